@@ -1,0 +1,204 @@
+/* pgb200.h -- C ABI of libpgb200.so: the B200 (sm_100a) hot paths of ProtGram-DirectGCN.
+ *
+ * The reference (iebeid/ProtGram-DirectGCN) is pure Python and has no FFI registry; the drop-in
+ * boundary is its Python class API.  Each entry point below replaces the *body* of the reference
+ * function cited next to it; the same-named Python classes under protgram-directgcn_b200/host/
+ * bind these with ctypes (see INTEGRATION.md for the stub a maintainer adds to the reference).
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (torch's allocator); the
+ *     library borrows it for the call, allocates nothing and keeps no global state.
+ *   - scratch is passed explicitly: (d_ws, ws_bytes); the matching *_ws_bytes() query is pure.
+ *   - `stream` is a cudaStream_t (passed as void*); every call is asynchronous on it.
+ *   - return 0 on success, a negative PG_E* code otherwise; pg_last_error() gives the
+ *     thread-local message.  There is no CPU fallback anywhere.
+ *
+ * Corpus buffer (input of hot path A): the byte string
+ *       [' ' only before global sequence #0]  seq_0 ' ' 0xFF  seq_1 ' ' 0xFF ...
+ *   i.e. each padded sequence of reference src/pipeline/data_builder.py:29-35 followed by one
+ *   separator byte PG_SEP.  Windows never contain a separator, so they never cross sequences
+ *   (data_builder.py:40-42,47-50); sequence bytes must be 7-bit ASCII.
+ *
+ * Dense n-gram tables: symbols are ranked by ascending byte value among the bytes present in
+ * the corpus (rank_of_byte), so the base-sigma number of an n-gram's ranks orders n-grams
+ * exactly like Python's sorted() on the strings (data_builder.py:164,172-173).
+ */
+#ifndef PGB200_H
+#define PGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_SEP 0xFF
+
+#define PG_OK 0
+#define PG_EINVAL (-1)   /* bad argument (size, alignment, null pointer)          */
+#define PG_ECUDA (-2)    /* a CUDA runtime call / kernel launch failed            */
+#define PG_EWORKSPACE (-3) /* workspace too small                                 */
+#define PG_ERANGE (-4)   /* table would not fit the index type (sigma^(n+1) etc.) */
+
+typedef void *pg_stream_t; /* cudaStream_t */
+
+int pg_version(void);
+const char *pg_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path A, part 1: n-gram transition counting
+ * ---------------------------------------------------------------------------------------- */
+
+/* Alphabet discovery: d_present256[b] = 1 for every byte value b != PG_SEP that occurs.
+ * (The reference's alphabet is data-defined: data_utils.py:207 upper-cases but never filters.)
+ * d_present256 must be zeroed by the caller (so shards can be OR-reduced across GPUs). */
+int pg_byte_presence(const uint8_t *d_buf, int64_t nbytes, uint32_t *d_present256, pg_stream_t stream);
+
+/* Synthetic protein-like corpus generated in place: nseq sequences of seq_len
+ * residues, residue (s, j) a pure function of (seed, first_seq + s, j) so any sharding sees the
+ * same corpus.  Layout = corpus buffer; bytes written = nseq*(seq_len+2) + leading_space. */
+int pg_synth_corpus(uint8_t *d_buf, int64_t first_seq, int64_t nseq, int seq_len, uint32_t seed,
+                    int leading_space, pg_stream_t stream);
+
+/* Replaces data_builder.py:45-54 (+ :203-220 text spill, :267-273 CSV re-parse + groupby.size()):
+ * for every separator-free window of n+1 bytes, d_bins[code(window)] += 1, where code is the
+ * base-sigma number of the n+1 symbol ranks.  d_bins has sigma^(n+1) uint64 entries and is
+ * ACCUMULATED into (zero it first; call once per corpus chunk / merge shards by summation).
+ * d_short_present (sigma^n bytes, caller-zeroed) receives a 1 for n-grams that occur only as a
+ * whole padded sequence of length exactly n (a node without any edge, data_builder.py:40 vs :47). */
+int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte,
+                   int sigma, unsigned long long *d_bins, uint8_t *d_short_present,
+                   pg_stream_t stream);
+
+/* Replaces data_builder.py:151-177 (distinct + sorted ids) and :281-286 (edge table).
+ * Step 1: d_sizes[0] = #nodes (distinct n-grams), d_sizes[1] = #unique transitions; also leaves
+ *         the node-id table and edge offsets in the workspace for step 2.
+ * Step 2: node codes (ascending = string order; id = position), and the edge table sorted by
+ *         (src, dst): exactly the coalesced row-major order of A_out_w (graph_utils.py:154). */
+size_t pg_graph_extract_ws_bytes(int n, int sigma);
+int pg_graph_extract_sizes(const unsigned long long *d_bins, const uint8_t *d_short_present, int n,
+                           int sigma, int64_t *d_sizes, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_graph_extract_fill(const unsigned long long *d_bins, int n, int sigma, int64_t num_nodes,
+                          int64_t num_edges, int64_t *d_node_code, int64_t *d_src, int64_t *d_dst,
+                          int64_t *d_count, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path A, part 2: adjacency + propagation matrices (graph_utils.py:140-287)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Stable LSD radix sort of 64-bit keys (low `key_bits` bits significant) carrying a 32-bit
+ * payload.  Result is left in d_keys / d_vals (the alt buffers are scratch). */
+size_t pg_sort_pairs_ws_bytes(int64_t n);
+int pg_sort_pairs(unsigned long long *d_keys, unsigned long long *d_keys_alt, uint32_t *d_vals,
+                  uint32_t *d_vals_alt, int64_t n, int key_bits, void *d_ws, size_t ws_bytes,
+                  pg_stream_t stream);
+
+/* Coalesce an arbitrary edge table (graph_utils.py:154 `.coalesce()`): sort by (src, dst) and
+ * sum duplicates.  d_sizes[0] receives the number of unique edges E'; outputs are written to
+ * the first E' slots of d_src_out/d_dst_out/d_w_out (each sized for `nnz`). */
+size_t pg_coo_coalesce_ws_bytes(int64_t nnz);
+int pg_coo_coalesce(const int64_t *d_src, const int64_t *d_dst, const float *d_w, int64_t nnz,
+                    int64_t num_nodes, int64_t *d_src_out, int64_t *d_dst_out, float *d_w_out,
+                    int64_t *d_sizes, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
+/* From the coalesced A_out_w (sorted, unique) build everything DirectedNgramGraph holds:
+ *   A_in_w            = A_out_w^T, coalesced                              (graph_utils.py:158)
+ *   shared pattern    = pattern(A) U pattern(A^T) U I, row-major sorted   (:173-195, :252-269)
+ *   mathcal_A_out/in  = sqrt(0.5*(An_ij^2 + An_ji^2) + eps) + [i==j],  An = D^-1 A   (:198-273)
+ *   A_undirected_norm = deg^-1/2 (sym(pattern) + I) deg^-1/2 with the reference's
+ *                       duplicate-self-loop semantics                      (:160-196)
+ * Step 1 sorts/merges and reports d_sizes[0] = P (pattern nnz); step 2 fills.
+ * d_rowptr is int64[num_nodes+1]; pattern columns are int32 (kernel format) -- the host side
+ * widens to the reference's int64 COO where that API is exposed. */
+size_t pg_normalize_ws_bytes(int64_t nnz, int64_t num_nodes);
+int pg_normalize_sizes(const int64_t *d_src, const int64_t *d_dst, const float *d_w, int64_t nnz,
+                       int64_t num_nodes, int64_t *d_sizes, void *d_ws, size_t ws_bytes,
+                       pg_stream_t stream);
+int pg_normalize_fill(const int64_t *d_src, const int64_t *d_dst, const float *d_w, int64_t nnz,
+                      int64_t num_nodes, float eps, int64_t pattern_nnz,
+                      int64_t *d_in_src, int64_t *d_in_dst, float *d_in_w,   /* A_in_w, nnz each */
+                      int64_t *d_rowptr, int32_t *d_col,                     /* shared pattern   */
+                      float *d_val_out, float *d_val_in, float *d_val_und,   /* P each           */
+                      void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
+/* CSR row pointers from sorted row ids; COO row ids from row pointers (int64 <-> CSR glue). */
+int pg_rowptr_from_sorted(const int64_t *d_rows, int64_t nnz, int64_t num_rows, int64_t *d_rowptr,
+                          pg_stream_t stream);
+int pg_coo_from_csr(const int64_t *d_rowptr, const int32_t *d_col, int64_t num_rows, int64_t nnz,
+                    int64_t *d_row_out, int64_t *d_col_out, pg_stream_t stream);
+
+/* Group an arbitrary edge list by one endpoint (the layer's general-edge-list contract,
+ * gnn_benchmarker.py:297-305): stable sort by `group` id -> CSR (rowptr, other endpoint, weight).
+ * d_w may be NULL (unweighted: protgram_directgcn.py:138-139) -> weights of 1. */
+size_t pg_edges_to_csr_ws_bytes(int64_t nnz);
+int pg_edges_to_csr(const int64_t *d_group, const int64_t *d_other, const float *d_w, int64_t nnz,
+                    int64_t num_nodes, int64_t *d_rowptr, int32_t *d_col, float *d_val,
+                    void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path B: DirectGCN propagation (protgram_directgcn.py:93-140) forward and backward
+ * ---------------------------------------------------------------------------------------- */
+
+/* Fan-out SpMM (forward aggregation): for v < nv:
+ *     Z[i, v*F : (v+1)*F] = sum_k val_v[k] * X[col[k], :]      k in row i of the shared CSR
+ * nv = 3 with one shared pattern is the fused dual-direction + undirected propagate
+ * (A_in X | A_out X | U X gathered once); nv = 1 is one propagate on its own CSR.
+ * X is [num_cols x F] with row stride ldx, Z is [num_rows x *] with row stride ldz; the nv
+ * output segments start at column z_off + v*F. */
+int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
+                   const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
+                   const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
+                   pg_stream_t stream);
+
+/* Fan-in SpMM (backward of the above over the transposed structure; forward of nothing else):
+ *     Y[i, :] = (d_init ? init[i, :] : 0) + sum_v sum_k val_v[k] * G[col[k], g_off + v*F : +F]
+ * With the symmetric shared pattern of reference-built graphs the transposed structure is the
+ * structure itself; general edge lists pass the CSR grouped by source. */
+int pg_spmm_fanin(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
+                  const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
+                  const float *d_g, int64_t ldg, int64_t g_off, const float *d_init, int64_t ldinit,
+                  float *d_y, int64_t ldy, int accumulate, pg_stream_t stream);
+
+/* Fused dense transform of one DirectGCN layer (the collapsed algebra of SURVEY.md 7.2):
+ *   A_ext[i, :] = [ a_i*Z_in[i] | b_i*Z_out[i] | c_i*Z_und[i] | X[i] (if has_res) | a_i b_i c_i | 1 (if has_res) ]
+ *   Y = A_ext @ W_ext (+ X if add_identity) + constant[i]        W_ext: [K_ext x F_out] row-major
+ *   H = leaky_relu(Y, slope) if slope != 1 else Y
+ * gates a,b,c are per-row vectors (gate_stride = 1) or scalars broadcast (gate_stride = 0).
+ * K_ext = 3*F_in + (has_res ? F_in : 0) + 3 + (has_res ? 1 : 0). */
+int pg_layer_gemm_fwd(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx,
+                      const float *d_gate_a, const float *d_gate_b, const float *d_gate_c,
+                      int gate_stride, const float *d_w_ext, const float *d_constant,
+                      int64_t ldconst, int64_t num_rows, int F_in, int F_out, int has_res,
+                      int add_identity, float slope, float *d_h, int64_t ldh, pg_stream_t stream);
+
+/* dY = dH * leaky_relu'(H)   (elementwise; also the gradient of `constant`). */
+int pg_lrelu_bwd(const float *d_dh, const float *d_h, float slope, int64_t numel, float *d_dy,
+                 pg_stream_t stream);
+
+/* dA = dY @ W_ext[:K_data]^T, then split: for the three Z segments
+ *     dgate_v[i] = <dA_v[i], Z_v[i]> + <dY[i], beta_v>,   dZ_v[i] = gate_v[i] * dA_v[i]
+ * and the residual segment (if has_res) goes to d_dxres.  Scalar gates (gate_stride 0) still
+ * get per-row dgate values; the host sums them. */
+int pg_layer_gemm_bwd_data(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z,
+                           int64_t ldz, const float *d_gate_a, const float *d_gate_b,
+                           const float *d_gate_c, int gate_stride, int64_t num_rows, int F_in,
+                           int F_out, int has_res, float *d_dz, int64_t lddz, float *d_dxres,
+                           int64_t lddxres, float *d_dgate /* [3 x num_rows] */, pg_stream_t stream);
+
+/* dW_ext = A_ext^T @ dY   ([K_ext x F_out]; split over rows, reduced deterministically). */
+size_t pg_layer_gemm_bwd_weight_ws_bytes(int64_t num_rows, int F_in, int F_out, int has_res);
+int pg_layer_gemm_bwd_weight(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx,
+                             const float *d_gate_a, const float *d_gate_b, const float *d_gate_c,
+                             int gate_stride, const float *d_dy, int64_t lddy, int64_t num_rows,
+                             int F_in, int F_out, int has_res, float *d_dw_ext, void *d_ws,
+                             size_t ws_bytes, pg_stream_t stream);
+
+/* Row-wise L2 normalisation  out = h / (||h||_2 + eps)   (models_utils.py:139-147). */
+int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_rows, int F, float eps,
+                         float *d_out, int64_t ldout, pg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB200_H */

@@ -1,0 +1,125 @@
+"""ctypes binding of libpgb200.so (include/pgb200.h).  No fallback: if the library is missing or
+there is no CUDA device, every hot-path call raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgb200.so")
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_P = c_void_p
+_SIGS = {
+    "pg_version": (c_int, []),
+    "pg_last_error": (c_char_p, []),
+    "pg_byte_presence": (c_int, [_P, c_int64, _P, _P]),
+    "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
+    "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
+    "pg_graph_extract_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pg_graph_extract_sizes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pg_graph_extract_fill": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pg_sort_pairs_ws_bytes": (c_size_t, [c_int64]),
+    "pg_sort_pairs": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "pg_coo_coalesce_ws_bytes": (c_size_t, [c_int64]),
+    "pg_coo_coalesce": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pg_normalize_ws_bytes": (c_size_t, [c_int64, c_int64]),
+    "pg_normalize_sizes": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "pg_normalize_fill": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, c_size_t, _P]),
+    "pg_rowptr_from_sorted": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "pg_coo_from_csr": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
+    "pg_edges_to_csr_ws_bytes": (c_size_t, [c_int64]),
+    "pg_edges_to_csr": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "pg_spmm_fanout": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P]),
+    "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
+                              c_int64, c_int, _P]),
+    "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
+                                  c_int, c_int, c_int, c_float, _P, c_int64, _P]),
+    "pg_lrelu_bwd": (c_int, [_P, _P, c_float, c_int64, _P, _P]),
+    "pg_layer_gemm_bwd_data": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, c_int64, c_int, c_int,
+                                       c_int, _P, c_int64, _P, c_int64, _P, _P]),
+    "pg_layer_gemm_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "pg_layer_gemm_bwd_weight": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int,
+                                         c_int, c_int, _P, _P, c_size_t, _P]),
+    "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
+}
+
+_lib = None
+launches = 0  # number of C-ABI calls that enqueue GPU work (bench.py reports it)
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """Load the shared library (does not need a GPU).  Raises NativeError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python protgram-directgcn_b200/build.py` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise NativeError("protgram-directgcn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def current_device() -> torch.device:
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def check_tensor(t: torch.Tensor, what: str = "input"):
+    """Hot-path inputs must live on the GPU: there is no CPU implementation to fall back to."""
+    if not t.is_cuda:
+        raise NativeError(f"{what} must be a CUDA tensor: the CUDA path has no CPU fallback")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor")
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; raise NativeError with pg_last_error() on failure."""
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise NativeError(f"{name} failed ({rc}): {lib.pg_last_error().decode()}")
+    launches += 1
+    return rc
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

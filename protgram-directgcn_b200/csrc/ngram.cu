@@ -1,0 +1,330 @@
+// Hot path A, part 1: residue n-grams -> dense transition table -> node ids + edge table.
+//
+// Replaces the per-residue Python of reference src/pipeline/data_builder.py:38-54 and the
+// Dask distinct()/groupby().size() of :151-177,267-273.  An edge IS an (n+1)-gram
+// (window i -> window i+1), so transition counting is an (n+1)-gram histogram over the
+// corpus buffer; node ids are ranks of present n-grams in base-sigma (= string) order.
+//
+// HBM traffic: 1 B/residue read (16 B vector loads, fully coalesced); the table updates are
+// L2 atomics (RED.ADD.64), which is the real limiter -- see DESIGN.md "count kernel".
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ alphabet discovery
+__global__ void __launch_bounds__(256) byte_presence_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
+                                                            uint32_t *__restrict__ present256) {
+    __shared__ uint32_t seen[256];
+    seen[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t nvec = nbytes / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(buf);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 q = v[i];
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            seen[w[k] & 0xFF] = 1;
+            seen[(w[k] >> 8) & 0xFF] = 1;
+            seen[(w[k] >> 16) & 0xFF] = 1;
+            seen[w[k] >> 24] = 1;
+        }
+    }
+    if (blockIdx.x == 0) {  // tail bytes
+        for (int64_t i = nvec * 16 + threadIdx.x; i < nbytes; i += blockDim.x) seen[buf[i]] = 1;
+    }
+    __syncthreads();
+    if (seen[threadIdx.x] && threadIdx.x != PG_SEP) present256[threadIdx.x] = 1;
+}
+
+// ------------------------------------------------------------------ synthetic corpus
+__constant__ uint32_t kAaCum16[20] = {5408,  6308,  9885,  14308, 16838, 21473, 22961, 26847, 30662, 37140,
+                                      38723, 41383, 44486, 47063, 50689, 54995, 58502, 63002, 63720, 65536};
+__constant__ char kAa[21] = "ACDEFGHIKLMNPQRSTVWY";
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) synth_corpus_kernel(uint8_t *__restrict__ buf, int64_t first_seq, int64_t nseq,
+                                                           int seq_len, uint32_t seed, int leading_space) {
+    const int64_t stride = seq_len + 2;
+    const int64_t total = nseq * stride;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / stride;
+        const int j = (int)(t - s * stride);
+        uint8_t out;
+        if (j == seq_len) out = ' ';
+        else if (j == seq_len + 1) out = PG_SEP;
+        else {
+            const unsigned long long g = (unsigned long long)(first_seq + s) * (unsigned long long)seq_len + j;
+            const uint32_t h = mix32((uint32_t)g ^ mix32((uint32_t)(g >> 32) ^ seed) ^ 0x9E3779B9u);
+            const uint32_t u = h >> 16;
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < 20; ++k) idx += (kAaCum16[k] <= u);
+            out = (uint8_t)kAa[idx];
+        }
+        buf[t + leading_space] = out;
+    }
+    if (leading_space && blockIdx.x == 0 && threadIdx.x == 0) buf[0] = ' ';
+}
+
+// ------------------------------------------------------------------ (n+1)-gram count
+// One thread owns the 16 windows that END in its 16-byte vector; the M-1 bytes of look-back
+// come from the previous vector (an L1 hit: the neighbouring thread loads it as its own).
+// The window code rolls: code = code*sigma + r_new - r_old*sigma^M, exact modulo 2^32 because
+// the true value is < sigma^M <= 2^32.
+template <int M>
+__global__ void __launch_bounds__(256) ngram_count_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
+                                                          const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
+                                                          uint32_t sigma_pow_m, uint32_t sigma_pow_n,
+                                                          unsigned long long *__restrict__ bins,
+                                                          uint8_t *__restrict__ short_present) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = rank_of_byte[threadIdx.x];
+    __syncthreads();
+    constexpr int LB = M - 1;  // look-back bytes (= n)
+    const int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p0 = vec * 16;
+    if (p0 >= nbytes) return;
+
+    uint8_t b[LB + 16];
+    {
+        uint32_t w[6];  // prev.z prev.w cur.x cur.y cur.z cur.w
+        if (p0 + 16 <= nbytes) {
+            const uint4 cur = *reinterpret_cast<const uint4 *>(buf + p0);
+            w[2] = cur.x; w[3] = cur.y; w[4] = cur.z; w[5] = cur.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int64_t i = p0 + k * 4 + t;
+                    x |= (uint32_t)(i < nbytes ? buf[i] : (uint8_t)PG_SEP) << (8 * t);
+                }
+                w[2 + k] = x;
+            }
+        }
+        if (p0 > 0) {
+            const uint2 prev = *reinterpret_cast<const uint2 *>(buf + p0 - 8);
+            w[0] = prev.x; w[1] = prev.y;
+        } else {
+            w[0] = w[1] = 0xFFFFFFFFu;  // before the buffer = separator
+        }
+#pragma unroll
+        for (int i = 0; i < LB + 16; ++i) {
+            const int pos = 8 - LB + i;  // byte index inside w[]
+            b[i] = (uint8_t)(w[pos >> 2] >> (8 * (pos & 3)));
+        }
+    }
+    uint32_t r[LB + 16];
+#pragma unroll
+    for (int i = 0; i < LB + 16; ++i) r[i] = lut[b[i]];
+
+    uint32_t code = 0;
+    int run = 0;
+#pragma unroll
+    for (int i = 0; i < LB + 16; ++i) {
+        code = code * sigma + r[i];
+        if (i >= M) code -= r[i - M] * sigma_pow_m;
+        run = (b[i] == PG_SEP) ? 0 : min(run + 1, M);
+        if (i >= LB) {
+            if (run == M) {
+                atomicAdd(&bins[code], 1ull);
+            } else if (run == LB) {
+                // a whole padded sequence of exactly n bytes ends here unless more follows
+                const int64_t q = p0 + (i - LB);
+                const uint8_t nxt = (q + 1 < nbytes) ? buf[q + 1] : (uint8_t)PG_SEP;
+                if (nxt == PG_SEP) short_present[code % sigma_pow_n] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ table -> ids / edges
+__global__ void __launch_bounds__(256) mark_present_kernel(const unsigned long long *__restrict__ bins, int64_t nbins,
+                                                           uint32_t sigma, uint32_t sigma_pow_n,
+                                                           int64_t *__restrict__ present, int64_t *__restrict__ edge_flag) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (int64_t)gridDim.x * blockDim.x) {
+        const bool nz = bins[k] != 0ull;
+        edge_flag[k] = nz ? 1 : 0;
+        if (nz) {
+            present[k / sigma] = 1;        // source n-gram  = leading n symbols
+            present[k % sigma_pow_n] = 1;  // target n-gram  = trailing n symbols
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) widen_flags_kernel(const uint8_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) emit_nodes_kernel(const int64_t *__restrict__ present, const int64_t *__restrict__ node_id,
+                                                         int64_t ngrams, int64_t *__restrict__ node_code) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngrams; g += (int64_t)gridDim.x * blockDim.x)
+        if (present[g]) node_code[node_id[g]] = g;
+}
+
+__global__ void __launch_bounds__(256) emit_edges_kernel(const unsigned long long *__restrict__ bins, int64_t nbins,
+                                                         const int64_t *__restrict__ edge_off, const int64_t *__restrict__ node_id,
+                                                         uint32_t sigma, uint32_t sigma_pow_n, int64_t *__restrict__ src,
+                                                         int64_t *__restrict__ dst, int64_t *__restrict__ count) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = bins[k];
+        if (c) {
+            const int64_t e = edge_off[k];
+            src[e] = node_id[k / sigma];
+            dst[e] = node_id[k % sigma_pow_n];
+            count[e] = (int64_t)c;
+        }
+    }
+}
+
+inline unsigned grid_for(int64_t n, int threads = 256, int per_sm = 8) {
+    int64_t want = pg_ceil_div(n, threads);
+    int64_t cap = (int64_t)PG_NUM_SMS * per_sm;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+bool table_sizes(int n, int sigma, int64_t *pow_n, int64_t *pow_m) {
+    if (n < 1 || n > 6 || sigma < 1 || sigma > 255) return false;
+    int64_t p = 1;
+    for (int k = 0; k < n; ++k) p *= sigma;
+    *pow_n = p;
+    *pow_m = p * sigma;
+    return *pow_m <= (1ll << 32);
+}
+
+struct ExtractWs {
+    int64_t *present, *node_id, *edge_off;
+    void *scan_ws;
+    size_t scan_bytes;
+};
+
+bool carve_extract(void *d_ws, size_t ws_bytes, int64_t pow_n, int64_t pow_m, ExtractWs *w) {
+    PgArena a(d_ws, ws_bytes);
+    w->present = a.take<int64_t>((size_t)pow_n);
+    w->node_id = a.take<int64_t>((size_t)pow_n);
+    w->edge_off = a.take<int64_t>((size_t)pow_m);
+    w->scan_bytes = pg_scan_ws_bytes(pow_m);
+    w->scan_ws = a.take<char>(w->scan_bytes);
+    return a.ok;
+}
+}  // namespace
+
+extern "C" int pg_byte_presence(const uint8_t *d_buf, int64_t nbytes, uint32_t *d_present256, pg_stream_t stream) {
+    PG_CHECK_ARG(d_buf && d_present256 && nbytes >= 0, "pg_byte_presence: bad arguments");
+    PG_CHECK_ARG(((uintptr_t)d_buf & 15) == 0, "pg_byte_presence: d_buf must be 16-byte aligned");
+    if (nbytes == 0) return PG_OK;
+    byte_presence_kernel<<<grid_for(nbytes / 16 + 1), 256, 0, pg_cu(stream)>>>(d_buf, nbytes, d_present256);
+    PG_CUDA_LAUNCH_CHECK("byte_presence_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_synth_corpus(uint8_t *d_buf, int64_t first_seq, int64_t nseq, int seq_len, uint32_t seed,
+                               int leading_space, pg_stream_t stream) {
+    PG_CHECK_ARG(d_buf && nseq >= 0 && seq_len >= 1 && first_seq >= 0, "pg_synth_corpus: bad arguments");
+    if (nseq == 0) return PG_OK;
+    synth_corpus_kernel<<<grid_for(nseq * (seq_len + 2), 256, 16), 256, 0, pg_cu(stream)>>>(
+        d_buf, first_seq, nseq, seq_len, seed, leading_space ? 1 : 0);
+    PG_CUDA_LAUNCH_CHECK("synth_corpus_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte, int sigma,
+                              unsigned long long *d_bins, uint8_t *d_short_present, pg_stream_t stream) {
+    int64_t pow_n, pow_m;
+    PG_CHECK_ARG(d_buf && d_rank_of_byte && d_bins && d_short_present && nbytes >= 0, "pg_ngram_count: null/negative argument");
+    PG_CHECK_ARG(((uintptr_t)d_buf & 15) == 0, "pg_ngram_count: d_buf must be 16-byte aligned");
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) {
+        pg_set_error("pg_ngram_count: table sigma^(n+1) out of range (n=%d sigma=%d; need 1<=n<=6, sigma^(n+1)<=2^32)", n, sigma);
+        return PG_ERANGE;
+    }
+    if (nbytes == 0) return PG_OK;
+    const int64_t nvec = pg_ceil_div(nbytes, 16);
+    const unsigned grid = (unsigned)pg_ceil_div(nvec, 256);
+    const uint32_t s = (uint32_t)sigma, pm = (uint32_t)pow_m /* wraps to 0 only at exactly 2^32 */, pn = (uint32_t)pow_n;
+    cudaStream_t st = pg_cu(stream);
+#define PG_LAUNCH_COUNT(M) \
+    ngram_count_kernel<M><<<grid, 256, 0, st>>>(d_buf, nbytes, d_rank_of_byte, s, pm, pn, d_bins, d_short_present)
+    switch (n + 1) {
+        case 2: PG_LAUNCH_COUNT(2); break;
+        case 3: PG_LAUNCH_COUNT(3); break;
+        case 4: PG_LAUNCH_COUNT(4); break;
+        case 5: PG_LAUNCH_COUNT(5); break;
+        case 6: PG_LAUNCH_COUNT(6); break;
+        case 7: PG_LAUNCH_COUNT(7); break;
+        default: pg_set_error("pg_ngram_count: unsupported n=%d", n); return PG_EINVAL;
+    }
+#undef PG_LAUNCH_COUNT
+    PG_CUDA_LAUNCH_CHECK("ngram_count_kernel");
+    return PG_OK;
+}
+
+extern "C" size_t pg_graph_extract_ws_bytes(int n, int sigma) {
+    int64_t pow_n, pow_m;
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) return 0;
+    return pg_align_up((size_t)pow_n * 8, 256) * 2 + pg_align_up((size_t)pow_m * 8, 256) +
+           pg_align_up(pg_scan_ws_bytes(pow_m), 256) + 1024;
+}
+
+extern "C" int pg_graph_extract_sizes(const unsigned long long *d_bins, const uint8_t *d_short_present, int n, int sigma,
+                                      int64_t *d_sizes, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    int64_t pow_n, pow_m;
+    PG_CHECK_ARG(d_bins && d_short_present && d_sizes && d_ws, "pg_graph_extract_sizes: null argument");
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) {
+        pg_set_error("pg_graph_extract_sizes: table out of range (n=%d sigma=%d)", n, sigma);
+        return PG_ERANGE;
+    }
+    ExtractWs w;
+    if (!carve_extract(d_ws, ws_bytes, pow_n, pow_m, &w)) {
+        pg_set_error("pg_graph_extract_sizes: workspace too small (%zu < %zu)", ws_bytes, pg_graph_extract_ws_bytes(n, sigma));
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    widen_flags_kernel<<<grid_for(pow_n), 256, 0, st>>>(d_short_present, pow_n, w.present);
+    PG_CUDA_LAUNCH_CHECK("widen_flags_kernel");
+    mark_present_kernel<<<grid_for(pow_m), 256, 0, st>>>(d_bins, pow_m, (uint32_t)sigma, (uint32_t)pow_n, w.present, w.edge_off);
+    PG_CUDA_LAUNCH_CHECK("mark_present_kernel");
+    int rc = pg_exclusive_scan_i64(w.present, w.node_id, pow_n, d_sizes + 0, w.scan_ws, w.scan_bytes, st);
+    if (rc != PG_OK) return rc;
+    rc = pg_exclusive_scan_i64(w.edge_off, w.edge_off, pow_m, d_sizes + 1, w.scan_ws, w.scan_bytes, st);
+    return rc;
+}
+
+extern "C" int pg_graph_extract_fill(const unsigned long long *d_bins, int n, int sigma, int64_t num_nodes, int64_t num_edges,
+                                     int64_t *d_node_code, int64_t *d_src, int64_t *d_dst, int64_t *d_count, void *d_ws,
+                                     size_t ws_bytes, pg_stream_t stream) {
+    int64_t pow_n, pow_m;
+    PG_CHECK_ARG(d_bins && d_ws && num_nodes >= 0 && num_edges >= 0, "pg_graph_extract_fill: bad argument");
+    PG_CHECK_ARG(num_nodes == 0 || d_node_code, "pg_graph_extract_fill: null node output");
+    PG_CHECK_ARG(num_edges == 0 || (d_src && d_dst && d_count), "pg_graph_extract_fill: null edge output");
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) {
+        pg_set_error("pg_graph_extract_fill: table out of range (n=%d sigma=%d)", n, sigma);
+        return PG_ERANGE;
+    }
+    ExtractWs w;
+    if (!carve_extract(d_ws, ws_bytes, pow_n, pow_m, &w)) {
+        pg_set_error("pg_graph_extract_fill: workspace too small");
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    if (num_nodes > 0) {
+        emit_nodes_kernel<<<grid_for(pow_n), 256, 0, st>>>(w.present, w.node_id, pow_n, d_node_code);
+        PG_CUDA_LAUNCH_CHECK("emit_nodes_kernel");
+    }
+    if (num_edges > 0) {
+        emit_edges_kernel<<<grid_for(pow_m), 256, 0, st>>>(d_bins, pow_m, w.edge_off, w.node_id, (uint32_t)sigma,
+                                                            (uint32_t)pow_n, d_src, d_dst, d_count);
+        PG_CUDA_LAUNCH_CHECK("emit_edges_kernel");
+    }
+    return PG_OK;
+}

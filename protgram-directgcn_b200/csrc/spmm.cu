@@ -1,0 +1,325 @@
+// Hot path B: the propagate() of DirectGCNLayer (reference src/models/protgram_directgcn.py:
+// 101-112,137-140) as CSR SpMM.  The reference runs 6 gather -> scale -> scatter_add passes
+// that each materialise an [E, F] temporary; here one pass gathers each neighbour row ONCE and
+// applies up to three edge values (A_in | A_out | U share one sparsity pattern on
+// reference-built graphs).
+//
+//   fan-out  Z[i, v*F:(v+1)*F] = sum_k val_v[k] * X[col[k], :]            (forward)
+//   fan-in   Y[i, :]           = init[i,:] + sum_v sum_k val_v[k] * G[col[k], v*F:(v+1)*F]   (backward)
+//
+// Mapping: a group of LPR lanes owns one row; every lane holds CHUNKS float4 of the feature
+// row (128-bit loads).  The group stages LPR (col, val) entries with one coalesced load each
+// and broadcasts them with width-limited shuffles, so index traffic is read once per row.
+// Accumulation order is the CSR order within the row -> bitwise reproducible run to run.
+// HBM-bound: algorithmic bytes per nnz = 4 (col) + 4*nv (vals) + 4*F (row gather when X is
+// not L2 resident); see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void fma4(float4 &acc, float s, const float4 &x) {
+    acc.x = fmaf(s, x.x, acc.x);
+    acc.y = fmaf(s, x.y, acc.y);
+    acc.z = fmaf(s, x.z, acc.z);
+    acc.w = fmaf(s, x.w, acc.w);
+}
+
+template <int NV, int LPR, int CHUNKS>
+__global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                          const float *__restrict__ val0, const float *__restrict__ val1,
+                                                          const float *__restrict__ val2, int64_t num_rows, int F,
+                                                          const float *__restrict__ x, int64_t ldx, float *__restrict__ z,
+                                                          int64_t ldz, int64_t z_off) {
+    constexpr int UNROLL = (CHUNKS == 1) ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (LPR - 1);                       // lane inside the row group
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    if (row >= num_rows) return;
+    const int nvec = F >> 2;                               // float4 per feature row
+    float4 acc[NV][CHUNKS];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) acc[v][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int64_t rb = rowptr[row], re = rowptr[row + 1];
+    for (int64_t base = rb; base < re; base += LPR) {
+        const int cnt = (int)min((int64_t)LPR, re - base);
+        int my_col = 0;
+        float my_v[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) my_v[v] = 0.f;
+        if (lg < cnt) {
+            my_col = col[base + lg];
+            my_v[0] = val0[base + lg];
+            if (NV > 1) my_v[1] = val1[base + lg];
+            if (NV > 2) my_v[NV - 1] = val2[base + lg];
+        }
+        int t = 0;
+        for (; t + UNROLL <= cnt; t += UNROLL) {
+            int c_[UNROLL];
+            float s_[UNROLL][NV];
+            float4 xr[UNROLL][CHUNKS];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                c_[u] = __shfl_sync(gmask, my_col, t + u, LPR);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s_[u][v] = __shfl_sync(gmask, my_v[v], t + u, LPR);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float4 *xp = reinterpret_cast<const float4 *>(x + (int64_t)c_[u] * ldx);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    const int f4 = lg + c * LPR;
+                    xr[u][c] = (f4 < nvec) ? __ldg(xp + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) fma4(acc[v][c], s_[u][v], xr[u][c]);
+        }
+        for (; t < cnt; ++t) {
+            const int cc = __shfl_sync(gmask, my_col, t, LPR);
+            float s[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) s[v] = __shfl_sync(gmask, my_v[v], t, LPR);
+            const float4 *xp = reinterpret_cast<const float4 *>(x + (int64_t)cc * ldx);
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int f4 = lg + c * LPR;
+                if (f4 < nvec) {
+                    const float4 xv = __ldg(xp + f4);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) fma4(acc[v][c], s[v], xv);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        float4 *zp = reinterpret_cast<float4 *>(z + row * ldz + z_off + (int64_t)v * F);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int f4 = lg + c * LPR;
+            if (f4 < nvec) zp[f4] = acc[v][c];
+        }
+    }
+}
+
+template <int NV, int LPR, int CHUNKS>
+__global__ void __launch_bounds__(256) spmm_fanin_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                         const float *__restrict__ val0, const float *__restrict__ val1,
+                                                         const float *__restrict__ val2, int64_t num_rows, int F,
+                                                         const float *__restrict__ g, int64_t ldg, int64_t g_off,
+                                                         const float *__restrict__ init, int64_t ldinit, float *__restrict__ y,
+                                                         int64_t ldy, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (LPR - 1);
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    if (row >= num_rows) return;
+    const int nvec = F >> 2;
+    float4 acc[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int f4 = lg + c * LPR;
+        acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f4 < nvec) {
+            if (init) acc[c] = __ldg(reinterpret_cast<const float4 *>(init + row * ldinit) + f4);
+            if (accumulate) {
+                const float4 o = reinterpret_cast<const float4 *>(y + row * ldy)[f4];
+                acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+            }
+        }
+    }
+    const int64_t rb = rowptr[row], re = rowptr[row + 1];
+    for (int64_t base = rb; base < re; base += LPR) {
+        const int cnt = (int)min((int64_t)LPR, re - base);
+        int my_col = 0;
+        float my_v[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) my_v[v] = 0.f;
+        if (lg < cnt) {
+            my_col = col[base + lg];
+            my_v[0] = val0[base + lg];
+            if (NV > 1) my_v[1] = val1[base + lg];
+            if (NV > 2) my_v[NV - 1] = val2[base + lg];
+        }
+        int t = 0;
+        for (; t + 2 <= cnt; t += 2) {
+            int c_[2];
+            float s_[2][NV];
+            float4 gr[2][NV][CHUNKS];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                c_[u] = __shfl_sync(gmask, my_col, t + u, LPR);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s_[u][v] = __shfl_sync(gmask, my_v[v], t + u, LPR);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 *gp = reinterpret_cast<const float4 *>(g + (int64_t)c_[u] * ldg + g_off + (int64_t)v * F);
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) {
+                        const int f4 = lg + c * LPR;
+                        gr[u][v][c] = (f4 < nvec) ? __ldg(gp + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) fma4(acc[c], s_[u][v], gr[u][v][c]);
+        }
+        for (; t < cnt; ++t) {
+            const int cc = __shfl_sync(gmask, my_col, t, LPR);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float s = __shfl_sync(gmask, my_v[v], t, LPR);
+                const float4 *gp = reinterpret_cast<const float4 *>(g + (int64_t)cc * ldg + g_off + (int64_t)v * F);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    const int f4 = lg + c * LPR;
+                    if (f4 < nvec) fma4(acc[c], s, __ldg(gp + f4));
+                }
+            }
+        }
+    }
+    float4 *yp = reinterpret_cast<float4 *>(y + row * ldy);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int f4 = lg + c * LPR;
+        if (f4 < nvec) yp[f4] = acc[c];
+    }
+}
+
+// Generic scalar kernels: any F / any alignment (one warp per row, lanes stride the features).
+template <int NV>
+__global__ void __launch_bounds__(256) spmm_fanout_scalar_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                                 const float *__restrict__ val0, const float *__restrict__ val1,
+                                                                 const float *__restrict__ val2, int64_t num_rows, int F,
+                                                                 const float *__restrict__ x, int64_t ldx, float *__restrict__ z,
+                                                                 int64_t ldz, int64_t z_off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= num_rows) return;
+    const int64_t rb = rowptr[row], re = rowptr[row + 1];
+    for (int f = lane; f < F; f += 32) {
+        float acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+        for (int64_t k = rb; k < re; ++k) {
+            const float xv = x[(int64_t)col[k] * ldx + f];
+            acc[0] = fmaf(val0[k], xv, acc[0]);
+            if (NV > 1) acc[1] = fmaf(val1[k], xv, acc[1]);
+            if (NV > 2) acc[NV - 1] = fmaf(val2[k], xv, acc[NV - 1]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) z[row * ldz + z_off + (int64_t)v * F + f] = acc[v];
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) spmm_fanin_scalar_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                                const float *__restrict__ val0, const float *__restrict__ val1,
+                                                                const float *__restrict__ val2, int64_t num_rows, int F,
+                                                                const float *__restrict__ g, int64_t ldg, int64_t g_off,
+                                                                const float *__restrict__ init, int64_t ldinit, float *__restrict__ y,
+                                                                int64_t ldy, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= num_rows) return;
+    const int64_t rb = rowptr[row], re = rowptr[row + 1];
+    for (int f = lane; f < F; f += 32) {
+        float acc = init ? init[row * ldinit + f] : 0.f;
+        if (accumulate) acc += y[row * ldy + f];
+        for (int64_t k = rb; k < re; ++k) {
+            const float *gp = g + (int64_t)col[k] * ldg + g_off + f;
+            acc = fmaf(val0[k], gp[0], acc);
+            if (NV > 1) acc = fmaf(val1[k], gp[F], acc);
+            if (NV > 2) acc = fmaf(val2[k], gp[2 * (int64_t)F], acc);
+        }
+        y[row * ldy + f] = acc;
+    }
+}
+
+inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// pick the row-group width: smallest power of two >= F/4, capped at 32 lanes x 4 chunks (F <= 512)
+inline bool pick_shape(int F, int *lpr, int *chunks) {
+    if (F % 4 != 0 || F > 512 || F < 4) return false;
+    const int nvec = F / 4;
+    int l = 4;
+    while (l < nvec && l < 32) l <<= 1;
+    int c = (nvec + l - 1) / l;
+    if (c == 3) c = 4;
+    *lpr = l;
+    *chunks = c;
+    return true;
+}
+}  // namespace
+
+#define PG_SPMM_DISPATCH(KERNEL, NV, ...)                                                             \
+    do {                                                                                              \
+        const unsigned grid = (unsigned)pg_ceil_div(num_rows * lpr, 256);                             \
+        if (lpr == 4) KERNEL<NV, 4, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                            \
+        else if (lpr == 8) KERNEL<NV, 8, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                       \
+        else if (lpr == 16) KERNEL<NV, 16, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                     \
+        else if (chunks == 1) KERNEL<NV, 32, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                   \
+        else if (chunks == 2) KERNEL<NV, 32, 2><<<grid, 256, 0, st>>>(__VA_ARGS__);                   \
+        else KERNEL<NV, 32, 4><<<grid, 256, 0, st>>>(__VA_ARGS__);                                    \
+    } while (0)
+
+extern "C" int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
+                              const float *d_val2, int nv, int64_t num_rows, int F, const float *d_x, int64_t ldx, float *d_z,
+                              int64_t ldz, int64_t z_off, pg_stream_t stream) {
+    cudaStream_t st = pg_cu(stream);
+    PG_CHECK_ARG(nv == 1 || nv == 3, "pg_spmm_fanout: nv must be 1 or 3 (got %d)", nv);
+    PG_CHECK_ARG(num_rows >= 0 && F >= 1 && ldx >= F && ldz >= z_off + (int64_t)nv * F && z_off >= 0, "pg_spmm_fanout: bad shape");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_rowptr && d_col && d_val0 && d_x && d_z && (nv == 1 || (d_val1 && d_val2)), "pg_spmm_fanout: null buffer");
+    int lpr = 0, chunks = 0;
+    const bool vec = pick_shape(F, &lpr, &chunks) && aligned16(d_x) && aligned16(d_z) && ldx % 4 == 0 && ldz % 4 == 0 && z_off % 4 == 0;
+    if (vec) {
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+    } else {
+        const unsigned grid = (unsigned)pg_ceil_div(num_rows * 32, 256);
+        if (nv == 3) spmm_fanout_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        else spmm_fanout_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+    }
+    PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_spmm_fanin(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
+                             const float *d_val2, int nv, int64_t num_rows, int F, const float *d_g, int64_t ldg, int64_t g_off,
+                             const float *d_init, int64_t ldinit, float *d_y, int64_t ldy, int accumulate, pg_stream_t stream) {
+    cudaStream_t st = pg_cu(stream);
+    PG_CHECK_ARG(nv == 1 || nv == 3, "pg_spmm_fanin: nv must be 1 or 3 (got %d)", nv);
+    PG_CHECK_ARG(num_rows >= 0 && F >= 1 && ldg >= g_off + (int64_t)nv * F && g_off >= 0 && ldy >= F, "pg_spmm_fanin: bad shape");
+    PG_CHECK_ARG(!d_init || ldinit >= F, "pg_spmm_fanin: bad init stride");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_rowptr && d_col && d_val0 && d_g && d_y && (nv == 1 || (d_val1 && d_val2)), "pg_spmm_fanin: null buffer");
+    int lpr = 0, chunks = 0;
+    const bool vec = pick_shape(F, &lpr, &chunks) && aligned16(d_g) && aligned16(d_y) && ldg % 4 == 0 && ldy % 4 == 0 &&
+                     g_off % 4 == 0 && (!d_init || (aligned16(d_init) && ldinit % 4 == 0));
+    if (vec) {
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+    } else {
+        const unsigned grid = (unsigned)pg_ceil_div(num_rows * 32, 256);
+        if (nv == 3) spmm_fanin_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        else spmm_fanin_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+    }
+    PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel");
+    return PG_OK;
+}

@@ -1,0 +1,69 @@
+"""Host-side corpus packing for hot path A: padded sequences -> the byte buffer the count kernel
+reads (include/pgb200.h, "corpus buffer"), the data-defined alphabet, and node-name decoding."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+
+SEP = 0xFF
+
+
+def pack_sequences(seqs: Sequence[str], global_first: bool = True) -> np.ndarray:
+    """seq_i -> [' ' if global sequence #0] seq_i ' ' 0xFF  (reference data_builder.py:29-35,97-102).
+    Raises ValueError for non-ASCII text (the reference windows per code point; the byte kernel
+    cannot reproduce that, so it refuses rather than silently diverging)."""
+    parts: List[bytes] = []
+    for i, s in enumerate(seqs):
+        try:
+            b = s.encode("ascii")
+        except UnicodeEncodeError as exc:
+            raise ValueError(f"sequence {i} holds non-ASCII characters; unsupported on the CUDA path") from exc
+        parts.append((b" " if (i == 0 and global_first) else b"") + b + b" \xff")
+    buf = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    return buf
+
+
+def to_device(buf: np.ndarray, device) -> torch.Tensor:
+    """Pinned staging + async H2D of the corpus buffer (16 B aligned by the allocator)."""
+    host = torch.from_numpy(np.ascontiguousarray(buf).copy()) if not isinstance(buf, torch.Tensor) else buf
+    if torch.device(device).type != "cuda":
+        return host
+    if not host.is_pinned():
+        host = host.pin_memory()
+    return host.to(device, non_blocking=True)
+
+
+def discover_alphabet(d_buf: torch.Tensor, group=None) -> Tuple[np.ndarray, torch.Tensor]:
+    """-> (symbols uint8[sigma] ascending, rank_of_byte uint8[256] on the device).
+    With a process group the 256-entry presence table is OR-reduced first so every rank packs
+    with the same alphabet."""
+    nat.require_cuda()
+    pres = torch.zeros(256, dtype=torch.int32, device=d_buf.device)
+    nat.call("pg_byte_presence", nat.ptr(d_buf), d_buf.numel(), nat.ptr(pres), nat.stream_ptr())
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(pres, op=dist.ReduceOp.MAX, group=group)
+    present = pres.cpu().numpy() != 0
+    return alphabet_from_presence(present, d_buf.device)
+
+
+def alphabet_from_presence(present: np.ndarray, device) -> Tuple[np.ndarray, torch.Tensor]:
+    symbols = np.nonzero(present)[0].astype(np.uint8)
+    rank = np.zeros(256, dtype=np.uint8)
+    rank[symbols] = np.arange(symbols.size, dtype=np.uint8)
+    return symbols, torch.from_numpy(rank).to(device)
+
+
+def decode_nodes(node_code: np.ndarray, symbols: np.ndarray, n: int) -> List[str]:
+    """base-sigma codes -> n-gram strings (most significant digit = first character)."""
+    sigma = int(symbols.size)
+    code = node_code.astype(np.int64).copy()
+    chars = np.empty((code.size, n), dtype=np.uint8)
+    for k in range(n - 1, -1, -1):
+        chars[:, k] = symbols[code % sigma]
+        code //= sigma
+    return [row.tobytes().decode("ascii") for row in chars]

@@ -1,0 +1,145 @@
+"""GraphBuilder -- drop-in for the reference's src/pipeline/data_builder.py:57-341.
+
+Same constructor (`GraphBuilder(config)`), same `run()` contract: for n = 1..GCN_NGRAM_MAX_N write
+`GRAPH_OBJECTS_DIR/ngram_graph_n{n}.pkl` holding a DirectedNgramGraph; print-and-continue on data
+errors, never raise from run() for them.  What changed is the body: the Dask bag / text spill /
+CSV re-parse / groupby pipeline (reference :118-220,267-273) is one pass of the count kernel over
+the corpus resident in HBM plus a scan/compaction (csrc/ngram.cu), and the graph object is built
+from the device edge table without the parquet round trip.
+
+Multi-GPU (one process per GPU, torch.distributed): each rank packs and counts a contiguous
+slice of the sequences; the dense tables are summed with an all-reduce (the merge step of
+SURVEY.md 8(e)); every rank then extracts the identical graph and rank 0 writes the pickles.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from . import corpus
+from .data_utils import DataLoader, DataUtils
+from .graph_utils import DirectedNgramGraph
+
+
+def table_sizes(n: int, sigma: int) -> Tuple[int, int]:
+    return sigma ** n, sigma ** (n + 1)
+
+
+def count_level(d_buf: torch.Tensor, n: int, d_rank: torch.Tensor, sigma: int,
+                bins: Optional[torch.Tensor] = None, short: Optional[torch.Tensor] = None):
+    """Accumulate the (n+1)-gram table of one corpus buffer.  -> (bins int64[sigma^(n+1)],
+    short_present uint8[sigma^n]).  Replaces reference data_builder.py:45-54,203-220,267-273."""
+    nat.require_cuda()
+    pow_n, pow_m = table_sizes(n, sigma)
+    dev = d_buf.device
+    if bins is None:
+        bins = torch.zeros(pow_m, dtype=torch.int64, device=dev)
+    if short is None:
+        short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
+    nat.call("pg_ngram_count", nat.ptr(d_buf), d_buf.numel(), n, nat.ptr(d_rank), sigma, nat.ptr(bins), nat.ptr(short),
+             nat.stream_ptr())
+    return bins, short
+
+
+def extract_level(bins: torch.Tensor, short: torch.Tensor, n: int, sigma: int):
+    """Dense table -> (node_code int64[N] ascending, src, dst, count int64[E] sorted by (src,dst)).
+    Replaces reference data_builder.py:151-177 (distinct + sorted ids) and :281-286."""
+    dev = bins.device
+    ws = nat.workspace(nat.query("pg_graph_extract_ws_bytes", n, sigma), dev)
+    sizes = torch.zeros(2, dtype=torch.int64, device=dev)
+    st = nat.stream_ptr()
+    nat.call("pg_graph_extract_sizes", nat.ptr(bins), nat.ptr(short), n, sigma, nat.ptr(sizes), nat.ptr(ws), ws.numel(), st)
+    num_nodes, num_edges = (int(v) for v in sizes.tolist())
+    node_code = torch.empty(num_nodes, dtype=torch.int64, device=dev)
+    src = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    dst = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    cnt = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    nat.call("pg_graph_extract_fill", nat.ptr(bins), n, sigma, num_nodes, num_edges, nat.ptr(node_code), nat.ptr(src),
+             nat.ptr(dst), nat.ptr(cnt), nat.ptr(ws), ws.numel(), st)
+    return node_code, src, dst, cnt
+
+
+def build_level_graph(d_buf: torch.Tensor, n: int, symbols: np.ndarray, d_rank: torch.Tensor, eps: float,
+                      group=None) -> DirectedNgramGraph:
+    """corpus buffer (device) -> DirectedNgramGraph for one n (count, merge, extract, normalise)."""
+    sigma = int(symbols.size)
+    bins, short = count_level(d_buf, n, d_rank, sigma)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
+        short_i = short.to(torch.int32)
+        dist.all_reduce(short_i, op=dist.ReduceOp.MAX, group=group)
+        short = short_i.to(torch.uint8)
+    node_code, src, dst, cnt = extract_level(bins, short, n, sigma)
+    names = corpus.decode_nodes(node_code.cpu().numpy(), symbols, n)
+    nodes = dict(enumerate(names))
+    return DirectedNgramGraph.from_edge_arrays(nodes, src, dst, cnt.to(torch.float32), epsilon_propagation=eps,
+                                               n_value=n, assume_coalesced=True)
+
+
+class GraphBuilder:
+    def __init__(self, config):
+        self.config = config
+        self.protein_sequence_file = str(config.GCN_INPUT_FASTA_PATH)
+        self.output_dir = str(config.GRAPH_OBJECTS_DIR)
+        self.n_max = config.GCN_NGRAM_MAX_N
+        self.num_workers_config = config.GRAPH_BUILDER_WORKERS if config.GRAPH_BUILDER_WORKERS is not None else 1
+        self.temp_dir = os.path.join(str(config.BASE_OUTPUT_DIR), "temp_graph_builder")
+        self.gcn_propagation_epsilon = getattr(config, "GCN_PROPAGATION_EPSILON", 1e-9)
+        self.process_group = getattr(config, "GRAPH_BUILDER_PROCESS_GROUP", None)  # optional, multi-GPU
+        print(f"GraphBuilder initialized: n_max={self.n_max}, output_dir='{self.output_dir}' (CUDA path)")
+
+    def _rank_world(self) -> Tuple[int, int]:
+        if self.process_group is None:
+            return 0, 1
+        import torch.distributed as dist
+        return dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+
+    def run(self):
+        t0 = time.monotonic()
+        DataUtils.print_header("PIPELINE STEP 1: Building N-gram Graphs")
+        nat.load()
+        nat.require_cuda()  # fail loudly: no CPU fallback
+        os.makedirs(self.output_dir, exist_ok=True)
+        if not os.path.exists(os.path.normpath(self.protein_sequence_file)):
+            print(f"ERROR: FASTA file not found at {self.protein_sequence_file}")
+            return
+        seqs: List[str] = [s for _, s in DataLoader.parse_sequences(self.protein_sequence_file)]
+        if not seqs:
+            print("ERROR: No sequences found in the FASTA file. Cannot proceed.")
+            return
+        print(f"  Loaded {len(seqs)} sequences from FASTA.")
+        rank, world = self._rank_world()
+        lo, hi = (len(seqs) * rank) // world, (len(seqs) * (rank + 1)) // world
+        dev = nat.current_device()
+        try:
+            buf = corpus.pack_sequences(seqs[lo:hi], global_first=(lo == 0))
+        except ValueError as exc:
+            print(f"ERROR: {exc}")
+            return
+        d_buf = corpus.to_device(buf, dev)
+        symbols, d_rank = corpus.discover_alphabet(d_buf, self.process_group)
+        for n in range(1, self.n_max + 1):
+            t_level = time.monotonic()
+            try:
+                graph = build_level_graph(d_buf, n, symbols, d_rank, self.gcn_propagation_epsilon, self.process_group)
+            except nat.NativeError:
+                raise
+            except Exception as exc:  # noqa: BLE001 - reference prints and continues with the next level
+                print(f"  [n={n}] ERROR building graph: {exc}")
+                continue
+            if graph.number_of_nodes == 0:
+                print(f"  Info: no n-grams for n={n}. No graph will be generated. Skipping.")
+                continue
+            if rank == 0:
+                out_path = os.path.join(self.output_dir, f"ngram_graph_n{n}.pkl")
+                DataUtils.save_object(graph, out_path)
+                print(f"  Graph for n={n} saved to {out_path}")
+            print(f"    Nodes: {graph.number_of_nodes}  Edges (unique weighted): {graph.number_of_edges}  "
+                  f"[{time.monotonic() - t_level:.3f}s]")
+        DataUtils.print_header(f"N-gram Graph Building FINISHED in {time.monotonic() - t0:.2f}s")

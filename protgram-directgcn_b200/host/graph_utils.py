@@ -1,0 +1,192 @@
+"""Graph / DirectedNgramGraph -- same public surface as the reference's src/utils/graph_utils.py
+(:19-125): constructor signature, attribute names, coalesced fp32 sparse-COO matrices with int64
+indices.  The matrix construction (reference :140-287) runs on the GPU through libpgb200.so:
+one radix sort of 2E+N tagged keys + two per-item passes (csrc/graph.cu) instead of ~14
+sparse coalesces.  There is no CPU fallback: building matrices without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+
+
+class Graph:
+    """Base container: id <-> n-gram maps (reference graph_utils.py:19-87)."""
+
+    def __init__(self, nodes: Dict[int, Any], edges: List[Tuple]):
+        self.idx_to_node_map_from_constructor = nodes if nodes is not None else {}
+        self.original_edges = edges if edges is not None else []
+        self.node_to_idx: Dict[Any, int] = {}
+        self.idx_to_node: Dict[int, Any] = {}
+        self.number_of_nodes: int = 0
+        self.node_sequences: List[Any] = []
+        self.edges: List[Tuple] = []
+        self.number_of_edges: int = 0
+        self._process_constructor_inputs()
+
+    def _process_constructor_inputs(self):
+        node_map = self.idx_to_node_map_from_constructor
+        if not node_map and not self.original_edges:
+            return
+        top = -1
+        for key in node_map.keys():
+            if isinstance(key, (int, np.integer)) and key >= 0:
+                top = max(top, int(key))
+        for e in self.original_edges:
+            if len(e) >= 2 and isinstance(e[0], (int, np.integer)) and isinstance(e[1], (int, np.integer)):
+                top = max(top, int(e[0]), int(e[1]))
+        self.number_of_nodes = top + 1
+        names = [node_map.get(i) for i in range(self.number_of_nodes)]
+        self.node_sequences = [str(nm) if nm is not None else f"__NODE_{i}__" for i, nm in enumerate(names)]
+        self.idx_to_node = dict(enumerate(self.node_sequences))
+        self.node_to_idx = {nm: i for i, nm in self.idx_to_node.items()}
+        self.edges = self.original_edges
+        self.number_of_edges = len(self.edges)
+
+
+def _coo(indices: torch.Tensor, values: torch.Tensor, n: int) -> torch.Tensor:
+    return torch.sparse_coo_tensor(indices, values, (n, n), is_coalesced=True)
+
+
+def _empty_coo(n: int, device="cpu") -> torch.Tensor:
+    return _coo(torch.empty((2, 0), dtype=torch.long, device=device),
+                torch.empty(0, dtype=torch.float32, device=device), n)
+
+
+def device_coalesce(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int):
+    """Arbitrary edge table -> row-major sorted, duplicates summed (reference :154 `.coalesce()`)."""
+    nnz = src.numel()
+    dev = src.device
+    so, do, wo = torch.empty_like(src), torch.empty_like(dst), torch.empty_like(w)
+    sizes = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = nat.workspace(nat.query("pg_coo_coalesce_ws_bytes", nnz), dev)
+    nat.call("pg_coo_coalesce", nat.ptr(src), nat.ptr(dst), nat.ptr(w), nnz, n, nat.ptr(so), nat.ptr(do), nat.ptr(wo),
+             nat.ptr(sizes), nat.ptr(ws), ws.numel(), nat.stream_ptr())
+    e = int(sizes.item())
+    return so[:e], do[:e], wo[:e]
+
+
+def device_normalize(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int, eps: float):
+    """Coalesced A_out_w (device, sorted unique) -> dict with A_in_w COO, shared CSR pattern and
+    the three value arrays.  Replaces reference :158-287."""
+    nnz = src.numel()
+    dev = src.device
+    ws = nat.workspace(nat.query("pg_normalize_ws_bytes", nnz, n), dev)
+    sizes = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = nat.stream_ptr()
+    nat.call("pg_normalize_sizes", nat.ptr(src), nat.ptr(dst), nat.ptr(w), nnz, n, nat.ptr(sizes), nat.ptr(ws), ws.numel(), st)
+    p = int(sizes.item())
+    in_src = torch.empty(nnz, dtype=torch.int64, device=dev)
+    in_dst = torch.empty(nnz, dtype=torch.int64, device=dev)
+    in_w = torch.empty(nnz, dtype=torch.float32, device=dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(p, dtype=torch.int32, device=dev)
+    v_out = torch.empty(p, dtype=torch.float32, device=dev)
+    v_in = torch.empty(p, dtype=torch.float32, device=dev)
+    v_und = torch.empty(p, dtype=torch.float32, device=dev)
+    nat.call("pg_normalize_fill", nat.ptr(src), nat.ptr(dst), nat.ptr(w), nnz, n, float(eps), p, nat.ptr(in_src),
+             nat.ptr(in_dst), nat.ptr(in_w), nat.ptr(rowptr), nat.ptr(col), nat.ptr(v_out), nat.ptr(v_in), nat.ptr(v_und),
+             nat.ptr(ws), ws.numel(), st)
+    return {"in_src": in_src, "in_dst": in_dst, "in_w": in_w, "rowptr": rowptr, "col": col,
+            "val_out": v_out, "val_in": v_in, "val_und": v_und, "pattern_nnz": p}
+
+
+def csr_to_coo_indices(rowptr: torch.Tensor, col: torch.Tensor, n: int) -> torch.Tensor:
+    """int32 CSR -> the reference's int64 [2, P] COO index layout."""
+    p = col.numel()
+    idx = torch.empty((2, p), dtype=torch.int64, device=col.device)
+    nat.call("pg_coo_from_csr", nat.ptr(rowptr), nat.ptr(col), n, p, nat.ptr(idx[0]), nat.ptr(idx[1]), nat.stream_ptr())
+    return idx
+
+
+class DirectedNgramGraph(Graph):
+    """Drop-in for reference graph_utils.py:90-287.  Attributes: A_out_w, A_in_w,
+    A_undirected_norm_sparse, mathcal_A_out, mathcal_A_in (coalesced sparse COO, fp32, int64
+    indices, on the CPU after construction exactly like the reference), node_to_idx, idx_to_node,
+    node_sequences, number_of_nodes, number_of_edges, n_value, epsilon_propagation."""
+
+    def __init__(self, nodes: Dict[int, Any], edge_file_path: Optional[str] = None,
+                 epsilon_propagation: float = 1e-9, n_value: Optional[int] = None):
+        super().__init__(nodes=nodes, edges=[])
+        self.epsilon_propagation = epsilon_propagation
+        self.n_value: Optional[int] = n_value
+        if self.number_of_nodes > 0 and edge_file_path and os.path.exists(edge_file_path):
+            print(f"    Loading edges from {os.path.basename(edge_file_path)}...")
+            try:
+                import pandas as pd
+                edge_df = pd.read_parquet(edge_file_path)
+                src = edge_df["source"].to_numpy(dtype=np.int64)
+                dst = edge_df["target"].to_numpy(dtype=np.int64)
+                w = edge_df["weight"].to_numpy(dtype=np.float32)  # int64 -> fp32 RN, reference :112
+                self._build_from_edges(src, dst, w)
+            except nat.NativeError:
+                raise  # a missing CUDA library / device is not a data error: fail loudly
+            except Exception as exc:  # noqa: BLE001 - reference :121-123 prints and falls back to empty
+                print(f"    Error reading edge file {edge_file_path}: {exc}. Initializing empty graph.")
+                self._initialize_empty_matrices()
+        else:
+            self._initialize_empty_matrices()
+
+    # -- construction from in-memory edge arrays (what GraphBuilder uses; no parquet round trip)
+    @classmethod
+    def from_edge_arrays(cls, nodes: Dict[int, Any], src, dst, weight, epsilon_propagation: float = 1e-9,
+                         n_value: Optional[int] = None, assume_coalesced: bool = False) -> "DirectedNgramGraph":
+        g = cls(nodes=nodes, edge_file_path=None, epsilon_propagation=epsilon_propagation, n_value=n_value)
+        if g.number_of_nodes > 0 and len(src) > 0:
+            g._build_from_edges(src, dst, weight, assume_coalesced=assume_coalesced)
+        return g
+
+    def _initialize_empty_matrices(self):
+        self.number_of_edges = 0
+        n = self.number_of_nodes
+        self.A_out_w = _empty_coo(n)
+        self.A_in_w = _empty_coo(n)
+        self.A_undirected_norm_sparse = _empty_coo(n)
+        self.mathcal_A_out = _empty_coo(n)
+        self.mathcal_A_in = _empty_coo(n)
+
+    def _build_from_edges(self, src, dst, w, assume_coalesced: bool = False, result_device="cpu"):
+        dev = nat.current_device()
+        as_dev = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(dev, dtype=dt)
+        src_d, dst_d, w_d = as_dev(src, torch.int64), as_dev(dst, torch.int64), as_dev(w, torch.float32)
+        n = self.number_of_nodes
+        self.number_of_edges = int(src_d.numel())  # reference :116 (rows of the edge table)
+        if not assume_coalesced:
+            src_d, dst_d, w_d = device_coalesce(src_d, dst_d, w_d, n)
+        if src_d.numel() == 0:
+            self._initialize_empty_matrices()
+            return
+        res = device_normalize(src_d, dst_d, w_d, n, self.epsilon_propagation)
+        pat = csr_to_coo_indices(res["rowptr"], res["col"], n)
+        out = lambda t: t.to(result_device)
+        pat_o = out(pat)
+        self.A_out_w = _coo(out(torch.stack([src_d, dst_d])), out(w_d), n)
+        self.A_in_w = _coo(out(torch.stack([res["in_src"], res["in_dst"]])), out(res["in_w"]), n)
+        self.A_undirected_norm_sparse = _coo(pat_o, out(res["val_und"]), n)
+        self.mathcal_A_out = _coo(pat_o, out(res["val_out"]), n)
+        self.mathcal_A_in = _coo(pat_o, out(res["val_in"]), n)
+
+    # reference :275-287 -- public: the trainer calls it after moving A_*_w to the device
+    def _create_propagation_matrices_for_gcn(self):
+        if self.number_of_nodes == 0:
+            self._initialize_empty_matrices()
+            return
+        a = self.A_out_w
+        target = a.device
+        if a._nnz() == 0:
+            self.mathcal_A_out = _empty_coo(self.number_of_nodes, target)
+            self.mathcal_A_in = _empty_coo(self.number_of_nodes, target)
+            return
+        dev = target if target.type == "cuda" else nat.current_device()
+        a = a.coalesce()
+        idx, val = a.indices().to(dev), a.values().to(dev, dtype=torch.float32)
+        res = device_normalize(idx[0].contiguous(), idx[1].contiguous(), val.contiguous(), self.number_of_nodes,
+                               self.epsilon_propagation)
+        pat = csr_to_coo_indices(res["rowptr"], res["col"], self.number_of_nodes).to(target)
+        self.mathcal_A_out = _coo(pat, res["val_out"].to(target), self.number_of_nodes)
+        self.mathcal_A_in = _coo(pat, res["val_in"].to(target), self.number_of_nodes)

@@ -1,0 +1,372 @@
+"""DirectGCNLayer / ProtGramDirectGCN -- drop-in for the reference's
+src/models/protgram_directgcn.py (same constructor signatures, parameter names => identical
+state_dict keys, same forward contracts), with the propagation and the dense transform running
+through libpgb200.so.
+
+Reference layer (:93-135): 6 x (gather -> scale -> scatter_add) + 4 Linears + 6 bias adds + 5 gate
+multiplies + constant.  Here (algebra checked to 7.8e-7):
+
+    Z      = [A_in X | A_out X | U X]                       one fan-out SpMM (X gathered once)
+    Y      = [a Z_in | b Z_out | c Z_und | X | a b c | 1] @ W_ext + constant     one fused GEMM
+    a = C_all*C_directed*C_in, b = C_all*C_directed*C_out, c = C_all*C_undirected
+    W_ext  = [ (W_in+W_sh)^T ; (W_out+W_sh)^T ; (W_und+W_sh)^T ; W_res^T ; beta_in ; beta_out ; beta_und ; b_res ]
+
+ProtGramDirectGCN additionally folds res_proj, the residual add and leaky_relu (:210-215) into
+the same GEMM epilogue.  Backward = lrelu' -> dW_ext GEMM (split over rows) -> dA GEMM + gate
+dot-products -> fan-in SpMM over the source-grouped structure (csrc/{spmm,gemm}.cu).
+No CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _native as nat
+from .models_utils import EmbeddingProcessor
+
+
+class Data:
+    """Minimal stand-in for torch_geometric.data.Data (attribute bag with .to()); the model only
+    uses getattr() on it (reference :196-203), so a real PyG Data works as well."""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+
+# ------------------------------------------------------------------------------------------------
+# edge lists -> cached CSR structures
+# ------------------------------------------------------------------------------------------------
+class _Csr:
+    __slots__ = ("rowptr", "col", "vals")
+
+    def __init__(self, rowptr, col, vals):
+        self.rowptr, self.col, self.vals = rowptr, col, vals
+
+
+def _edges_to_csr(group: torch.Tensor, other: torch.Tensor, w: Optional[torch.Tensor], n: int) -> _Csr:
+    nnz = group.numel()
+    dev = group.device
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(nnz, dtype=torch.float32, device=dev)
+    ws = nat.workspace(nat.query("pg_edges_to_csr_ws_bytes", nnz), dev)
+    nat.call("pg_edges_to_csr", nat.ptr(group), nat.ptr(other), nat.ptr(w), nnz, n, nat.ptr(rowptr), nat.ptr(col), nat.ptr(val),
+             nat.ptr(ws), ws.numel(), nat.stream_ptr())
+    return _Csr(rowptr, col, [val])
+
+
+class EdgeStructure:
+    """CSR views of the three edge lists of one graph.
+
+    by_dst: rows = message targets (ei[1]), cols = sources (ei[0])  -> forward  out[t] += w*x[s]
+    by_src: rows = sources, cols = targets                          -> backward dx[s] += w*dy[t]
+    `shared` = the three edge_index tensors are identical (reference-built graphs): one pattern,
+    three value arrays, so the nv=3 kernels gather each neighbour row once."""
+
+    def __init__(self, eis, ews, n: int):
+        self.n = n
+        same = all(e.shape == eis[0].shape for e in eis) and all(
+            e.data_ptr() == eis[0].data_ptr() or torch.equal(e, eis[0]) for e in eis[1:])
+        self.shared = bool(same)
+        prep = lambda e: e.to(torch.int64).contiguous()
+        fw = lambda w: None if w is None else w.to(torch.float32).contiguous()
+        self.by_dst: List[_Csr] = []
+        self.by_src: List[_Csr] = []
+        for ei, ew in zip(eis, ews):
+            ei = prep(ei)
+            self.by_dst.append(_edges_to_csr(ei[1], ei[0], fw(ew), n))
+            self.by_src.append(_edges_to_csr(ei[0], ei[1], fw(ew), n))
+        if self.shared:
+            # stable sort => the permutation is the same for the three value arrays
+            for lst in (self.by_dst, self.by_src):
+                merged = _Csr(lst[0].rowptr, lst[0].col, [c.vals[0] for c in lst])
+                lst[:] = [merged]
+            d, s = self.by_dst[0], self.by_src[0]
+            if torch.equal(d.rowptr, s.rowptr) and torch.equal(d.col, s.col) and all(
+                    torch.equal(a, b) for a, b in zip(d.vals, s.vals)):
+                self.by_src = self.by_dst  # symmetric matrices: transposed structure == structure
+        self.nnz_total = sum(int(e.shape[1]) for e in eis)
+
+
+_STRUCT_CACHE: Dict[tuple, EdgeStructure] = {}
+
+
+def get_structure(eis, ews, n: int) -> EdgeStructure:
+    key = tuple((t.data_ptr(), tuple(t.shape), t._version) if t is not None else None for t in (*eis, *ews)) + (n,)
+    st = _STRUCT_CACHE.get(key)
+    if st is None:
+        if len(_STRUCT_CACHE) > 16:
+            _STRUCT_CACHE.clear()
+        st = EdgeStructure(eis, ews, n)
+        st._keepalive = (eis, ews)  # data_ptr keys stay valid while cached
+        _STRUCT_CACHE[key] = st
+    return st
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels as autograd function
+# ------------------------------------------------------------------------------------------------
+def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int) -> torch.Tensor:
+    n = x.shape[0]
+    z = torch.empty((n, 3 * f_in), dtype=torch.float32, device=x.device)
+    st = nat.stream_ptr()
+    if struct.shared:
+        c = struct.by_dst[0]
+        nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
+                 3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, st)
+    else:
+        for v, c in enumerate(struct.by_dst):
+            nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
+                     nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, st)
+    return z
+
+
+def _fanin(struct: EdgeStructure, dz: torch.Tensor, f_in: int, init: Optional[torch.Tensor]) -> torch.Tensor:
+    n = dz.shape[0]
+    dx = torch.empty((n, f_in), dtype=torch.float32, device=dz.device)
+    st = nat.stream_ptr()
+    ldinit = init.stride(0) if init is not None else 0
+    if struct.shared:
+        c = struct.by_src[0]
+        nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
+                 3, n, f_in, nat.ptr(dz), dz.stride(0), 0, nat.ptr(init), ldinit, nat.ptr(dx), dx.stride(0), 0, st)
+    else:
+        for v, c in enumerate(struct.by_src):
+            nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
+                     nat.ptr(dz), dz.stride(0), v * f_in, nat.ptr(init) if v == 0 else None, ldinit, nat.ptr(dx),
+                     dx.stride(0), 0 if v == 0 else 1, st)
+    return dx
+
+
+class _DirectGCNFused(torch.autograd.Function):
+    """H = act( [aZ_in | bZ_out | cZ_und | X? | a b c | 1?] @ W_ext (+X) + constant )."""
+
+    @staticmethod
+    def forward(ctx, x, ga, gb, gc, w_ext, const_rows, struct, has_res, add_identity, slope):
+        nat.check_tensor(x, "x")
+        x = x.contiguous().float()
+        ga, gb, gc = (g.contiguous().float() for g in (ga, gb, gc))
+        w_ext = w_ext.contiguous().float()
+        n, f_in = x.shape
+        f_out = w_ext.shape[1]
+        gate_stride = 1 if ga.numel() == n else 0
+        if ga.numel() not in (1, n):
+            raise ValueError(f"gate vectors must have 1 or {n} entries, got {ga.numel()}")
+        z = _fanout(struct, x, f_in)
+        h = torch.empty((n, f_out), dtype=torch.float32, device=x.device)
+        if const_rows is not None:
+            const_rows = const_rows.contiguous().float()
+        nat.call("pg_layer_gemm_fwd", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
+                 gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), const_rows.stride(0) if const_rows is not None else 0,
+                 n, f_in, f_out, int(has_res), int(add_identity), float(slope), nat.ptr(h), h.stride(0), nat.stream_ptr())
+        ctx.save_for_backward(x, ga, gb, gc, w_ext, z, h)
+        ctx.struct, ctx.has_res, ctx.add_identity, ctx.slope = struct, bool(has_res), bool(add_identity), float(slope)
+        ctx.gate_stride, ctx.has_const = gate_stride, const_rows is not None
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, ga, gb, gc, w_ext, z, h = ctx.saved_tensors
+        n, f_in = x.shape
+        f_out = w_ext.shape[1]
+        st = nat.stream_ptr()
+        dh = dh.contiguous().float()
+        if ctx.slope != 1.0:
+            dy = torch.empty_like(dh)
+            nat.call("pg_lrelu_bwd", nat.ptr(dh), nat.ptr(h), ctx.slope, dh.numel(), nat.ptr(dy), st)
+        else:
+            dy = dh
+        has_res = int(ctx.has_res)
+        # dW_ext = A_ext^T dY
+        dw = torch.empty_like(w_ext)
+        ws = nat.workspace(nat.query("pg_layer_gemm_bwd_weight_ws_bytes", n, f_in, f_out, has_res), x.device)
+        nat.call("pg_layer_gemm_bwd_weight", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb),
+                 nat.ptr(gc), ctx.gate_stride, nat.ptr(dy), dy.stride(0), n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws),
+                 ws.numel(), st)
+        # dA = dY W_ext^T  -> dZ (gated), dXres, dgates
+        dz = torch.empty_like(z)
+        dxres = torch.empty_like(x) if ctx.has_res else None
+        dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
+        nat.call("pg_layer_gemm_bwd_data", nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), nat.ptr(ga),
+                 nat.ptr(gb), nat.ptr(gc), ctx.gate_stride, n, f_in, f_out, has_res, nat.ptr(dz), dz.stride(0),
+                 nat.ptr(dxres), dxres.stride(0) if dxres is not None else 0, nat.ptr(dgate), st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            init = dxres if ctx.has_res else (dy if ctx.add_identity else None)
+            dx = _fanin(ctx.struct, dz, f_in, init)
+        if ctx.gate_stride == 1:
+            dga, dgb, dgc = (dgate[v].reshape(ga.shape) for v in range(3))
+        else:
+            dga, dgb, dgc = (dgate[v].sum().reshape(ga.shape) for v in range(3))
+        dconst = dy if ctx.has_const else None
+        return dx, dga, dgb, dgc, dw, dconst, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------------
+class DirectGCNLayer(nn.Module):
+    """Same parameters / init as reference :26-91 (state_dict compatible)."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_nodes: int, use_vector_coeffs: bool = True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_nodes = num_nodes
+        self.use_vector_coeffs = use_vector_coeffs
+        self.lin_main_in = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin_main_out = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin_undirected = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias_main_in = nn.Parameter(torch.Tensor(out_channels))
+        self.bias_main_out = nn.Parameter(torch.Tensor(out_channels))
+        self.bias_undirected = nn.Parameter(torch.Tensor(out_channels))
+        self.lin_shared = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias_directed_shared_in = nn.Parameter(torch.Tensor(out_channels))
+        self.bias_directed_shared_out = nn.Parameter(torch.Tensor(out_channels))
+        self.bias_undirected_shared = nn.Parameter(torch.Tensor(out_channels))
+        if self.use_vector_coeffs and self.num_nodes > 0:
+            for name in ("C_in_vec", "C_out_vec", "C_directed_vec", "C_undirected_vec", "C_all_vec"):
+                setattr(self, name, nn.Parameter(torch.Tensor(num_nodes, 1)))
+        else:
+            self.use_vector_coeffs = False
+            for name in ("C_in", "C_out", "C_directed", "C_undirected", "C_all"):
+                setattr(self, name, nn.Parameter(torch.Tensor(1)))
+        self.constant = nn.Parameter(torch.Tensor(num_nodes, out_channels)) if self.num_nodes > 0 else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in (self.lin_main_in, self.lin_main_out, self.lin_shared, self.lin_undirected):
+            nn.init.xavier_uniform_(lin.weight)
+        for b in (self.bias_main_in, self.bias_main_out, self.bias_directed_shared_in, self.bias_directed_shared_out,
+                  self.bias_undirected, self.bias_undirected_shared):
+            nn.init.zeros_(b)
+        sfx = "_vec" if self.use_vector_coeffs else ""
+        for name in ("C_in", "C_out", "C_directed", "C_undirected", "C_all"):
+            nn.init.ones_(getattr(self, name + sfx))
+        if self.constant is not None:
+            nn.init.xavier_uniform_(self.constant)
+
+    # -- parameter packing (tiny torch ops; autograd splits dW_ext back onto the 4 Linears / 6 biases)
+    def _gates(self, original_indices):
+        sfx = "_vec" if self.use_vector_coeffs else ""
+        c_in, c_out, c_dir, c_und, c_all = (getattr(self, k + sfx) for k in ("C_in", "C_out", "C_directed", "C_undirected", "C_all"))
+        if self.use_vector_coeffs and original_indices is not None:
+            c_in, c_out, c_dir, c_und, c_all = (t[original_indices] for t in (c_in, c_out, c_dir, c_und, c_all))
+        cd = c_all * c_dir
+        return (cd * c_in).reshape(-1), (cd * c_out).reshape(-1), (c_all * c_und).reshape(-1)
+
+    def _constant_rows(self, original_indices):
+        # reference :116-128: the constant is only added on the vector-coefficient path
+        if not self.use_vector_coeffs or self.constant is None:
+            return None
+        return self.constant if original_indices is None else self.constant[original_indices]
+
+    def _w_ext(self, res_weight=None, res_bias=None):
+        ws = self.lin_shared.weight
+        blocks = [(self.lin_main_in.weight + ws).t(), (self.lin_main_out.weight + ws).t(), (self.lin_undirected.weight + ws).t()]
+        if res_weight is not None:
+            blocks.append(res_weight.t())
+        blocks.append(torch.stack([self.bias_main_in + self.bias_directed_shared_in,
+                                   self.bias_main_out + self.bias_directed_shared_out,
+                                   self.bias_undirected + self.bias_undirected_shared]))
+        if res_weight is not None:
+            rb = res_bias if res_bias is not None else torch.zeros(self.out_channels, device=ws.device, dtype=ws.dtype)
+            blocks.append(rb.unsqueeze(0))
+        return torch.cat(blocks, dim=0)
+
+    def _run(self, x, edges, original_indices, res_weight, res_bias, add_identity, slope):
+        ei_in, ew_in, ei_out, ew_out, ei_und, ew_und = edges
+        nat.check_tensor(x, "x")
+        struct = get_structure((ei_in, ei_out, ei_und), (ew_in, ew_out, ew_und), x.shape[0])
+        ga, gb, gc = self._gates(original_indices)
+        return _DirectGCNFused.apply(x, ga, gb, gc, self._w_ext(res_weight, res_bias), self._constant_rows(original_indices),
+                                     struct, res_weight is not None, add_identity, slope)
+
+    def forward(self, x: torch.Tensor,
+                edge_index_in: torch.Tensor, edge_weight_in: Optional[torch.Tensor],
+                edge_index_out: torch.Tensor, edge_weight_out: Optional[torch.Tensor],
+                edge_index_undirected: torch.Tensor, edge_weight_undirected: Optional[torch.Tensor],
+                original_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reference :93-135 (no residual, no activation: those belong to the stack)."""
+        return self._run(x, (edge_index_in, edge_weight_in, edge_index_out, edge_weight_out, edge_index_undirected,
+                             edge_weight_undirected), original_indices, None, None, False, 1.0)
+
+
+class ProtGramDirectGCN(nn.Module):
+    """Reference :143-222."""
+
+    LEAKY_SLOPE = 0.01  # F.leaky_relu default (reference :215)
+
+    def __init__(self, layer_dims: List[int], num_graph_nodes: Optional[int], task_num_output_classes: int, n_gram_len: int,
+                 one_gram_dim: int, max_pe_len: int, dropout: float, use_vector_coeffs: bool, l2_eps: float = 1e-12):
+        super().__init__()
+        self.n_gram_len = n_gram_len
+        self.one_gram_dim = one_gram_dim
+        self.dropout = dropout
+        self.l2_eps = l2_eps
+        self.pe_layer = None
+        if one_gram_dim > 0 and max_pe_len > 0:
+            self.pe_layer = nn.Embedding(max_pe_len, one_gram_dim)
+        self.convs = nn.ModuleList()
+        self.res_projs = nn.ModuleList()
+        if not layer_dims or len(layer_dims) < 2:
+            raise ValueError("layer_dims must contain at least input and output dimensions (length >= 2).")
+        for i in range(len(layer_dims) - 1):
+            in_dim, out_dim = layer_dims[i], layer_dims[i + 1]
+            nodes = num_graph_nodes if num_graph_nodes is not None else 0
+            self.convs.append(DirectGCNLayer(in_dim, out_dim, nodes, use_vector_coeffs and nodes > 0))
+            self.res_projs.append(nn.Linear(in_dim, out_dim) if in_dim != out_dim else nn.Identity())
+        final_dim = layer_dims[-1]
+        hidden = final_dim // 2 if final_dim > 1 else 1
+        self.decoder_fc = nn.Sequential(nn.Linear(final_dim, hidden), nn.ReLU(), nn.Dropout(p=0.5),
+                                        nn.Linear(hidden, task_num_output_classes))
+
+    def _apply_pe(self, x: torch.Tensor) -> torch.Tensor:
+        if self.pe_layer is None:
+            return x
+        if self.n_gram_len > 0 and self.one_gram_dim > 0 and x.shape[1] == self.n_gram_len * self.one_gram_dim:
+            k = min(self.n_gram_len, self.pe_layer.num_embeddings)
+            if k > 0:
+                xr = x.clone().view(-1, self.n_gram_len, self.one_gram_dim)
+                xr[:, :k, :] += self.pe_layer.weight[:k].unsqueeze(0)
+                return xr.view(-1, self.n_gram_len * self.one_gram_dim)
+        return x
+
+    def embed(self, data, return_layers: bool = False):
+        """The layer stack only (PE + L fused layers) -> final hidden state h (reference :208-218).
+        With return_layers=True also returns the list of per-layer activations."""
+        x = getattr(data, "x", None)
+        ei_in, ew_in = getattr(data, "edge_index_in", None), getattr(data, "edge_weight_in", None)
+        ei_out, ew_out = getattr(data, "edge_index_out", None), getattr(data, "edge_weight_out", None)
+        ei_und, ew_und = getattr(data, "edge_index_undirected_norm", None), getattr(data, "edge_weight_undirected_norm", None)
+        original_indices = getattr(data, "original_indices", None)
+        if x is None or ei_in is None or ei_out is None or ei_und is None:
+            raise ValueError("ProtGramDirectGCN requires 'x', 'edge_index_in', 'edge_index_out', and "
+                             "'edge_index_undirected_norm' in the Data object.")
+        edges = (ei_in, ew_in, ei_out, ew_out, ei_und, ew_und)
+        h = self._apply_pe(x)
+        layers = []
+        for conv, res in zip(self.convs, self.res_projs):
+            if isinstance(res, nn.Linear):
+                h = conv._run(h, edges, original_indices, res.weight, res.bias, False, self.LEAKY_SLOPE)
+            else:
+                h = conv._run(h, edges, original_indices, None, None, True, self.LEAKY_SLOPE)
+            h = F.dropout(h, p=self.dropout, training=self.training)
+            layers.append(h)
+        return (h, layers) if return_layers else h
+
+    def forward(self, data) -> Tuple[torch.Tensor, torch.Tensor]:
+        h = self.embed(data)
+        task_logits = self.decoder_fc(h)
+        emb = EmbeddingProcessor.l2_normalize_torch(h, eps=self.l2_eps)
+        return F.log_softmax(task_logits, dim=-1), emb

@@ -1,0 +1,295 @@
+"""Executable specification of every compute entry point of include/pgb200.h in plain
+torch / numpy -- TEST INFRASTRUCTURE ONLY.
+
+Two uses:
+  * `-m gpu` tests call the real CUDA entry point and the function here on the same seeded
+    inputs (the "plain PyTorch fp32 reference of the same op").
+  * `install(monkeypatch)` swaps protgram_directgcn_b200._native's call/ptr/... for this module
+    so the HOST logic above the C ABI (parameter packing, autograd wiring, structure caching,
+    rank sharding) can be exercised on CPU-only machines.  The product never imports this file,
+    and without the monkeypatch every hot-path call on a CPU tensor raises NativeError.
+
+Argument order of each spec_* function == the C prototype (pointers are tensors; outputs are
+written in place), so `call(name, *args)` can dispatch positionally.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+SEP = 0xFF
+
+
+# --------------------------------------------------------------------------- builder
+def pg_byte_presence(buf, nbytes, present256, stream=None):
+    seen = torch.bincount(buf[:nbytes].to(torch.int64), minlength=256) > 0
+    seen[SEP] = False
+    present256[seen] = 1
+
+
+def pg_ngram_count(buf, nbytes, n, rank_of_byte, sigma, bins, short_present, stream=None):
+    b = buf[:nbytes].cpu().numpy()
+    rank = rank_of_byte.cpu().numpy().astype(np.int64)
+    m = n + 1
+    is_sep = b == SEP
+    if nbytes >= m:
+        L = nbytes - m + 1
+        ok = np.ones(L, dtype=bool)
+        code = np.zeros(L, dtype=np.int64)
+        for k in range(m):
+            ok &= ~is_sep[k:k + L]
+            code = code * sigma + rank[b[k:k + L]]
+        add = np.bincount(code[ok], minlength=sigma ** m)
+        bins += torch.from_numpy(add).to(bins.device)
+    # whole padded sequences of exactly n bytes
+    bounds = np.concatenate([[-1], np.nonzero(is_sep)[0], [nbytes]])
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        if hi - lo - 1 == n:
+            code = 0
+            for k in range(lo + 1, hi):
+                code = code * sigma + int(rank[b[k]])
+            short_present[code] = 1
+
+
+_extract_state = {}
+
+
+def pg_graph_extract_ws_bytes(n, sigma):
+    return 256
+
+
+def pg_graph_extract_sizes(bins, short_present, n, sigma, sizes, ws, ws_bytes, stream=None):
+    pow_n = sigma ** n
+    nz = torch.nonzero(bins != 0).flatten()
+    present = short_present.clone().to(torch.bool)
+    present[nz // sigma] = True
+    present[nz % pow_n] = True
+    sizes[0] = int(present.sum())
+    sizes[1] = nz.numel()
+    _extract_state[id(ws)] = (present, nz)
+
+
+def pg_graph_extract_fill(bins, n, sigma, num_nodes, num_edges, node_code, src, dst, count, ws, ws_bytes, stream=None):
+    present, nz = _extract_state.pop(id(ws))
+    pow_n = sigma ** n
+    ids = torch.cumsum(present.to(torch.int64), 0) - 1
+    node_code.copy_(torch.nonzero(present).flatten())
+    src.copy_(ids[nz // sigma])
+    dst.copy_(ids[nz % pow_n])
+    count.copy_(bins[nz])
+
+
+# --------------------------------------------------------------------------- graph
+def pg_sort_pairs_ws_bytes(n):
+    return 256
+
+
+def pg_sort_pairs(keys, keys_alt, vals, vals_alt, n, key_bits, ws, ws_bytes, stream=None):
+    k = keys[:n].cpu().numpy().view(np.uint64)
+    mask = np.uint64((1 << key_bits) - 1) if key_bits < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort(k & mask, kind="stable")
+    keys[:n] = torch.from_numpy(k[order].view(np.int64)).to(keys.device)
+    vals[:n] = vals[:n][torch.from_numpy(order).to(vals.device)]
+
+
+def _coalesce(src, dst, w, n):
+    key = src * n + dst
+    order = torch.argsort(key, stable=True)
+    key, w = key[order], w[order]
+    uniq, inv = torch.unique_consecutive(key, return_inverse=True)
+    out = torch.zeros(uniq.numel(), dtype=torch.float32, device=w.device).index_add_(0, inv, w)
+    return uniq // n, uniq % n, out
+
+
+def pg_coo_coalesce_ws_bytes(nnz):
+    return 256
+
+
+def pg_coo_coalesce(src, dst, w, nnz, n, src_out, dst_out, w_out, sizes, ws, ws_bytes, stream=None):
+    s, d, v = _coalesce(src[:nnz], dst[:nnz], w[:nnz], n)
+    e = s.numel()
+    src_out[:e], dst_out[:e], w_out[:e] = s, d, v
+    sizes[0] = e
+
+
+_norm_state = {}
+
+
+def pg_normalize_ws_bytes(nnz, n):
+    return 256
+
+
+def _normalize(src, dst, w, n, eps):
+    f32 = torch.float32
+    rs_out = torch.zeros(n, dtype=torch.float64).index_add_(0, src, w.double()).to(f32)
+    rs_in = torch.zeros(n, dtype=torch.float64).index_add_(0, dst, w.double()).to(f32)
+    inv = lambda r: torch.where(r != 0, 1.0 / r, torch.zeros_like(r))
+    io, ii = inv(rs_out), inv(rs_in)
+    loops = torch.arange(n)
+    rows = torch.cat([src, dst, loops])
+    cols = torch.cat([dst, src, loops])
+    key = rows * n + cols
+    ukey = torch.unique(key)
+    r, c = ukey // n, ukey % n
+    pos = lambda rr, cc: torch.searchsorted(ukey, rr * n + cc)
+    P = ukey.numel()
+    w_rc = torch.zeros(P, dtype=f32)
+    w_cr = torch.zeros(P, dtype=f32)
+    w_rc[pos(src, dst)] = w
+    w_cr[pos(dst, src)] = w
+    has_sym = torch.zeros(P, dtype=torch.bool)
+    has_sym[pos(src, dst)] = True
+    has_sym[pos(dst, src)] = True
+    diag = r == c
+
+    def mathcal(inv_deg, a_rc, a_cr):
+        a = a_rc * inv_deg[r]
+        b = a_cr * inv_deg[c]
+        s = (a * a + b * b) * 0.5
+        v = torch.sqrt(s + torch.tensor(eps, dtype=f32))
+        v = torch.where(diag, v + 1.0, v)
+        return torch.where(has_sym, v, torch.ones_like(v))
+
+    v_out = mathcal(io, w_rc, w_cr)
+    v_in = mathcal(ii, w_cr, w_rc)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
+    native = torch.zeros(n, dtype=torch.bool)
+    native[r[diag & has_sym]] = True
+    deg = (rowptr[1:] - rowptr[:-1] + native.to(torch.int64)).to(f32)
+    dis = 1.0 / torch.sqrt(deg)
+    v_und = dis[r] * dis[c]
+    v_und = torch.where(diag & native[r], v_und + v_und, v_und)
+    i_src, i_dst, i_w = _coalesce(dst, src, w, n)
+    return i_src, i_dst, i_w, rowptr, c.to(torch.int32), v_out, v_in, v_und
+
+
+def pg_normalize_sizes(src, dst, w, nnz, n, sizes, ws, ws_bytes, stream=None):
+    res = _normalize(src[:nnz], dst[:nnz], w[:nnz], n, 0.0)
+    sizes[0] = res[4].numel()
+
+
+def pg_normalize_fill(src, dst, w, nnz, n, eps, pattern_nnz, in_src, in_dst, in_w, rowptr, col, val_out, val_in,
+                      val_und, ws, ws_bytes, stream=None):
+    res = _normalize(src[:nnz], dst[:nnz], w[:nnz], n, eps)
+    for out, r in zip((in_src, in_dst, in_w, rowptr, col, val_out, val_in, val_und), res):
+        out.copy_(r)
+
+
+def pg_rowptr_from_sorted(rows, nnz, num_rows, rowptr, stream=None):
+    rowptr[0] = 0
+    rowptr[1:] = torch.cumsum(torch.bincount(rows[:nnz], minlength=num_rows), 0)
+
+
+def pg_coo_from_csr(rowptr, col, num_rows, nnz, row_out, col_out, stream=None):
+    counts = rowptr[1:] - rowptr[:-1]
+    row_out.copy_(torch.repeat_interleave(torch.arange(num_rows, device=col.device), counts))
+    col_out.copy_(col.to(torch.int64))
+
+
+def pg_edges_to_csr_ws_bytes(nnz):
+    return 256
+
+
+def pg_edges_to_csr(group, other, w, nnz, n, rowptr, col, val, ws, ws_bytes, stream=None):
+    order = torch.argsort(group, stable=True)
+    col.copy_(other[order].to(torch.int32))
+    val.copy_(w[order] if w is not None else torch.ones(nnz, dtype=torch.float32, device=group.device))
+    pg_rowptr_from_sorted(group[order], nnz, n, rowptr)
+
+
+# --------------------------------------------------------------------------- DirectGCN
+def _rows_of(rowptr, num_rows):
+    counts = rowptr[1:num_rows + 1] - rowptr[:num_rows]
+    return torch.repeat_interleave(torch.arange(num_rows, device=rowptr.device), counts)
+
+
+def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_off, stream=None):
+    rows = _rows_of(rowptr, num_rows)
+    xg = x[:, :F][col.long()]
+    for v, val in enumerate((v0, v1, v2)[:nv]):
+        acc = torch.zeros(num_rows, F, dtype=torch.float32, device=x.device).index_add_(0, rows, val.view(-1, 1) * xg)
+        z[:, z_off + v * F: z_off + (v + 1) * F] = acc
+
+
+def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, stream=None):
+    rows = _rows_of(rowptr, num_rows)
+    acc = torch.zeros(num_rows, F, dtype=torch.float32, device=g.device)
+    if init is not None:
+        acc += init[:, :F]
+    if accumulate:
+        acc += y[:, :F]
+    for v, val in enumerate((v0, v1, v2)[:nv]):
+        acc.index_add_(0, rows, val.view(-1, 1) * g[:, g_off + v * F: g_off + (v + 1) * F][col.long()])
+    y[:, :F] = acc
+
+
+def _a_ext(z, x, ga, gb, gc, n, f_in, has_res):
+    gate = lambda g: g.reshape(-1, 1).expand(n, 1)
+    blocks = [z[:, :f_in] * gate(ga), z[:, f_in:2 * f_in] * gate(gb), z[:, 2 * f_in:3 * f_in] * gate(gc)]
+    if has_res:
+        blocks.append(x[:, :f_in])
+    blocks += [gate(ga), gate(gb), gate(gc)]
+    if has_res:
+        blocks.append(torch.ones(n, 1, dtype=torch.float32, device=z.device))
+    return torch.cat(blocks, dim=1)
+
+
+def pg_layer_gemm_fwd(z, ldz, x, ldx, ga, gb, gc, gate_stride, w_ext, constant, ldconst, n, f_in, f_out, has_res,
+                      add_identity, slope, h, ldh, stream=None):
+    y = _a_ext(z, x, ga, gb, gc, n, f_in, has_res) @ w_ext
+    if add_identity:
+        y = y + x[:, :f_out]
+    if constant is not None:
+        y = y + constant
+    h.copy_(torch.where(y > 0, y, y * slope) if slope != 1.0 else y)
+
+
+def pg_lrelu_bwd(dh, h, slope, numel, dy, stream=None):
+    dy.copy_(torch.where(h > 0, dh, dh * slope))
+
+
+def pg_layer_gemm_bwd_data(dy, lddy, w_ext, z, ldz, ga, gb, gc, gate_stride, n, f_in, f_out, has_res, dz, lddz,
+                           dxres, lddxres, dgate, stream=None):
+    k_data = 3 * f_in + (f_in if has_res else 0)
+    da = dy @ w_ext[:k_data].t()
+    gates = [g.reshape(-1, 1).expand(n, 1) for g in (ga, gb, gc)]
+    for v in range(3):
+        seg = slice(v * f_in, (v + 1) * f_in)
+        dgate[v] = (da[:, seg] * z[:, seg]).sum(1) + dy @ w_ext[k_data + v]
+        dz[:, seg] = da[:, seg] * gates[v]
+    if has_res:
+        dxres.copy_(da[:, 3 * f_in:])
+
+
+def pg_layer_gemm_bwd_weight_ws_bytes(n, f_in, f_out, has_res):
+    return 256
+
+
+def pg_layer_gemm_bwd_weight(z, ldz, x, ldx, ga, gb, gc, gate_stride, dy, lddy, n, f_in, f_out, has_res, dw_ext, ws,
+                             ws_bytes, stream=None):
+    dw_ext.copy_(_a_ext(z, x, ga, gb, gc, n, f_in, has_res).t() @ dy)
+
+
+def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
+    out.copy_(h / (torch.norm(h, p=2, dim=1, keepdim=True) + eps))
+
+
+# --------------------------------------------------------------------------- monkeypatch glue
+def install(monkeypatch, nat):
+    """Route protgram_directgcn_b200._native through this module (CPU tensors, tests only)."""
+    spec = globals()
+
+    def call(name, *args):
+        nat.launches += 1
+        spec[name](*args)
+        return 0
+
+    monkeypatch.setattr(nat, "call", call)
+    monkeypatch.setattr(nat, "query", lambda name, *a: int(spec[name](*a)))
+    monkeypatch.setattr(nat, "ptr", lambda t: t)
+    monkeypatch.setattr(nat, "stream_ptr", lambda: None)
+    monkeypatch.setattr(nat, "require_cuda", lambda: None)
+    monkeypatch.setattr(nat, "check_tensor", lambda t, what="input": None)
+    monkeypatch.setattr(nat, "current_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(nat, "workspace", lambda nbytes, device: torch.empty(8, dtype=torch.uint8))

@@ -1,0 +1,198 @@
+"""Host logic above the C ABI, exercised on CPU by swapping the native entry points for their
+executable specification (tests/kernel_spec.py).  What this covers: FASTA ingest, corpus packing,
+alphabet ranking, node decoding, DirectedNgramGraph assembly, GraphBuilder.run() file contract,
+DirectGCN parameter packing + autograd wiring, state_dict compatibility -- all against the
+reference-generated goldens.  The CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import protgram_directgcn_b200 as pg
+from protgram_directgcn_b200 import _native as nat
+from protgram_directgcn_b200.host import protgram_directgcn as model_mod
+from tests import kernel_spec
+from tests.helpers import BUILD_FIXTURES, MATS, MODEL_FIXTURES, fasta_sequences, load, rel_err
+
+
+@pytest.fixture
+def spec_native(monkeypatch):
+    kernel_spec.install(monkeypatch, nat)
+    model_mod._STRUCT_CACHE.clear()
+    yield
+    model_mod._STRUCT_CACHE.clear()
+
+
+def check_graph_against_golden(graph, g, n, val_tol=2e-7):
+    assert graph.number_of_nodes == int(g[f"n{n}_number_of_nodes"])
+    assert graph.number_of_edges == int(g[f"n{n}_number_of_edges"])
+    assert graph.node_sequences == list(g[f"n{n}_nodes"])
+    assert graph.node_to_idx == {s: i for i, s in enumerate(g[f"n{n}_nodes"])}
+    assert graph.n_value == n
+    for m in MATS:
+        t = getattr(graph, m)
+        assert t.is_sparse and t.is_coalesced() and t.dtype == torch.float32 and t.indices().dtype == torch.int64
+        assert tuple(t.shape) == (graph.number_of_nodes,) * 2
+        assert np.array_equal(t.indices().cpu().numpy(), g[f"n{n}_{m}_idx"]), (n, m)
+        if m in ("A_out_w", "A_in_w"):
+            assert np.array_equal(t.values().cpu().numpy(), g[f"n{n}_{m}_val"]), (n, m)  # counts: bit exact
+        else:
+            assert rel_err(t.values().cpu().numpy(), g[f"n{n}_{m}_val"]) <= val_tol, (n, m)
+
+
+@pytest.mark.parametrize("name", sorted(BUILD_FIXTURES))
+def test_graph_builder_run_matches_reference(name, tmp_path, spec_native):
+    g = load(name)
+    cfg = pg.Config()
+    cfg.GCN_INPUT_FASTA_PATH = fasta_sequences(str(g["fasta"]), tmp_path)
+    cfg.BASE_OUTPUT_DIR = tmp_path / "out"
+    cfg.GRAPH_OBJECTS_DIR = cfg.BASE_OUTPUT_DIR / "1_graph_objects"
+    cfg.GCN_NGRAM_MAX_N = BUILD_FIXTURES[name]
+    cfg.GRAPH_BUILDER_WORKERS = 1
+    pg.GraphBuilder(cfg).run()
+    for n in range(1, BUILD_FIXTURES[name] + 1):
+        path = cfg.GRAPH_OBJECTS_DIR / f"ngram_graph_n{n}.pkl"
+        assert path.exists()  # the only thing the reference's own smoke test asserts (unit_tests.py:79-80)
+        graph = pg.DataUtils.load_object(str(path))
+        assert isinstance(graph, pg.DirectedNgramGraph)
+        check_graph_against_golden(graph, g, n)
+
+
+def test_directed_ngram_graph_from_parquet_unsorted(tmp_path, spec_native):
+    """Constructor contract of reference graph_utils.py:91-125: nodes dict + parquet edge table in
+    arbitrary row order."""
+    import pandas as pd
+    g = load("build_protein")
+    n = 2
+    idx = g[f"n{n}_A_out_w_idx"]
+    perm = np.random.default_rng(0).permutation(idx.shape[1])
+    df = pd.DataFrame({"source": idx[0][perm], "target": idx[1][perm],
+                       "weight": g[f"n{n}_A_out_w_val"][perm].astype(np.int64)})
+    path = str(tmp_path / "edges.parquet")
+    df.to_parquet(path, index=False)
+    nodes = dict(enumerate(g[f"n{n}_nodes"].tolist()))
+    graph = pg.DirectedNgramGraph(nodes, path, epsilon_propagation=1e-9, n_value=n)
+    check_graph_against_golden(graph, g, n)
+    # the trainer re-creates the propagation matrices after loading (protgram_directgcn_trainer.py:299)
+    graph.mathcal_A_out = None
+    graph._create_propagation_matrices_for_gcn()
+    check_graph_against_golden(graph, g, n)
+
+
+def test_empty_and_missing_inputs(tmp_path, spec_native, capsys):
+    g = pg.DirectedNgramGraph({0: "A", 1: "C"}, None)
+    assert g.number_of_nodes == 2 and g.number_of_edges == 0
+    for m in MATS:
+        assert getattr(g, m)._nnz() == 0 and tuple(getattr(g, m).shape) == (2, 2)
+    g0 = pg.DirectedNgramGraph({}, None)
+    assert g0.number_of_nodes == 0
+    cfg = pg.Config()
+    cfg.GCN_INPUT_FASTA_PATH = tmp_path / "nope.fasta"
+    cfg.BASE_OUTPUT_DIR = tmp_path / "o"
+    cfg.GRAPH_OBJECTS_DIR = tmp_path / "o" / "g"
+    pg.GraphBuilder(cfg).run()  # prints, never raises (reference data_builder.py:110-112)
+    assert "not found" in capsys.readouterr().out
+    empty = tmp_path / "empty.fasta"
+    empty.write_text(">only_header\n\n")
+    cfg.GCN_INPUT_FASTA_PATH = empty
+    pg.GraphBuilder(cfg).run()
+    assert "No sequences found" in capsys.readouterr().out
+
+
+def _load_model(g):
+    dims = [int(d) for d in g["dims"]]
+    model = pg.ProtGramDirectGCN(layer_dims=dims, num_graph_nodes=int(g["num_graph_nodes"]),
+                                 task_num_output_classes=int(g["num_classes"]), n_gram_len=int(g["n_gram_len"]),
+                                 one_gram_dim=int(g["one_gram_dim"]), max_pe_len=16, dropout=0.0,
+                                 use_vector_coeffs=bool(g["use_vec"]))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    assert set(sd) == set(model.state_dict()), "state_dict keys must equal the reference's"
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+def _data(g, device="cpu"):
+    kw = {"x": torch.from_numpy(g["x"]).clone().to(device).requires_grad_(True)}
+    for k, name in (("in", "in"), ("out", "out"), ("und", "undirected_norm")):
+        kw[f"edge_index_{name}"] = torch.from_numpy(g[f"ei_{k}"]).to(device)
+        kw[f"edge_weight_{name}"] = torch.from_numpy(g[f"ew_{k}"]).to(device) if f"ew_{k}" in g.files else None
+    if "original_indices" in g.files:
+        kw["original_indices"] = torch.from_numpy(g["original_indices"]).to(device)
+    return pg.Data(**kw)
+
+
+def run_model_case(g, device, tol_fwd, tol_bwd):
+    model = _load_model(g).to(device)
+    data = _data(g, device)
+    model.eval()
+    # per-layer embeddings: the golden holds the reference's conv outputs; the stack applies
+    # leaky_relu(conv + res_proj(h)) on top (protgram_directgcn.py:210-215)
+    with torch.no_grad():
+        _, layers = model.embed(data, return_layers=True)
+        sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+        h_ref = torch.from_numpy(g["x"])
+        if "pe_layer.weight" in sd and int(g["one_gram_dim"]) > 0 and h_ref.shape[1] == int(g["n_gram_len"]) * int(g["one_gram_dim"]):
+            k = min(int(g["n_gram_len"]), sd["pe_layer.weight"].shape[0])
+            h_ref = h_ref.clone().view(-1, int(g["n_gram_len"]), int(g["one_gram_dim"]))
+            h_ref[:, :k, :] += sd["pe_layer.weight"][:k].unsqueeze(0)
+            h_ref = h_ref.view(g["x"].shape[0], -1)
+        for i, h_mine in enumerate(layers):
+            res = h_ref @ sd[f"res_projs.{i}.weight"].t() + sd[f"res_projs.{i}.bias"] if f"res_projs.{i}.weight" in sd else h_ref
+            h_ref = torch.nn.functional.leaky_relu(torch.from_numpy(g[f"layer{i}_out"]) + res)
+            assert rel_err(h_mine.cpu().numpy(), h_ref.numpy()) <= tol_fwd, f"layer {i}"
+    logp, emb = model(data=data)
+    assert rel_err(logp.detach().cpu().numpy(), g["logp"]) <= tol_fwd
+    assert rel_err(emb.detach().cpu().numpy(), g["emb"]) <= tol_fwd
+    y = torch.from_numpy(g["y"]).to(device)
+    wvec = torch.from_numpy(g["wvec"]).to(device)
+    loss = torch.nn.functional.nll_loss(logp, y) + (emb * wvec).sum()
+    assert abs(float(loss) - float(g["loss"])) <= tol_fwd * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    assert rel_err(data.x.grad.cpu().numpy(), g["grad_x"]) <= tol_bwd
+    for k, p in model.named_parameters():
+        ref = g["grad:" + k]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(ref)
+        assert rel_err(got, ref) <= tol_bwd or float(np.max(np.abs(ref))) < 1e-12, k
+    return model
+
+
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
+def test_model_host_logic_matches_reference(name, spec_native):
+    run_model_case(load(name), "cpu", 1e-5, 1e-4)
+
+
+def test_directgcn_layer_alone_matches_oracle(spec_native):
+    """DirectGCNLayer.forward on its own (no residual / activation), reference :93-135."""
+    from oracle import directgcn_oracle
+    g = load("model_general_scalar")
+    model = _load_model(g)
+    data = _data(g)
+    layer = model.convs[0]
+    out = layer(data.x, data.edge_index_in, data.edge_weight_in, data.edge_index_out, data.edge_weight_out,
+                data.edge_index_undirected_norm, data.edge_weight_undirected_norm)
+    p = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    ref = directgcn_oracle.directgcn_layer(p, "convs.0.", data.x.detach(), data.edge_index_in, data.edge_weight_in,
+                                           data.edge_index_out, data.edge_weight_out, data.edge_index_undirected_norm,
+                                           data.edge_weight_undirected_norm)
+    assert rel_err(out.detach().numpy(), ref.numpy()) <= 1e-5
+
+
+def test_missing_inputs_raise_value_error(spec_native):
+    g = load("model_cluster_batch")
+    model = _load_model(g)
+    with pytest.raises(ValueError):
+        model(data=pg.Data(x=torch.zeros(3, 10)))
+    with pytest.raises(ValueError):
+        pg.ProtGramDirectGCN([4], 3, 2, 1, 0, 0, 0.0, True)
+
+
+def test_no_cpu_fallback():
+    """Without the test-only spec, CPU tensors must raise: the product has no CPU path."""
+    g = load("model_cluster_batch")
+    model = _load_model(g)
+    with pytest.raises(nat.NativeError):
+        model(data=_data(g))
+    if not torch.cuda.is_available():
+        with pytest.raises(nat.NativeError):
+            pg.DirectedNgramGraph.from_edge_arrays({0: "A", 1: "C"}, np.array([0]), np.array([1]), np.array([2.0]))
