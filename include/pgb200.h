@@ -45,6 +45,8 @@ typedef void *pg_stream_t; /* cudaStream_t */
 
 int pg_version(void);
 const char *pg_last_error(void);
+/* diagnostics only: kernels launched by this library since it was loaded (process-wide) */
+unsigned long long pg_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Hot path A, part 1: n-gram transition counting

@@ -21,6 +21,7 @@ _P = c_void_p
 _SIGS = {
     "pg_version": (c_int, []),
     "pg_last_error": (c_char_p, []),
+    "pg_launch_count": (ctypes.c_uint64, []),
     "pg_byte_presence": (c_int, [_P, c_int64, _P, _P]),
     "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
     "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
@@ -119,6 +120,11 @@ def call(name: str, *args):
 
 def query(name: str, *args) -> int:
     return int(getattr(load(), name)(*args))
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libpgb200.so in this process (bench.py's gpu_launches)."""
+    return int(load().pg_launch_count())
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

@@ -9,6 +9,7 @@
 #define PG_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
 void pg_set_error(const char *fmt, ...);
+void pg_count_launch();  // diagnostics: number of kernels this library has launched (pg_launch_count)
 
 #define PG_CHECK_ARG(cond, ...)        \
     do {                               \
@@ -25,6 +26,7 @@ void pg_set_error(const char *fmt, ...);
             pg_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(_e)); \
             return PG_ECUDA;                                                          \
         }                                                                             \
+        pg_count_launch();                                                            \
     } while (0)
 
 #define PG_CUDA_CALL(expr)                                                          \

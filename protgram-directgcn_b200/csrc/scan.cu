@@ -14,6 +14,9 @@ void pg_set_error(const char *fmt, ...) {
 }
 extern "C" const char *pg_last_error(void) { return g_err; }
 extern "C" int pg_version(void) { return 100; }
+static unsigned long long g_launches = 0;
+void pg_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" unsigned long long pg_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 // ---------------------------------------------------------------------------- scan
 namespace {

@@ -208,19 +208,19 @@ def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_o
     rows = _rows_of(rowptr, num_rows)
     xg = x[:, :F][col.long()]
     for v, val in enumerate((v0, v1, v2)[:nv]):
-        acc = torch.zeros(num_rows, F, dtype=torch.float32, device=x.device).index_add_(0, rows, val.view(-1, 1) * xg)
+        acc = torch.zeros(num_rows, F, dtype=x.dtype, device=x.device).index_add_(0, rows, val.to(x.dtype).view(-1, 1) * xg)
         z[:, z_off + v * F: z_off + (v + 1) * F] = acc
 
 
 def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, stream=None):
     rows = _rows_of(rowptr, num_rows)
-    acc = torch.zeros(num_rows, F, dtype=torch.float32, device=g.device)
+    acc = torch.zeros(num_rows, F, dtype=g.dtype, device=g.device)
     if init is not None:
         acc += init[:, :F]
     if accumulate:
         acc += y[:, :F]
     for v, val in enumerate((v0, v1, v2)[:nv]):
-        acc.index_add_(0, rows, val.view(-1, 1) * g[:, g_off + v * F: g_off + (v + 1) * F][col.long()])
+        acc.index_add_(0, rows, val.to(g.dtype).view(-1, 1) * g[:, g_off + v * F: g_off + (v + 1) * F][col.long()])
     y[:, :F] = acc
 
 

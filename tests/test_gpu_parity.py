@@ -35,7 +35,7 @@ def test_radix_sort_pairs_stable(n, key_bits):
     hi = min(key_bits, 62)
     keys = torch.randint(0, 2 ** hi, (n,), generator=g, dtype=torch.int64)
     if n > 10:
-        keys[n // 2:] = keys[: n - n // 2]  # many duplicates: stability is observable
+        keys[n // 2:] = keys[: n - n // 2].clone()  # many duplicates: stability is observable
     if key_bits == 64:
         keys[::3] |= -(2 ** 63)  # top bit set: unsigned order
     vals = torch.arange(n, dtype=torch.int32)
@@ -71,11 +71,12 @@ def test_spmm_fanout_fanin_vs_spec(F, nv):
     x = torch.from_numpy(rng.standard_normal((n, F)).astype(np.float32))
     g = torch.from_numpy(rng.standard_normal((n, 3 * F)).astype(np.float32))
     init = torch.from_numpy(rng.standard_normal((n, F)).astype(np.float32))
-    z_ref = torch.zeros(n, 3 * F)
-    y_ref = torch.zeros(n, F)
+    # ground truth in float64 (hub rows sum up to 15 000 terms: fp32 results differ by summation order)
+    z_ref = torch.zeros(n, 3 * F, dtype=torch.float64)
+    y_ref = torch.zeros(n, F, dtype=torch.float64)
     z_off = 0 if nv == 3 else F
-    spec.pg_spmm_fanout(rowptr, col, *vals, nv, n, F, x, F, z_ref, 3 * F, z_off)
-    spec.pg_spmm_fanin(rowptr, col, *vals, nv, n, F, g, 3 * F, z_off, init, F, y_ref, F, 0)
+    spec.pg_spmm_fanout(rowptr, col, *vals, nv, n, F, x.double(), F, z_ref, 3 * F, z_off)
+    spec.pg_spmm_fanin(rowptr, col, *vals, nv, n, F, g.double(), 3 * F, z_off, init.double(), F, y_ref, F, 0)
     d = lambda t: t.to(DEV)
     rp, cl, vs = d(rowptr), d(col), [d(v) for v in vals]
     xd, gd, initd = d(x), d(g), d(init)
@@ -86,8 +87,8 @@ def test_spmm_fanout_fanin_vs_spec(F, nv):
              nat.ptr(z), 3 * F, z_off, st)
     nat.call("pg_spmm_fanin", nat.ptr(rp), nat.ptr(cl), nat.ptr(vs[0]), nat.ptr(vs[1]), nat.ptr(vs[2]), nv, n, F, nat.ptr(gd), 3 * F,
              z_off, nat.ptr(initd), F, nat.ptr(y), F, 0, st)
-    assert rel_err(z.cpu().numpy(), z_ref.numpy()) <= 2e-6
-    assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= 2e-6
+    assert rel_err(z.cpu().numpy(), z_ref.numpy()) <= 5e-6
+    assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= 5e-6
     # run-to-run bitwise reproducibility (fixed accumulation order)
     z2 = torch.zeros_like(z)
     nat.call("pg_spmm_fanout", nat.ptr(rp), nat.ptr(cl), nat.ptr(vs[0]), nat.ptr(vs[1]), nat.ptr(vs[2]), nv, n, F, nat.ptr(xd), F,
