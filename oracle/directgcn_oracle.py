@@ -99,3 +99,43 @@ def protgram_forward(p: Dict[str, torch.Tensor], x, ei_in, ew_in, ei_out, ew_out
     logits = z @ p["decoder_fc.3.weight"].t() + p["decoder_fc.3.bias"]
     out = (F.log_softmax(logits, dim=-1), l2_normalize(h, l2_eps))
     return out + (conv_outs,) if return_layers else out
+
+
+def init_params(layer_dims, num_nodes: int, num_classes: int, one_gram_dim: int = 0, max_pe_len: int = 0,
+                seed: int = 42) -> Dict[str, torch.Tensor]:
+    """Fresh parameters with the reference's shapes and initialisers (protgram_directgcn.py:34-91,
+    :156-180): xavier-uniform Linear weights and `constant`, zero biases, unit gates, default
+    nn.Linear init for res_projs / decoder.  Leaf tensors with requires_grad=True."""
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+
+    def xavier(*shape):
+        fan_out, fan_in = shape[0], shape[1]
+        a = (6.0 / (fan_in + fan_out)) ** 0.5
+        return (torch.rand(*shape, generator=g) * 2 - 1) * a
+
+    def linear(prefix, fin, fout):
+        bound = 1.0 / fin ** 0.5
+        p[prefix + ".weight"] = (torch.rand(fout, fin, generator=g) * 2 - 1) * bound
+        p[prefix + ".bias"] = (torch.rand(fout, generator=g) * 2 - 1) * bound
+
+    if one_gram_dim > 0 and max_pe_len > 0:
+        p["pe_layer.weight"] = torch.randn(max_pe_len, one_gram_dim, generator=g)
+    for i in range(len(layer_dims) - 1):
+        fin, fout = layer_dims[i], layer_dims[i + 1]
+        pre = f"convs.{i}."
+        for k in ("lin_main_in", "lin_main_out", "lin_undirected", "lin_shared"):
+            p[pre + k + ".weight"] = xavier(fout, fin)
+        for k in ("bias_main_in", "bias_main_out", "bias_undirected", "bias_directed_shared_in",
+                  "bias_directed_shared_out", "bias_undirected_shared"):
+            p[pre + k] = torch.zeros(fout)
+        for k in ("C_in_vec", "C_out_vec", "C_directed_vec", "C_undirected_vec", "C_all_vec"):
+            p[pre + k] = torch.ones(num_nodes, 1)
+        p[pre + "constant"] = xavier(num_nodes, fout)
+        if fin != fout:
+            linear(f"res_projs.{i}", fin, fout)
+    final = layer_dims[-1]
+    hidden = final // 2 if final > 1 else 1
+    linear("decoder_fc.0", final, hidden)
+    linear("decoder_fc.3", hidden, num_classes)
+    return {k: v.requires_grad_(True) for k, v in p.items()}

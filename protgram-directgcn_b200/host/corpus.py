@@ -61,9 +61,14 @@ def alphabet_from_presence(present: np.ndarray, device) -> Tuple[np.ndarray, tor
 def decode_nodes(node_code: np.ndarray, symbols: np.ndarray, n: int) -> List[str]:
     """base-sigma codes -> n-gram strings (most significant digit = first character)."""
     sigma = int(symbols.size)
-    code = node_code.astype(np.int64).copy()
+    code = np.asarray(node_code, dtype=np.int64).copy()
     chars = np.empty((code.size, n), dtype=np.uint8)
     for k in range(n - 1, -1, -1):
         chars[:, k] = symbols[code % sigma]
         code //= sigma
-    return [row.tobytes().decode("ascii") for row in chars]
+    if code.size == 0:
+        return []
+    # fixed-width bytes -> str in one vectorised cast; numpy strips trailing NULs only, and NUL
+    # cannot occur (it would have to be a corpus byte), so trailing spaces survive
+    return np.ascontiguousarray(chars).view(f"S{n}").ravel().astype(f"U{n}").tolist() if 0 not in symbols else \
+        [row.tobytes().decode("ascii") for row in chars]

@@ -135,10 +135,11 @@ class DirectedNgramGraph(Graph):
     # -- construction from in-memory edge arrays (what GraphBuilder uses; no parquet round trip)
     @classmethod
     def from_edge_arrays(cls, nodes: Dict[int, Any], src, dst, weight, epsilon_propagation: float = 1e-9,
-                         n_value: Optional[int] = None, assume_coalesced: bool = False) -> "DirectedNgramGraph":
+                         n_value: Optional[int] = None, assume_coalesced: bool = False,
+                         result_device="cpu") -> "DirectedNgramGraph":
         g = cls(nodes=nodes, edge_file_path=None, epsilon_propagation=epsilon_propagation, n_value=n_value)
         if g.number_of_nodes > 0 and len(src) > 0:
-            g._build_from_edges(src, dst, weight, assume_coalesced=assume_coalesced)
+            g._build_from_edges(src, dst, weight, assume_coalesced=assume_coalesced, result_device=result_device)
         return g
 
     def _initialize_empty_matrices(self):
@@ -149,6 +150,29 @@ class DirectedNgramGraph(Graph):
         self.A_undirected_norm_sparse = _empty_coo(n)
         self.mathcal_A_out = _empty_coo(n)
         self.mathcal_A_in = _empty_coo(n)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_pg_device", None)  # device-side CSR sidecar never enters the pickle
+        return state
+
+    def gcn_data(self, x: torch.Tensor, device, **extra):
+        """Data object for ProtGramDirectGCN with the three propagation matrices attached the way
+        the reference trainer does (protgram_directgcn_trainer.py:362-367).  When this graph was
+        built in this process the device CSR from the normalisation kernels is handed to the layer
+        directly, so the edge lists are not re-sorted."""
+        from .protgram_directgcn import Data, register_symmetric_structure
+        dev = torch.device(device)
+        side = getattr(self, "_pg_device", None)
+        if side is not None and side["pattern"].device == dev:
+            ei = side["pattern"]
+            ew = (side["val_in"], side["val_out"], side["val_und"])
+            register_symmetric_structure(ei, ew, self.number_of_nodes, side["rowptr"], side["col"])
+        else:
+            ei = self.mathcal_A_in.indices().to(dev)
+            ew = tuple(t.values().to(dev) for t in (self.mathcal_A_in, self.mathcal_A_out, self.A_undirected_norm_sparse))
+        return Data(x=x.to(dev), edge_index_in=ei, edge_weight_in=ew[0], edge_index_out=ei, edge_weight_out=ew[1],
+                    edge_index_undirected_norm=ei, edge_weight_undirected_norm=ew[2], num_nodes=self.number_of_nodes, **extra)
 
     def _build_from_edges(self, src, dst, w, assume_coalesced: bool = False, result_device="cpu"):
         dev = nat.current_device()
@@ -163,6 +187,8 @@ class DirectedNgramGraph(Graph):
             return
         res = device_normalize(src_d, dst_d, w_d, n, self.epsilon_propagation)
         pat = csr_to_coo_indices(res["rowptr"], res["col"], n)
+        self._pg_device = {"pattern": pat, "rowptr": res["rowptr"], "col": res["col"], "val_in": res["val_in"],
+                           "val_out": res["val_out"], "val_und": res["val_und"]}
         out = lambda t: t.to(result_device)
         pat_o = out(pat)
         self.A_out_w = _coo(out(torch.stack([src_d, dst_d])), out(w_d), n)

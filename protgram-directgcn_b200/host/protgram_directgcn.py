@@ -101,8 +101,27 @@ class EdgeStructure:
 _STRUCT_CACHE: Dict[tuple, EdgeStructure] = {}
 
 
+def _cache_key(eis, ews, n):
+    return tuple((t.data_ptr(), tuple(t.shape), t._version) if t is not None else None for t in (*eis, *ews)) + (n,)
+
+
+def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Tensor, col: torch.Tensor) -> None:
+    """Hand the layer a ready CSR for a shared, row-major sorted, value-symmetric pattern (what the
+    normalisation kernels emit for reference-built graphs): ews = (in, out, undirected) values in
+    pattern order.  Symmetry makes grouped-by-target == grouped-by-source == the row CSR."""
+    st = EdgeStructure.__new__(EdgeStructure)
+    st.n, st.shared = n, True
+    csr = _Csr(rowptr, col, [w.contiguous() for w in ews])
+    st.by_dst, st.by_src = [csr], [csr]
+    st.nnz_total = 3 * int(col.numel())
+    st._keepalive = (ei, ews)
+    if len(_STRUCT_CACHE) > 16:
+        _STRUCT_CACHE.clear()
+    _STRUCT_CACHE[_cache_key((ei, ei, ei), ews, n)] = st
+
+
 def get_structure(eis, ews, n: int) -> EdgeStructure:
-    key = tuple((t.data_ptr(), tuple(t.shape), t._version) if t is not None else None for t in (*eis, *ews)) + (n,)
+    key = _cache_key(eis, ews, n)
     st = _STRUCT_CACHE.get(key)
     if st is None:
         if len(_STRUCT_CACHE) > 16:
