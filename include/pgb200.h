@@ -73,6 +73,10 @@ int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d
                    int sigma, unsigned long long *d_bins, uint8_t *d_short_present,
                    pg_stream_t stream);
 
+/* Test hook: 1 forces the global-atomics variant of pg_ngram_count (default: shared-memory
+ * privatised tables whenever sigma^(n+1) fits), so parity tests can cover both. */
+void pg_debug_force_global_count(int on);
+
 /* Replaces data_builder.py:151-177 (distinct + sorted ids) and :281-286 (edge table).
  * Step 1: d_sizes[0] = #nodes (distinct n-grams), d_sizes[1] = #unique transitions; also leaves
  *         the node-id table and edge offsets in the workspace for step 2.

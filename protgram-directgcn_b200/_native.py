@@ -25,6 +25,7 @@ _SIGS = {
     "pg_byte_presence": (c_int, [_P, c_int64, _P, _P]),
     "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
     "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
+    "pg_debug_force_global_count": (None, [c_int]),
     "pg_graph_extract_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_graph_extract_sizes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_graph_extract_fill": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -48,6 +48,9 @@ def discover_alphabet(d_buf: torch.Tensor, group=None) -> Tuple[np.ndarray, torc
         import torch.distributed as dist
         dist.all_reduce(pres, op=dist.ReduceOp.MAX, group=group)
     present = pres.cpu().numpy() != 0
+    if present[128:].any():
+        # the kernels treat every byte >= 0x80 as the sequence separator (7-bit ASCII contract)
+        raise ValueError("corpus buffer holds non-ASCII bytes; unsupported on the CUDA path")
     return alphabet_from_presence(present, d_buf.device)
 
 

@@ -209,8 +209,17 @@ def test_synth_corpus_matches_cpu_twin_and_is_shard_independent():
     assert np.array_equal(a, ref[1 + 600 * 52:])
 
 
+@pytest.fixture(params=["smem", "global"])
+def count_variant(request):
+    """pg_ngram_count has two kernels (shared-memory privatised tables / global REDs): run both."""
+    lib = nat.load()
+    lib.pg_debug_force_global_count(1 if request.param == "global" else 0)
+    yield request.param
+    lib.pg_debug_force_global_count(0)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
-def test_count_and_extract_vs_c_oracle(n):
+def test_count_and_extract_vs_c_oracle(n, count_variant):
     """~1.4 M residues, 20-letter alphabet: dense tables and extracted graph bit-exact vs oracle/ngram_count.c"""
     from oracle import c_oracle
     d_buf = _device_corpus(4000, 350)
@@ -226,6 +235,22 @@ def test_count_and_extract_vs_c_oracle(n):
     assert corpus.decode_nodes(node_code.cpu().numpy(), symbols, n) == nodes_ref
     assert np.array_equal(src.cpu().numpy(), src_ref) and np.array_equal(dst.cpu().numpy(), dst_ref)
     assert np.array_equal(cnt.cpu().numpy(), cnt_ref)
+
+
+def test_count_lane_overflow_homopolymer(count_variant):
+    """Adversarial for the 16-bit shared-memory lanes: 3 M identical windows (one homopolymer per
+    sequence) must still count exactly (lane drains at 32768 into the 64-bit table)."""
+    from oracle import c_oracle
+    seqs = ["A" * 3000] * 1000 + ["AC" * 700] * 300
+    buf = c_oracle.pack_corpus(seqs)
+    symbols, rank = c_oracle.alphabet(buf)
+    d_buf = corpus.to_device(buf, DEV)
+    d_rank = torch.from_numpy(rank).to(DEV)
+    for n in (1, 3):
+        ref, _ = c_oracle.count_level(buf, n, rank, symbols.size)
+        bins, _ = data_builder.count_level(d_buf, n, d_rank, symbols.size)
+        assert np.array_equal(bins.cpu().numpy().astype(np.uint64), ref)
+        assert int(bins.max()) > 2_900_000
 
 
 def test_count_ragged_tail_and_chunked_accumulation():

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Runs the two dominant kernels a few times at benchmark size, for `ncu --set full` captures:
+   ngram_count (C2 corpus, n=3) and the nv=3 fan-out / fan-in SpMM on the R-MAT graph of bench.py.
+usage: python tools/run_kernels.py [count] [spmm] [--log2 N]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["count", "spmm"]
+    log2 = int(sys.argv[sys.argv.index("--log2") + 1]) if "--log2" in sys.argv else 21
+    torch.cuda.set_device(0)
+    pipe = bench.B200Pipeline(0, 1, torch.device("cuda", 0))
+    if "count" in which:
+        symbols, d_rank = pipe.corpus.discover_alphabet(pipe.d_buf)
+        for _ in range(3):
+            bins, short = pipe.db.count_level(pipe.d_buf, bench.N_LEVEL, d_rank, int(symbols.size))
+        torch.cuda.synchronize()
+        print("count ok", int(bins.sum()))
+    if "spmm" in which:
+        out = bench.spmm_large_leg(pipe, 6548.5, log2, iters=2)
+        print({k: (v if not isinstance(v, dict) else {a: round(b, 3) for a, b in v.items()}) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
