@@ -114,6 +114,7 @@ class B200Pipeline:
         from protgram_directgcn_b200.host import corpus, data_builder, graph_utils
         self.pg, self.nat, self.corpus, self.db, self.gu = pg, nat, corpus, data_builder, graph_utils
         self.rank, self.world, self.dev = rank, world, device
+        self.use_cuda_graph = True
         self.group = None
         if world > 1:
             import torch.distributed as dist
@@ -124,7 +125,7 @@ class B200Pipeline:
         self.h_buf = None
         self.count_ms = []
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        self.model = self.opt = self.x = self.labels = None
+        self.model = self.opt = self.x = self.labels = self.graphed = None
 
     # ---- hot path A on a device-resident corpus; returns the device edge table + matrices
     def build(self, d_buf, materialise_host: bool):
@@ -145,9 +146,8 @@ class B200Pipeline:
             dist.all_reduce(s32, op=dist.ReduceOp.MAX, group=self.group)
             short = s32.to(torch.uint8)
         node_code, src, dst, cnt = db.extract_level(bins, short, N_LEVEL, sigma)
-        names = self.corpus.decode_nodes(node_code.cpu().numpy(), symbols, N_LEVEL)   # node ids <-> n-gram strings
-        nodes = dict(enumerate(names))
-        graph = self.gu.DirectedNgramGraph.from_edge_arrays(nodes, src, dst, cnt.to(torch.float32), n_value=N_LEVEL,
+        names = self.corpus.decode_nodes(node_code.cpu().numpy(), symbols, N_LEVEL)   # node id -> n-gram string
+        graph = self.gu.DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), n_value=N_LEVEL,
                                                             assume_coalesced=True,
                                                             result_device="cpu" if materialise_host else self.dev)
         return graph
@@ -159,14 +159,30 @@ class B200Pipeline:
         n = graph.number_of_nodes
         self.num_nodes = n
         self.model = self.pg.ProtGramDirectGCN(DIMS, n, n, N_LEVEL, 0, 512, DROPOUT, True).to(self.dev)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR, fused=True)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR, fused=True, capturable=True)
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         g = torch.Generator().manual_seed(SEED)
         self.x = torch.randn(n, DIMS[0], generator=g).to(self.dev)
         self.labels = next_node_labels(graph.A_out_w.coalesce().cpu(), n).to(self.dev)
+        self.graphed = None
+        if self.use_cuda_graph:
+            from protgram_directgcn_b200.host.graphed_step import GraphedDirectGCNStep
+            cap = int(graph.mathcal_A_out._nnz() * 1.05) + 1024
+            self.graphed = GraphedDirectGCNStep(self.model, self.opt, self.x, self.labels, n, cap, l2_lambda=L2_LAMBDA)
 
     def train_and_extract(self, graph):
         self.ensure_model(graph)
+        if self.graphed is not None:
+            side = getattr(graph, "_pg_device", None)
+            if side is None or side["col"].device != self.dev:   # graph object came back from the host: trainer-style .to(device)
+                m_in, m_out, m_un = graph.mathcal_A_in.to(self.dev), graph.mathcal_A_out.to(self.dev), graph.A_undirected_norm_sparse.to(self.dev)
+                rowptr = torch.zeros(graph.number_of_nodes + 1, dtype=torch.int64, device=self.dev)
+                rows = m_in.indices()[0].contiguous()
+                self.nat.call("pg_rowptr_from_sorted", self.nat.ptr(rows), rows.numel(), graph.number_of_nodes, self.nat.ptr(rowptr), self.nat.stream_ptr())
+                self.graphed.load_structure(rowptr, m_in.indices()[1].to(torch.int32), m_in.values(), m_out.values(), m_un.values())
+            else:
+                self.graphed.load_structure(side["rowptr"], side["col"], side["val_in"], side["val_out"], side["val_und"])
+            return self.graphed.replay()
         data = graph.gcn_data(self.x, self.dev)
         self.model.train()
         self.opt.zero_grad(set_to_none=True)
@@ -259,6 +275,38 @@ def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iter
     return out
 
 
+def phase_breakdown(pipe, reps=5):
+    """Untimed diagnostic: wall-clock per phase of the resident step with a device sync after each phase."""
+    import collections
+    nat, db = pipe.nat, pipe.db
+    acc = collections.OrderedDict()
+
+    def lap(name, t):
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        acc[name] = acc.get(name, 0.0) + (now - t) * 1e3 / reps
+        return now
+
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        symbols, d_rank = pipe.corpus.discover_alphabet(pipe.d_buf, None)
+        t = lap("alphabet", t)
+        sigma = int(symbols.size)
+        bins, short = db.count_level(pipe.d_buf, N_LEVEL, d_rank, sigma)
+        t = lap("count", t)
+        node_code, src, dst, cnt = db.extract_level(bins, short, N_LEVEL, sigma)
+        t = lap("extract", t)
+        names = pipe.corpus.decode_nodes(node_code.cpu().numpy(), symbols, N_LEVEL)
+        t = lap("node_names", t)
+        graph = pipe.gu.DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), n_value=N_LEVEL,
+                                                            assume_coalesced=True, result_device=pipe.dev)
+        t = lap("graph_object+normalise", t)
+        pipe.train_and_extract(graph)
+        t = lap("directgcn_step", t)
+    return {k: round(v, 3) for k, v in acc.items()}
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -272,6 +320,7 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     pipe = B200Pipeline(rank, world, dev)
+    pipe.use_cuda_graph = not args.no_cuda_graph
     nat = pipe.nat
     peak_gbs, peak_src = peaks()
 
@@ -287,6 +336,7 @@ def run_b200(args):
         pipe.count_ms.clear()
         barrier()
         l0 = nat.kernel_launches()
+        r0 = pipe.graphed.replays if pipe.graphed is not None else 0
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
@@ -303,7 +353,10 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps, wall / steps, nat.kernel_launches() - l0, last
+        launches = nat.kernel_launches() - l0
+        if pipe.graphed is not None:  # kernels replayed from the captured CUDA graph do not pass the host-side counter
+            launches += (pipe.graphed.replays - r0) * pipe.graphed.kernels_per_replay
+        return ms / steps, wall / steps, launches, last
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -328,7 +381,8 @@ def run_b200(args):
         "config": {"workload": WORKLOAD, "residues_per_step_per_gpu": NSEQ * SEQ_LEN, "n": N_LEVEL, "layer_dims": DIMS,
                    "nodes": graph.number_of_nodes, "unique_edges": graph.number_of_edges, "pattern_nnz": int(graph.mathcal_A_out._nnz()),
                    "l2_handling": "inputs larger than L2 (corpus 176 MB per GPU > 126 MB L2)",
-                   "multi_gpu": "corpus sharded by sequence range, tables merged by NCCL all-reduce, n=3 DirectGCN replicated"},
+                   "multi_gpu": "corpus sharded by sequence range, tables merged by NCCL all-reduce, n=3 DirectGCN replicated",
+                   "directgcn_step": "eager" if args.no_cuda_graph else "CUDA graph replay (fwd+loss+bwd+Adam+eval fwd captured once)"},
         "clocks": clocks, "gpu_launches": int(launches / max(1, args.steps)),
         "e2e": {"value": residues / (e2e_ms * 1e-3), "unit": "residues/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d + gcn_h2d),
                 "d2h_bytes_per_step": int(d2h)},
@@ -342,6 +396,19 @@ def run_b200(args):
                             "share_of_step": count_ms / ms_step,
                             "note": "1 B/residue read; limiter is L2 atomic throughput (175 M RED.ADD.64 per launch), see DESIGN.md"}
         line["build"] = {"count_residues_per_s": NSEQ * SEQ_LEN / (count_ms * 1e-3)}
+    if rank == 0:
+        line["phases_ms"] = phase_breakdown(pipe)
+    if rank == 0 and args.profile_host:
+        import cProfile
+        import pstats
+        prof = cProfile.Profile()
+        prof.enable()
+        for _ in range(10):
+            pipe.step_resident()
+        torch.cuda.synchronize()
+        prof.disable()
+        with open(args.profile_host, "w") as fh:
+            pstats.Stats(prof, stream=fh).sort_stats("cumulative").print_stats(45)
     if rank == 0 and world == 1 and not args.no_large:
         try:
             line["spmm_large"] = spmm_large_leg(pipe, peak_gbs, args.large_log2_nodes)
@@ -469,7 +536,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-large", action="store_true", help="skip the large-graph SpMM leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the DirectGCN step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--large-log2-nodes", type=int, default=21)
+    ap.add_argument("--profile-host", default=None, help="write a cProfile of 10 resident steps to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,7 +71,8 @@ def decode_nodes(node_code: np.ndarray, symbols: np.ndarray, n: int) -> List[str
         code //= sigma
     if code.size == 0:
         return []
-    # fixed-width bytes -> str in one vectorised cast; numpy strips trailing NULs only, and NUL
-    # cannot occur (it would have to be a corpus byte), so trailing spaces survive
-    return np.ascontiguousarray(chars).view(f"S{n}").ravel().astype(f"U{n}").tolist() if 0 not in symbols else \
-        [row.tobytes().decode("ascii") for row in chars]
+    # 7-bit ASCII bytes widened to UCS4 code points and viewed as fixed-width unicode: one vectorised
+    # cast instead of 8k Python-level decodes (numpy 'U' strips trailing NULs only; NUL never ranks).
+    if 0 in symbols:
+        return [row.tobytes().decode("ascii") for row in chars]
+    return chars.astype(np.uint32).view(f"U{n}").ravel().tolist()

@@ -76,9 +76,8 @@ def build_level_graph(d_buf: torch.Tensor, n: int, symbols: np.ndarray, d_rank: 
         dist.all_reduce(short_i, op=dist.ReduceOp.MAX, group=group)
         short = short_i.to(torch.uint8)
     node_code, src, dst, cnt = extract_level(bins, short, n, sigma)
-    names = corpus.decode_nodes(node_code.cpu().numpy(), symbols, n)
-    nodes = dict(enumerate(names))
-    return DirectedNgramGraph.from_edge_arrays(nodes, src, dst, cnt.to(torch.float32), epsilon_propagation=eps,
+    names = corpus.decode_nodes(node_code.cpu().numpy(), symbols, n)   # id -> n-gram string, id order
+    return DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), epsilon_propagation=eps,
                                                n_value=n, assume_coalesced=True)
 
 

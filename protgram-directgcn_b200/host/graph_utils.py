@@ -15,14 +15,59 @@ import torch
 from .. import _native as nat
 
 
-class Graph:
+class _LazyMaps:
+    """idx_to_node / node_to_idx are views derived from node_sequences; they are built on first
+    access (an 8k-entry dict costs more host time than the whole GPU graph build) and always
+    written into pickles, so a pickled graph has the reference's attribute layout."""
+
+    def _maps(self):
+        d = self.__dict__
+        if d.get("_idx_to_node") is None:
+            names = d.get("node_sequences", [])
+            d["_idx_to_node"] = dict(zip(range(len(names)), names))
+            d["_node_to_idx"] = dict(zip(names, range(len(names))))
+        return d["_idx_to_node"], d["_node_to_idx"]
+
+    @property
+    def idx_to_node(self):
+        return self._maps()[0]
+
+    @idx_to_node.setter
+    def idx_to_node(self, value):
+        self._maps()
+        self.__dict__["_idx_to_node"] = value
+
+    @property
+    def node_to_idx(self):
+        return self._maps()[1]
+
+    @node_to_idx.setter
+    def node_to_idx(self, value):
+        self._maps()
+        self.__dict__["_node_to_idx"] = value
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        i2n, n2i = self._maps()
+        state.pop("_idx_to_node", None)
+        state.pop("_node_to_idx", None)
+        state["idx_to_node"], state["node_to_idx"] = i2n, n2i
+        state.pop("_pg_device", None)  # device-side CSR sidecar never enters the pickle
+        return state
+
+    def __setstate__(self, state):
+        state = dict(state)
+        self.__dict__["_idx_to_node"] = state.pop("idx_to_node", None)
+        self.__dict__["_node_to_idx"] = state.pop("node_to_idx", None)
+        self.__dict__.update(state)
+
+
+class Graph(_LazyMaps):
     """Base container: id <-> n-gram maps (reference graph_utils.py:19-87)."""
 
     def __init__(self, nodes: Dict[int, Any], edges: List[Tuple]):
         self.idx_to_node_map_from_constructor = nodes if nodes is not None else {}
         self.original_edges = edges if edges is not None else []
-        self.node_to_idx: Dict[Any, int] = {}
-        self.idx_to_node: Dict[int, Any] = {}
         self.number_of_nodes: int = 0
         self.node_sequences: List[Any] = []
         self.edges: List[Tuple] = []
@@ -31,6 +76,12 @@ class Graph:
 
     def _process_constructor_inputs(self):
         node_map = self.idx_to_node_map_from_constructor
+        if isinstance(node_map, list):
+            # internal fast path: GraphBuilder hands over the decoded names in id order
+            self.idx_to_node_map_from_constructor = {}
+            self.number_of_nodes = len(node_map)
+            self.node_sequences = node_map
+            return
         if not node_map and not self.original_edges:
             return
         top = -1
@@ -43,8 +94,6 @@ class Graph:
         self.number_of_nodes = top + 1
         names = [node_map.get(i) for i in range(self.number_of_nodes)]
         self.node_sequences = [str(nm) if nm is not None else f"__NODE_{i}__" for i, nm in enumerate(names)]
-        self.idx_to_node = dict(enumerate(self.node_sequences))
-        self.node_to_idx = {nm: i for i, nm in self.idx_to_node.items()}
         self.edges = self.original_edges
         self.number_of_edges = len(self.edges)
 
@@ -151,11 +200,6 @@ class DirectedNgramGraph(Graph):
         self.mathcal_A_out = _empty_coo(n)
         self.mathcal_A_in = _empty_coo(n)
 
-    def __getstate__(self):
-        state = dict(self.__dict__)
-        state.pop("_pg_device", None)  # device-side CSR sidecar never enters the pickle
-        return state
-
     def gcn_data(self, x: torch.Tensor, device, **extra):
         """Data object for ProtGramDirectGCN with the three propagation matrices attached the way
         the reference trainer does (protgram_directgcn_trainer.py:362-367).  When this graph was
@@ -167,7 +211,7 @@ class DirectedNgramGraph(Graph):
         if side is not None and side["pattern"].device == dev:
             ei = side["pattern"]
             ew = (side["val_in"], side["val_out"], side["val_und"])
-            register_symmetric_structure(ei, ew, self.number_of_nodes, side["rowptr"], side["col"])
+            register_symmetric_structure(ei, ew, self.number_of_nodes, side["rowptr"], side["col"], static=False)
         else:
             ei = self.mathcal_A_in.indices().to(dev)
             ew = tuple(t.values().to(dev) for t in (self.mathcal_A_in, self.mathcal_A_out, self.A_undirected_norm_sparse))

@@ -102,19 +102,28 @@ _STRUCT_CACHE: Dict[tuple, EdgeStructure] = {}
 
 
 def _cache_key(eis, ews, n):
-    return tuple((t.data_ptr(), tuple(t.shape), t._version) if t is not None else None for t in (*eis, *ews)) + (n,)
+    return tuple((t.data_ptr(), tuple(t.shape)) if t is not None else None for t in (*eis, *ews)) + (n,)
 
 
-def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Tensor, col: torch.Tensor) -> None:
+def _versions(eis, ews):
+    return tuple(t._version if t is not None else -1 for t in (*eis, *ews))
+
+
+def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Tensor, col: torch.Tensor,
+                                 static: bool = True) -> None:
     """Hand the layer a ready CSR for a shared, row-major sorted, value-symmetric pattern (what the
     normalisation kernels emit for reference-built graphs): ews = (in, out, undirected) values in
-    pattern order.  Symmetry makes grouped-by-target == grouped-by-source == the row CSR."""
+    pattern order.  Symmetry makes grouped-by-target == grouped-by-source == the row CSR.
+    static=True: the buffers are rewritten in place by their owner (CUDA-graph replay), so the
+    cached structure stays valid across version bumps of the tensors."""
     st = EdgeStructure.__new__(EdgeStructure)
     st.n, st.shared = n, True
     csr = _Csr(rowptr, col, [w.contiguous() for w in ews])
     st.by_dst, st.by_src = [csr], [csr]
     st.nnz_total = 3 * int(col.numel())
     st._keepalive = (ei, ews)
+    st._static = static
+    st._vers = _versions((ei, ei, ei), ews)
     if len(_STRUCT_CACHE) > 16:
         _STRUCT_CACHE.clear()
     _STRUCT_CACHE[_cache_key((ei, ei, ei), ews, n)] = st
@@ -123,11 +132,15 @@ def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Te
 def get_structure(eis, ews, n: int) -> EdgeStructure:
     key = _cache_key(eis, ews, n)
     st = _STRUCT_CACHE.get(key)
+    if st is not None and not getattr(st, "_static", False) and st._vers != _versions(eis, ews):
+        st = None  # tensors were modified in place since the CSR was built
     if st is None:
         if len(_STRUCT_CACHE) > 16:
             _STRUCT_CACHE.clear()
         st = EdgeStructure(eis, ews, n)
         st._keepalive = (eis, ews)  # data_ptr keys stay valid while cached
+        st._static = False
+        st._vers = _versions(eis, ews)
         _STRUCT_CACHE[key] = st
     return st
 
