@@ -276,6 +276,18 @@ def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
 
 
 # --------------------------------------------------------------------------- monkeypatch glue
+class _Setter:
+    """monkeypatch-like setter for worker processes (no pytest fixture there)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def install_plain(nat):
+    install(_Setter, nat)
+
+
 def install(monkeypatch, nat):
     """Route protgram_directgcn_b200._native through this module (CPU tensors, tests only)."""
     spec = globals()

@@ -1,0 +1,145 @@
+"""N > 1 paths on CPU: world_size-2 gloo process groups, native entry points replaced by their
+executable spec (tests/kernel_spec.py) so only the host-side sharding / collective logic is under
+test here.  The same code runs over NCCL on the GPU box (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import BUILD_FIXTURES, MATS, fasta_sequences, load
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _init(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from protgram_directgcn_b200 import _native as nat
+    from tests import kernel_spec
+    kernel_spec.install_plain(nat)
+    return nat
+
+
+def _builder_worker(rank, world, port, fasta_path, out_dir, n_max, q):
+    try:
+        _init(rank, world, port)
+        import protgram_directgcn_b200 as pg
+        cfg = pg.Config()
+        cfg.GCN_INPUT_FASTA_PATH = fasta_path
+        cfg.BASE_OUTPUT_DIR = out_dir
+        cfg.GRAPH_OBJECTS_DIR = os.path.join(out_dir, "graphs")
+        cfg.GCN_NGRAM_MAX_N = n_max
+        cfg.GRAPH_BUILDER_PROCESS_GROUP = dist.group.WORLD
+        pg.GraphBuilder(cfg).run()
+        dist.barrier()
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["build_protein", "build_ragged"])
+def test_sharded_builder_equals_reference(name, tmp_path):
+    """Corpus split over 2 ranks by sequence range, tables merged by all-reduce: bit-exact nodes,
+    edges and counts against the reference goldens (== the single-rank result)."""
+    g = load(name)
+    fasta = fasta_sequences(str(g["fasta"]), tmp_path)
+    n_max = BUILD_FIXTURES[name]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_builder_worker, args=(r, 2, port, fasta, str(tmp_path), n_max, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+    import protgram_directgcn_b200 as pg
+    from tests.test_host_logic_cpu import check_graph_against_golden
+    for n in range(1, n_max + 1):
+        graph = pg.DataUtils.load_object(os.path.join(str(tmp_path), "graphs", f"ngram_graph_n{n}.pkl"))
+        check_graph_against_golden(graph, g, n)
+
+
+def _prop_worker(rank, world, port, payload, q):
+    try:
+        nat = _init(rank, world, port)
+        from protgram_directgcn_b200.host.partitioned import RowPartitionedPropagation, row_range
+        from protgram_directgcn_b200.host.protgram_directgcn import _Csr
+        rowptr, col, vals, x, gz, n, symmetric, t_rowptr_list, t_col_list, t_vals_list = payload
+        lo, hi, per = row_range(n, rank, world)
+        transposed = None
+        if not symmetric:
+            transposed = _Csr(t_rowptr_list[rank], t_col_list[rank], t_vals_list[rank])
+        prop = RowPartitionedPropagation(rowptr, col, vals, n, symmetric=symmetric, transposed=transposed)
+        xl = x[lo:hi].clone().requires_grad_(True)
+        z = prop(xl)
+        gl = torch.zeros_like(z)
+        gl[: hi - lo] = gz[lo:hi]
+        z.backward(gl)
+        q.put((rank, z.detach()[: hi - lo].numpy(), xl.grad.numpy()))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_row_partitioned_propagation_equals_single(symmetric):
+    from protgram_directgcn_b200.host.partitioned import row_range
+    rng = np.random.default_rng(4 if symmetric else 5)
+    n, f, world = 301, 12, 2
+    dense = [np.where(rng.random((n, n)) < 0.03, rng.standard_normal((n, n)), 0.0).astype(np.float32) for _ in range(3)]
+    mask = (dense[0] != 0) | (dense[1] != 0) | (dense[2] != 0)
+    if symmetric:
+        mask = mask | mask.T
+        dense = [np.where(mask, (d + d.T) / 2 + 0.1, 0).astype(np.float32) for d in dense]
+    else:
+        dense = [np.where(mask, d + 0.1, 0).astype(np.float32) for d in dense]
+    rows, cols = np.nonzero(mask)
+    rowptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64))
+    col = torch.from_numpy(cols.astype(np.int32))
+    vals = [torch.from_numpy(d[rows, cols]) for d in dense]
+    x = torch.from_numpy(rng.standard_normal((n, f)).astype(np.float32))
+    gz = torch.from_numpy(rng.standard_normal((n, 3 * f)).astype(np.float32))
+    # single-process truth
+    z_ref = torch.cat([torch.from_numpy(d) @ x for d in dense], dim=1)
+    dx_ref = sum(torch.from_numpy(d).t() @ gz[:, v * f:(v + 1) * f] for v, d in enumerate(dense))
+    # source-grouped CSR of each rank's row block (general case): rows = global source id, cols = local target index
+    t_rp, t_col, t_vals = [], [], []
+    for r in range(world):
+        lo, hi, per = row_range(n, r, world)
+        blk = mask[lo:hi]
+        tr, ts = np.nonzero(blk)            # local target, global source
+        order = np.lexsort((tr, ts))
+        ts_s, tr_s = ts[order], tr[order]
+        t_rp.append(torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(ts_s, minlength=world * per))]).astype(np.int64)))
+        t_col.append(torch.from_numpy(tr_s.astype(np.int32)))
+        t_vals.append([torch.from_numpy(d[lo:hi][tr_s, ts_s]) for d in dense])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    payload = (rowptr, col, vals, x, gz, n, symmetric, t_rp, t_col, t_vals)
+    procs = [ctx.Process(target=_prop_worker, args=(r, world, port, payload, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(r[1], str) for r in res), res
+    z = np.concatenate([r[1] for r in res])
+    dx = np.concatenate([r[2][: row_range(n, r[0], world)[1] - row_range(n, r[0], world)[0]] for r in res])
+    assert np.max(np.abs(z - z_ref.numpy())) <= 1e-4 * np.max(np.abs(z_ref.numpy()))
+    assert np.max(np.abs(dx - dx_ref.numpy())) <= 1e-4 * np.max(np.abs(dx_ref.numpy()))
