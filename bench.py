@@ -254,11 +254,13 @@ def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iter
     y = torch.empty(n, F, device=dev)
     st = nat.stream_ptr()
     args = (nat.ptr(res["rowptr"]), nat.ptr(res["col"]), nat.ptr(res["val_in"]), nat.ptr(res["val_out"]), nat.ptr(res["val_und"]), 3, n, F)
-    fo = lambda: nat.call("pg_spmm_fanout", *args, nat.ptr(x), F, nat.ptr(z), 3 * F, 0, st)
-    fi = lambda: nat.call("pg_spmm_fanin", *args, nat.ptr(z), 3 * F, 0, None, 0, nat.ptr(y), F, 0, st)
+    plan = nat.SpmmPlan(res["rowptr"])
+    fo = lambda: nat.call("pg_spmm_fanout", *args, nat.ptr(x), F, nat.ptr(z), 3 * F, 0, plan.ref(3 * F), st)
+    fi = lambda: nat.call("pg_spmm_fanin", *args, nat.ptr(z), 3 * F, 0, None, 0, nat.ptr(y), F, 0, plan.ref(3 * F), st)
     out = {"graph": f"R-MAT 2^{log2_nodes} nodes, {e} directed edges before dedupe, pattern nnz {P}", "F": F, "pattern_nnz": P}
     deg = (res["rowptr"][1:] - res["rowptr"][:-1])
     out["max_row_nnz"] = int(deg.max())
+    out["long_rows"] = {"chunk": plan.chunk, "rows": plan.n_long, "slices": plan.n_items}
     for name, fn, bytes_alg in (("fanout_fwd", fo, 8 * (n + 1) + 16 * P + 4 * F * P + 12 * n * F),
                                 ("fanin_bwd", fi, 8 * (n + 1) + 16 * P + 12 * F * P + 4 * n * F)):
         for _ in range(2):
@@ -311,6 +313,8 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its banner there)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)

@@ -146,6 +146,21 @@ int pg_edges_to_csr(const int64_t *d_group, const int64_t *d_other, const float 
  * Hot path B: DirectGCN propagation (protgram_directgcn.py:93-140) forward and backward
  * ---------------------------------------------------------------------------------------- */
 
+/* Load-balancing plan for skewed degree distributions (optional, NULL = one lane group per row).
+ * Rows with more than `chunk` stored entries ("long" rows) are cut into n_items slices of `chunk`
+ * entries, one lane group each; slices write partial sums into d_partials, which a second kernel
+ * adds up in slice order, so results stay bitwise reproducible.  The plan only depends on rowptr
+ * and is built once per graph by the host (host/protgram_directgcn.py: SpmmPlan). */
+typedef struct pg_spmm_plan {
+    int32_t chunk;              /* entries per slice; rows with nnz > chunk are long          */
+    int64_t n_long;             /* number of long rows (0 => plan ignored)                   */
+    int64_t n_items;            /* total number of slices                                    */
+    const int32_t *d_long_rows; /* [n_long]   row ids, ascending                             */
+    const int64_t *d_item_ptr;  /* [n_long+1] first slice of each long row                   */
+    const int32_t *d_item_row;  /* [n_items]  index into d_long_rows                         */
+    float *d_partials;          /* scratch: n_items x max(nv*F) floats                       */
+} pg_spmm_plan;
+
 /* Fan-out SpMM (forward aggregation): for v < nv:
  *     Z[i, v*F : (v+1)*F] = sum_k val_v[k] * X[col[k], :]      k in row i of the shared CSR
  * nv = 3 with one shared pattern is the fused dual-direction + undirected propagate
@@ -155,7 +170,7 @@ int pg_edges_to_csr(const int64_t *d_group, const int64_t *d_other, const float 
 int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
                    const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
                    const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
-                   pg_stream_t stream);
+                   const pg_spmm_plan *plan, pg_stream_t stream);
 
 /* Fan-in SpMM (backward of the above over the transposed structure; forward of nothing else):
  *     Y[i, :] = (d_init ? init[i, :] : 0) + sum_v sum_k val_v[k] * G[col[k], g_off + v*F : +F]
@@ -164,7 +179,7 @@ int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d
 int pg_spmm_fanin(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
                   const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
                   const float *d_g, int64_t ldg, int64_t g_off, const float *d_init, int64_t ldinit,
-                  float *d_y, int64_t ldy, int accumulate, pg_stream_t stream);
+                  float *d_y, int64_t ldy, int accumulate, const pg_spmm_plan *plan, pg_stream_t stream);
 
 /* Fused dense transform of one DirectGCN layer (the collapsed algebra of SURVEY.md 7.2):
  *   A_ext[i, :] = [ a_i*Z_in[i] | b_i*Z_out[i] | c_i*Z_und[i] | X[i] (if has_res) | a_i b_i c_i | 1 (if has_res) ]

@@ -41,9 +41,9 @@ _SIGS = {
     "pg_coo_from_csr": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "pg_edges_to_csr_ws_bytes": (c_size_t, [c_int64]),
     "pg_edges_to_csr": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
-    "pg_spmm_fanout": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P]),
+    "pg_spmm_fanout": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P, _P]),
     "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
-                              c_int64, c_int, _P]),
+                              c_int64, c_int, _P, _P]),
     "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
                                   c_int, c_int, c_int, c_float, _P, c_int64, _P]),
     "pg_lrelu_bwd": (c_int, [_P, _P, c_float, c_int64, _P, _P]),
@@ -54,6 +54,49 @@ _SIGS = {
                                          c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
 }
+
+class SpmmPlanStruct(ctypes.Structure):
+    """Mirror of `pg_spmm_plan` (include/pgb200.h)."""
+    _fields_ = [("chunk", ctypes.c_int32), ("n_long", c_int64), ("n_items", c_int64), ("d_long_rows", _P),
+                ("d_item_ptr", _P), ("d_item_row", _P), ("d_partials", _P)]
+
+
+class SpmmPlan:
+    """Long-row work split for the SpMM kernels, built once per CSR structure (depends on rowptr only).
+    Keeps its device arrays alive; `.ref(width)` returns the pointer to pass as `plan` (None if the
+    structure has no long rows)."""
+
+    CHUNK = 512
+
+    def __init__(self, rowptr: torch.Tensor, chunk: int = CHUNK):
+        deg = rowptr[1:] - rowptr[:-1]
+        long_rows = torch.nonzero(deg > chunk).flatten()
+        self.chunk = int(chunk)
+        self.n_long = int(long_rows.numel())
+        self.n_items = 0
+        self._struct = None
+        self._partials = None
+        if self.n_long:
+            per = (deg[long_rows] + chunk - 1) // chunk
+            item_ptr = torch.zeros(self.n_long + 1, dtype=torch.int64, device=rowptr.device)
+            item_ptr[1:] = torch.cumsum(per, 0)
+            self.n_items = int(item_ptr[-1])
+            self.long_rows = long_rows.to(torch.int32).contiguous()
+            self.item_ptr = item_ptr
+            self.item_row = torch.repeat_interleave(torch.arange(self.n_long, device=rowptr.device, dtype=torch.int32), per).contiguous()
+
+    def ref(self, width: int):
+        if not self.n_long:
+            return None
+        need = self.n_items * int(width)
+        if self._partials is None or self._partials.numel() < need:
+            self._partials = torch.empty(need, dtype=torch.float32, device=self.long_rows.device)
+            self._struct = None
+        if self._struct is None:
+            self._struct = SpmmPlanStruct(self.chunk, self.n_long, self.n_items, ptr(self.long_rows), ptr(self.item_ptr),
+                                          ptr(self.item_row), ptr(self._partials))
+        return ctypes.byref(self._struct)
+
 
 _lib = None
 launches = 0  # number of C-ABI calls that enqueue GPU work (bench.py reports it)

@@ -24,18 +24,50 @@ __device__ __forceinline__ void fma4(float4 &acc, float s, const float4 &x) {
     acc.w = fmaf(s, x.w, acc.w);
 }
 
+// Work mapping.  Rows mode: group g owns row g; rows longer than `skip_above` nnz are left to the
+// long-row pass.  Items mode (long_rows != nullptr): group g owns one `chunk`-nnz slice of a long
+// row and writes a partial sum to its own output row g (combined afterwards in item order, so the
+// result stays bitwise reproducible however skewed the degrees are).
+struct RowMap {
+    int64_t num_groups;
+    int64_t skip_above;           // rows mode: 0 = no limit
+    const int32_t *long_rows;     // items mode
+    const int64_t *item_ptr;
+    const int32_t *item_row;
+    int32_t chunk;
+};
+
+__device__ __forceinline__ bool map_group(const RowMap &m, const int64_t *__restrict__ rowptr, int64_t g, int64_t *rb,
+                                          int64_t *re, int64_t *out_row) {
+    if (m.long_rows != nullptr) {
+        const int32_t li = m.item_row[g];
+        const int64_t row = m.long_rows[li];
+        const int64_t b = rowptr[row] + (g - m.item_ptr[li]) * (int64_t)m.chunk;
+        *rb = b;
+        *re = min(b + m.chunk, rowptr[row + 1]);
+        *out_row = g;
+        return true;
+    }
+    *rb = rowptr[g];
+    *re = rowptr[g + 1];
+    *out_row = g;
+    return !(m.skip_above > 0 && *re - *rb > m.skip_above);
+}
+
 template <int NV, int LPR, int CHUNKS>
 __global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                           const float *__restrict__ val0, const float *__restrict__ val1,
-                                                          const float *__restrict__ val2, int64_t num_rows, int F,
+                                                          const float *__restrict__ val2, RowMap map, int F,
                                                           const float *__restrict__ x, int64_t ldx, float *__restrict__ z,
                                                           int64_t ldz, int64_t z_off) {
     constexpr int UNROLL = (CHUNKS == 1) ? 4 : 2;
     const int lane = threadIdx.x & 31;
     const int lg = lane & (LPR - 1);                       // lane inside the row group
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    if (row >= num_rows) return;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    if (gid >= map.num_groups) return;
+    int64_t rb, re, row;
+    if (!map_group(map, rowptr, gid, &rb, &re, &row)) return;
     const int nvec = F >> 2;                               // float4 per feature row
     float4 acc[NV][CHUNKS];
 #pragma unroll
@@ -43,7 +75,6 @@ __global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restr
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) acc[v][c] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const int64_t rb = rowptr[row], re = rowptr[row + 1];
     for (int64_t base = rb; base < re; base += LPR) {
         const int cnt = (int)min((int64_t)LPR, re - base);
         int my_col = 0;
@@ -114,15 +145,17 @@ __global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restr
 template <int NV, int LPR, int CHUNKS>
 __global__ void __launch_bounds__(256) spmm_fanin_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                          const float *__restrict__ val0, const float *__restrict__ val1,
-                                                         const float *__restrict__ val2, int64_t num_rows, int F,
+                                                         const float *__restrict__ val2, RowMap map, int F,
                                                          const float *__restrict__ g, int64_t ldg, int64_t g_off,
                                                          const float *__restrict__ init, int64_t ldinit, float *__restrict__ y,
                                                          int64_t ldy, int accumulate) {
     const int lane = threadIdx.x & 31;
     const int lg = lane & (LPR - 1);
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    if (row >= num_rows) return;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    if (gid >= map.num_groups) return;
+    int64_t rb, re, row;
+    if (!map_group(map, rowptr, gid, &rb, &re, &row)) return;
     const int nvec = F >> 2;
     float4 acc[CHUNKS];
 #pragma unroll
@@ -137,7 +170,6 @@ __global__ void __launch_bounds__(256) spmm_fanin_kernel(const int64_t *__restri
             }
         }
     }
-    const int64_t rb = rowptr[row], re = rowptr[row + 1];
     for (int64_t base = rb; base < re; base += LPR) {
         const int cnt = (int)min((int64_t)LPR, re - base);
         int my_col = 0;
@@ -251,6 +283,23 @@ __global__ void __launch_bounds__(256) spmm_fanin_scalar_kernel(const int64_t *_
     }
 }
 
+// Combine the partial sums of the long rows in item order (fixed order => reproducible).
+__global__ void __launch_bounds__(256) spmm_reduce_long_kernel(const int32_t *__restrict__ long_rows, const int64_t *__restrict__ item_ptr,
+                                                               int64_t n_long, int width, const float *__restrict__ partials,
+                                                               float *__restrict__ out, int64_t ldo, int64_t o_off,
+                                                               const float *__restrict__ init, int64_t ldinit, int accumulate) {
+    const int64_t li = blockIdx.x;
+    if (li >= n_long) return;
+    const int64_t row = long_rows[li];
+    const int64_t ib = item_ptr[li], ie = item_ptr[li + 1];
+    for (int f = threadIdx.x; f < width; f += blockDim.x) {
+        float acc = init ? init[row * ldinit + f] : 0.f;
+        if (accumulate) acc += out[row * ldo + o_off + f];
+        for (int64_t it = ib; it < ie; ++it) acc += partials[it * width + f];
+        out[row * ldo + o_off + f] = acc;
+    }
+}
+
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 // pick the row-group width: smallest power of two >= F/4, capped at 32 lanes x 4 chunks (F <= 512)
@@ -265,11 +314,30 @@ inline bool pick_shape(int F, int *lpr, int *chunks) {
     *chunks = c;
     return true;
 }
+
+inline RowMap rows_map(int64_t num_rows, const pg_spmm_plan *plan) {
+    RowMap m;
+    m.num_groups = num_rows;
+    m.skip_above = (plan && plan->n_long > 0) ? plan->chunk : 0;
+    m.long_rows = nullptr; m.item_ptr = nullptr; m.item_row = nullptr; m.chunk = 0;
+    return m;
+}
+inline RowMap items_map(const pg_spmm_plan *plan) {
+    RowMap m;
+    m.num_groups = plan->n_items;
+    m.skip_above = 0;
+    m.long_rows = plan->d_long_rows; m.item_ptr = plan->d_item_ptr; m.item_row = plan->d_item_row; m.chunk = plan->chunk;
+    return m;
+}
+inline bool plan_ok(const pg_spmm_plan *plan) {
+    return !plan || plan->n_long == 0 ||
+           (plan->chunk > 0 && plan->n_items >= plan->n_long && plan->d_long_rows && plan->d_item_ptr && plan->d_item_row && plan->d_partials);
+}
 }  // namespace
 
-#define PG_SPMM_DISPATCH(KERNEL, NV, ...)                                                             \
+#define PG_SPMM_DISPATCH(KERNEL, NV, GROUPS, ...)                                                     \
     do {                                                                                              \
-        const unsigned grid = (unsigned)pg_ceil_div(num_rows * lpr, 256);                             \
+        const unsigned grid = (unsigned)pg_ceil_div((GROUPS) * lpr, 256);                             \
         if (lpr == 4) KERNEL<NV, 4, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                            \
         else if (lpr == 8) KERNEL<NV, 8, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                       \
         else if (lpr == 16) KERNEL<NV, 16, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);                     \
@@ -280,46 +348,74 @@ inline bool pick_shape(int F, int *lpr, int *chunks) {
 
 extern "C" int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
                               const float *d_val2, int nv, int64_t num_rows, int F, const float *d_x, int64_t ldx, float *d_z,
-                              int64_t ldz, int64_t z_off, pg_stream_t stream) {
+                              int64_t ldz, int64_t z_off, const pg_spmm_plan *plan, pg_stream_t stream) {
     cudaStream_t st = pg_cu(stream);
     PG_CHECK_ARG(nv == 1 || nv == 3, "pg_spmm_fanout: nv must be 1 or 3 (got %d)", nv);
     PG_CHECK_ARG(num_rows >= 0 && F >= 1 && ldx >= F && ldz >= z_off + (int64_t)nv * F && z_off >= 0, "pg_spmm_fanout: bad shape");
+    PG_CHECK_ARG(plan_ok(plan), "pg_spmm_fanout: malformed plan");
     if (num_rows == 0) return PG_OK;
     PG_CHECK_ARG(d_rowptr && d_col && d_val0 && d_x && d_z && (nv == 1 || (d_val1 && d_val2)), "pg_spmm_fanout: null buffer");
+    const float *v1 = nv == 3 ? d_val1 : d_val0, *v2 = nv == 3 ? d_val2 : d_val0;
     int lpr = 0, chunks = 0;
     const bool vec = pick_shape(F, &lpr, &chunks) && aligned16(d_x) && aligned16(d_z) && ldx % 4 == 0 && ldz % 4 == 0 && z_off % 4 == 0;
     if (vec) {
-        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
-        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        const RowMap rm = rows_map(num_rows, plan);
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off);
+        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off);
+        PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel");
+        if (plan && plan->n_long > 0) {
+            const RowMap im = items_map(plan);
+            const int64_t w = (int64_t)nv * F;
+            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0);
+            else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0);
+            PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel(long rows)");
+            spmm_reduce_long_kernel<<<(unsigned)plan->n_long, 256, 0, st>>>(plan->d_long_rows, plan->d_item_ptr, plan->n_long, (int)w,
+                                                                            plan->d_partials, d_z, ldz, z_off, nullptr, 0, 0);
+            PG_CUDA_LAUNCH_CHECK("spmm_reduce_long_kernel");
+        }
     } else {
         const unsigned grid = (unsigned)pg_ceil_div(num_rows * 32, 256);
-        if (nv == 3) spmm_fanout_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
-        else spmm_fanout_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        if (nv == 3) spmm_fanout_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        else spmm_fanout_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        PG_CUDA_LAUNCH_CHECK("spmm_fanout_scalar_kernel");
     }
-    PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel");
     return PG_OK;
 }
 
 extern "C" int pg_spmm_fanin(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
                              const float *d_val2, int nv, int64_t num_rows, int F, const float *d_g, int64_t ldg, int64_t g_off,
-                             const float *d_init, int64_t ldinit, float *d_y, int64_t ldy, int accumulate, pg_stream_t stream) {
+                             const float *d_init, int64_t ldinit, float *d_y, int64_t ldy, int accumulate,
+                             const pg_spmm_plan *plan, pg_stream_t stream) {
     cudaStream_t st = pg_cu(stream);
     PG_CHECK_ARG(nv == 1 || nv == 3, "pg_spmm_fanin: nv must be 1 or 3 (got %d)", nv);
     PG_CHECK_ARG(num_rows >= 0 && F >= 1 && ldg >= g_off + (int64_t)nv * F && g_off >= 0 && ldy >= F, "pg_spmm_fanin: bad shape");
     PG_CHECK_ARG(!d_init || ldinit >= F, "pg_spmm_fanin: bad init stride");
+    PG_CHECK_ARG(plan_ok(plan), "pg_spmm_fanin: malformed plan");
     if (num_rows == 0) return PG_OK;
     PG_CHECK_ARG(d_rowptr && d_col && d_val0 && d_g && d_y && (nv == 1 || (d_val1 && d_val2)), "pg_spmm_fanin: null buffer");
+    const float *v1 = nv == 3 ? d_val1 : d_val0, *v2 = nv == 3 ? d_val2 : d_val0;
     int lpr = 0, chunks = 0;
     const bool vec = pick_shape(F, &lpr, &chunks) && aligned16(d_g) && aligned16(d_y) && ldg % 4 == 0 && ldy % 4 == 0 &&
                      g_off % 4 == 0 && (!d_init || (aligned16(d_init) && ldinit % 4 == 0));
     if (vec) {
-        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
-        else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        const RowMap rm = rows_map(num_rows, plan);
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel");
+        if (plan && plan->n_long > 0) {
+            const RowMap im = items_map(plan);
+            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_g, ldg, g_off, nullptr, 0, plan->d_partials, (int64_t)F, 0);
+            else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_g, ldg, g_off, nullptr, 0, plan->d_partials, (int64_t)F, 0);
+            PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel(long rows)");
+            spmm_reduce_long_kernel<<<(unsigned)plan->n_long, 256, 0, st>>>(plan->d_long_rows, plan->d_item_ptr, plan->n_long, F, plan->d_partials,
+                                                                            d_y, ldy, 0, d_init, ldinit, accumulate);
+            PG_CUDA_LAUNCH_CHECK("spmm_reduce_long_kernel");
+        }
     } else {
         const unsigned grid = (unsigned)pg_ceil_div(num_rows * 32, 256);
-        if (nv == 3) spmm_fanin_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val1, d_val2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
-        else spmm_fanin_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, d_val0, d_val0, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        if (nv == 3) spmm_fanin_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        else spmm_fanin_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_g, ldg, g_off, d_init, ldinit, d_y, ldy, accumulate);
+        PG_CUDA_LAUNCH_CHECK("spmm_fanin_scalar_kernel");
     }
-    PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel");
     return PG_OK;
 }

@@ -45,6 +45,7 @@ class GraphedDirectGCNStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.kernels_per_replay = 0
         self.replays = 0
+        self._no_long_rows_checked = True  # set False to validate every load_structure (costs a host sync)
         self._warmup = warmup
 
     def load_structure(self, rowptr: torch.Tensor, col: torch.Tensor, val_in: torch.Tensor, val_out: torch.Tensor,
@@ -54,6 +55,12 @@ class GraphedDirectGCNStep:
         if rowptr.numel() != self.num_nodes + 1 or p > self.capacity:
             raise ValueError(f"structure does not fit the captured step (nodes {rowptr.numel() - 1} vs {self.num_nodes}, "
                              f"nnz {p} vs capacity {self.capacity})")
+        if self.graph is not None and not self._no_long_rows_checked:
+            # the long-row split of the SpMM is planned from rowptr at capture time; a replayed graph
+            # must therefore stay in the "no long rows" regime (always true for n-gram graphs: <= 2*sigma+1)
+            from .. import _native as nat
+            if int((rowptr[1:] - rowptr[:-1]).max()) > nat.SpmmPlan.CHUNK:
+                raise ValueError("captured step cannot take a structure with rows longer than the SpMM chunk; re-capture")
         self.rowptr.copy_(rowptr, non_blocking=True)
         self.col[:p].copy_(col, non_blocking=True)
         for dst, src in zip(self.vals, (val_in, val_out, val_und)):

@@ -63,7 +63,7 @@ def _spmm_fanout(csr: _Csr, x_full: torch.Tensor, rows: int, f: int) -> torch.Te
     z = torch.empty((rows, nv * f), dtype=torch.float32, device=x_full.device)
     v = csr.vals + [None] * (3 - nv)
     nat.call("pg_spmm_fanout", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, rows, f,
-             nat.ptr(x_full), x_full.stride(0), nat.ptr(z), z.stride(0), 0, nat.stream_ptr())
+             nat.ptr(x_full), x_full.stride(0), nat.ptr(z), z.stride(0), 0, csr.plan(3 * f), nat.stream_ptr())
     return z
 
 
@@ -72,7 +72,7 @@ def _spmm_fanin(csr: _Csr, g_full: torch.Tensor, rows: int, f: int) -> torch.Ten
     y = torch.empty((rows, f), dtype=torch.float32, device=g_full.device)
     v = csr.vals + [None] * (3 - nv)
     nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, rows, f,
-             nat.ptr(g_full), g_full.stride(0), 0, None, 0, nat.ptr(y), y.stride(0), 0, nat.stream_ptr())
+             nat.ptr(g_full), g_full.stride(0), 0, None, 0, nat.ptr(y), y.stride(0), 0, csr.plan(3 * f), nat.stream_ptr())
     return y
 
 

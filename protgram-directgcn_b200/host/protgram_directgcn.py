@@ -47,10 +47,17 @@ class Data:
 # edge lists -> cached CSR structures
 # ------------------------------------------------------------------------------------------------
 class _Csr:
-    __slots__ = ("rowptr", "col", "vals")
+    __slots__ = ("rowptr", "col", "vals", "_plan")
 
     def __init__(self, rowptr, col, vals):
         self.rowptr, self.col, self.vals = rowptr, col, vals
+        self._plan = None
+
+    def plan(self, width: int):
+        """Long-row split for skewed degree distributions (built on first use, cached)."""
+        if self._plan is None:
+            self._plan = nat.SpmmPlan(self.rowptr)
+        return self._plan.ref(width)
 
 
 def _edges_to_csr(group: torch.Tensor, other: torch.Tensor, w: Optional[torch.Tensor], n: int) -> _Csr:
@@ -155,11 +162,11 @@ def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int) -> torch.Tensor:
     if struct.shared:
         c = struct.by_dst[0]
         nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
-                 3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, st)
+                 3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, c.plan(3 * f_in), st)
     else:
         for v, c in enumerate(struct.by_dst):
             nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
-                     nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, st)
+                     nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, c.plan(3 * f_in), st)
     return z
 
 
@@ -171,12 +178,13 @@ def _fanin(struct: EdgeStructure, dz: torch.Tensor, f_in: int, init: Optional[to
     if struct.shared:
         c = struct.by_src[0]
         nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
-                 3, n, f_in, nat.ptr(dz), dz.stride(0), 0, nat.ptr(init), ldinit, nat.ptr(dx), dx.stride(0), 0, st)
+                 3, n, f_in, nat.ptr(dz), dz.stride(0), 0, nat.ptr(init), ldinit, nat.ptr(dx), dx.stride(0), 0,
+                 c.plan(3 * f_in), st)
     else:
         for v, c in enumerate(struct.by_src):
             nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
                      nat.ptr(dz), dz.stride(0), v * f_in, nat.ptr(init) if v == 0 else None, ldinit, nat.ptr(dx),
-                     dx.stride(0), 0 if v == 0 else 1, st)
+                     dx.stride(0), 0 if v == 0 else 1, c.plan(3 * f_in), st)
     return dx
 
 

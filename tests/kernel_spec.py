@@ -204,7 +204,7 @@ def _rows_of(rowptr, num_rows):
     return torch.repeat_interleave(torch.arange(num_rows, device=rowptr.device), counts)
 
 
-def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_off, stream=None):
+def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_off, plan=None, stream=None):
     rows = _rows_of(rowptr, num_rows)
     xg = x[:, :F][col.long()]
     for v, val in enumerate((v0, v1, v2)[:nv]):
@@ -212,7 +212,8 @@ def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_o
         z[:, z_off + v * F: z_off + (v + 1) * F] = acc
 
 
-def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, stream=None):
+def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, plan=None,
+                  stream=None):
     rows = _rows_of(rowptr, num_rows)
     acc = torch.zeros(num_rows, F, dtype=g.dtype, device=g.device)
     if init is not None:

@@ -64,7 +64,9 @@ def _random_csr(rng, n_rows, n_cols, avg, skew=False):
 
 @pytest.mark.parametrize("F", [4, 12, 24, 64, 128, 256, 512, 7, 130, 1024])
 @pytest.mark.parametrize("nv", [1, 3])
-def test_spmm_fanout_fanin_vs_spec(F, nv):
+@pytest.mark.parametrize("chunk", [0, 96])
+def test_spmm_fanout_fanin_vs_spec(F, nv, chunk):
+    """chunk = 0: one lane group per row; chunk = 96: the hub rows go through the long-row split."""
     rng = np.random.default_rng(F * 10 + nv)
     n = 300 if F >= 512 else 1000
     rowptr, col, vals = _random_csr(rng, n, n, 9, skew=True)
@@ -83,16 +85,20 @@ def test_spmm_fanout_fanin_vs_spec(F, nv):
     z = torch.zeros(n, 3 * F, device=DEV)
     y = torch.empty(n, F, device=DEV)
     st = nat.stream_ptr()
+    plan = nat.SpmmPlan(rp, chunk=chunk) if chunk else None
+    pref = (lambda w: plan.ref(w)) if plan is not None else (lambda w: None)
+    if chunk:
+        assert plan.n_long >= 1 and plan.n_items > plan.n_long
     nat.call("pg_spmm_fanout", nat.ptr(rp), nat.ptr(cl), nat.ptr(vs[0]), nat.ptr(vs[1]), nat.ptr(vs[2]), nv, n, F, nat.ptr(xd), F,
-             nat.ptr(z), 3 * F, z_off, st)
+             nat.ptr(z), 3 * F, z_off, pref(3 * F), st)
     nat.call("pg_spmm_fanin", nat.ptr(rp), nat.ptr(cl), nat.ptr(vs[0]), nat.ptr(vs[1]), nat.ptr(vs[2]), nv, n, F, nat.ptr(gd), 3 * F,
-             z_off, nat.ptr(initd), F, nat.ptr(y), F, 0, st)
+             z_off, nat.ptr(initd), F, nat.ptr(y), F, 0, pref(3 * F), st)
     assert rel_err(z.cpu().numpy(), z_ref.numpy()) <= 5e-6
     assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= 5e-6
     # run-to-run bitwise reproducibility (fixed accumulation order)
     z2 = torch.zeros_like(z)
     nat.call("pg_spmm_fanout", nat.ptr(rp), nat.ptr(cl), nat.ptr(vs[0]), nat.ptr(vs[1]), nat.ptr(vs[2]), nv, n, F, nat.ptr(xd), F,
-             nat.ptr(z2), 3 * F, z_off, st)
+             nat.ptr(z2), 3 * F, z_off, pref(3 * F), st)
     assert torch.equal(z, z2)
 
 

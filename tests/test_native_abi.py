@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound():
 def test_argument_errors_are_reported_not_crashed():
     lib = nat.load()
     # pure argument validation happens before any CUDA call
-    rc = lib.pg_spmm_fanout(None, None, None, None, None, 2, 10, 8, None, 8, None, 24, 0, None)
+    rc = lib.pg_spmm_fanout(None, None, None, None, None, 2, 10, 8, None, 8, None, 24, 0, None, None)
     assert rc == -1 and b"nv must be 1 or 3" in lib.pg_last_error()
     rc = lib.pg_ngram_count(None, 0, 3, None, 21, None, None, None)
     assert rc == -1
