@@ -408,7 +408,7 @@ def run_b200(args):
         prof = cProfile.Profile()
         prof.enable()
         for _ in range(10):
-            pipe.step_resident()
+            pipe.step_e2e() if args.profile_e2e else pipe.step_resident()
         torch.cuda.synchronize()
         prof.disable()
         with open(args.profile_host, "w") as fh:
@@ -543,6 +543,7 @@ def main():
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the DirectGCN step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--large-log2-nodes", type=int, default=21)
     ap.add_argument("--profile-host", default=None, help="write a cProfile of 10 resident steps to this file")
+    ap.add_argument("--profile-e2e", action="store_true", help="profile e2e steps instead of resident ones")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

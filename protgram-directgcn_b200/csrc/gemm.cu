@@ -57,70 +57,125 @@ __device__ __forceinline__ float4 ld4_guard(const float *p, int64_t ld, int64_t 
     return make_float4(t[0], t[1], t[2], t[3]);
 }
 
-constexpr int BM = 128, BN = 64, BK = 16;
-constexpr int APAD = 4;
+constexpr int BN = 64, BK = 16, PAD = 4;
 
 // -------------------------------------------------------------------------------------------
-// forward:  H[M, F_out] = epilogue(A_ext @ W_ext)
+// One SIMT fp32 mainloop for the three GEMMs of a layer: C[m, n] = sum_k A(m, k) * B(k, n).
+// 256 threads, (BM x 64) output tile, BK = 16, operands staged k-major in shared memory with a
+// register-prefetched double buffer (one __syncthreads per k-tile).  The operand functors do the
+// layout work (gating, virtual columns, transposes), the epilogue functors the fusion.
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layer_gemm_fwd_kernel(AExt A, const float *__restrict__ w_ext, int F_out, bool w_vec,
-                                                             const float *__restrict__ constant, int64_t ldconst,
-                                                             int add_identity, float slope, float *__restrict__ h, int64_t ldh,
-                                                             bool h_vec) {
-    __shared__ __align__(16) float As[BK][BM + APAD];
-    __shared__ __align__(16) float Bs[BK][BN];
-    const int tid = threadIdx.x;
-    const int tm = tid >> 4, tn = tid & 15;          // 16 x 16 threads, 8 x 4 outputs each
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
-    float acc[8][4];
+struct OpA_Ext {  // forward: A(m, k) = A_ext[m, k]
+    AExt A;
+    template <int BM_>
+    __device__ __forceinline__ void load(float4 (&r)[BM_ / 64], int64_t m0, int64_t k0, int tid) const {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    for (int k0 = 0; k0 < A.k_ext; k0 += BK) {
-        // A tile: 128 rows x 16 k = 512 float4, two per thread, stored k-major
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
             const int idx = tid + rep * 256;
-            const int r = idx >> 2, kq = (idx & 3) * 4;
-            const float4 v = A.at4(m0 + r, k0 + kq);
-            As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+            r[rep] = A.at4(m0 + (idx >> 2), (int)k0 + (idx & 3) * 4);
         }
-        {   // B tile: 16 k x 64 n = 256 float4, one per thread
-            const int kr = tid >> 4, nq = (tid & 15) * 4;
-            const float4 v = ld4_guard(w_ext, F_out, k0 + kr, A.k_ext, n0 + nq, F_out, w_vec);
-            *reinterpret_cast<float4 *>(&Bs[kr][nq]) = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][tm * 8]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][tm * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tn * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-        }
-        __syncthreads();
     }
-    // epilogue: + identity residual + constant, leaky_relu
+    template <int BM_>
+    __device__ __forceinline__ void store(float (*As)[BM_ + PAD], const float4 (&r)[BM_ / 64], int tid) const {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t r = m0 + tm * 8 + i;
-        if (r >= A.M) continue;
-        const int c0 = n0 + tn * 4;
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            const int m = idx >> 2, kq = (idx & 3) * 4;
+            As[kq + 0][m] = r[rep].x; As[kq + 1][m] = r[rep].y; As[kq + 2][m] = r[rep].z; As[kq + 3][m] = r[rep].w;
+        }
+    }
+};
+
+struct OpA_Plain {  // backward data: A(m, k) = dY[m, k]
+    const float *p;
+    int64_t ld, M;
+    int ncols;
+    bool vec;
+    template <int BM_>
+    __device__ __forceinline__ void load(float4 (&r)[BM_ / 64], int64_t m0, int64_t k0, int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            r[rep] = ld4_guard(p, ld, m0 + (idx >> 2), M, (int)k0 + (idx & 3) * 4, ncols, vec);
+        }
+    }
+    template <int BM_>
+    __device__ __forceinline__ void store(float (*As)[BM_ + PAD], const float4 (&r)[BM_ / 64], int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            const int m = idx >> 2, kq = (idx & 3) * 4;
+            As[kq + 0][m] = r[rep].x; As[kq + 1][m] = r[rep].y; As[kq + 2][m] = r[rep].z; As[kq + 3][m] = r[rep].w;
+        }
+    }
+};
+
+struct OpA_ExtT {  // backward weights: A(m = ext column, k = node row) = A_ext[k, m]
+    AExt A;        // A.M = end of this split's row range (rows beyond read as zero)
+    template <int BM_>
+    __device__ __forceinline__ void load(float4 (&r)[BM_ / 64], int64_t m0, int64_t k0, int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            r[rep] = A.at4(k0 + idx / (BM_ / 4), (int)m0 + (idx % (BM_ / 4)) * 4);
+        }
+    }
+    template <int BM_>
+    __device__ __forceinline__ void store(float (*As)[BM_ + PAD], const float4 (&r)[BM_ / 64], int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            *reinterpret_cast<float4 *>(&As[idx / (BM_ / 4)][(idx % (BM_ / 4)) * 4]) = r[rep];
+        }
+    }
+};
+
+struct OpB_Rows {  // B(k, n) = p[k, n]  (W_ext for the forward, dY for the weight gradient)
+    const float *p;
+    int64_t ld, nrows;
+    int ncols;
+    bool vec;
+    __device__ __forceinline__ void load(float4 &r, int n0, int64_t k0, int tid) const {
+        r = ld4_guard(p, ld, k0 + (tid >> 4), nrows, n0 + (tid & 15) * 4, ncols, vec);
+    }
+    __device__ __forceinline__ void store(float (*Bs)[BN + PAD], const float4 &r, int tid) const {
+        *reinterpret_cast<float4 *>(&Bs[tid >> 4][(tid & 15) * 4]) = r;
+    }
+};
+
+struct OpB_Trans {  // B(k, n) = p[n, k]  (W_ext^T for the data gradient)
+    const float *p;
+    int64_t ld, nrows;  // nrows = extent of n
+    int ncols;          // extent of k
+    bool vec;
+    __device__ __forceinline__ void load(float4 &r, int n0, int64_t k0, int tid) const {
+        r = ld4_guard(p, ld, n0 + (tid >> 2), nrows, (int)k0 + (tid & 3) * 4, ncols, vec);
+    }
+    __device__ __forceinline__ void store(float (*Bs)[BN + PAD], const float4 &r, int tid) const {
+        const int n = tid >> 2, kq = (tid & 3) * 4;
+        Bs[kq + 0][n] = r.x; Bs[kq + 1][n] = r.y; Bs[kq + 2][n] = r.z; Bs[kq + 3][n] = r.w;
+    }
+};
+
+struct Epi_Fwd {  // H = leaky_relu(acc (+ X) + constant)
+    const float *x;
+    int64_t ldx;
+    const float *constant;
+    int64_t ldconst;
+    float *h;
+    int64_t ldh, M;
+    int F_out, add_identity;
+    float slope;
+    bool h_vec;
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int) const {
+        if (r >= M) return;
         float y[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + j;
-            float v = acc[i][j];
+            float v = acc[j];
             if (c < F_out) {
-                if (add_identity) v += A.x[r * A.ldx + c];
+                if (add_identity) v += x[r * ldx + c];
                 if (constant) v += constant[r * ldconst + c];
                 if (slope != 1.f) v = v > 0.f ? v : v * slope;
             }
@@ -134,67 +189,107 @@ __global__ void __launch_bounds__(256) layer_gemm_fwd_kernel(AExt A, const float
                 if (c0 + j < F_out) h[r * ldh + c0 + j] = y[j];
         }
     }
-}
+};
 
-// -------------------------------------------------------------------------------------------
-// backward (data):  dA[M, k_data] = dY[M, F_out] @ W_ext[:k_data, :]^T   -> dZ (raw) | dXres
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layer_gemm_bwd_data_kernel(const float *__restrict__ dy, int64_t lddy, bool dy_vec,
-                                                                  const float *__restrict__ w_ext, bool w_vec, int64_t M, int F_in,
-                                                                  int F_out, int k_data, float *__restrict__ dz, int64_t lddz,
-                                                                  float *__restrict__ dxres, int64_t lddxres) {
-    __shared__ __align__(16) float As[BK][BM + APAD];   // dY tile, k (= f) major
-    __shared__ __align__(16) float Bs[BK][BN + APAD];   // W_ext^T tile: Bs[f][kd]
-    const int tid = threadIdx.x;
-    const int tm = tid >> 4, tn = tid & 15;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;                     // column of dA = row of W_ext
-    float acc[8][4];
+struct Epi_BwdData {  // dA columns -> dZ (raw, gated later) | dXres
+    float *dz;
+    int64_t lddz;
+    float *dxres;
+    int64_t lddxres, M;
+    int F_in, k_data;
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int) const {
+        if (r >= M) return;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            if (c >= k_data) continue;
+            if (c < 3 * F_in) dz[r * lddz + c] = acc[j];
+            else dxres[r * lddxres + (c - 3 * F_in)] = acc[j];
+        }
+    }
+};
+
+struct Epi_Partial {  // split-K partial of dW_ext
+    float *partial;
+    int rows, cols;  // k_ext, F_out
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int z) const {
+        if (r >= rows) return;
+        float *out = partial + (int64_t)z * rows * cols + r * cols;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < cols) out[c0 + j] = acc[j];
+    }
+};
+
+template <int BM_, class OpA, class OpB, class Epi>
+__global__ void __launch_bounds__(256) gemm_kernel(OpA opa, OpB opb, Epi epi, int64_t k_total, int64_t k_per_z) {
+    constexpr int TM = BM_ / 16;
+    __shared__ __align__(16) float As[2][BK][BM_ + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+    const int tid = threadIdx.x;
+    const int tm = tid >> 4, tn = tid & 15;  // 16 x 16 threads, TM x 4 outputs each
+    const int64_t m0 = (int64_t)blockIdx.x * BM_;
+    const int n0 = blockIdx.y * BN;
+    const int64_t kb = (int64_t)blockIdx.z * k_per_z;
+    const int64_t ke = min(k_total, kb + k_per_z);
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    for (int k0 = 0; k0 < F_out; k0 += BK) {
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
-            const int idx = tid + rep * 256;
-            const int r = idx >> 2, kq = (idx & 3) * 4;
-            const float4 v = ld4_guard(dy, lddy, m0 + r, M, k0 + kq, F_out, dy_vec);
-            As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    float4 ra[BM_ / 64], rb;
+    if (kb < ke) {
+        opa.template load<BM_>(ra, m0, kb, tid);
+        opb.load(rb, n0, kb, tid);
+        opa.template store<BM_>(As[0], ra, tid);
+        opb.store(Bs[0], rb, tid);
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+        const bool more = k0 + BK < ke;
+        if (more) {
+            opa.template load<BM_>(ra, m0, k0 + BK, tid);
+            opb.load(rb, n0, k0 + BK, tid);
         }
-        {   // 64 rows of W_ext (kd) x 16 f = 256 float4, one per thread, stored f-major
-            const int r = tid >> 2, kq = (tid & 3) * 4;
-            const float4 v = ld4_guard(w_ext, F_out, n0 + r, k_data, k0 + kq, F_out, w_vec);
-            Bs[kq + 0][r] = v.x; Bs[kq + 1][r] = v.y; Bs[kq + 2][r] = v.z; Bs[kq + 3][r] = v.w;
-        }
-        __syncthreads();
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][tm * 8]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][tm * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tn * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+            float a[TM];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TM; i += 4) {
+                const float4 av = *reinterpret_cast<const float4 *>(&As[cur][k][tm * TM + i]);
+                a[i] = av.x; a[i + 1] = av.y; a[i + 2] = av.z; a[i + 3] = av.w;
+            }
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[cur][k][tn * 4]);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t r = m0 + tm * 8 + i;
-        if (r >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + tn * 4 + j;
-            if (c >= k_data) continue;
-            if (c < 3 * F_in) dz[r * lddz + c] = acc[i][j];
-            else dxres[r * lddxres + (c - 3 * F_in)] = acc[i][j];
+        if (more) {
+            opa.template store<BM_>(As[cur ^ 1], ra, tid);
+            opb.store(Bs[cur ^ 1], rb, tid);
         }
+        __syncthreads();
+        cur ^= 1;
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) epi(acc[i], m0 + tm * TM + i, n0 + tn * 4, (int)blockIdx.z);
+}
+
+template <class OpA, class OpB, class Epi>
+int launch_gemm(OpA opa, OpB opb, Epi epi, int64_t M, int64_t N, int64_t k_total, int64_t k_per_z, int z, cudaStream_t st) {
+    const int64_t tiles128 = pg_ceil_div(M, 128) * pg_ceil_div(N, BN) * z;
+    if (tiles128 >= 2 * PG_NUM_SMS) {
+        dim3 grid((unsigned)pg_ceil_div(M, 128), (unsigned)pg_ceil_div(N, BN), (unsigned)z);
+        gemm_kernel<128, OpA, OpB, Epi><<<grid, 256, 0, st>>>(opa, opb, epi, k_total, k_per_z);
+    } else {  // small problems: more, smaller tiles to fill 148 SMs
+        dim3 grid((unsigned)pg_ceil_div(M, 64), (unsigned)pg_ceil_div(N, BN), (unsigned)z);
+        gemm_kernel<64, OpA, OpB, Epi><<<grid, 256, 0, st>>>(opa, opb, epi, k_total, k_per_z);
+    }
+    PG_CUDA_LAUNCH_CHECK("gemm_kernel");
+    return PG_OK;
 }
 
 // gate gradients + gating of dZ:  one warp per row
@@ -228,61 +323,6 @@ __global__ void __launch_bounds__(256) gate_grad_kernel(float *__restrict__ dz, 
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) dot[v] += __shfl_xor_sync(0xffffffffu, dot[v], s);
             if (lane == 0) dgate[(int64_t)v * M + r] = dot[v];
-        }
-    }
-}
-
-// -------------------------------------------------------------------------------------------
-// backward (weights):  dW_ext[k_ext, F_out] = A_ext^T @ dY, rows split into `splits` slices
-// -------------------------------------------------------------------------------------------
-constexpr int WM = 64, WN = 64, WR = 16;  // output tile 64 (k_ext) x 64 (f), 16 rows per step
-
-__global__ void __launch_bounds__(256) layer_gemm_bwd_weight_kernel(AExt A, const float *__restrict__ dy, int64_t lddy, bool dy_vec,
-                                                                    int F_out, int64_t rows_per_split, float *__restrict__ partial) {
-    __shared__ __align__(16) float As[WR][WM];
-    __shared__ __align__(16) float Bs[WR][WN];
-    const int tid = threadIdx.x;
-    const int tm = tid >> 4, tn = tid & 15;          // 16 x 16 threads, 4 x 4 outputs each
-    const int kx0 = blockIdx.x * WM;
-    const int n0 = blockIdx.y * WN;
-    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
-    const int64_t r_end = min(A.M, r_begin + rows_per_split);
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    AExt Ac = A;
-    Ac.M = r_end;  // rows beyond the slice read as zero
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += WR) {
-        {   // 16 rows x 64 kx = 256 float4 each
-            const int rr = tid >> 4, q = (tid & 15) * 4;
-            *reinterpret_cast<float4 *>(&As[rr][q]) = Ac.at4(r0 + rr, kx0 + q);
-            *reinterpret_cast<float4 *>(&Bs[rr][q]) = ld4_guard(dy, lddy, r0 + rr, r_end, n0 + q, F_out, dy_vec);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < WR; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[k][tm * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tn * 4]);
-            const float aa[4] = {a.x, a.y, a.z, a.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float *out = partial + (int64_t)blockIdx.z * A.k_ext * F_out;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int kx = kx0 + tm * 4 + i;
-        if (kx >= A.k_ext) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + tn * 4 + j;
-            if (c < F_out) out[(int64_t)kx * F_out + c] = acc[i][j];
         }
     }
 }
@@ -341,9 +381,9 @@ AExt make_aext(const float *z, int64_t ldz, const float *x, int64_t ldx, const f
 }
 
 int split_count(int64_t M, int k_ext, int F_out) {
-    const int64_t tiles = pg_ceil_div(k_ext, WM) * pg_ceil_div(F_out, WN);
+    const int64_t tiles = pg_ceil_div(k_ext, 64) * pg_ceil_div(F_out, BN);
     int64_t s = pg_ceil_div(2 * PG_NUM_SMS, tiles);
-    const int64_t max_s = pg_ceil_div(M, 4 * WR);
+    const int64_t max_s = pg_ceil_div(M, 4 * BK);
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
     if (s > 1024) s = 1024;
@@ -365,11 +405,10 @@ extern "C" int pg_layer_gemm_fwd(const float *d_z, int64_t ldz, const float *d_x
     AExt A = make_aext(d_z, ldz, d_x, ldx, d_gate_a, d_gate_b, d_gate_c, gate_stride, num_rows, F_in, has_res);
     const bool w_vec = F_out % 4 == 0 && al16(d_w_ext);
     const bool h_vec = F_out % 4 == 0 && al16(d_h) && ldh % 4 == 0;
-    dim3 grid((unsigned)pg_ceil_div(num_rows, BM), (unsigned)pg_ceil_div(F_out, BN));
-    layer_gemm_fwd_kernel<<<grid, 256, 0, pg_cu(stream)>>>(A, d_w_ext, F_out, w_vec, d_constant, ldconst, add_identity, slope, d_h,
-                                                           ldh, h_vec);
-    PG_CUDA_LAUNCH_CHECK("layer_gemm_fwd_kernel");
-    return PG_OK;
+    OpA_Ext opa{A};
+    OpB_Rows opb{d_w_ext, F_out, A.k_ext, F_out, w_vec};
+    Epi_Fwd epi{d_x, ldx, d_constant, ldconst, d_h, ldh, num_rows, F_out, add_identity, slope, h_vec};
+    return launch_gemm(opa, opb, epi, num_rows, F_out, A.k_ext, A.k_ext, 1, pg_cu(stream));
 }
 
 extern "C" int pg_lrelu_bwd(const float *d_dh, const float *d_h, float slope, int64_t numel, float *d_dy, pg_stream_t stream) {
@@ -395,10 +434,13 @@ extern "C" int pg_layer_gemm_bwd_data(const float *d_dy, int64_t lddy, const flo
     const bool dy_vec = F_out % 4 == 0 && al16(d_dy) && lddy % 4 == 0;
     const bool w_vec = F_out % 4 == 0 && al16(d_w_ext);
     cudaStream_t st = pg_cu(stream);
-    dim3 grid((unsigned)pg_ceil_div(num_rows, BM), (unsigned)pg_ceil_div(k_data, BN));
-    layer_gemm_bwd_data_kernel<<<grid, 256, 0, st>>>(d_dy, lddy, dy_vec, d_w_ext, w_vec, num_rows, F_in, F_out, k_data, d_dz, lddz,
-                                                     d_dxres, lddxres);
-    PG_CUDA_LAUNCH_CHECK("layer_gemm_bwd_data_kernel");
+    {
+        OpA_Plain opa{d_dy, lddy, num_rows, F_out, dy_vec};
+        OpB_Trans opb{d_w_ext, F_out, k_data, F_out, w_vec};
+        Epi_BwdData epi{d_dz, lddz, d_dxres, lddxres, num_rows, F_in, k_data};
+        int rc = launch_gemm(opa, opb, epi, num_rows, k_data, F_out, F_out, 1, st);
+        if (rc != PG_OK) return rc;
+    }
     gate_grad_kernel<<<grid_for(num_rows * 32), 256, 0, st>>>(d_dz, lddz, d_z, ldz, d_dy, lddy, d_w_ext, d_gate_a, d_gate_b, d_gate_c,
                                                               gate_stride, num_rows, F_in, F_out, k_data, d_dgate);
     PG_CUDA_LAUNCH_CHECK("gate_grad_kernel");
@@ -430,11 +472,15 @@ extern "C" int pg_layer_gemm_bwd_weight(const float *d_z, int64_t ldz, const flo
         return PG_EWORKSPACE;
     }
     int64_t rows_per_split = pg_ceil_div(num_rows, splits);
-    rows_per_split = pg_ceil_div(rows_per_split, WR) * WR;
+    rows_per_split = pg_ceil_div(rows_per_split, BK) * BK;
     const bool dy_vec = F_out % 4 == 0 && al16(d_dy) && lddy % 4 == 0;
-    dim3 grid((unsigned)pg_ceil_div(A.k_ext, WM), (unsigned)pg_ceil_div(F_out, WN), (unsigned)splits);
-    layer_gemm_bwd_weight_kernel<<<grid, 256, 0, st>>>(A, d_dy, lddy, dy_vec, F_out, rows_per_split, (float *)d_ws);
-    PG_CUDA_LAUNCH_CHECK("layer_gemm_bwd_weight_kernel");
+    {
+        OpA_ExtT opa{A};
+        OpB_Rows opb{d_dy, lddy, num_rows, F_out, dy_vec};
+        Epi_Partial epi{(float *)d_ws, A.k_ext, F_out};
+        int rc = launch_gemm(opa, opb, epi, A.k_ext, F_out, num_rows, rows_per_split, splits, st);
+        if (rc != PG_OK) return rc;
+    }
     reduce_splits_kernel<<<grid_for(numel), 256, 0, st>>>((const float *)d_ws, splits, numel, d_dw_ext);
     PG_CUDA_LAUNCH_CHECK("reduce_splits_kernel");
     return PG_OK;

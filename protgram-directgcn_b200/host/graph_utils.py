@@ -233,13 +233,17 @@ class DirectedNgramGraph(Graph):
         pat = csr_to_coo_indices(res["rowptr"], res["col"], n)
         self._pg_device = {"pattern": pat, "rowptr": res["rowptr"], "col": res["col"], "val_in": res["val_in"],
                            "val_out": res["val_out"], "val_und": res["val_und"]}
-        out = lambda t: t.to(result_device)
-        pat_o = out(pat)
-        self.A_out_w = _coo(out(torch.stack([src_d, dst_d])), out(w_d), n)
-        self.A_in_w = _coo(out(torch.stack([res["in_src"], res["in_dst"]])), out(res["in_w"]), n)
-        self.A_undirected_norm_sparse = _coo(pat_o, out(res["val_und"]), n)
-        self.mathcal_A_out = _coo(pat_o, out(res["val_out"]), n)
-        self.mathcal_A_in = _coo(pat_o, out(res["val_in"]), n)
+        a_out_idx = torch.stack([src_d, dst_d])
+        a_in_idx = torch.stack([res["in_src"], res["in_dst"]])
+        tensors = [a_out_idx, w_d, a_in_idx, res["in_w"], pat, res["val_und"], res["val_out"], res["val_in"]]
+        # (pinned per-call staging was tried and dropped: cudaHostAlloc churn made the step time erratic)
+        tensors = [t.to(result_device) for t in tensors]
+        a_out_idx, w_o, a_in_idx, in_w, pat_o, v_und, v_out, v_in = tensors
+        self.A_out_w = _coo(a_out_idx, w_o, n)
+        self.A_in_w = _coo(a_in_idx, in_w, n)
+        self.A_undirected_norm_sparse = _coo(pat_o, v_und, n)
+        self.mathcal_A_out = _coo(pat_o, v_out, n)
+        self.mathcal_A_in = _coo(pat_o, v_in, n)
 
     # reference :275-287 -- public: the trainer calls it after moving A_*_w to the device
     def _create_propagation_matrices_for_gcn(self):

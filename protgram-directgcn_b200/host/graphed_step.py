@@ -15,6 +15,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+from .models_utils import EmbeddingProcessor
 from .protgram_directgcn import Data, register_symmetric_structure
 
 
@@ -80,9 +81,11 @@ class GraphedDirectGCNStep:
         self.opt.step()
         emb = None
         if self.with_extraction:
+            # extract_gcn_node_embeddings (models_utils.py:265-273) keeps only the embedding: run the layer
+            # stack + L2 normalisation and skip the decoder / log_softmax whose output it discards
             self.model.eval()
             with torch.no_grad():
-                _, emb = self.model(data=self.data)
+                emb = EmbeddingProcessor.l2_normalize_torch(self.model.embed(self.data), eps=self.model.l2_eps)
         return loss, emb
 
     def capture(self) -> None:
