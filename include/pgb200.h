@@ -193,6 +193,21 @@ int pg_layer_gemm_fwd(const float *d_z, int64_t ldz, const float *d_x, int64_t l
                       int64_t ldconst, int64_t num_rows, int F_in, int F_out, int has_res,
                       int add_identity, float slope, float *d_h, int64_t ldh, pg_stream_t stream);
 
+/* Same contract as pg_layer_gemm_fwd, computed on the tcgen05 tensor cores with a 3 x TF32 operand
+ * split (fp32-level accuracy, see csrc/gemm_tc.cu).  Requires F_in % 4 == 0, F_out % 16 == 0,
+ * F_out <= 256 (pg_layer_gemm_fwd_tc_supported) and 16-byte aligned operands; d_ws holds the
+ * pre-split weight image.  pg_layer_gemm_fwd_tc_check (host-synchronising, for tests) reports a
+ * tensor-pipeline watchdog expiry instead of letting a mis-programmed MMA hang the device. */
+int pg_layer_gemm_fwd_tc_supported(int F_in, int F_out);
+size_t pg_layer_gemm_fwd_tc_ws_bytes(int F_in, int F_out, int has_res);
+int pg_layer_gemm_fwd_tc(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx,
+                         const float *d_gate_a, const float *d_gate_b, const float *d_gate_c,
+                         int gate_stride, const float *d_w_ext, const float *d_constant,
+                         int64_t ldconst, int64_t num_rows, int F_in, int F_out, int has_res,
+                         int add_identity, float slope, float *d_h, int64_t ldh, void *d_ws,
+                         size_t ws_bytes, pg_stream_t stream);
+int pg_layer_gemm_fwd_tc_check(const void *d_ws, int F_in, int F_out, int has_res, pg_stream_t stream);
+
 /* dY = dH * leaky_relu'(H)   (elementwise; also the gradient of `constant`). */
 int pg_lrelu_bwd(const float *d_dh, const float *d_h, float slope, int64_t numel, float *d_dy,
                  pg_stream_t stream);

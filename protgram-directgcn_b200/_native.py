@@ -46,6 +46,11 @@ _SIGS = {
                               c_int64, c_int, _P, _P]),
     "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
                                   c_int, c_int, c_int, c_float, _P, c_int64, _P]),
+    "pg_layer_gemm_fwd_tc_supported": (c_int, [c_int, c_int]),
+    "pg_layer_gemm_fwd_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pg_layer_gemm_fwd_tc": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
+                                     c_int, c_int, c_int, c_float, _P, c_int64, _P, c_size_t, _P]),
+    "pg_layer_gemm_fwd_tc_check": (c_int, [_P, c_int, c_int, c_int, _P]),
     "pg_lrelu_bwd": (c_int, [_P, _P, c_float, c_int64, _P, _P]),
     "pg_layer_gemm_bwd_data": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, c_int64, c_int, c_int,
                                        c_int, _P, c_int64, _P, c_int64, _P, _P]),

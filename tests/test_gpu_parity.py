@@ -408,3 +408,38 @@ def test_cuda_graph_step_matches_eager():
     assert abs(losses_g[0] - losses_e[0]) <= 1e-2 * abs(losses_e[0])
     for a, b in zip(m1.parameters(), m2.parameters()):
         assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("n,f_in,f_out,has_res,vec_gate", [(1000, 64, 256, 1, 1), (4096, 256, 256, 0, 1), (777, 128, 128, 1, 1),
+                                                           (5000, 128, 64, 1, 0), (300, 32, 16, 1, 1), (129, 4, 32, 0, 1)])
+def test_layer_gemm_fwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
+    """tcgen05 (3 x TF32 split) forward transform against the fp32 spec: the 1e-4 north-star bar must
+    hold with margin (asserted 2e-5), i.e. the operand split really recovers fp32-level accuracy."""
+    g = torch.Generator().manual_seed(n + f_in)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    z, x = rnd(n, 3 * f_in), rnd(n, f_in)
+    gates = [rnd(n) if vec_gate else rnd(1) for _ in range(3)]
+    k_ext = 3 * f_in + (f_in if has_res else 0) + 3 + (1 if has_res else 0)
+    w_ext = rnd(k_ext, f_out) * 0.2
+    const = rnd(n, f_out)
+    add_identity = int((not has_res) and f_in == f_out)
+    gs = 1 if vec_gate else 0
+    h_ref = torch.empty(n, f_out, dtype=torch.float64)
+    spec.pg_layer_gemm_fwd(z.double(), 3 * f_in, x.double(), f_in, *[t.double() for t in gates], gs, w_ext.double(), const.double(),
+                           f_out, n, f_in, f_out, has_res, add_identity, 0.01, h_ref, f_out)
+    assert nat.query("pg_layer_gemm_fwd_tc_supported", f_in, f_out) == 1
+    d = lambda t: t.to(DEV).contiguous()
+    zd, xd, wd, cd = d(z), d(x), d(w_ext), d(const)
+    gd = [d(t) for t in gates]
+    h = torch.full((n, f_out), float("nan"), device=DEV)
+    ws = _ws(nat.query("pg_layer_gemm_fwd_tc_ws_bytes", f_in, f_out, has_res))
+    st = nat.stream_ptr()
+    nat.call("pg_layer_gemm_fwd_tc", nat.ptr(zd), 3 * f_in, nat.ptr(xd), f_in, nat.ptr(gd[0]), nat.ptr(gd[1]), nat.ptr(gd[2]), gs,
+             nat.ptr(wd), nat.ptr(cd), f_out, n, f_in, f_out, has_res, add_identity, 0.01, nat.ptr(h), f_out, nat.ptr(ws), ws.numel(), st)
+    nat.call("pg_layer_gemm_fwd_tc_check", nat.ptr(ws), f_in, f_out, has_res, st)
+    assert rel_err(h.cpu().numpy(), h_ref.numpy()) <= 2e-5
+    # and against the SIMT kernel (same contract)
+    h2 = torch.empty(n, f_out, device=DEV)
+    nat.call("pg_layer_gemm_fwd", nat.ptr(zd), 3 * f_in, nat.ptr(xd), f_in, nat.ptr(gd[0]), nat.ptr(gd[1]), nat.ptr(gd[2]), gs, nat.ptr(wd),
+             nat.ptr(cd), f_out, n, f_in, f_out, has_res, add_identity, 0.01, nat.ptr(h2), f_out, st)
+    assert rel_err(h.cpu().numpy(), h2.cpu().numpy()) <= 2e-5
