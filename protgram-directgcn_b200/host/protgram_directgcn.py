@@ -188,6 +188,21 @@ def _fanin(struct: EdgeStructure, dz: torch.Tensor, f_in: int, init: Optional[to
     return dx
 
 
+# Dense transform backend: "auto" = tcgen05 tensor cores (3 x TF32 split, fp32-level accuracy) when the
+# hidden width makes it a real contraction (F_out >= 128, north_star) and the shape is supported,
+# SIMT fp32 otherwise; "off" / "force" for tests and A/B timing.
+import os as _os
+
+TC_MODE = _os.environ.get("PGB200_TC", "auto")
+TC_MIN_WIDTH, TC_MIN_ROWS = 128, 4096
+
+
+def _use_tensor_cores(n: int, f_in: int, f_out: int) -> bool:
+    if TC_MODE == "off" or not nat.query("pg_layer_gemm_fwd_tc_supported", f_in, f_out):
+        return False
+    return TC_MODE == "force" or (f_out >= TC_MIN_WIDTH and n >= TC_MIN_ROWS)
+
+
 class _DirectGCNFused(torch.autograd.Function):
     """H = act( [aZ_in | bZ_out | cZ_und | X? | a b c | 1?] @ W_ext (+X) + constant )."""
 
@@ -206,9 +221,16 @@ class _DirectGCNFused(torch.autograd.Function):
         h = torch.empty((n, f_out), dtype=torch.float32, device=x.device)
         if const_rows is not None:
             const_rows = const_rows.contiguous().float()
-        nat.call("pg_layer_gemm_fwd", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
-                 gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), const_rows.stride(0) if const_rows is not None else 0,
-                 n, f_in, f_out, int(has_res), int(add_identity), float(slope), nat.ptr(h), h.stride(0), nat.stream_ptr())
+        ldc = const_rows.stride(0) if const_rows is not None else 0
+        if _use_tensor_cores(n, f_in, f_out) and ldc % 4 == 0:
+            ws = nat.workspace(nat.query("pg_layer_gemm_fwd_tc_ws_bytes", f_in, f_out, int(has_res)), x.device)
+            nat.call("pg_layer_gemm_fwd_tc", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
+                     gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), ldc, n, f_in, f_out, int(has_res), int(add_identity),
+                     float(slope), nat.ptr(h), h.stride(0), nat.ptr(ws), ws.numel(), nat.stream_ptr())
+        else:
+            nat.call("pg_layer_gemm_fwd", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
+                     gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), ldc, n, f_in, f_out, int(has_res), int(add_identity),
+                     float(slope), nat.ptr(h), h.stride(0), nat.stream_ptr())
         ctx.save_for_backward(x, ga, gb, gc, w_ext, z, h)
         ctx.struct, ctx.has_res, ctx.add_identity, ctx.slope = struct, bool(has_res), bool(add_identity), float(slope)
         ctx.gate_stride, ctx.has_const = gate_stride, const_rows is not None

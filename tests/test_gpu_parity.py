@@ -324,7 +324,7 @@ def test_model_matches_reference_gpu(name):
     run_model_case(g, DEV, 2e-5, 1e-4)
 
 
-def test_per_layer_embeddings_vs_oracle_c2_shape():
+def test_per_layer_embeddings_vs_oracle_c2_shape(tol=2e-5):
     """N = 8 000-node random n-gram-like graph, layer dims 64 -> 256 -> 128 -> 64 (reference
     GCN_HIDDEN_LAYER_DIMS): per-layer conv outputs and final embedding vs the CPU oracle."""
     from oracle import directgcn_oracle, graph_oracle
@@ -356,8 +356,8 @@ def test_per_layer_embeddings_vs_oracle_c2_shape():
     for i, conv_ref in enumerate(layers_ref):
         res = h @ params[f"res_projs.{i}.weight"].t() + params[f"res_projs.{i}.bias"] if f"res_projs.{i}.weight" in params else h
         h = torch.nn.functional.leaky_relu(conv_ref + res)
-        assert rel_err(outs[i].numpy(), h.numpy()) <= 2e-5, f"layer {i}"
-    assert rel_err(emb, emb_ref.numpy()) <= 2e-5
+        assert rel_err(outs[i].numpy(), h.numpy()) <= tol, f"layer {i}"
+    assert rel_err(emb, emb_ref.numpy()) <= tol
 
 
 def test_cuda_graph_step_matches_eager():
@@ -443,3 +443,15 @@ def test_layer_gemm_fwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
     nat.call("pg_layer_gemm_fwd", nat.ptr(zd), 3 * f_in, nat.ptr(xd), f_in, nat.ptr(gd[0]), nat.ptr(gd[1]), nat.ptr(gd[2]), gs, nat.ptr(wd),
              nat.ptr(cd), f_out, n, f_in, f_out, has_res, add_identity, 0.01, nat.ptr(h2), f_out, st)
     assert rel_err(h.cpu().numpy(), h2.cpu().numpy()) <= 2e-5
+
+
+def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
+    """Force the tcgen05 dense transform inside the model and re-check the reference goldens
+    (model_refgraph has widths 24/40/16/8 -> only the 16-wide layer qualifies; the C2-shaped oracle
+    check below covers 256/128/64)."""
+    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    model_mod._STRUCT_CACHE.clear()
+    run_model_case(load("model_refgraph"), DEV, 2e-5, 1e-4)
+    # 3 x TF32 (truncating split, lo*lo dropped) carries ~2^-21 per product: after three stacked layers
+    # the worst element sits at ~2e-5 of the layer maximum -- 5x inside the 1e-4 north-star bar
+    test_per_layer_embeddings_vs_oracle_c2_shape(tol=5e-5)
