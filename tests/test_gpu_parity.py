@@ -455,3 +455,70 @@ def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     # 3 x TF32 (truncating split, lo*lo dropped) carries ~2^-21 per product: after three stacked layers
     # the worst element sits at ~2e-5 of the layer maximum -- 5x inside the 1e-4 north-star bar
     test_per_layer_embeddings_vs_oracle_c2_shape(tol=5e-5)
+
+
+def test_c3_n4_graph_and_hidden256_layers_sampled_oracle():
+    """BASELINE config C3 shape: n = 4 graph (~168 k nodes, ~3.2 M directed edges, pattern ~6.6 M) and a
+    3-layer DirectGCN with hidden 256 (tcgen05 dense transform in auto mode).  The CPU oracle cannot run
+    6 x [6.6 M x 256] propagates in seconds, so every layer is checked on 256 sampled target rows: the
+    oracle layer is evaluated on the sub edge lists that end in the sample, fed with the GPU's own
+    previous-layer activations."""
+    from oracle import directgcn_oracle
+    nseq, L, n = 300_000, 350, 4
+    d_buf = _device_corpus(nseq, L)
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    graph = data_builder.build_level_graph(d_buf, n, symbols, d_rank, 1e-9)
+    N = graph.number_of_nodes
+    assert 160_000 <= N <= 170_000 and 3_000_000 <= graph.number_of_edges <= 3_400_000
+    assert int(graph.A_out_w.values().double().sum()) == nseq * (L + 1 - n) + 1   # every window counted once (counts < 2^24: exact in fp32)
+    pat = graph.mathcal_A_out.indices()
+    assert torch.equal(pat, graph.mathcal_A_in.indices()) and torch.equal(pat, graph.A_undirected_norm_sparse.indices())
+    torch.manual_seed(3)
+    model = pg.ProtGramDirectGCN([64, 256, 256, 256], N, 8, n, 0, 512, 0.5, True)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.ndim == 1 or p.shape[-1] == 1:
+                p.add_(0.2 * torch.randn_like(p))
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.randn(N, 64)
+    model = model.to(DEV).eval()
+    data = graph.gcn_data(x, DEV)
+    with torch.no_grad():
+        _, layers = model.embed(data, return_layers=True)
+    layers = [t.cpu() for t in layers]
+    sample = torch.from_numpy(np.random.default_rng(0).choice(N, 256, replace=False))
+    in_sample = torch.zeros(N, dtype=torch.bool)
+    in_sample[sample] = True
+    sub = []
+    for t in (graph.mathcal_A_in, graph.mathcal_A_out, graph.A_undirected_norm_sparse):
+        keep = in_sample[t.indices()[1]]
+        sub += [t.indices()[:, keep], t.values()[keep]]
+    h_prev = x
+    for i, h_gpu in enumerate(layers):
+        conv = directgcn_oracle.directgcn_layer(params, f"convs.{i}.", h_prev, *sub)
+        res = h_prev @ params[f"res_projs.{i}.weight"].t() + params[f"res_projs.{i}.bias"] if f"res_projs.{i}.weight" in params else h_prev
+        ref = torch.nn.functional.leaky_relu(conv + res)[sample]
+        assert rel_err(h_gpu[sample].numpy(), ref.numpy()) <= 5e-5, f"layer {i}"   # north-star bar 1e-4
+        h_prev = h_gpu
+
+
+def test_c4_n5_reduced_vs_c_oracle():
+    """BASELINE config C4 at reduced size: n = 5 (85.8 M-bin table, global-atomics kernel) over
+    400 k x 350 residues, dense table bit-exact against oracle/ngram_count.c; the n = 4 table is its
+    marginal up to the per-sequence boundary windows."""
+    from oracle import c_oracle
+    nseq, L = 400_000, 350
+    d_buf = _device_corpus(nseq, L)
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    sigma = int(symbols.size)
+    bins5, short5 = data_builder.count_level(d_buf, 5, d_rank, sigma)
+    assert int(bins5.sum()) == nseq * (L + 1 - 5) + 1
+    h_buf = d_buf.cpu().numpy()
+    _, rank = c_oracle.alphabet(h_buf)
+    ref, _ = c_oracle.count_level(h_buf, 5, rank, sigma)
+    assert np.array_equal(bins5.cpu().numpy().astype(np.uint64), ref)
+    bins4, _ = data_builder.count_level(d_buf, 4, d_rank, sigma)
+    marg = bins5.view(sigma ** 5, sigma).sum(1)
+    assert int((bins4 - marg).sum()) == nseq and int((bins4 - marg).min()) >= 0
+    node_code, src, dst, cnt = data_builder.extract_level(bins5, short5, 5, sigma)
+    assert 3_000_000 <= node_code.numel() <= 3_500_000 and int(cnt.sum()) == int(bins5.sum())
