@@ -394,11 +394,13 @@ def run_b200(args):
     }
     if count_ms:
         alg = pipe.nbytes
-        line["roofline"] = {"kernel": f"ngram_count_kernel<{N_LEVEL + 1}>", "bound": "hbm", "achieved": alg / (count_ms * 1e-3) / 1e9,
-                            "peak": peak_gbs, "unit": "GB/s", "frac": alg / (count_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+        line["roofline"] = {"kernel": f"ngram_count_smem_kernel<{N_LEVEL + 1}>", "bound": "hbm", "achieved": alg / (count_ms * 1e-3) / 1e9,
+                            "peak": peak_gbs, "unit": "GB/s", "frac": alg / (count_ms * 1e-3) / 1e9 / peak_gbs,
+                            "traffic": 181_936_896,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_ncu_count_smem_v2.txt)
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": count_ms,
                             "share_of_step": count_ms / ms_step,
-                            "note": "1 B/residue read; limiter is L2 atomic throughput (175 M RED.ADD.64 per launch), see DESIGN.md"}
+                            "note": "1 B/residue read (DRAM traffic == algorithmic bytes); the kernel is bound by the 175 M shared-memory "
+                                    "table updates + key arithmetic (issue-bound, IPC 0.7), not by HBM: see DESIGN.md section 4"}
         line["build"] = {"count_residues_per_s": NSEQ * SEQ_LEN / (count_ms * 1e-3)}
     if rank == 0:
         line["phases_ms"] = phase_breakdown(pipe)

@@ -2,7 +2,7 @@
 reads (include/pgb200.h, "corpus buffer"), the data-defined alphabet, and node-name decoding."""
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -27,6 +27,30 @@ def pack_sequences(seqs: Sequence[str], global_first: bool = True) -> np.ndarray
     return buf
 
 
+def stream_chunks(seqs: Iterable[str], chunk_bytes: int = 1 << 28, rank: int = 0, world: int = 1, block: int = 4096):
+    """Pack an iterator of sequences into corpus-buffer chunks of ~chunk_bytes, cut at sequence
+    boundaries, without ever holding the whole corpus as Python strings.  With world > 1 the
+    sequences are dealt to ranks in blocks of `block` (counting is order independent); the leading
+    space of global sequence #0 stays with the rank that owns it.  Yields np.uint8 arrays."""
+    parts: List[bytes] = []
+    size = 0
+    for i, s in enumerate(seqs):
+        if (i // block) % world != rank:
+            continue
+        try:
+            b = s.encode("ascii")
+        except UnicodeEncodeError as exc:
+            raise ValueError(f"sequence {i} holds non-ASCII characters; unsupported on the CUDA path") from exc
+        piece = (b" " if i == 0 else b"") + b + b" \xff"
+        parts.append(piece)
+        size += len(piece)
+        if size >= chunk_bytes:
+            yield np.frombuffer(b"".join(parts), dtype=np.uint8)
+            parts, size = [], 0
+    if parts:
+        yield np.frombuffer(b"".join(parts), dtype=np.uint8)
+
+
 def to_device(buf: np.ndarray, device) -> torch.Tensor:
     """Pinned staging + async H2D of the corpus buffer (16 B aligned by the allocator)."""
     host = torch.from_numpy(np.ascontiguousarray(buf).copy()) if not isinstance(buf, torch.Tensor) else buf
@@ -37,13 +61,17 @@ def to_device(buf: np.ndarray, device) -> torch.Tensor:
     return host.to(device, non_blocking=True)
 
 
-def discover_alphabet(d_buf: torch.Tensor, group=None) -> Tuple[np.ndarray, torch.Tensor]:
+def discover_alphabet(d_buf, group=None) -> Tuple[np.ndarray, torch.Tensor]:
     """-> (symbols uint8[sigma] ascending, rank_of_byte uint8[256] on the device).
-    With a process group the 256-entry presence table is OR-reduced first so every rank packs
-    with the same alphabet."""
+    d_buf: one corpus buffer or a list of chunks (device tensors, or host arrays uploaded one at a time).  With a process group the 256-entry presence table
+    is OR-reduced first so every rank packs with the same alphabet."""
     nat.require_cuda()
-    pres = torch.zeros(256, dtype=torch.int32, device=d_buf.device)
-    nat.call("pg_byte_presence", nat.ptr(d_buf), d_buf.numel(), nat.ptr(pres), nat.stream_ptr())
+    chunks = list(d_buf) if isinstance(d_buf, (list, tuple)) else [d_buf]
+    dev = next((c.device for c in chunks if torch.is_tensor(c) and c.is_cuda), None) or nat.current_device()
+    pres = torch.zeros(256, dtype=torch.int32, device=dev)
+    for c in chunks:
+        c_dev = c if torch.is_tensor(c) and c.is_cuda else to_device(c, dev)   # host chunks stream through one at a time
+        nat.call("pg_byte_presence", nat.ptr(c_dev), c_dev.numel(), nat.ptr(pres), nat.stream_ptr())
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(pres, op=dist.ReduceOp.MAX, group=group)
@@ -51,7 +79,7 @@ def discover_alphabet(d_buf: torch.Tensor, group=None) -> Tuple[np.ndarray, torc
     if present[128:].any():
         # the kernels treat every byte >= 0x80 as the sequence separator (7-bit ASCII contract)
         raise ValueError("corpus buffer holds non-ASCII bytes; unsupported on the CUDA path")
-    return alphabet_from_presence(present, d_buf.device)
+    return alphabet_from_presence(present, dev)
 
 
 def alphabet_from_presence(present: np.ndarray, device) -> Tuple[np.ndarray, torch.Tensor]:

@@ -64,11 +64,19 @@ def extract_level(bins: torch.Tensor, short: torch.Tensor, n: int, sigma: int):
     return node_code, src, dst, cnt
 
 
-def build_level_graph(d_buf: torch.Tensor, n: int, symbols: np.ndarray, d_rank: torch.Tensor, eps: float,
+def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, eps: float,
                       group=None) -> DirectedNgramGraph:
-    """corpus buffer (device) -> DirectedNgramGraph for one n (count, merge, extract, normalise)."""
+    """corpus buffer(s) -> DirectedNgramGraph for one n (count, merge, extract, normalise).
+    d_buf: a device corpus buffer, or a list of chunks (device tensors or host arrays that are
+    uploaded one at a time: corpora larger than HBM stream through, the tables accumulate)."""
     sigma = int(symbols.size)
-    bins, short = count_level(d_buf, n, d_rank, sigma)
+    chunks = list(d_buf) if isinstance(d_buf, (list, tuple)) else [d_buf]
+    bins = short = None
+    for c in chunks:
+        c_dev = c if torch.is_tensor(c) and c.is_cuda else corpus.to_device(c, d_rank.device)
+        bins, short = count_level(c_dev, n, d_rank, sigma, bins, short)
+    if bins is None:
+        bins, short = count_level(torch.empty(0, dtype=torch.uint8, device=d_rank.device), n, d_rank, sigma)
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
@@ -108,21 +116,38 @@ class GraphBuilder:
         if not os.path.exists(os.path.normpath(self.protein_sequence_file)):
             print(f"ERROR: FASTA file not found at {self.protein_sequence_file}")
             return
-        seqs: List[str] = [s for _, s in DataLoader.parse_sequences(self.protein_sequence_file)]
-        if not seqs:
-            print("ERROR: No sequences found in the FASTA file. Cannot proceed.")
-            return
-        print(f"  Loaded {len(seqs)} sequences from FASTA.")
         rank, world = self._rank_world()
-        lo, hi = (len(seqs) * rank) // world, (len(seqs) * (rank + 1)) // world
         dev = nat.current_device()
+        chunk_bytes = int(getattr(self.config, "GRAPH_BUILDER_CHUNK_BYTES", 1 << 28))
+        hbm_budget = int(getattr(self.config, "GRAPH_BUILDER_RESIDENT_BYTES", 0.5 * torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 1 << 62))
+        n_seqs = [0]
+
+        def sequences():
+            for _, s in DataLoader.parse_sequences(self.protein_sequence_file):
+                n_seqs[0] += 1
+                yield s
+
+        chunks, resident = [], 0
         try:
-            buf = corpus.pack_sequences(seqs[lo:hi], global_first=(lo == 0))
+            for buf in corpus.stream_chunks(sequences(), chunk_bytes, rank, world):
+                if resident + buf.size <= hbm_budget:      # keep the corpus in HBM across the n levels
+                    chunks.append(corpus.to_device(buf, dev))
+                    resident += buf.size
+                else:                                       # larger than the budget: re-streamed per level
+                    chunks.append(buf)
         except ValueError as exc:
             print(f"ERROR: {exc}")
             return
-        d_buf = corpus.to_device(buf, dev)
-        symbols, d_rank = corpus.discover_alphabet(d_buf, self.process_group)
+        if n_seqs[0] == 0:
+            print("ERROR: No sequences found in the FASTA file. Cannot proceed.")
+            return
+        print(f"  Loaded {n_seqs[0]} sequences from FASTA ({len(chunks)} corpus chunk(s) on this rank).")
+        try:
+            symbols, d_rank = corpus.discover_alphabet(chunks, self.process_group)
+        except ValueError as exc:
+            print(f"ERROR: {exc}")
+            return
+        d_buf = chunks
         for n in range(1, self.n_max + 1):
             t_level = time.monotonic()
             try:

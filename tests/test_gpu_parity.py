@@ -179,6 +179,22 @@ def test_graph_builder_run_matches_reference_gpu(name, tmp_path):
             assert torch.equal(dense, dense.t())
 
 
+@pytest.mark.parametrize("chunk_bytes,resident", [(256, 1 << 40), (256, 0), (1000, 1500)])
+def test_graph_builder_streamed_chunks_gpu(chunk_bytes, resident, tmp_path):
+    """Chunked corpus (device-resident or re-uploaded per level) == the one-buffer build == the reference."""
+    g = load("build_protein")
+    cfg = pg.Config()
+    cfg.GCN_INPUT_FASTA_PATH = fasta_sequences(str(g["fasta"]), tmp_path)
+    cfg.BASE_OUTPUT_DIR = tmp_path / "out"
+    cfg.GRAPH_OBJECTS_DIR = cfg.BASE_OUTPUT_DIR / "1_graph_objects"
+    cfg.GCN_NGRAM_MAX_N = BUILD_FIXTURES["build_protein"]
+    cfg.GRAPH_BUILDER_CHUNK_BYTES = chunk_bytes
+    cfg.GRAPH_BUILDER_RESIDENT_BYTES = resident
+    pg.GraphBuilder(cfg).run()
+    for n in range(1, BUILD_FIXTURES["build_protein"] + 1):
+        check_graph_against_golden(pg.DataUtils.load_object(str(cfg.GRAPH_OBJECTS_DIR / f"ngram_graph_n{n}.pkl")), g, n)
+
+
 def test_directed_ngram_graph_general_edge_table(tmp_path):
     """Unsorted parquet with duplicate rows and float weights (coalesce path) vs the graph oracle."""
     import pandas as pd

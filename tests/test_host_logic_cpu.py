@@ -59,6 +59,39 @@ def test_graph_builder_run_matches_reference(name, tmp_path, spec_native):
         check_graph_against_golden(graph, g, n)
 
 
+@pytest.mark.parametrize("chunk_bytes,resident", [(64, 1 << 40), (64, 0), (200, 300)])
+def test_graph_builder_streamed_chunks_match_reference(chunk_bytes, resident, tmp_path, spec_native):
+    """Corpora larger than HBM stream through in chunks cut at sequence boundaries (resident or
+    re-uploaded per level); the tables accumulate and the graphs are those of the one-buffer build."""
+    g = load("build_ragged")
+    cfg = pg.Config()
+    cfg.GCN_INPUT_FASTA_PATH = fasta_sequences(str(g["fasta"]), tmp_path)
+    cfg.BASE_OUTPUT_DIR = tmp_path / "out"
+    cfg.GRAPH_OBJECTS_DIR = cfg.BASE_OUTPUT_DIR / "1_graph_objects"
+    cfg.GCN_NGRAM_MAX_N = BUILD_FIXTURES["build_ragged"]
+    cfg.GRAPH_BUILDER_CHUNK_BYTES = chunk_bytes
+    cfg.GRAPH_BUILDER_RESIDENT_BYTES = resident
+    pg.GraphBuilder(cfg).run()
+    for n in range(1, BUILD_FIXTURES["build_ragged"] + 1):
+        check_graph_against_golden(pg.DataUtils.load_object(str(cfg.GRAPH_OBJECTS_DIR / f"ngram_graph_n{n}.pkl")), g, n)
+
+
+def test_stream_chunks_partition_the_corpus():
+    from protgram_directgcn_b200.host import corpus
+    seqs = ["ACDE", "", "K", "LMNPQ" * 7, "RST", "VW", "Y" * 40] * 5
+    whole = corpus.pack_sequences(seqs).tobytes()
+    for world in (1, 2, 3):
+        pieces = []
+        for rank in range(world):
+            chunks = list(corpus.stream_chunks(iter(seqs), chunk_bytes=50, rank=rank, world=world, block=2))
+            assert all(c.size and c[-1] == corpus.SEP for c in chunks)          # cut at sequence boundaries only
+            pieces += [p for c in chunks for p in c.tobytes().split(b"\xff")[:-1]]
+        assert sorted(pieces) == sorted(whole.split(b"\xff")[:-1])              # same multiset of padded sequences
+        assert sum(p.startswith(b" ") and len(p) > 1 for p in pieces) == 1                      # one leading space: global sequence #0
+    with pytest.raises(ValueError):
+        list(corpus.stream_chunks(iter(["AC\u00e9"])))
+
+
 def test_directed_ngram_graph_from_parquet_unsorted(tmp_path, spec_native):
     """Constructor contract of reference graph_utils.py:91-125: nodes dict + parquet edge table in
     arbitrary row order."""
