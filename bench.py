@@ -13,7 +13,9 @@ One STEP = one pass of the hot path over one corpus batch:
 metric = residues/s through the whole step (whole job, all ranks).  `value` has the corpus
 already resident in HBM; `e2e` runs the same step from PINNED HOST bytes through the
 reference-facing classes (H2D of the corpus, graph object materialised on the host like the
-reference's, trainer-style .to(device), embeddings read back to numpy).
+reference's, trainer-style .to(device), embeddings read back to numpy); every e2e step issues one
+full H2D copy of the corpus, double-buffered on a copy stream so that the upload of batch i+1
+overlaps the graph/DirectGCN kernels of batch i (host/corpus.py:CorpusUploader).
 
     python bench.py [--gpus N --steps K --warmup W]            our arm   (torchrun for N > 1)
     python bench.py --impl reference [...]                     the reference algorithm on host cores
@@ -123,12 +125,13 @@ class B200Pipeline:
         self.d_buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         nat.call("pg_synth_corpus", nat.ptr(self.d_buf), rank * NSEQ, NSEQ, SEQ_LEN, SEED, int(rank == 0), nat.stream_ptr())
         self.h_buf = None
+        self.up = None
         self.count_ms = []
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.model = self.opt = self.x = self.labels = self.graphed = None
 
     # ---- hot path A on a device-resident corpus; returns the device edge table + matrices
-    def build(self, d_buf, materialise_host: bool):
+    def build(self, d_buf, materialise_host: bool, after_count=None):
         nat, db = self.nat, self.db
         symbols, d_rank = self.corpus.discover_alphabet(d_buf, self.group)
         sigma = int(symbols.size)
@@ -139,6 +142,8 @@ class B200Pipeline:
         db.count_level(d_buf, N_LEVEL, d_rank, sigma, bins, short)
         self.ev[1].record()
         self._pending_count_event = True
+        if after_count is not None:
+            after_count()          # d_buf has no reader left: the uploader may reuse the slot / prefetch the next batch
         if self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=self.group)
@@ -207,8 +212,15 @@ class B200Pipeline:
     def step_e2e(self):
         if self.h_buf is None:
             self.h_buf = self.d_buf.cpu().pin_memory()
-        d_buf = self.h_buf.to(self.dev, non_blocking=True)                       # H2D: the corpus bytes
-        graph = self.build(d_buf, materialise_host=True)                         # graph object on the host (reference contract)
+            self.up = self.corpus.CorpusUploader(self.dev)
+            self.up.submit(self.h_buf)
+
+        def prefetch_next():                                                     # H2D of the NEXT step's corpus bytes, issued every
+            self.up.release()                                                    # step: it runs on the copy stream under this
+            self.up.submit(self.h_buf)                                           # step's extract/normalise/DirectGCN kernels
+
+        d_buf = self.up.acquire()                                                # H2D of this step's bytes (waits for the copy)
+        graph = self.build(d_buf, materialise_host=True, after_count=prefetch_next)  # graph object on the host (reference contract)
         loss, emb = self.train_and_extract(graph)
         emb_host = emb.cpu().numpy()                                              # D2H: embeddings (models_utils.py:265-273)
         return float(loss.item()), emb_host, graph
@@ -230,24 +242,48 @@ def next_node_labels(a_out: torch.Tensor, n: int) -> torch.Tensor:
     return labels
 
 
-def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iters=5):
-    """DirectGCN propagation where X does not fit L2: R-MAT power-law digraph, hidden 128 (config C5's
-    per-GPU shape scaled to one GPU).  Reports the fan-out (forward) and fan-in (backward) SpMM."""
-    nat, gu = pipe.nat, pipe.gu
-    dev = pipe.dev
+def rmat_graph(pipe, log2_nodes, edges_per_node):
+    """R-MAT power-law digraph (a,b,c,d = .57,.19,.19,.05; integer weights 1..7), seeded identically on every
+    rank, pushed through the reference normalisation (coalesce + a8/a9) on the device -> shared-pattern CSR."""
+    gu, dev = pipe.gu, pipe.dev
     n = 1 << log2_nodes
     e = n * edges_per_node
     g = torch.Generator(device=dev).manual_seed(SEED)
     src = torch.zeros(e, dtype=torch.int64, device=dev)
     dst = torch.zeros(e, dtype=torch.int64, device=dev)
-    for _ in range(log2_nodes):  # R-MAT quadrants a,b,c,d = .57,.19,.19,.05 -> (src bit, dst bit) = 00,01,10,11
+    for _ in range(log2_nodes):  # quadrant -> (src bit, dst bit) = 00,01,10,11
         r = torch.rand(e, generator=g, device=dev)
         src = src * 2 + (r >= 0.76).to(torch.int64)
         dst = dst * 2 + (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).to(torch.int64)
+        del r
     w = torch.randint(1, 8, (e,), generator=g, device=dev).to(torch.float32)
     s, d, wv = gu.device_coalesce(src, dst, w, n)
+    del src, dst, w
     res = gu.device_normalize(s, d, wv, n, 1e-9)
-    del src, dst, w, s, d, wv
+    del s, d, wv
+    for k in ("in_src", "in_dst", "in_w"):
+        res.pop(k)
+    torch.cuda.empty_cache()
+    return n, e, res
+
+
+def _time_ms(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+
+def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iters=5):
+    """DirectGCN propagation where X does not fit L2: R-MAT power-law digraph, hidden 128 (config C5's
+    per-GPU shape scaled to one GPU).  Reports the fan-out (forward) and fan-in (backward) SpMM."""
+    nat, dev = pipe.nat, pipe.dev
+    n, e, res = rmat_graph(pipe, log2_nodes, edges_per_node)
     P = int(res["pattern_nnz"])
     x = torch.randn(n, F, device=dev)
     z = torch.empty(n, 3 * F, device=dev)
@@ -263,17 +299,69 @@ def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iter
     out["long_rows"] = {"chunk": plan.chunk, "rows": plan.n_long, "slices": plan.n_items}
     for name, fn, bytes_alg in (("fanout_fwd", fo, 8 * (n + 1) + 16 * P + 4 * F * P + 12 * n * F),
                                 ("fanin_bwd", fi, 8 * (n + 1) + 16 * P + 12 * F * P + 4 * n * F)):
-        for _ in range(2):
-            fn()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        for a, b in evs:
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        ms = _time_ms(fn, iters)
         out[name] = {"ms": ms, "edges_per_s": 3 * P / (ms * 1e-3), "algorithmic_bytes": bytes_alg,
                      "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_alg / (ms * 1e-3) / 1e9 / peak_gbs}
+    return out
+
+
+def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_node=16, F=128, iters=5):
+    """Config C5's shape, weak-scaled: R-MAT graph with 2^log2_nodes_per_gpu nodes PER GPU, hidden 128, rows
+    partitioned over the ranks (SURVEY 8e).  forward = NCCL all-gather of X over NVLink + local fan-out SpMM;
+    backward = all-gather of dZ + local fan-in (symmetric matrices).  Times are max over ranks; edges/s is the
+    whole job (3 * pattern nnz of the full graph per pass).  Every rank builds the full graph redundantly (setup,
+    untimed) and keeps its row block."""
+    import math
+    from protgram_directgcn_b200.host import partitioned as part
+    nat, dev, world = pipe.nat, pipe.dev, pipe.world
+    log2_nodes = log2_nodes_per_gpu + int(round(math.log2(world)))
+    n, e, res = rmat_graph(pipe, log2_nodes, edges_per_node)
+    P = int(res["pattern_nnz"])
+    prop = part.RowPartitionedPropagation(res["rowptr"], res["col"], [res["val_in"], res["val_out"], res["val_und"]], n,
+                                          group=dist.group.WORLD, symmetric=True)
+    p_local = int(prop.local.col.numel())
+    del res
+    torch.cuda.empty_cache()
+    per = prop.per
+    x_local = torch.randn(per, F, device=dev)
+    dz_local = torch.randn(per, 3 * F, device=dev)
+    holder = {}
+
+    def ag_x():
+        holder["x"] = part._all_gather_rows(x_local, prop.group)
+
+    def ag_dz():
+        holder["g"] = part._all_gather_rows(dz_local, prop.group)
+
+    def fwd():
+        ag_x()
+        holder["z"] = part._spmm_fanout(prop.local, holder["x"], per, F)
+
+    def bwd():
+        ag_dz()
+        holder["dx"] = part._spmm_fanin(prop.local, holder["g"], per, F)
+
+    ag_x(); ag_dz()
+    local_fo = lambda: part._spmm_fanout(prop.local, holder["x"], per, F)
+    local_fi = lambda: part._spmm_fanin(prop.local, holder["g"], per, F)
+    out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}), {e} directed edges before dedupe, pattern nnz {P}",
+           "F": F, "pattern_nnz": P, "rows_per_gpu": per, "partition": "1-D rows, global int32 columns",
+           "exchange": "NCCL all_gather_into_tensor (fwd: X [N,F]; bwd: dZ [N,3F])"}
+    mx = lambda v: (lambda t: (dist.all_reduce(t, op=dist.ReduceOp.MAX), float(t.item()))[1])(torch.tensor([v], device=dev))
+    for name, fn, comm, local, width in (("fwd", fwd, ag_x, local_fo, F), ("bwd", bwd, ag_dz, local_fi, 3 * F)):
+        dist.barrier()
+        ms = mx(_time_ms(fn, iters))
+        dist.barrier()
+        ms_comm = mx(_time_ms(comm, iters))
+        dist.barrier()
+        ms_local = mx(_time_ms(local, iters))
+        recv = 4 * width * per * (world - 1)                                      # bytes received per GPU
+        alg_local = 8 * (per + 1) + 16 * p_local + (4 * F * p_local + 12 * per * F if name == "fwd" else 12 * F * p_local + 4 * per * F)
+        out[name] = {"ms": ms, "edges_per_s": 3 * P / (ms * 1e-3), "ms_all_gather": ms_comm, "ms_local_spmm": ms_local,
+                     "nvlink_recv_bytes_per_gpu": recv, "nvlink_gbs_per_gpu": recv / (ms_comm * 1e-3) / 1e9,
+                     "nvlink_frac_of_900": recv / (ms_comm * 1e-3) / 1e9 / 900.0,
+                     "local_spmm_algorithmic_bytes": alg_local, "local_spmm_gbs": alg_local / (ms_local * 1e-3) / 1e9,
+                     "local_spmm_frac_of_hbm_peak": alg_local / (ms_local * 1e-3) / 1e9 / peak_gbs}
     return out
 
 
@@ -349,6 +437,8 @@ def run_b200(args):
         for _ in range(steps):
             last = fn()
             pipe.collect_count_ms()
+        if getattr(pipe, "up", None) is not None:   # the prefetch issued by the last step belongs to the timed region
+            torch.cuda.current_stream().wait_stream(pipe.up.copy_stream)
         t1.record()
         barrier()
         wall = time.perf_counter() - w0
@@ -420,6 +510,13 @@ def run_b200(args):
             line["spmm_large"] = spmm_large_leg(pipe, peak_gbs, args.large_log2_nodes)
         except Exception as exc:  # noqa: BLE001 - the headline must still print
             line["spmm_large"] = {"error": repr(exc)}
+    if world > 1 and not args.no_large:
+        try:
+            leg = spmm_partitioned_leg(pipe, peak_gbs, dist, args.large_log2_nodes)
+        except Exception as exc:  # noqa: BLE001 - the headline must still print
+            leg = {"error": repr(exc)}
+        if rank == 0:
+            line["spmm_partitioned"] = leg
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(sample_seqs=6000, procs=1)
     if rank == 0:

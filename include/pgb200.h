@@ -71,11 +71,18 @@ int pg_synth_corpus(uint8_t *d_buf, int64_t first_seq, int64_t nseq, int seq_len
  * whole padded sequence of length exactly n (a node without any edge, data_builder.py:40 vs :47). */
 int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte,
                    int sigma, unsigned long long *d_bins, uint8_t *d_short_present,
-                   pg_stream_t stream);
+                   void *d_ws, size_t ws_bytes, pg_stream_t stream);
+/* Workspace of pg_ngram_count (256-byte aligned device memory, contents irrelevant): a status
+ * word + a scratch table for the 8-bit-lane shared-memory variant, whose result is only merged
+ * into d_bins when the kernel proved it exact (else a strictly exact variant recounts, all on
+ * the stream, no host round trip).  d_ws may be NULL: the strictly exact variants are used. */
+size_t pg_ngram_count_ws_bytes(int n, int sigma);
 
-/* Test hook: 1 forces the global-atomics variant of pg_ngram_count (default: shared-memory
- * privatised tables whenever sigma^(n+1) fits), so parity tests can cover both. */
-void pg_debug_force_global_count(int on);
+/* Test hook: pins the variant of pg_ngram_count so parity tests can cover every kernel.
+ * AUTO: widest shared-memory lanes that fit one CTA (32/16 bit: strict; 8 bit: scratch + hazard
+ * check + gated strict recount), L2 REDs for tables beyond 4 key-range splits or tiny corpora. */
+enum { PG_COUNT_AUTO = 0, PG_COUNT_GLOBAL = 1, PG_COUNT_STRICT = 2, PG_COUNT_FAST8 = 3, PG_COUNT_FAST8_FORCE_HAZARD = 4 };
+void pg_debug_count_variant(int variant);
 
 /* Replaces data_builder.py:151-177 (distinct + sorted ids) and :281-286 (edge table).
  * Step 1: d_sizes[0] = #nodes (distinct n-grams), d_sizes[1] = #unique transitions; also leaves
@@ -233,6 +240,24 @@ int pg_layer_gemm_bwd_weight(const float *d_z, int64_t ldz, const float *d_x, in
 /* Row-wise L2 normalisation  out = h / (||h||_2 + eps)   (models_utils.py:139-147). */
 int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_rows, int F, float eps,
                          float *d_out, int64_t ldout, pg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row f1: loss of the next-node task, forward AND backward in one pass
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces F.log_softmax(task_logits, dim=-1) (protgram_directgcn.py:221) + F.nll_loss(.., y)
+ * (protgram_directgcn_trainer.py:90,94; reduction 'mean') and their autograd backward.
+ * d_logits [n, ld] (c <= ld columns used) is OVERWRITTEN with d(loss)/d(logits) =
+ * (softmax(row) - onehot(label)) * grad_scale; rows whose label is outside [0, c) are ignored
+ * (zero gradient, zero loss: ignore_index semantics), grad_scale = 1 / #counted rows.
+ * d_row_loss[n] = -log_softmax(row)[label]; d_loss[0] = grad_scale * sum(d_row_loss);
+ * d_colsum[c] = column sums of the gradient (= gradient of the decoder bias).
+ * All reductions run in a fixed order (bitwise reproducible). */
+#define PG_SOFTMAX_NLL_MAX_CLASSES 28672
+size_t pg_softmax_nll_ws_bytes(int64_t n, int64_t c);
+int pg_softmax_nll(float *d_logits, int64_t ld, int64_t n, int64_t c, const int64_t *d_labels,
+                   float grad_scale, float *d_row_loss, float *d_colsum, float *d_loss, void *d_ws,
+                   size_t ws_bytes, pg_stream_t stream);
 
 #ifdef __cplusplus
 }

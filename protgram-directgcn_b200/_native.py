@@ -24,8 +24,9 @@ _SIGS = {
     "pg_launch_count": (ctypes.c_uint64, []),
     "pg_byte_presence": (c_int, [_P, c_int64, _P, _P]),
     "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
-    "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
-    "pg_debug_force_global_count": (None, [c_int]),
+    "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "pg_ngram_count_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pg_debug_count_variant": (None, [c_int]),
     "pg_graph_extract_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_graph_extract_sizes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_graph_extract_fill": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -58,6 +59,8 @@ _SIGS = {
     "pg_layer_gemm_bwd_weight": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int,
                                          c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
+    "pg_softmax_nll_ws_bytes": (c_size_t, [c_int64, c_int64]),
+    "pg_softmax_nll": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
 }
 
 class SpmmPlanStruct(ctypes.Structure):
@@ -102,6 +105,8 @@ class SpmmPlan:
                                           ptr(self.item_row), ptr(self._partials))
         return ctypes.byref(self._struct)
 
+
+SOFTMAX_NLL_MAX_CLASSES = 28672  # PG_SOFTMAX_NLL_MAX_CLASSES (include/pgb200.h)
 
 _lib = None
 launches = 0  # number of C-ABI calls that enqueue GPU work (bench.py reports it)

@@ -161,12 +161,14 @@ __device__ __forceinline__ uint32_t scan_vector(const uint8_t *__restrict__ buf,
 // Variant G: every window is one RED.ADD.64 into the dense table in L2.  Measured on B200:
 // ~200 G updates/s for >= 194k bins, collapsing to 12 G/s at 441 bins (same-address serialisation),
 // so it is only used when the table does not fit the shared-memory variant below.
+// `gate` (optional): the kernel is a no-op unless *gate != 0 (strict recount after a flagged hazard).
 template <int M>
 __global__ void __launch_bounds__(256) ngram_count_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
                                                           const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
                                                           uint32_t sigma_pow_m, uint32_t sigma_pow_n,
                                                           unsigned long long *__restrict__ bins,
-                                                          uint8_t *__restrict__ short_present) {
+                                                          uint8_t *__restrict__ short_present, const int *__restrict__ gate) {
+    if (gate != nullptr && *gate == 0) return;
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = rank_of_byte[threadIdx.x];
     __syncthreads();
@@ -179,72 +181,125 @@ __global__ void __launch_bounds__(256) ngram_count_kernel(const uint8_t *__restr
         if ((valid >> k) & 1u) atomicAdd(&bins[codes[k]], 1ull);
 }
 
-// Variant S: privatised table in shared memory, 16-bit lanes (two per word), persistent CTAs.
-// The table is cut into `splits` contiguous key ranges; CTA b serves range b % splits and walks
-// the corpus tiles of group b / splits, so `splits` CTAs read the same bytes (second read = L2
-// hit) and each keeps the windows of its range.  Shared-memory atomics run at ~1.3 T updates/s on
-// B200 (vs 0.2 T/s for L2 REDs).  Overflow: the single add that observes a lane at 32767 moves
-// 32768 to the global table and subtracts it again; a lane can only carry into its neighbour
-// after 32768 further in-flight adds, far more than 1024 threads x 16 windows can have pending.
+// Variant S: privatised table in shared memory, persistent CTAs (one per SM, 1024 threads).
+// Shared-memory atomics run at ~1.3 T updates/s on B200 (vs 0.2 T/s for L2 REDs).  The table is
+// packed into LB-bit lanes of 32-bit words, LB = the widest of 32/16/8 whose table fits one CTA, so
+// that ONE CTA holds the whole key space and every corpus byte is scanned once:
+//   LB = 32  no overflow possible, fire-and-forget adds                     (<= 56k bins)
+//   LB = 16  the single add that observes a lane at 32767 moves 32768 to `out` and subtracts it again;
+//            a lane can only carry into its neighbour after 32768 further in-flight adds, more than
+//            1024 threads x 16 windows can have pending: STRICTLY exact        (<= 112k bins)
+//   LB = 8   same scheme with 127 -> 128.  The slack is only 128 adds, which a pathological corpus
+//            (one window repeated >= 128 times inside a 16 KB tile, e.g. homopolymers) can exhaust
+//            before the subtraction lands.  A carry needs some add to OBSERVE a lane >= 192 first
+//            (adds move a lane by +1), and until the first carry every observation is exact, so
+//            "no add observed >= 192" proves the result exact.  Such an observation raises *status;
+//            the 8-bit kernel therefore counts into a zeroed SCRATCH table, which is merged into
+//            the real table only if *status stayed 0, else a strict variant recounts (gate).
+// Larger tables are cut into `splits` contiguous key ranges (SPLIT = true): CTA b serves range
+// b % splits and walks the tiles of group b / splits (second read of a tile = L2 hit).
 constexpr int kSmemCountThreads = 1024;
-template <int M>
+constexpr int64_t kSmemTableBytes = 224 * 1024;  // of the 227 KB per CTA (lut + counters take the rest)
+
+template <int M, int LB, bool SPLIT>
 __global__ void __launch_bounds__(kSmemCountThreads, 1) ngram_count_smem_kernel(
     const uint8_t *__restrict__ buf, int64_t nbytes, const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
-    uint32_t sigma_pow_m, uint32_t sigma_pow_n, unsigned long long *__restrict__ bins, uint8_t *__restrict__ short_present,
-    int splits, uint32_t lanes_per_split) {
-    extern __shared__ unsigned tbl[];  // lanes_per_split 16-bit lanes
+    uint32_t sigma_pow_m, uint32_t sigma_pow_n, unsigned long long *__restrict__ out, uint8_t *__restrict__ short_present,
+    int splits, uint32_t lanes_per_split, int *__restrict__ status, const int *__restrict__ gate) {
+    constexpr uint32_t PER_WORD = 32 / LB;                 // lanes per 32-bit word
+    constexpr uint32_t LSH = LB == 32 ? 0 : (LB == 16 ? 1 : 2);
+    constexpr uint32_t LANE_MASK = LB == 32 ? 0xFFFFFFFFu : ((1u << (LB % 32)) - 1u);
+    constexpr uint32_t HALF = LB == 32 ? 0u : (1u << ((LB - 1) % 32));  // drain quantum (128 / 32768)
+    extern __shared__ unsigned tbl[];
     __shared__ uint8_t lut[256];
+    if (gate != nullptr && *gate == 0) return;
     if (threadIdx.x < 256) lut[threadIdx.x] = rank_of_byte[threadIdx.x];
-    const uint32_t words = (lanes_per_split + 1) / 2;
+    const uint32_t words = (lanes_per_split + PER_WORD - 1) / PER_WORD;
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) tbl[i] = 0;
     __syncthreads();
-    const int split = blockIdx.x % splits;
-    const int64_t group = blockIdx.x / splits, groups = gridDim.x / splits;
+    const int split = SPLIT ? blockIdx.x % splits : 0;
+    const int64_t group = SPLIT ? blockIdx.x / splits : blockIdx.x, groups = SPLIT ? gridDim.x / splits : gridDim.x;
     const uint32_t lo = (uint32_t)split * lanes_per_split;
     const uint32_t hi = min(lo + lanes_per_split, sigma_pow_m);
     const uint32_t span = hi > lo ? hi - lo : 0u;
     uint8_t *sp = (split == 0) ? short_present : nullptr;
     const int64_t nvec = (nbytes + 15) / 16;
+    bool hazard = false;
     for (int64_t vec = group * blockDim.x + threadIdx.x; vec < nvec; vec += groups * blockDim.x) {
         uint32_t codes[16];
-        const uint32_t valid = scan_vector<M>(buf, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, sp, codes);
-        unsigned old[16];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {  // 16 independent shared-memory atomics, issued back to back
-            const uint32_t l = codes[k] - lo;
-            const bool ok = ((valid >> k) & 1u) && l < span;
-            old[k] = 0;
-            if (ok) {
-                old[k] = atomicAdd(&tbl[l >> 1], 1u << ((l & 1u) * 16u));
-                mine |= 1u << k;
-            }
-        }
-        uint32_t full = 0;  // lanes that just went 32767 -> 32768
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t sh = ((codes[k] - lo) & 1u) * 16u;
-            if (((mine >> k) & 1u) && ((old[k] >> sh) & 0xFFFFu) == 32767u) full |= 1u << k;
-        }
-        if (full) {  // rare: move 32768 counts of that lane to the 64-bit table
+        uint32_t valid = scan_vector<M>(buf, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, sp, codes);
+        if (SPLIT) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                if ((full >> k) & 1u) {
-                    const uint32_t l = codes[k] - lo;
-                    atomicSub(&tbl[l >> 1], 32768u << ((l & 1u) * 16u));
-                    atomicAdd(&bins[codes[k]], 32768ull);
+                codes[k] -= lo;
+                if (codes[k] >= span) {
+                    valid &= ~(1u << k);
+                    codes[k] = 0;
+                }
+            }
+        }
+        if (LB == 32) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) atomicAdd(&tbl[codes[k]], (valid >> k) & 1u);
+        } else {
+            // Branch-free: invalid windows add 0.  `att` collects "this add saw its lane at >= HALF-1"
+            // (top lane bit of old+inc); only then (rare) the slow path looks at the lane values.
+            unsigned old[16];
+            uint32_t att = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {  // 16 independent shared-memory atomics, issued back to back
+                const uint32_t sh = (codes[k] * LB) & 31u;
+                const uint32_t inc = ((valid >> k) & 1u) << sh;
+                old[k] = atomicAdd(&tbl[codes[k] >> LSH], inc);
+                att |= (old[k] + inc) & (inc << (LB - 1));
+            }
+            if (att) {
+                // re-derive the codes (cheaper than keeping 16 more registers live in the hot loop)
+                uint32_t valid2 = scan_vector<M>(buf, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, nullptr, codes);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    uint32_t c = codes[k];
+                    if (SPLIT) {
+                        c -= lo;
+                        if (c >= span) continue;
+                    }
+                    if (!((valid2 >> k) & 1u)) continue;
+                    const uint32_t sh = (c * LB) & 31u;
+                    const uint32_t lane = (old[k] >> sh) & LANE_MASK;
+                    if (lane == HALF - 1u) {  // this add took the lane to HALF: move HALF counts to the 64-bit table
+                        atomicSub(&tbl[c >> LSH], HALF << sh);
+                        atomicAdd(&out[c + lo], (unsigned long long)HALF);
+                    }
+                    if (LB == 8 && lane >= 192u) hazard = true;
                 }
             }
         }
     }
+    if (LB == 8 && hazard) *status = 1;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
         const unsigned w = tbl[i];
-        const uint32_t k = lo + 2 * i;
-        if (w & 0xFFFFu) atomicAdd(&bins[k], (unsigned long long)(w & 0xFFFFu));
-        if (w >> 16) atomicAdd(&bins[k + 1], (unsigned long long)(w >> 16));
+        if (w == 0u) continue;
+        const uint32_t k = lo + PER_WORD * i;
+#pragma unroll
+        for (uint32_t j = 0; j < PER_WORD; ++j) {
+            const unsigned long long c = LB == 32 ? w : ((w >> ((j * LB) % 32)) & LANE_MASK);
+            if (c) atomicAdd(&out[k + j], c);
+        }
     }
 }
+
+// bins += scratch unless the 8-bit count flagged a hazard (then the gated strict recount supplies the counts)
+__global__ void __launch_bounds__(256) merge_scratch_kernel(const unsigned long long *__restrict__ scratch, int64_t nbins,
+                                                            const int *__restrict__ status, unsigned long long *__restrict__ bins) {
+    if (*status != 0) return;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = scratch[k];
+        if (c) bins[k] += c;
+    }
+}
+
+__global__ void set_flag_kernel(int *flag, int v) { *flag = v; }
 
 // ------------------------------------------------------------------ table -> ids / edges
 __global__ void __launch_bounds__(256) mark_present_kernel(const unsigned long long *__restrict__ bins, int64_t nbins,
@@ -337,70 +392,128 @@ extern "C" int pg_synth_corpus(uint8_t *d_buf, int64_t first_seq, int64_t nseq, 
     return PG_OK;
 }
 
-// test hook: force the global-atomics variant so both variants are covered by the parity tests
-static bool g_force_global_count = false;
-extern "C" void pg_debug_force_global_count(int on) { g_force_global_count = on != 0; }
+// test hook: pin the count variant so the parity tests cover every kernel (see pgb200.h)
+static int g_count_variant = PG_COUNT_AUTO;
+extern "C" void pg_debug_count_variant(int v) { g_count_variant = v; }
 
-extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte, int sigma,
-                              unsigned long long *d_bins, uint8_t *d_short_present, pg_stream_t stream) {
-    int64_t pow_n, pow_m;
-    PG_CHECK_ARG(d_buf && d_rank_of_byte && d_bins && d_short_present && nbytes >= 0, "pg_ngram_count: null/negative argument");
-    PG_CHECK_ARG(((uintptr_t)d_buf & 15) == 0, "pg_ngram_count: d_buf must be 16-byte aligned");
-    if (!table_sizes(n, sigma, &pow_n, &pow_m)) {
-        pg_set_error("pg_ngram_count: table sigma^(n+1) out of range (n=%d sigma=%d; need 1<=n<=6, sigma^(n+1)<=2^32)", n, sigma);
-        return PG_ERANGE;
-    }
-    if (nbytes == 0) return PG_OK;
-    const int64_t nvec = pg_ceil_div(nbytes, 16);
-    const uint32_t s = (uint32_t)sigma, pm = (uint32_t)pow_m, pn = (uint32_t)pow_n;
-    cudaStream_t st = pg_cu(stream);
-    // shared-memory variant when the table fits <= kMaxSplits CTAs x 100k 16-bit lanes
-    constexpr int64_t kLanesMax = 100 * 1024;  // 200 KB of the 227 KB per CTA
-    constexpr int kMaxSplits = 4;
-    const int splits = (int)pg_ceil_div(pow_m, kLanesMax);
-    const bool use_smem = splits <= kMaxSplits && nvec >= 4 * kSmemCountThreads && !g_force_global_count;
-    if (use_smem) {
-        const uint32_t lanes = (uint32_t)pg_ceil_div(pow_m, splits);
-        const uint32_t lanes_even = (lanes + 1) & ~1u;  // whole words per split
-        const size_t smem = (size_t)(lanes_even / 2) * sizeof(unsigned);
-        int64_t groups = PG_NUM_SMS / splits;
-        const int64_t max_groups = pg_ceil_div(nvec, kSmemCountThreads);
-        if (groups > max_groups) groups = max_groups;
-        const unsigned grid = (unsigned)(groups * splits);
-#define PG_LAUNCH_SMEM(M)                                                                                              \
-    do {                                                                                                               \
-        PG_CUDA_CALL(cudaFuncSetAttribute(ngram_count_smem_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        ngram_count_smem_kernel<M><<<grid, kSmemCountThreads, smem, st>>>(d_buf, nbytes, d_rank_of_byte, s, pm, pn, d_bins,      \
-                                                                          d_short_present, splits, lanes_even);          \
+namespace {
+struct CountArgs {
+    const uint8_t *buf;
+    int64_t nbytes;
+    const uint8_t *rank;
+    uint32_t sigma, pow_m, pow_n;
+    uint8_t *short_present;
+    cudaStream_t st;
+};
+
+template <int LB, bool SPLIT>
+int launch_smem_count(int m, const CountArgs &a, unsigned long long *out, int splits, int *status, const int *gate) {
+    const uint32_t per_word = 32 / LB;
+    uint32_t lanes = (uint32_t)pg_ceil_div(a.pow_m, splits);
+    lanes = (lanes + per_word - 1) / per_word * per_word;  // whole words per split
+    const size_t smem = (size_t)(lanes / per_word) * sizeof(unsigned);
+    const int64_t nvec = pg_ceil_div(a.nbytes, 16);
+    int64_t groups = PG_NUM_SMS / splits;
+    const int64_t max_groups = pg_ceil_div(nvec, kSmemCountThreads);
+    if (groups > max_groups) groups = max_groups;
+    const unsigned grid = (unsigned)(groups * splits);
+#define PG_LAUNCH_SMEM(MM)                                                                                                  \
+    do {                                                                                                                    \
+        PG_CUDA_CALL(cudaFuncSetAttribute(ngram_count_smem_kernel<MM, LB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                                      \
+        ngram_count_smem_kernel<MM, LB, SPLIT><<<grid, kSmemCountThreads, smem, a.st>>>(                                     \
+            a.buf, a.nbytes, a.rank, a.sigma, a.pow_m, a.pow_n, out, a.short_present, splits, lanes, status, gate);          \
     } while (0)
-        switch (n + 1) {
-            case 2: PG_LAUNCH_SMEM(2); break;
-            case 3: PG_LAUNCH_SMEM(3); break;
-            case 4: PG_LAUNCH_SMEM(4); break;
-            case 5: PG_LAUNCH_SMEM(5); break;
-            case 6: PG_LAUNCH_SMEM(6); break;
-            case 7: PG_LAUNCH_SMEM(7); break;
-            default: pg_set_error("pg_ngram_count: unsupported n=%d", n); return PG_EINVAL;
-        }
-#undef PG_LAUNCH_SMEM
-        PG_CUDA_LAUNCH_CHECK("ngram_count_smem_kernel");
-        return PG_OK;
+    switch (m) {
+        case 2: PG_LAUNCH_SMEM(2); break;
+        case 3: PG_LAUNCH_SMEM(3); break;
+        case 4: PG_LAUNCH_SMEM(4); break;
+        case 5: PG_LAUNCH_SMEM(5); break;
+        case 6: PG_LAUNCH_SMEM(6); break;
+        case 7: PG_LAUNCH_SMEM(7); break;
+        default: pg_set_error("pg_ngram_count: unsupported n=%d", m - 1); return PG_EINVAL;
     }
-    const unsigned grid = (unsigned)pg_ceil_div(nvec, 256);
-#define PG_LAUNCH_COUNT(M) \
-    ngram_count_kernel<M><<<grid, 256, 0, st>>>(d_buf, nbytes, d_rank_of_byte, s, pm, pn, d_bins, d_short_present)
-    switch (n + 1) {
+#undef PG_LAUNCH_SMEM
+    PG_CUDA_LAUNCH_CHECK("ngram_count_smem_kernel");
+    return PG_OK;
+}
+
+int launch_global_count(int m, const CountArgs &a, unsigned long long *bins, const int *gate) {
+    const unsigned grid = (unsigned)pg_ceil_div(pg_ceil_div(a.nbytes, 16), 256);
+#define PG_LAUNCH_COUNT(MM) \
+    ngram_count_kernel<MM><<<grid, 256, 0, a.st>>>(a.buf, a.nbytes, a.rank, a.sigma, a.pow_m, a.pow_n, bins, a.short_present, gate)
+    switch (m) {
         case 2: PG_LAUNCH_COUNT(2); break;
         case 3: PG_LAUNCH_COUNT(3); break;
         case 4: PG_LAUNCH_COUNT(4); break;
         case 5: PG_LAUNCH_COUNT(5); break;
         case 6: PG_LAUNCH_COUNT(6); break;
         case 7: PG_LAUNCH_COUNT(7); break;
-        default: pg_set_error("pg_ngram_count: unsupported n=%d", n); return PG_EINVAL;
+        default: pg_set_error("pg_ngram_count: unsupported n=%d", m - 1); return PG_EINVAL;
     }
 #undef PG_LAUNCH_COUNT
     PG_CUDA_LAUNCH_CHECK("ngram_count_kernel");
     return PG_OK;
+}
+
+constexpr int kMaxSplits = 4;
+inline int splits_for(int64_t pow_m, int lane_bits) { return (int)pg_ceil_div(pow_m * lane_bits / 8, kSmemTableBytes); }
+
+// the strictly exact variants: 32-bit lanes, 16-bit lanes (<= 4 key-range splits), else L2 REDs
+int launch_strict_count(int m, const CountArgs &a, unsigned long long *bins, const int *gate, bool allow_smem) {
+    if (allow_smem && splits_for(a.pow_m, 32) == 1) return launch_smem_count<32, false>(m, a, bins, 1, nullptr, gate);
+    const int s16 = splits_for(a.pow_m, 16);
+    if (allow_smem && s16 == 1) return launch_smem_count<16, false>(m, a, bins, 1, nullptr, gate);
+    if (allow_smem && s16 <= kMaxSplits) return launch_smem_count<16, true>(m, a, bins, s16, nullptr, gate);
+    return launch_global_count(m, a, bins, gate);
+}
+}  // namespace
+
+extern "C" size_t pg_ngram_count_ws_bytes(int n, int sigma) {
+    int64_t pow_n, pow_m;
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) return 0;
+    if (splits_for(pow_m, 16) == 1 || splits_for(pow_m, 8) > kMaxSplits) return 256;  // strict variants need no scratch
+    return 256 + pg_align_up((size_t)pow_m * 8, 256);
+}
+
+extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte, int sigma,
+                              unsigned long long *d_bins, uint8_t *d_short_present, void *d_ws, size_t ws_bytes,
+                              pg_stream_t stream) {
+    int64_t pow_n, pow_m;
+    PG_CHECK_ARG(d_buf && d_rank_of_byte && d_bins && d_short_present && nbytes >= 0, "pg_ngram_count: null/negative argument");
+    PG_CHECK_ARG(((uintptr_t)d_buf & 15) == 0, "pg_ngram_count: d_buf must be 16-byte aligned");
+    PG_CHECK_ARG(nbytes < (1ll << 40), "pg_ngram_count: at most 2^40 bytes per call (count the corpus in chunks)");
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) {
+        pg_set_error("pg_ngram_count: table sigma^(n+1) out of range (n=%d sigma=%d; need 1<=n<=6, sigma^(n+1)<=2^32)", n, sigma);
+        return PG_ERANGE;
+    }
+    if (nbytes == 0) return PG_OK;
+    const int64_t nvec = pg_ceil_div(nbytes, 16);
+    CountArgs a{d_buf, nbytes, d_rank_of_byte, (uint32_t)sigma, (uint32_t)pow_m, (uint32_t)pow_n, d_short_present, pg_cu(stream)};
+    const int m = n + 1;
+    const int variant = g_count_variant;
+    const bool big_enough = nvec >= 4 * kSmemCountThreads;  // tiny corpora: zeroing + flushing 148 tables costs more than REDs
+    if (variant == PG_COUNT_GLOBAL) return launch_global_count(m, a, d_bins, nullptr);
+    if (variant == PG_COUNT_STRICT) return launch_strict_count(m, a, d_bins, nullptr, true);
+    const int s8 = splits_for(pow_m, 8);
+    const size_t need = 256 + pg_align_up((size_t)pow_m * 8, 256);
+    const bool fast8 = splits_for(pow_m, 16) > 1 && s8 <= kMaxSplits && d_ws != nullptr && ws_bytes >= need &&
+                       ((uintptr_t)d_ws & 255) == 0;
+    if (!fast8 || (variant == PG_COUNT_AUTO && !big_enough)) return launch_strict_count(m, a, d_bins, nullptr, big_enough);
+    // 8-bit lanes: count into the zeroed scratch, merge if no hazard was observed, else recount strictly
+    int *status = (int *)d_ws;
+    unsigned long long *scratch = (unsigned long long *)((char *)d_ws + 256);
+    PG_CUDA_CALL(cudaMemsetAsync(d_ws, 0, need, a.st));
+    int rc = s8 == 1 ? launch_smem_count<8, false>(m, a, scratch, 1, status, nullptr)
+                     : launch_smem_count<8, true>(m, a, scratch, s8, status, nullptr);
+    if (rc != PG_OK) return rc;
+    if (variant == PG_COUNT_FAST8_FORCE_HAZARD) {
+        set_flag_kernel<<<1, 1, 0, a.st>>>(status, 1);
+        PG_CUDA_LAUNCH_CHECK("set_flag_kernel");
+    }
+    merge_scratch_kernel<<<grid_for(pow_m), 256, 0, a.st>>>(scratch, pow_m, status, d_bins);
+    PG_CUDA_LAUNCH_CHECK("merge_scratch_kernel");
+    return launch_strict_count(m, a, d_bins, status, true);  // no-op kernels unless *status != 0
 }
 
 extern "C" size_t pg_graph_extract_ws_bytes(int n, int sigma) {

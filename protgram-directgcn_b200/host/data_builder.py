@@ -41,8 +41,9 @@ def count_level(d_buf: torch.Tensor, n: int, d_rank: torch.Tensor, sigma: int,
         bins = torch.zeros(pow_m, dtype=torch.int64, device=dev)
     if short is None:
         short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
+    ws = nat.workspace(nat.query("pg_ngram_count_ws_bytes", n, sigma), dev)
     nat.call("pg_ngram_count", nat.ptr(d_buf), d_buf.numel(), n, nat.ptr(d_rank), sigma, nat.ptr(bins), nat.ptr(short),
-             nat.stream_ptr())
+             nat.ptr(ws), ws.numel(), nat.stream_ptr())
     return bins, short
 
 
@@ -72,9 +73,19 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
     sigma = int(symbols.size)
     chunks = list(d_buf) if isinstance(d_buf, (list, tuple)) else [d_buf]
     bins = short = None
-    for c in chunks:
-        c_dev = c if torch.is_tensor(c) and c.is_cuda else corpus.to_device(c, d_rank.device)
-        bins, short = count_level(c_dev, n, d_rank, sigma, bins, short)
+    host_idx = [i for i, c in enumerate(chunks) if not (torch.is_tensor(c) and c.is_cuda)]
+    up = corpus.CorpusUploader(d_rank.device) if host_idx else None
+    if up is not None:
+        up.submit(chunks[host_idx[0]])
+    for i, c in enumerate(chunks):
+        if torch.is_tensor(c) and c.is_cuda:
+            bins, short = count_level(c, n, d_rank, sigma, bins, short)
+            continue
+        nxt = host_idx.index(i) + 1
+        if nxt < len(host_idx):
+            up.submit(chunks[host_idx[nxt]])            # upload of the next chunk runs under this chunk's count
+        bins, short = count_level(up.acquire(), n, d_rank, sigma, bins, short)
+        up.release()
     if bins is None:
         bins, short = count_level(torch.empty(0, dtype=torch.uint8, device=d_rank.device), n, d_rank, sigma)
     if group is not None:

@@ -70,8 +70,7 @@ class GraphedDirectGCNStep:
     def _step(self):
         self.model.train()
         self.opt.zero_grad(set_to_none=True)
-        logp, _ = self.model(data=self.data)
-        nll = F.nll_loss(logp, self.labels)
+        nll = self.model.nll_loss(self.data, self.labels)   # fused decoder output + log_softmax + nll (row f1)
         nll.backward()
         loss = nll.detach()
         if self.l2_lambda > 0.0:

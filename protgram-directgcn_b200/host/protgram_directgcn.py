@@ -275,6 +275,59 @@ class _DirectGCNFused(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# row f1: decoder output layer + log_softmax + nll_loss, forward and backward in one pass
+# ------------------------------------------------------------------------------------------------
+class _LinearLogSoftmaxNLL(torch.autograd.Function):
+    """loss = nll_loss(log_softmax(d @ W^T + b), labels)   (reference protgram_directgcn.py:219-221 +
+    protgram_directgcn_trainer.py:94).  The logits GEMM and the two gradient GEMMs are library GEMMs;
+    everything between them (log_softmax, nll, their backward, the bias gradient: 10 passes over the
+    N x C matrix in the reference) is one pass of pg_softmax_nll that overwrites the logits with
+    d(loss)/d(logits).  labels outside [0, C) are ignored (ignore_index semantics)."""
+
+    @staticmethod
+    def forward(ctx, d, weight, bias, labels, has_ignored):
+        nat.check_tensor(d, "decoder input")
+        n, c = d.shape[0], weight.shape[0]
+        dev = d.device
+        logits = torch.addmm(bias, d, weight.t()) if bias is not None else d @ weight.t()
+        # grad_scale is a host scalar of the C ABI: with every row counted (the trainer's case) it is 1/n and no
+        # device->host read is needed; masked labels take the exact count from the device
+        scale = 1.0 / max(n, 1)
+        if has_ignored:
+            scale = 1.0 / max(1, int(((labels >= 0) & (labels < c)).sum().item()))
+        row_loss = torch.empty(n, dtype=torch.float32, device=dev)
+        colsum = torch.empty(c, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = nat.workspace(nat.query("pg_softmax_nll_ws_bytes", n, c), dev)
+        nat.call("pg_softmax_nll", nat.ptr(logits), logits.stride(0), n, c, nat.ptr(labels), scale, nat.ptr(row_loss),
+                 nat.ptr(colsum), nat.ptr(loss), nat.ptr(ws), ws.numel(), nat.stream_ptr())
+        ctx.save_for_backward(d, weight, logits, colsum)   # logits now holds dloss/dlogits
+        ctx.has_bias = bias is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d, weight, g, colsum = ctx.saved_tensors
+        dd = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dd = (g @ weight).mul_(grad_out)
+        if ctx.needs_input_grad[1]:
+            dw = (g.t() @ d).mul_(grad_out)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum * grad_out
+        return dd, dw, db, None, None
+
+
+def linear_log_softmax_nll(d: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor,
+                           has_ignored: bool = False) -> torch.Tensor:
+    """Fused `F.nll_loss(F.log_softmax(F.linear(d, weight, bias), -1), labels)` (mean over counted rows).
+    Pass has_ignored=True when some labels lie outside [0, C) (costs one device->host read of the count)."""
+    if weight.shape[0] > nat.SOFTMAX_NLL_MAX_CLASSES:
+        return F.nll_loss(F.log_softmax(F.linear(d, weight, bias), dim=-1), labels)   # torch CUDA ops, no row cache that large
+    return _LinearLogSoftmaxNLL.apply(d.contiguous(), weight.contiguous(), bias, labels.contiguous(), bool(has_ignored))
+
+
+# ------------------------------------------------------------------------------------------------
 # modules
 # ------------------------------------------------------------------------------------------------
 class DirectGCNLayer(nn.Module):
@@ -426,6 +479,15 @@ class ProtGramDirectGCN(nn.Module):
             h = F.dropout(h, p=self.dropout, training=self.training)
             layers.append(h)
         return (h, layers) if return_layers else h
+
+    def nll_loss(self, data, labels: torch.Tensor, has_ignored: bool = False) -> torch.Tensor:
+        """`F.nll_loss(self(data)[0], labels)` of the reference trainer (protgram_directgcn_trainer.py:92-94)
+        without materialising log_softmax: the decoder's output Linear, log_softmax and nll_loss (and their
+        backward) run through the fused loss (row f1)."""
+        h = self.embed(data)
+        d = self.decoder_fc[:-1](h)
+        last = self.decoder_fc[-1]
+        return linear_log_softmax_nll(d, last.weight, last.bias, labels, has_ignored)
 
     def forward(self, data) -> Tuple[torch.Tensor, torch.Tensor]:
         h = self.embed(data)

@@ -27,7 +27,11 @@ def pg_byte_presence(buf, nbytes, present256, stream=None):
     present256[seen] = 1
 
 
-def pg_ngram_count(buf, nbytes, n, rank_of_byte, sigma, bins, short_present, stream=None):
+def pg_ngram_count_ws_bytes(n, sigma):
+    return 256
+
+
+def pg_ngram_count(buf, nbytes, n, rank_of_byte, sigma, bins, short_present, ws=None, ws_bytes=0, stream=None):
     b = buf[:nbytes].cpu().numpy()
     rank = rank_of_byte.cpu().numpy().astype(np.int64)
     m = n + 1
@@ -278,6 +282,26 @@ def pg_layer_gemm_bwd_weight(z, ldz, x, ldx, ga, gb, gc, gate_stride, dy, lddy, 
 
 def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
     out.copy_(h / (torch.norm(h, p=2, dim=1, keepdim=True) + eps))
+
+
+def pg_softmax_nll_ws_bytes(n, c):
+    return 256
+
+
+def pg_softmax_nll(logits, ld, n, c, labels, grad_scale, row_loss, colsum, loss, ws=None, ws_bytes=0, stream=None):
+    """Executable specification of csrc/decoder.cu (torch fp32, the reference's own ops)."""
+    x = logits[:, :c]
+    ok = (labels >= 0) & (labels < c)
+    logp = torch.log_softmax(x, dim=-1)
+    safe = torch.where(ok, labels, torch.zeros_like(labels))
+    rl = -logp.gather(1, safe[:, None])[:, 0]
+    row_loss.copy_(torch.where(ok, rl, torch.zeros_like(rl)))
+    g = torch.exp(logp)
+    g[torch.arange(n), safe] -= 1.0
+    g = g * grad_scale * ok[:, None].to(g.dtype)
+    x.copy_(g)
+    colsum.copy_(g.sum(0))
+    loss.copy_(row_loss.sum() * grad_scale)
 
 
 # --------------------------------------------------------------------------- monkeypatch glue

@@ -161,6 +161,47 @@ def test_l2_normalize_rows():
     assert rel_err(out.cpu().numpy(), ref.numpy()) <= 1e-6
 
 
+@pytest.mark.parametrize("n,c,ld,ignored", [(1, 1, 1, False), (7, 5, 8, False), (300, 1000, 1000, True), (513, 513, 520, False),
+                                            (2000, 8401, 8401, False), (64, 28672, 28672, True)])
+def test_softmax_nll_fused_vs_fp64(n, c, ld, ignored):
+    """pg_softmax_nll (row f1) against log_softmax + nll_loss + autograd in fp64: loss, dlogits, bias gradient;
+    large-magnitude logits exercise the max subtraction; rerun must be bitwise identical (fixed-order sums)."""
+    g = torch.Generator().manual_seed(n * 31 + c)
+    logits = (torch.randn(n, c, generator=g) * 8.0).to(DEV)
+    labels = torch.randint(0, c, (n,), generator=g).to(DEV)
+    if ignored:
+        labels[::4] = -100
+        labels[1::8] = c + 3
+    ok = (labels >= 0) & (labels < c)
+    scale = 1.0 / max(1, int(ok.sum()))
+    x64 = logits.double().requires_grad_(True)
+    if bool(ok.any()):
+        ref = torch.nn.functional.nll_loss(torch.log_softmax(x64[ok], -1), labels[ok])
+        ref.backward()
+        gref = x64.grad
+    else:
+        ref, gref = torch.zeros((), dtype=torch.float64), torch.zeros_like(x64)
+    outs = []
+    for _ in range(2):
+        buf = torch.full((n, ld), 123.0, device=DEV)
+        buf[:, :c] = logits
+        row_loss = torch.empty(n, device=DEV)
+        colsum = torch.empty(c, device=DEV)
+        loss = torch.empty((), device=DEV)
+        ws = nat.workspace(nat.query("pg_softmax_nll_ws_bytes", n, c), DEV)
+        nat.call("pg_softmax_nll", nat.ptr(buf), ld, n, c, nat.ptr(labels), scale, nat.ptr(row_loss), nat.ptr(colsum), nat.ptr(loss),
+                 nat.ptr(ws), ws.numel(), nat.stream_ptr())
+        outs.append((buf.clone(), colsum.clone(), loss.clone()))
+    buf, colsum, loss = outs[0]
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert abs(float(loss) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    assert rel_err(buf[:, :c].cpu().numpy(), gref.cpu().numpy()) <= 1e-5
+    assert rel_err(colsum.cpu().numpy(), gref.sum(0).cpu().numpy()) <= 1e-5 or float(gref.sum(0).abs().max()) < 1e-7
+    if ld > c:
+        assert bool((buf[:, c:] == 123.0).all())          # padding columns untouched
+    assert float(row_loss[~ok].abs().sum()) == 0.0
+
+
 # ------------------------------------------------------------------------------- builder
 @pytest.mark.parametrize("name", sorted(BUILD_FIXTURES))
 def test_graph_builder_run_matches_reference_gpu(name, tmp_path):
@@ -231,13 +272,18 @@ def test_synth_corpus_matches_cpu_twin_and_is_shard_independent():
     assert np.array_equal(a, ref[1 + 600 * 52:])
 
 
-@pytest.fixture(params=["smem", "global"])
+COUNT_VARIANTS = {"auto": 0, "global": 1, "strict": 2, "fast8_forced_hazard": 4}
+
+
+@pytest.fixture(params=sorted(COUNT_VARIANTS))
 def count_variant(request):
-    """pg_ngram_count has two kernels (shared-memory privatised tables / global REDs): run both."""
+    """pg_ngram_count picks among shared-memory tables with 32/16/8-bit lanes and global REDs; the 8-bit
+    variant counts into a scratch table that is merged only when proven exact, else a gated strict
+    recount runs.  Pin each path (include/pgb200.h PG_COUNT_*): all must give the oracle's table."""
     lib = nat.load()
-    lib.pg_debug_force_global_count(1 if request.param == "global" else 0)
+    lib.pg_debug_count_variant(COUNT_VARIANTS[request.param])
     yield request.param
-    lib.pg_debug_force_global_count(0)
+    lib.pg_debug_count_variant(0)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
@@ -259,11 +305,14 @@ def test_count_and_extract_vs_c_oracle(n, count_variant):
     assert np.array_equal(cnt.cpu().numpy(), cnt_ref)
 
 
-def test_count_lane_overflow_homopolymer(count_variant):
-    """Adversarial for the 16-bit shared-memory lanes: 3 M identical windows (one homopolymer per
-    sequence) must still count exactly (lane drains at 32768 into the 64-bit table)."""
+@pytest.mark.parametrize("extra", ["", "DEFGHIKLMNPQRSTV", "DEFGHIKLMNPQRSTVWY"])
+def test_count_lane_overflow_homopolymer(count_variant, extra):
+    """Adversarial for the packed shared-memory lanes: 3 M identical windows (one homopolymer per
+    sequence) must still count exactly.  The extra letters size the n=3 table for each lane width:
+    3^4 bins -> 32-bit lanes; 19^4 = 130k -> 8-bit lanes, 1 split (the hazard check must fire and the strict
+    recount take over); 21^4 -> the C2 table; n=1 tables are tiny -> 32-bit lanes."""
     from oracle import c_oracle
-    seqs = ["A" * 3000] * 1000 + ["AC" * 700] * 300
+    seqs = ["A" * 3000] * 1000 + ["AC" * 700] * 300 + ([extra] if extra else [])
     buf = c_oracle.pack_corpus(seqs)
     symbols, rank = c_oracle.alphabet(buf)
     d_buf = corpus.to_device(buf, DEV)

@@ -183,6 +183,20 @@ def run_model_case(g, device, tol_fwd, tol_bwd):
     assert abs(float(loss) - float(g["loss"])) <= tol_fwd * max(1.0, abs(float(g["loss"])))
     loss.backward()
     assert rel_err(data.x.grad.cpu().numpy(), g["grad_x"]) <= tol_bwd
+    # row f1: the fused decoder-output + log_softmax + nll path must give the reference's loss and gradient too
+    grads_unfused = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    data2 = _data(g, device)
+    h = model.embed(data2)
+    emb2 = pg.EmbeddingProcessor.l2_normalize_torch(h, eps=model.l2_eps)
+    last = model.decoder_fc[-1]
+    loss2 = model_mod.linear_log_softmax_nll(model.decoder_fc[:-1](h), last.weight, last.bias, y) + (emb2 * wvec).sum()
+    assert abs(float(loss2) - float(g["loss"])) <= tol_fwd * max(1.0, abs(float(g["loss"])))
+    loss2.backward()
+    assert rel_err(data2.x.grad.cpu().numpy(), g["grad_x"]) <= tol_bwd
+    for k, p in model.named_parameters():
+        if k in grads_unfused:
+            assert rel_err(p.grad.cpu().numpy(), grads_unfused[k].cpu().numpy()) <= tol_bwd, k
     for k, p in model.named_parameters():
         ref = g["grad:" + k]
         got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(ref)
@@ -209,6 +223,25 @@ def test_directgcn_layer_alone_matches_oracle(spec_native):
                                            data.edge_index_out, data.edge_weight_out, data.edge_index_undirected_norm,
                                            data.edge_weight_undirected_norm)
     assert rel_err(out.detach().numpy(), ref.numpy()) <= 1e-5
+
+
+def test_fused_loss_ignores_out_of_range_labels(spec_native):
+    """ignore_index semantics of the fused loss (row f1) == F.nll_loss(..., ignore_index=-100)."""
+    g = load("model_refgraph")
+    model = _load_model(g)
+    model.eval()
+    y = torch.from_numpy(g["y"]).clone()
+    y[::3] = -100
+    ref = torch.nn.functional.nll_loss(model(data=_data(g))[0], y)
+    ref.backward()
+    grads_ref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    out = model.nll_loss(_data(g), y, has_ignored=True)
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    for k, p in model.named_parameters():
+        if k in grads_ref:
+            assert rel_err(p.grad.numpy(), grads_ref[k].numpy()) <= 1e-5, k
 
 
 def test_missing_inputs_raise_value_error(spec_native):

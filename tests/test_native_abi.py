@@ -26,6 +26,8 @@ def test_header_symbols_exported_and_bound():
     assert lib.pg_version() >= 100
     assert nat.query("pg_sort_pairs_ws_bytes", 10_000) > 0
     assert nat.query("pg_graph_extract_ws_bytes", 3, 21) > 21 ** 4 * 8
+    assert nat.query("pg_ngram_count_ws_bytes", 3, 21) >= 256 + 21 ** 4 * 8   # 8-bit lanes: scratch table
+    assert nat.query("pg_ngram_count_ws_bytes", 1, 21) == 256                 # strict variants: status word only
 
 
 def test_argument_errors_are_reported_not_crashed():
@@ -33,7 +35,7 @@ def test_argument_errors_are_reported_not_crashed():
     # pure argument validation happens before any CUDA call
     rc = lib.pg_spmm_fanout(None, None, None, None, None, 2, 10, 8, None, 8, None, 24, 0, None, None)
     assert rc == -1 and b"nv must be 1 or 3" in lib.pg_last_error()
-    rc = lib.pg_ngram_count(None, 0, 3, None, 21, None, None, None)
+    rc = lib.pg_ngram_count(None, 0, 3, None, 21, None, None, None, 0, None)
     assert rc == -1
     with pytest.raises(nat.NativeError):
         nat.call("pg_sort_pairs", None, None, None, None, -5, 8, None, 0, None)
