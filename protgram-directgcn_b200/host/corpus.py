@@ -96,7 +96,7 @@ class CorpusUploader:
             host = host.pin_memory()
         k = self._next
         self._next = (k + 1) % len(self.slots)
-        if any(sl == k for sl, _, _ in self.pending) or k in self.in_use:
+        if any(p[0] == k for p in self.pending) or k in self.in_use:
             raise RuntimeError("CorpusUploader: all slots are busy (acquire/release before submitting more)")
         n = host.numel()
         with torch.cuda.stream(self.copy_stream):
@@ -114,7 +114,9 @@ class CorpusUploader:
         k, view, ev, _host = self.pending.pop(0)
         if self.passthrough:
             return view
-        torch.cuda.current_stream(self.device).wait_event(ev)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        view.record_stream(cur)   # the slot was allocated on the copy stream: tell the allocator who else reads it
         self.in_use.append(k)
         return view
 
