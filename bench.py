@@ -257,6 +257,11 @@ def rmat_graph(pipe, log2_nodes, edges_per_node):
         dst = dst * 2 + (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).to(torch.int64)
         del r
     w = torch.randint(1, 8, (e,), generator=g, device=dev).to(torch.float32)
+    # R-MAT puts every hub at the low ids; relabel the nodes with a seeded random permutation (what any 1-D
+    # partitioner does for power-law graphs) so that equal row blocks carry equal numbers of nonzeros
+    perm = torch.randperm(n, generator=g, device=dev)
+    src, dst = perm[src], perm[dst]
+    del perm
     s, d, wv = gu.device_coalesce(src, dst, w, n)
     del src, dst, w
     res = gu.device_normalize(s, d, wv, n, 1e-9)
@@ -293,7 +298,7 @@ def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iter
     plan = nat.SpmmPlan(res["rowptr"])
     fo = lambda: nat.call("pg_spmm_fanout", *args, nat.ptr(x), F, nat.ptr(z), 3 * F, 0, plan.ref(3 * F), st)
     fi = lambda: nat.call("pg_spmm_fanin", *args, nat.ptr(z), 3 * F, 0, None, 0, nat.ptr(y), F, 0, plan.ref(3 * F), st)
-    out = {"graph": f"R-MAT 2^{log2_nodes} nodes, {e} directed edges before dedupe, pattern nnz {P}", "F": F, "pattern_nnz": P}
+    out = {"graph": f"R-MAT 2^{log2_nodes} nodes (ids randomly relabelled), {e} directed edges before dedupe, pattern nnz {P}", "F": F, "pattern_nnz": P}
     deg = (res["rowptr"][1:] - res["rowptr"][:-1])
     out["max_row_nnz"] = int(deg.max())
     out["long_rows"] = {"chunk": plan.chunk, "rows": plan.n_long, "slices": plan.n_items}
@@ -344,10 +349,11 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     ag_x(); ag_dz()
     local_fo = lambda: part._spmm_fanout(prop.local, holder["x"], per, F)
     local_fi = lambda: part._spmm_fanin(prop.local, holder["g"], per, F)
-    out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}), {e} directed edges before dedupe, pattern nnz {P}",
+    mx = lambda v: (lambda t: (dist.all_reduce(t, op=dist.ReduceOp.MAX), float(t.item()))[1])(torch.tensor([v], device=dev, dtype=torch.float64))
+    out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}, ids randomly relabelled), {e} directed edges before dedupe, pattern nnz {P}",
            "F": F, "pattern_nnz": P, "rows_per_gpu": per, "partition": "1-D rows, global int32 columns",
+           "local_nnz_max_over_mean": mx(float(p_local)) / (P / world),
            "exchange": "NCCL all_gather_into_tensor (fwd: X [N,F]; bwd: dZ [N,3F])"}
-    mx = lambda v: (lambda t: (dist.all_reduce(t, op=dist.ReduceOp.MAX), float(t.item()))[1])(torch.tensor([v], device=dev))
     for name, fn, comm, local, width in (("fwd", fwd, ag_x, local_fo, F), ("bwd", bwd, ag_dz, local_fi, 3 * F)):
         dist.barrier()
         ms = mx(_time_ms(fn, iters))
@@ -434,9 +440,12 @@ def run_b200(args):
         w0 = time.perf_counter()
         t0.record()
         last = None
+        marks = []
         for _ in range(steps):
             last = fn()
             pipe.collect_count_ms()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         if getattr(pipe, "up", None) is not None:   # the prefetch issued by the last step belongs to the timed region
             torch.cuda.current_stream().wait_stream(pipe.up.copy_stream)
         t1.record()
@@ -447,6 +456,7 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        pipe.step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([t0] + marks[:-1], marks)]   # diagnostic: per-step device time
         launches = nat.kernel_launches() - l0
         if pipe.graphed is not None:  # kernels replayed from the captured CUDA graph do not pass the host-side counter
             launches += (pipe.graphed.replays - r0) * pipe.graphed.kernels_per_replay
@@ -456,6 +466,7 @@ def run_b200(args):
     sampler.start()
     ms_step, wall_step, launches, last = timed(pipe.step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
+    step_ms_resident = pipe.step_ms
     count_ms = statistics.mean(pipe.count_ms) if pipe.count_ms else None
     loss, emb, graph = last
     residues = NSEQ * SEQ_LEN * world
@@ -481,6 +492,7 @@ def run_b200(args):
         "e2e": {"value": residues / (e2e_ms * 1e-3), "unit": "residues/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d + gcn_h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "wall_ms_per_step": wall_step * 1e3,
+        "per_step_ms": {"resident": step_ms_resident, "e2e": pipe.step_ms},
     }
     if count_ms:
         alg = pipe.nbytes

@@ -241,6 +241,32 @@ int pg_layer_gemm_bwd_weight(const float *d_z, int64_t ldz, const float *d_x, in
 int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_rows, int F, float eps,
                          float *d_out, int64_t ldout, pg_stream_t stream);
 
+/* Parameter side of one DirectGCNLayer (protgram_directgcn.py:34-66): the reference's own tensors,
+ * row-major [F_out, F_in] weights, [F_out] biases, gate vectors of num_gate entries (N, or 1 for the
+ * scalar-coefficient variant).  w_res / b_res: the stack's res_proj Linear (:159-160), NULL without. */
+typedef struct pg_layer_params {
+    const float *w_in, *w_out, *w_und, *w_sh;                       /* lin_main_in/out, lin_undirected, lin_shared .weight */
+    const float *b_in, *b_out, *b_und, *bs_in, *bs_out, *bs_und;   /* bias_main_*, bias_undirected, bias_*_shared* */
+    const float *w_res, *b_res;
+    const float *c_in, *c_out, *c_dir, *c_und, *c_all;             /* C_in, C_out, C_directed, C_undirected, C_all (_vec) */
+} pg_layer_params;
+typedef struct pg_layer_param_grads {
+    float *w_in, *w_out, *w_und, *w_sh, *b_in, *b_out, *b_und, *bs_in, *bs_out, *bs_und, *w_res, *b_res;
+    float *c_in, *c_out, *c_dir, *c_und, *c_all;
+} pg_layer_param_grads;
+
+/* -> the operands of pg_layer_gemm_*: W_ext [3F_in (+F_in) + 3 (+1), F_out] and the gates
+ * a = (C_all*C_dir)*C_in, b = (C_all*C_dir)*C_out, c = C_all*C_und.  Same fp32 operations as the
+ * reference's tensor ops (:101-133), so bit-identical to composing them. */
+int pg_pack_layer_params(const pg_layer_params *params, int64_t num_gate, int F_in, int F_out,
+                         int has_res, float *d_w_ext, float *d_gate_a, float *d_gate_b,
+                         float *d_gate_c, pg_stream_t stream);
+/* Backward of the packing: dW_ext, da, db, dc -> gradients of every reference parameter. */
+int pg_unpack_layer_param_grads(const pg_layer_params *params, const float *d_dw_ext,
+                                const float *d_dgate_a, const float *d_dgate_b,
+                                const float *d_dgate_c, int64_t num_gate, int F_in, int F_out,
+                                int has_res, const pg_layer_param_grads *grads, pg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Row f1: loss of the next-node task, forward AND backward in one pass
  * ---------------------------------------------------------------------------------------- */

@@ -59,9 +59,26 @@ _SIGS = {
     "pg_layer_gemm_bwd_weight": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int,
                                          c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
+    "pg_pack_layer_params": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "pg_unpack_layer_param_grads": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "pg_softmax_nll_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "pg_softmax_nll": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
 }
+
+LAYER_PARAM_FIELDS = ("w_in", "w_out", "w_und", "w_sh", "b_in", "b_out", "b_und", "bs_in", "bs_out", "bs_und", "w_res", "b_res",
+                      "c_in", "c_out", "c_dir", "c_und", "c_all")
+
+
+class LayerParamsStruct(ctypes.Structure):
+    """Mirror of `pg_layer_params` / `pg_layer_param_grads` (include/pgb200.h): 17 device pointers."""
+    _fields_ = [(name, _P) for name in LAYER_PARAM_FIELDS]
+
+
+def layer_params(**tensors):
+    """-> (by-reference argument, keep-alive) for pg_pack_layer_params / pg_unpack_layer_param_grads."""
+    st = LayerParamsStruct(**{k: ptr(tensors.get(k)) for k in LAYER_PARAM_FIELDS})
+    return ctypes.byref(st), (st, tensors)
+
 
 class SpmmPlanStruct(ctypes.Structure):
     """Mirror of `pg_spmm_plan` (include/pgb200.h)."""

@@ -91,13 +91,9 @@ __device__ __forceinline__ uint32_t sep_nibble(uint32_t w) {
 // Output: codes[k] = code of the window ending at byte p0+k, bit k of the returned mask = that
 // window is separator-free.  (Branch-free so the 16 table updates of a thread can be in flight
 // together.)
-template <int M>
-__device__ __forceinline__ uint32_t scan_vector(const uint8_t *__restrict__ buf, int64_t nbytes, int64_t p0,
-                                                const uint8_t *lut, uint32_t sigma, uint32_t sigma_pow_m,
-                                                uint32_t sigma_pow_n, uint8_t *__restrict__ short_present,
-                                                uint32_t (&codes)[16]) {
-    constexpr int LB = M - 1;  // look-back bytes (= n)
-    uint32_t w[6];             // prev.x prev.y cur.x cur.y cur.z cur.w   (24 bytes, positions 0..23)
+// The 24 bytes a thread works on: prev.x prev.y cur.x cur.y cur.z cur.w (buffer positions p0-8 .. p0+15);
+// bytes outside the buffer read as separators.
+__device__ __forceinline__ void load_vector(const uint8_t *__restrict__ buf, int64_t nbytes, int64_t p0, uint32_t (&w)[6]) {
     if (p0 + 16 <= nbytes) {
         const uint4 cur = *reinterpret_cast<const uint4 *>(buf + p0);
         w[2] = cur.x; w[3] = cur.y; w[4] = cur.z; w[5] = cur.w;
@@ -119,6 +115,13 @@ __device__ __forceinline__ uint32_t scan_vector(const uint8_t *__restrict__ buf,
     } else {
         w[0] = w[1] = 0xFFFFFFFFu;  // before the buffer = separator
     }
+}
+
+template <int M>
+__device__ __forceinline__ uint32_t scan_words(const uint32_t (&w)[6], int64_t nbytes, int64_t p0, const uint8_t *lut,
+                                               uint32_t sigma, uint32_t sigma_pow_m, uint32_t sigma_pow_n,
+                                               uint8_t *__restrict__ short_present, uint32_t (&codes)[16]) {
+    constexpr int LB = M - 1;  // look-back bytes (= n)
     uint32_t sep = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) sep |= sep_nibble(w[k]) << (4 * k);
@@ -156,6 +159,16 @@ __device__ __forceinline__ uint32_t scan_vector(const uint8_t *__restrict__ buf,
         }
     }
     return (valid >> 8) & 0xFFFFu;
+}
+
+template <int M>
+__device__ __forceinline__ uint32_t scan_vector(const uint8_t *__restrict__ buf, int64_t nbytes, int64_t p0,
+                                                const uint8_t *lut, uint32_t sigma, uint32_t sigma_pow_m,
+                                                uint32_t sigma_pow_n, uint8_t *__restrict__ short_present,
+                                                uint32_t (&codes)[16]) {
+    uint32_t w[6];
+    load_vector(buf, nbytes, p0, w);
+    return scan_words<M>(w, nbytes, p0, lut, sigma, sigma_pow_m, sigma_pow_n, short_present, codes);
 }
 
 // Variant G: every window is one RED.ADD.64 into the dense table in L2.  Measured on B200:
@@ -225,9 +238,19 @@ __global__ void __launch_bounds__(kSmemCountThreads, 1) ngram_count_smem_kernel(
     uint8_t *sp = (split == 0) ? short_present : nullptr;
     const int64_t nvec = (nbytes + 15) / 16;
     bool hazard = false;
-    for (int64_t vec = group * blockDim.x + threadIdx.x; vec < nvec; vec += groups * blockDim.x) {
+    // the loads of the next vector are issued before this one is processed (the loop body is ~400
+    // instructions per warp: one iteration of lookahead hides the whole HBM latency)
+    const int64_t vstep = groups * blockDim.x;
+    int64_t vec = group * blockDim.x + threadIdx.x;
+    uint32_t wn[6];
+    if (vec < nvec) load_vector(buf, nbytes, vec * 16, wn);
+    for (; vec < nvec; vec += vstep) {
+        uint32_t wc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wc[k] = wn[k];
+        if (vec + vstep < nvec) load_vector(buf, nbytes, (vec + vstep) * 16, wn);
         uint32_t codes[16];
-        uint32_t valid = scan_vector<M>(buf, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, sp, codes);
+        uint32_t valid = scan_words<M>(wc, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, sp, codes);
         if (SPLIT) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {

@@ -275,6 +275,48 @@ class _DirectGCNFused(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# parameter packing: 17 reference parameters -> (W_ext, a, b, c), one kernel each way
+# ------------------------------------------------------------------------------------------------
+class _PackLayerParams(torch.autograd.Function):
+    """(W_ext, a, b, c) of one layer from the reference's parameters (csrc/params.cu).  Replaces ~12 tiny
+    tensor ops in forward and ~25 in autograd's backward per layer; bit-identical in forward."""
+
+    @staticmethod
+    def forward(ctx, has_res, *params):
+        names = nat.LAYER_PARAM_FIELDS
+        t = {k: (None if v is None else v.detach().contiguous().float()) for k, v in zip(names, params)}
+        w_in = t["w_in"]
+        f_out, f_in = w_in.shape
+        num_gate = t["c_in"].numel()
+        k_ext = 3 * f_in + (f_in + 1 if has_res else 0) + 3
+        dev = w_in.device
+        w_ext = torch.empty((k_ext, f_out), dtype=torch.float32, device=dev)
+        ga, gb, gc = (torch.empty(num_gate, dtype=torch.float32, device=dev) for _ in range(3))
+        ref, keep = nat.layer_params(**t)
+        nat.call("pg_pack_layer_params", ref, num_gate, f_in, f_out, int(has_res), nat.ptr(w_ext), nat.ptr(ga), nat.ptr(gb),
+                 nat.ptr(gc), nat.stream_ptr())
+        ctx.tensors, ctx.has_res, ctx.shapes = t, bool(has_res), [None if v is None else v.shape for v in params]
+        return w_ext, ga, gb, gc
+
+    @staticmethod
+    def backward(ctx, dw_ext, dga, dgb, dgc):
+        t, names = ctx.tensors, nat.LAYER_PARAM_FIELDS
+        f_out, f_in = t["w_in"].shape
+        num_gate = t["c_in"].numel()
+        dev = t["w_in"].device
+        k_ext = 3 * f_in + (f_in + 1 if ctx.has_res else 0) + 3
+        dw_ext = torch.zeros((k_ext, f_out), device=dev) if dw_ext is None else dw_ext.contiguous()
+        dga, dgb, dgc = (torch.zeros(num_gate, device=dev) if g is None else g.contiguous().reshape(-1) for g in (dga, dgb, dgc))
+        grads = {k: (None if t[k] is None else torch.empty_like(t[k])) for k in names}
+        p_ref, keep_p = nat.layer_params(**t)
+        g_ref, keep_g = nat.layer_params(**grads)
+        nat.call("pg_unpack_layer_param_grads", p_ref, nat.ptr(dw_ext), nat.ptr(dga), nat.ptr(dgb), nat.ptr(dgc), num_gate, f_in, f_out,
+                 int(ctx.has_res), g_ref, nat.stream_ptr())
+        out = [None if grads[k] is None else grads[k].reshape(shape) for k, shape in zip(names, ctx.shapes)]
+        return (None, *out)
+
+
+# ------------------------------------------------------------------------------------------------
 # row f1: decoder output layer + log_softmax + nll_loss, forward and backward in one pass
 # ------------------------------------------------------------------------------------------------
 class _LinearLogSoftmaxNLL(torch.autograd.Function):
@@ -399,12 +441,24 @@ class DirectGCNLayer(nn.Module):
             blocks.append(rb.unsqueeze(0))
         return torch.cat(blocks, dim=0)
 
+    def _packed(self, res_weight=None, res_bias=None):
+        sfx = "_vec" if self.use_vector_coeffs else ""
+        c = [getattr(self, k + sfx) for k in ("C_in", "C_out", "C_directed", "C_undirected", "C_all")]
+        return _PackLayerParams.apply(res_weight is not None, self.lin_main_in.weight, self.lin_main_out.weight,
+                                      self.lin_undirected.weight, self.lin_shared.weight, self.bias_main_in, self.bias_main_out,
+                                      self.bias_undirected, self.bias_directed_shared_in, self.bias_directed_shared_out,
+                                      self.bias_undirected_shared, res_weight, res_bias, *c)
+
     def _run(self, x, edges, original_indices, res_weight, res_bias, add_identity, slope):
         ei_in, ew_in, ei_out, ew_out, ei_und, ew_und = edges
         nat.check_tensor(x, "x")
         struct = get_structure((ei_in, ei_out, ei_und), (ew_in, ew_out, ew_und), x.shape[0])
-        ga, gb, gc = self._gates(original_indices)
-        return _DirectGCNFused.apply(x, ga, gb, gc, self._w_ext(res_weight, res_bias), self._constant_rows(original_indices),
+        if original_indices is None or not self.use_vector_coeffs:
+            w_ext, ga, gb, gc = self._packed(res_weight, res_bias)      # one kernel (csrc/params.cu)
+        else:                                                             # cluster mini-batch: gates gathered per sub-graph node
+            ga, gb, gc = self._gates(original_indices)
+            w_ext = self._w_ext(res_weight, res_bias)
+        return _DirectGCNFused.apply(x, ga, gb, gc, w_ext, self._constant_rows(original_indices),
                                      struct, res_weight is not None, add_identity, slope)
 
     def forward(self, x: torch.Tensor,

@@ -284,6 +284,37 @@ def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
     out.copy_(h / (torch.norm(h, p=2, dim=1, keepdim=True) + eps))
 
 
+def pg_pack_layer_params(p, num_gate, F_in, F_out, has_res, w_ext, ga, gb, gc, stream=None):
+    """Executable specification of csrc/params.cu: the reference's tensor-op composition."""
+    blocks = [(p.w_in + p.w_sh).t(), (p.w_out + p.w_sh).t(), (p.w_und + p.w_sh).t()]
+    if has_res:
+        blocks.append(p.w_res.t())
+    blocks.append(torch.stack([p.b_in + p.bs_in, p.b_out + p.bs_out, p.b_und + p.bs_und]))
+    if has_res:
+        blocks.append((p.b_res if p.b_res is not None else torch.zeros(F_out)).reshape(1, -1))
+    w_ext.copy_(torch.cat(blocks, 0))
+    cd = p.c_all.reshape(-1) * p.c_dir.reshape(-1)
+    ga.copy_(cd * p.c_in.reshape(-1))
+    gb.copy_(cd * p.c_out.reshape(-1))
+    gc.copy_(p.c_all.reshape(-1) * p.c_und.reshape(-1))
+
+
+def pg_unpack_layer_param_grads(p, dw_ext, dga, dgb, dgc, num_gate, F_in, F_out, has_res, d, stream=None):
+    blk = [dw_ext[v * F_in:(v + 1) * F_in].t() for v in range(3)]
+    d.w_in.copy_(blk[0]); d.w_out.copy_(blk[1]); d.w_und.copy_(blk[2]); d.w_sh.copy_(blk[0] + blk[1] + blk[2])
+    k_data = 3 * F_in + (F_in if has_res else 0)
+    if has_res:
+        d.w_res.copy_(dw_ext[3 * F_in:4 * F_in].t())
+        if d.b_res is not None:
+            d.b_res.copy_(dw_ext[k_data + 3])
+    for j, (a, b) in enumerate(((d.b_in, d.bs_in), (d.b_out, d.bs_out), (d.b_und, d.bs_und))):
+        a.copy_(dw_ext[k_data + j]); b.copy_(dw_ext[k_data + j])
+    call, cdir, cin, cout, cund = (t.reshape(-1) for t in (p.c_all, p.c_dir, p.c_in, p.c_out, p.c_und))
+    s = dga * cin + dgb * cout
+    d.c_in.reshape(-1).copy_(dga * call * cdir); d.c_out.reshape(-1).copy_(dgb * call * cdir)
+    d.c_dir.reshape(-1).copy_(s * call); d.c_und.reshape(-1).copy_(dgc * call); d.c_all.reshape(-1).copy_(s * cdir + dgc * cund)
+
+
 def pg_softmax_nll_ws_bytes(n, c):
     return 256
 
@@ -329,6 +360,8 @@ def install(monkeypatch, nat):
     monkeypatch.setattr(nat, "call", call)
     monkeypatch.setattr(nat, "query", lambda name, *a: int(spec[name](*a)))
     monkeypatch.setattr(nat, "ptr", lambda t: t)
+    import types
+    monkeypatch.setattr(nat, "layer_params", lambda **t: (types.SimpleNamespace(**{k: t.get(k) for k in nat.LAYER_PARAM_FIELDS}), None))
     monkeypatch.setattr(nat, "stream_ptr", lambda: None)
     monkeypatch.setattr(nat, "require_cuda", lambda: None)
     monkeypatch.setattr(nat, "check_tensor", lambda t, what="input": None)

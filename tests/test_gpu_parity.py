@@ -161,6 +161,31 @@ def test_l2_normalize_rows():
     assert rel_err(out.cpu().numpy(), ref.numpy()) <= 1e-6
 
 
+@pytest.mark.parametrize("f_in,f_out,n_gate,has_res", [(64, 256, 1000, True), (16, 16, 1, False), (24, 40, 77, True), (128, 64, 1, True)])
+def test_pack_layer_params_matches_tensor_ops(f_in, f_out, n_gate, has_res):
+    """csrc/params.cu vs the reference's tensor-op composition (DirectGCNLayer._w_ext/_gates): forward bit-identical,
+    backward equal to autograd through the composition."""
+    torch.manual_seed(f_in * 7 + f_out)
+    layer = pg.DirectGCNLayer(f_in, f_out, n_gate if n_gate > 1 else 0, n_gate > 1).to(DEV)
+    with torch.no_grad():
+        for p_ in layer.parameters():
+            p_.copy_(torch.randn_like(p_))
+    res = torch.nn.Linear(f_in, f_out).to(DEV) if has_res else None
+    rw, rb = (res.weight, res.bias) if has_res else (None, None)
+    w_ref = layer._w_ext(rw, rb)
+    g_ref = layer._gates(None)
+    w, ga, gb, gc = layer._packed(rw, rb)
+    assert torch.equal(w, w_ref) and all(torch.equal(a, b) for a, b in zip((ga, gb, gc), g_ref))
+    cw = torch.randn_like(w)
+    cg = [torch.randn_like(t) for t in g_ref]
+    params = list(layer.parameters()) + (list(res.parameters()) if has_res else [])
+    params = [p_ for p_ in params if p_ is not layer.constant]
+    ref_grads = torch.autograd.grad((w_ref * cw).sum() + sum((a * b).sum() for a, b in zip(g_ref, cg)), params)
+    grads = torch.autograd.grad((w * cw).sum() + sum((a * b).sum() for a, b in zip((ga, gb, gc), cg)), params)
+    for a, b in zip(grads, ref_grads):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+
+
 @pytest.mark.parametrize("n,c,ld,ignored", [(1, 1, 1, False), (7, 5, 8, False), (300, 1000, 1000, True), (513, 513, 520, False),
                                             (2000, 8401, 8401, False), (64, 28672, 28672, True)])
 def test_softmax_nll_fused_vs_fp64(n, c, ld, ignored):
