@@ -73,14 +73,17 @@ int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d
                    int sigma, unsigned long long *d_bins, uint8_t *d_short_present,
                    void *d_ws, size_t ws_bytes, pg_stream_t stream);
 /* Workspace of pg_ngram_count (256-byte aligned device memory, contents irrelevant): a status
- * word + a scratch table for the 8-bit-lane shared-memory variant, whose result is only merged
- * into d_bins when the kernel proved it exact (else a strictly exact variant recounts, all on
- * the stream, no host round trip).  d_ws may be NULL: the strictly exact variants are used. */
+ * word, one packed shared-memory table per CTA (written with plain stores and summed by a reduce
+ * kernel: no flush atomics) and, for the 8-bit-lane variant, a scratch table for drained lanes;
+ * that variant's result is only merged into d_bins when the kernel proved it exact, else a
+ * strictly exact variant recounts (all on the stream, no host round trip).
+ * d_ws may be NULL: every window is then one L2 atomic on d_bins (slower, same result). */
 size_t pg_ngram_count_ws_bytes(int n, int sigma);
 
 /* Test hook: pins the variant of pg_ngram_count so parity tests can cover every kernel.
  * AUTO: widest shared-memory lanes that fit one CTA (32/16 bit: strict; 8 bit: scratch + hazard
- * check + gated strict recount), L2 REDs for tables beyond 4 key-range splits or tiny corpora. */
+ * check + gated strict recount), L2 REDs for tables beyond 4 key-range splits or tiny corpora.
+ * STRICT: the 32/16-bit variants even for tiny corpora; FAST8*: the 8-bit variant where it applies. */
 enum { PG_COUNT_AUTO = 0, PG_COUNT_GLOBAL = 1, PG_COUNT_STRICT = 2, PG_COUNT_FAST8 = 3, PG_COUNT_FAST8_FORCE_HAZARD = 4 };
 void pg_debug_count_variant(int variant);
 

@@ -72,12 +72,23 @@ __global__ void __launch_bounds__(kThreads) softmax_nll_kernel(float *__restrict
     for (int j = threadIdx.x; j < c; j += kThreads) out[j] = colsum[j];
 }
 
+// colsum[j] = sum_p partial[p][j]: a CTA owns 32 columns, its 8 warps take every 8th partial (coalesced 128 B
+// rows), the 8 sub-sums are combined in warp order -> fixed summation order
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float *__restrict__ partial, int parts, int c,
                                                             float *__restrict__ colsum) {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c; j += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * c + j];  // fixed order
-        colsum[j] = s;
+    __shared__ float sub[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (j < c)
+        for (int p = warp; p < parts; p += 8) s += partial[(int64_t)p * c + j];
+    sub[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && j < c) {
+        float t = sub[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += sub[w][lane];
+        colsum[j] = t;
     }
 }
 
@@ -133,8 +144,7 @@ extern "C" int pg_softmax_nll(float *d_logits, int64_t ld, int64_t n, int64_t c,
     PG_CUDA_CALL(cudaFuncSetAttribute(softmax_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     softmax_nll_kernel<<<grid, kThreads, smem, st>>>(d_logits, ld, n, (int)c, d_labels, grad_scale, d_row_loss, (float *)d_ws);
     PG_CUDA_LAUNCH_CHECK("softmax_nll_kernel");
-    int g2 = (int)pg_ceil_div(c, 256);
-    if (g2 > PG_NUM_SMS * 4) g2 = PG_NUM_SMS * 4;
+    const int g2 = (int)pg_ceil_div(c, 32);
     colsum_reduce_kernel<<<g2, 256, 0, st>>>((const float *)d_ws, grid, (int)c, d_colsum);
     PG_CUDA_LAUNCH_CHECK("colsum_reduce_kernel");
     loss_reduce_kernel<<<1, kThreads, 0, st>>>(d_row_loss, n, grad_scale, d_loss);

@@ -186,23 +186,25 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
 
     if (warp < TC_PRODUCERS / 32) {
         // ------------------------------------------------------------------ A producers
-        constexpr int PER = (TC_BM * TC_CHUNKS) / TC_PRODUCERS;  // 4 float4 per thread per tile
-        float4 v[2][PER];  // tiles kt and kt+1 in registers: two tiles of global loads are always in flight
+        constexpr int PER = (TC_BM * TC_CHUNKS) / TC_PRODUCERS;  // float4 per thread per tile
+        constexpr int PF = 2;                                    // k-tiles of global loads kept in flight (registers); 4 measured slower (C3 0.59 -> 0.69 ms)
+        float4 v[PF][PER];
 #pragma unroll
-        for (int d = 0; d < 2; ++d)
+        for (int d = 0; d < PF; ++d)
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int idx = i * TC_PRODUCERS + tid;
                 v[d][i] = (d < k_tiles) ? A.at4(m0 + idx / TC_CHUNKS, d * TC_BK + (idx % TC_CHUNKS) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        for (int kt = 0; kt < k_tiles; kt += 2) {
+        for (int kt = 0; kt < k_tiles; kt += PF) {
 #pragma unroll
-            for (int d = 0; d < 2; ++d) {
+            for (int d = 0; d < PF; ++d) {
                 const int t = kt + d;
                 if (t < k_tiles) {
-                    uint8_t *st = smem + (size_t)d * stage_bytes;  // stage == t & 1 == d (kt is even)
+                    const int sg = d & 1;                              // stage == t & 1 (kt is a multiple of PF, PF even)
+                    uint8_t *st = smem + (size_t)sg * stage_bytes;
                     if (t >= 2 && !bail) {
-                        if (!mbar_wait(&empty[d], (uint32_t)(((t >> 1) - 1) & 1))) bail = 1;
+                        if (!mbar_wait(&empty[sg], (uint32_t)(((t >> 1) - 1) & 1))) bail = 1;
                     }
 #pragma unroll
                     for (int i = 0; i < PER; ++i) {
@@ -215,9 +217,9 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
                         *reinterpret_cast<float4 *>(st + a_bytes + kc * TC_LBO_A + r * 16) = lo;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-                    mbar_arrive(&full[d]);
-                    if (t + 2 < k_tiles) {  // refill the register slot with the tile two steps ahead
-                        const int k0 = (t + 2) * TC_BK;
+                    mbar_arrive(&full[sg]);
+                    if (t + PF < k_tiles) {  // refill the register slot with the tile PF steps ahead
+                        const int k0 = (t + PF) * TC_BK;
 #pragma unroll
                         for (int i = 0; i < PER; ++i) {
                             const int idx = i * TC_PRODUCERS + tid;

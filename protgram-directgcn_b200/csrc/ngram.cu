@@ -218,7 +218,8 @@ template <int M, int LB, bool SPLIT>
 __global__ void __launch_bounds__(kSmemCountThreads, 1) ngram_count_smem_kernel(
     const uint8_t *__restrict__ buf, int64_t nbytes, const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
     uint32_t sigma_pow_m, uint32_t sigma_pow_n, unsigned long long *__restrict__ out, uint8_t *__restrict__ short_present,
-    int splits, uint32_t lanes_per_split, int *__restrict__ status, const int *__restrict__ gate) {
+    int splits, uint32_t lanes_per_split, int *__restrict__ status, const int *__restrict__ gate,
+    unsigned *__restrict__ partials) {
     constexpr uint32_t PER_WORD = 32 / LB;                 // lanes per 32-bit word
     constexpr uint32_t LSH = LB == 32 ? 0 : (LB == 16 ? 1 : 2);
     constexpr uint32_t LANE_MASK = LB == 32 ? 0xFFFFFFFFu : ((1u << (LB % 32)) - 1u);
@@ -300,25 +301,49 @@ __global__ void __launch_bounds__(kSmemCountThreads, 1) ngram_count_smem_kernel(
     }
     if (LB == 8 && hazard) *status = 1;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
-        const unsigned w = tbl[i];
-        if (w == 0u) continue;
-        const uint32_t k = lo + PER_WORD * i;
-#pragma unroll
-        for (uint32_t j = 0; j < PER_WORD; ++j) {
-            const unsigned long long c = LB == 32 ? w : ((w >> ((j * LB) % 32)) & LANE_MASK);
-            if (c) atomicAdd(&out[k + j], c);
-        }
-    }
+    // The packed table goes to this CTA's slice of the workspace with plain coalesced stores; the
+    // reduce kernel below sums the slices.  (Flushing with one RED per non-zero bin and CTA cost
+    // 148 x 194k = 28.8 M L2 atomics = half of the kernel's time at C2.)
+    unsigned *mine = partials + (size_t)blockIdx.x * words;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) mine[i] = tbl[i];
 }
 
-// bins += scratch unless the 8-bit count flagged a hazard (then the gated strict recount supplies the counts)
-__global__ void __launch_bounds__(256) merge_scratch_kernel(const unsigned long long *__restrict__ scratch, int64_t nbins,
-                                                            const int *__restrict__ status, unsigned long long *__restrict__ bins) {
-    if (*status != 0) return;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long c = scratch[k];
-        if (c) bins[k] += c;
+// bins[k] += sum over the CTAs' packed tables (+ the drained counts in `scratch`, 8-bit variant).
+// run_if: -1 always; 0 only if *status == 0 (8-bit result proven exact); 1 only if *status != 0
+// (strict recount after a flagged hazard).  One thread per 32-bit word = 32/LB bins; fixed order.
+template <int LB>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const unsigned *__restrict__ partials, int groups, int splits,
+                                                              uint32_t lanes_per_split, uint32_t sigma_pow_m,
+                                                              const unsigned long long *__restrict__ scratch,
+                                                              const int *__restrict__ status, int run_if,
+                                                              unsigned long long *__restrict__ bins) {
+    if (run_if >= 0 && (*status != 0) != (run_if != 0)) return;
+    constexpr uint32_t PER_WORD = 32 / LB;
+    constexpr uint32_t LANE_MASK = LB == 32 ? 0xFFFFFFFFu : ((1u << (LB % 32)) - 1u);
+    const uint32_t words = lanes_per_split / PER_WORD;
+    const int64_t total = (int64_t)splits * words;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        const int split = (int)(w / words);
+        const uint32_t wi = (uint32_t)(w - (int64_t)split * words);
+        unsigned long long acc[PER_WORD];
+#pragma unroll
+        for (uint32_t j = 0; j < PER_WORD; ++j) acc[j] = 0ull;
+        const unsigned *src = partials + (size_t)split * words + wi;
+#pragma unroll 4
+        for (int g = 0; g < groups; ++g) {
+            const unsigned v = src[(size_t)g * splits * words];
+#pragma unroll
+            for (uint32_t j = 0; j < PER_WORD; ++j) acc[j] += LB == 32 ? v : ((v >> ((j * LB) % 32)) & LANE_MASK);
+        }
+        const uint32_t k0 = (uint32_t)split * lanes_per_split + wi * PER_WORD;
+#pragma unroll
+        for (uint32_t j = 0; j < PER_WORD; ++j) {
+            const uint32_t k = k0 + j;
+            if (k < sigma_pow_m) {
+                const unsigned long long c = acc[j] + (scratch != nullptr ? scratch[k] : 0ull);
+                if (c) bins[k] += c;
+            }
+        }
     }
 }
 
@@ -429,23 +454,44 @@ struct CountArgs {
     cudaStream_t st;
 };
 
+// Workspace of the shared-memory variants: [status word, 256 B][drain scratch: sigma^(n+1) x u64, 8-bit
+// variant only][one packed table per CTA: 148 x <= 224 KB].
+constexpr size_t kPartialBytes = (size_t)PG_NUM_SMS * kSmemTableBytes;
+constexpr int kMaxSplits = 4;
+inline int splits_for(int64_t pow_m, int lane_bits) { return (int)pg_ceil_div(pow_m * lane_bits / 8, kSmemTableBytes); }
+inline bool uses_fast8(int64_t pow_m) { return splits_for(pow_m, 16) > 1 && splits_for(pow_m, 8) <= kMaxSplits; }
+inline size_t scratch_bytes(int64_t pow_m) { return uses_fast8(pow_m) ? pg_align_up((size_t)pow_m * 8, 256) : 0; }
+
+struct CountWs {
+    int *status;
+    unsigned long long *scratch;  // null unless the 8-bit variant applies
+    unsigned *partials;
+};
+
+// count into per-CTA packed tables + reduce them into `bins`.  spill = where drained lanes go (bins, or
+// the scratch for the 8-bit variant); run_if / gate as in reduce_partials_kernel.
 template <int LB, bool SPLIT>
-int launch_smem_count(int m, const CountArgs &a, unsigned long long *out, int splits, int *status, const int *gate) {
+int launch_smem_count(int m, const CountArgs &a, unsigned long long *bins, unsigned long long *spill, int splits, const CountWs &ws,
+                      int run_if) {
     const uint32_t per_word = 32 / LB;
     uint32_t lanes = (uint32_t)pg_ceil_div(a.pow_m, splits);
     lanes = (lanes + per_word - 1) / per_word * per_word;  // whole words per split
-    const size_t smem = (size_t)(lanes / per_word) * sizeof(unsigned);
+    const uint32_t words = lanes / per_word;
+    const size_t smem = (size_t)words * sizeof(unsigned);
     const int64_t nvec = pg_ceil_div(a.nbytes, 16);
     int64_t groups = PG_NUM_SMS / splits;
     const int64_t max_groups = pg_ceil_div(nvec, kSmemCountThreads);
     if (groups > max_groups) groups = max_groups;
     const unsigned grid = (unsigned)(groups * splits);
+    const int *gate = run_if == 1 ? ws.status : nullptr;
+    int *status = LB == 8 ? ws.status : nullptr;
 #define PG_LAUNCH_SMEM(MM)                                                                                                  \
     do {                                                                                                                    \
         PG_CUDA_CALL(cudaFuncSetAttribute(ngram_count_smem_kernel<MM, LB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                      \
         ngram_count_smem_kernel<MM, LB, SPLIT><<<grid, kSmemCountThreads, smem, a.st>>>(                                     \
-            a.buf, a.nbytes, a.rank, a.sigma, a.pow_m, a.pow_n, out, a.short_present, splits, lanes, status, gate);          \
+            a.buf, a.nbytes, a.rank, a.sigma, a.pow_m, a.pow_n, spill, a.short_present, splits, lanes, status, gate,         \
+            ws.partials);                                                                                                    \
     } while (0)
     switch (m) {
         case 2: PG_LAUNCH_SMEM(2); break;
@@ -458,6 +504,10 @@ int launch_smem_count(int m, const CountArgs &a, unsigned long long *out, int sp
     }
 #undef PG_LAUNCH_SMEM
     PG_CUDA_LAUNCH_CHECK("ngram_count_smem_kernel");
+    const int64_t total_words = (int64_t)splits * words;
+    reduce_partials_kernel<LB><<<grid_for(total_words, 256, 4), 256, 0, a.st>>>(
+        ws.partials, (int)groups, splits, lanes, a.pow_m, LB == 8 ? ws.scratch : nullptr, ws.status, run_if, bins);
+    PG_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return PG_OK;
 }
 
@@ -479,24 +529,23 @@ int launch_global_count(int m, const CountArgs &a, unsigned long long *bins, con
     return PG_OK;
 }
 
-constexpr int kMaxSplits = 4;
-inline int splits_for(int64_t pow_m, int lane_bits) { return (int)pg_ceil_div(pow_m * lane_bits / 8, kSmemTableBytes); }
-
-// the strictly exact variants: 32-bit lanes, 16-bit lanes (<= 4 key-range splits), else L2 REDs
-int launch_strict_count(int m, const CountArgs &a, unsigned long long *bins, const int *gate, bool allow_smem) {
-    if (allow_smem && splits_for(a.pow_m, 32) == 1) return launch_smem_count<32, false>(m, a, bins, 1, nullptr, gate);
+// the strictly exact variants: 32-bit lanes, 16-bit lanes (<= 4 key-range splits), else L2 REDs.
+// run_if = -1: unconditional; 1: only if *ws.status != 0 (recount after a flagged hazard).
+int launch_strict_count(int m, const CountArgs &a, unsigned long long *bins, const CountWs *ws, int run_if, bool allow_smem) {
+    allow_smem = allow_smem && ws != nullptr;
+    if (allow_smem && splits_for(a.pow_m, 32) == 1) return launch_smem_count<32, false>(m, a, bins, bins, 1, *ws, run_if);
     const int s16 = splits_for(a.pow_m, 16);
-    if (allow_smem && s16 == 1) return launch_smem_count<16, false>(m, a, bins, 1, nullptr, gate);
-    if (allow_smem && s16 <= kMaxSplits) return launch_smem_count<16, true>(m, a, bins, s16, nullptr, gate);
-    return launch_global_count(m, a, bins, gate);
+    if (allow_smem && s16 == 1) return launch_smem_count<16, false>(m, a, bins, bins, 1, *ws, run_if);
+    if (allow_smem && s16 <= kMaxSplits) return launch_smem_count<16, true>(m, a, bins, bins, s16, *ws, run_if);
+    return launch_global_count(m, a, bins, run_if == 1 ? ws->status : nullptr);
 }
 }  // namespace
 
 extern "C" size_t pg_ngram_count_ws_bytes(int n, int sigma) {
     int64_t pow_n, pow_m;
     if (!table_sizes(n, sigma, &pow_n, &pow_m)) return 0;
-    if (splits_for(pow_m, 16) == 1 || splits_for(pow_m, 8) > kMaxSplits) return 256;  // strict variants need no scratch
-    return 256 + pg_align_up((size_t)pow_m * 8, 256);
+    if (splits_for(pow_m, 8) > kMaxSplits) return 256;  // L2 REDs only: no workspace needed
+    return 256 + scratch_bytes(pow_m) + kPartialBytes;
 }
 
 extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte, int sigma,
@@ -515,28 +564,30 @@ extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const
     CountArgs a{d_buf, nbytes, d_rank_of_byte, (uint32_t)sigma, (uint32_t)pow_m, (uint32_t)pow_n, d_short_present, pg_cu(stream)};
     const int m = n + 1;
     const int variant = g_count_variant;
-    const bool big_enough = nvec >= 4 * kSmemCountThreads;  // tiny corpora: zeroing + flushing 148 tables costs more than REDs
-    if (variant == PG_COUNT_GLOBAL) return launch_global_count(m, a, d_bins, nullptr);
-    if (variant == PG_COUNT_STRICT) return launch_strict_count(m, a, d_bins, nullptr, true);
-    const int s8 = splits_for(pow_m, 8);
-    const size_t need = 256 + pg_align_up((size_t)pow_m * 8, 256);
-    const bool fast8 = splits_for(pow_m, 16) > 1 && s8 <= kMaxSplits && d_ws != nullptr && ws_bytes >= need &&
-                       ((uintptr_t)d_ws & 255) == 0;
-    if (!fast8 || (variant == PG_COUNT_AUTO && !big_enough)) return launch_strict_count(m, a, d_bins, nullptr, big_enough);
-    // 8-bit lanes: count into the zeroed scratch, merge if no hazard was observed, else recount strictly
-    int *status = (int *)d_ws;
-    unsigned long long *scratch = (unsigned long long *)((char *)d_ws + 256);
-    PG_CUDA_CALL(cudaMemsetAsync(d_ws, 0, need, a.st));
-    int rc = s8 == 1 ? launch_smem_count<8, false>(m, a, scratch, 1, status, nullptr)
-                     : launch_smem_count<8, true>(m, a, scratch, s8, status, nullptr);
-    if (rc != PG_OK) return rc;
+    // tiny corpora: zeroing and reducing 148 tables costs more than the L2 REDs
+    const bool big_enough = nvec >= 4 * kSmemCountThreads;
+    const bool have_ws = d_ws != nullptr && ((uintptr_t)d_ws & 255) == 0 && ws_bytes >= pg_ngram_count_ws_bytes(n, sigma) &&
+                         splits_for(pow_m, 8) <= kMaxSplits;
+    if (variant == PG_COUNT_GLOBAL || !have_ws) return launch_global_count(m, a, d_bins, nullptr);
+    CountWs ws;
+    ws.status = (int *)d_ws;
+    ws.scratch = uses_fast8(pow_m) ? (unsigned long long *)((char *)d_ws + 256) : nullptr;
+    ws.partials = (unsigned *)((char *)d_ws + 256 + scratch_bytes(pow_m));
+    const bool fast8 = uses_fast8(pow_m) && variant != PG_COUNT_STRICT;
+    if (!fast8) return launch_strict_count(m, a, d_bins, &ws, -1, variant == PG_COUNT_STRICT || big_enough);
+    if (variant == PG_COUNT_AUTO && !big_enough) return launch_global_count(m, a, d_bins, nullptr);
+    // 8-bit lanes: drained counts go to the zeroed scratch; the reduce merges tables + scratch into d_bins
+    // only if no hazard was observed, else the gated strict variant recounts into d_bins
+    PG_CUDA_CALL(cudaMemsetAsync(d_ws, 0, 256 + scratch_bytes(pow_m), a.st));
     if (variant == PG_COUNT_FAST8_FORCE_HAZARD) {
-        set_flag_kernel<<<1, 1, 0, a.st>>>(status, 1);
+        set_flag_kernel<<<1, 1, 0, a.st>>>(ws.status, 1);  // the count below can only set it as well
         PG_CUDA_LAUNCH_CHECK("set_flag_kernel");
     }
-    merge_scratch_kernel<<<grid_for(pow_m), 256, 0, a.st>>>(scratch, pow_m, status, d_bins);
-    PG_CUDA_LAUNCH_CHECK("merge_scratch_kernel");
-    return launch_strict_count(m, a, d_bins, status, true);  // no-op kernels unless *status != 0
+    const int s8 = splits_for(pow_m, 8);
+    int rc = s8 == 1 ? launch_smem_count<8, false>(m, a, d_bins, ws.scratch, 1, ws, 0)
+                     : launch_smem_count<8, true>(m, a, d_bins, ws.scratch, s8, ws, 0);
+    if (rc != PG_OK) return rc;
+    return launch_strict_count(m, a, d_bins, &ws, 1, true);  // no-op kernels unless *status != 0
 }
 
 extern "C" size_t pg_graph_extract_ws_bytes(int n, int sigma) {

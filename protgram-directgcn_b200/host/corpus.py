@@ -172,3 +172,44 @@ def decode_nodes(node_code: np.ndarray, symbols: np.ndarray, n: int) -> List[str
     if 0 in symbols:
         return [row.tobytes().decode("ascii") for row in chars]
     return chars.astype(np.uint32).view(f"U{n}").ravel().tolist()
+
+
+_PINNED_POOL: List[torch.Tensor] = []   # reusable pinned staging buffers (cudaHostAlloc costs ~1 ms a call)
+
+
+class LazyNodeNames:
+    """Node names of one level, decoded lazily: the packed codes start an async device->pinned-host
+    copy at construction and are turned into strings on `resolve()` (first access of
+    `graph.node_sequences`), so the host-side decode runs under whatever GPU work follows the
+    extraction instead of stalling the stream."""
+
+    def __init__(self, node_code: torch.Tensor, symbols: np.ndarray, n: int):
+        self.symbols, self.n, self.count = symbols, int(n), int(node_code.numel())
+        self._names = None
+        if not node_code.is_cuda:
+            self._host, self._event = node_code, None
+            return
+        need = max(self.count, 1)
+        buf = next((b for b in _PINNED_POOL if b.numel() >= need), None)
+        if buf is not None:
+            _PINNED_POOL.remove(buf)
+        else:
+            buf = torch.empty(max(need, 1 << 16), dtype=torch.int64).pin_memory()
+        self._buf = buf
+        self._host = buf[:self.count]
+        self._host.copy_(node_code, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+    def __len__(self) -> int:
+        return self.count
+
+    def resolve(self) -> List[str]:
+        if self._names is None:
+            if self._event is not None:
+                self._event.synchronize()
+            self._names = decode_nodes(self._host.numpy(), self.symbols, self.n)
+            if self._event is not None:
+                _PINNED_POOL.append(self._buf)
+                self._buf = self._host = None
+        return self._names

@@ -95,7 +95,7 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
         dist.all_reduce(short_i, op=dist.ReduceOp.MAX, group=group)
         short = short_i.to(torch.uint8)
     node_code, src, dst, cnt = extract_level(bins, short, n, sigma)
-    names = corpus.decode_nodes(node_code.cpu().numpy(), symbols, n)   # id -> n-gram string, id order
+    names = corpus.LazyNodeNames(node_code, symbols, n)   # id -> n-gram string, id order; decoded on first access
     return DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), epsilon_propagation=eps,
                                                n_value=n, assume_coalesced=True)
 

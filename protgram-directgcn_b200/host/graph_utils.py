@@ -15,15 +15,59 @@ import torch
 from .. import _native as nat
 
 
+MATRIX_ATTRS = ("A_out_w", "A_in_w", "A_undirected_norm_sparse", "mathcal_A_out", "mathcal_A_in")
+
+
+def _matrix_property(name):
+    key = "_m_" + name
+
+    def get(self):
+        self.wait_ready()
+        try:
+            return self.__dict__[key]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def set_(self, value):
+        self.__dict__[key] = value
+
+    return property(get, set_)
+
+
 class _LazyMaps:
     """idx_to_node / node_to_idx are views derived from node_sequences; they are built on first
     access (an 8k-entry dict costs more host time than the whole GPU graph build) and always
     written into pickles, so a pickled graph has the reference's attribute layout."""
 
+    @property
+    def node_sequences(self):
+        """id -> n-gram list.  GraphBuilder hands over the packed node codes still on their way from
+        the device (corpus.LazyNodeNames); they are decoded on first access, i.e. under the GPU work
+        that was enqueued in the meantime."""
+        d = self.__dict__
+        lazy = d.get("_lazy_names")
+        if lazy is not None:
+            d["_node_sequences"] = lazy.resolve()
+            d["_lazy_names"] = None
+        return d.setdefault("_node_sequences", [])
+
+    @node_sequences.setter
+    def node_sequences(self, value):
+        self.__dict__["_node_sequences"] = value
+        self.__dict__["_lazy_names"] = None
+
+    def wait_ready(self):
+        """Block until the host copies of the matrices (started asynchronously by the GPU build on a side
+        stream) have landed.  Every access to a matrix attribute goes through here."""
+        ev = self.__dict__.get("_ready_event")
+        if ev is not None:
+            ev.synchronize()
+            self.__dict__["_ready_event"] = None
+
     def _maps(self):
         d = self.__dict__
         if d.get("_idx_to_node") is None:
-            names = d.get("node_sequences", [])
+            names = self.node_sequences
             d["_idx_to_node"] = dict(zip(range(len(names)), names))
             d["_node_to_idx"] = dict(zip(names, range(len(names))))
         return d["_idx_to_node"], d["_node_to_idx"]
@@ -51,6 +95,14 @@ class _LazyMaps:
         i2n, n2i = self._maps()
         state.pop("_idx_to_node", None)
         state.pop("_node_to_idx", None)
+        self.wait_ready()
+        state.pop("_ready_event", None)
+        for m in MATRIX_ATTRS:
+            if "_m_" + m in state:
+                state[m] = state.pop("_m_" + m)
+        state.pop("_lazy_names", None)
+        state.pop("_node_sequences", None)
+        state["node_sequences"] = self.node_sequences
         state["idx_to_node"], state["node_to_idx"] = i2n, n2i
         state.pop("_pg_device", None)  # device-side CSR sidecar never enters the pickle
         return state
@@ -59,7 +111,16 @@ class _LazyMaps:
         state = dict(state)
         self.__dict__["_idx_to_node"] = state.pop("idx_to_node", None)
         self.__dict__["_node_to_idx"] = state.pop("node_to_idx", None)
+        self.__dict__["_node_sequences"] = state.pop("node_sequences", [])
+        self.__dict__["_lazy_names"] = None
+        for m in MATRIX_ATTRS:
+            if m in state:
+                self.__dict__["_m_" + m] = state.pop(m)
         self.__dict__.update(state)
+
+
+for _m in MATRIX_ATTRS:   # plain attributes in the reference; here they first wait for the async host copy
+    setattr(_LazyMaps, _m, _matrix_property(_m))
 
 
 class Graph(_LazyMaps):
@@ -81,6 +142,12 @@ class Graph(_LazyMaps):
             self.idx_to_node_map_from_constructor = {}
             self.number_of_nodes = len(node_map)
             self.node_sequences = node_map
+            return
+        if hasattr(node_map, "resolve"):
+            # ... or the packed codes still in flight from the device (decoded on first access)
+            self.idx_to_node_map_from_constructor = {}
+            self.number_of_nodes = len(node_map)
+            self.__dict__["_lazy_names"] = node_map
             return
         if not node_map and not self.original_edges:
             return
@@ -105,6 +172,29 @@ def _coo(indices: torch.Tensor, values: torch.Tensor, n: int) -> torch.Tensor:
 def _empty_coo(n: int, device="cpu") -> torch.Tensor:
     return _coo(torch.empty((2, 0), dtype=torch.long, device=device),
                 torch.empty(0, dtype=torch.float32, device=device), n)
+
+
+_D2H_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _async_to_host(tensors):
+    """Device tensors -> pinned host tensors (torch's caching host allocator recycles the blocks), copied on
+    a side stream so the caller's stream is free to run the next kernels.  -> (host tensors, done event)."""
+    dev = tensors[0].device
+    side = _D2H_STREAMS.get(dev.index)
+    if side is None:
+        side = _D2H_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    out = []
+    with torch.cuda.stream(side):
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            t.record_stream(side)
+            out.append(h)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return out, ev
 
 
 def device_coalesce(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int):
@@ -236,8 +326,10 @@ class DirectedNgramGraph(Graph):
         a_out_idx = torch.stack([src_d, dst_d])
         a_in_idx = torch.stack([res["in_src"], res["in_dst"]])
         tensors = [a_out_idx, w_d, a_in_idx, res["in_w"], pat, res["val_und"], res["val_out"], res["val_in"]]
-        # (pinned per-call staging was tried and dropped: cudaHostAlloc churn made the step time erratic)
-        tensors = [t.to(result_device) for t in tensors]
+        if torch.device(result_device).type == "cpu" and dev.type == "cuda":
+            tensors, self.__dict__["_ready_event"] = _async_to_host(tensors)   # lands under whatever the caller enqueues next
+        else:
+            tensors = [t.to(result_device) for t in tensors]
         a_out_idx, w_o, a_in_idx, in_w, pat_o, v_und, v_out, v_in = tensors
         self.A_out_w = _coo(a_out_idx, w_o, n)
         self.A_in_w = _coo(a_in_idx, in_w, n)

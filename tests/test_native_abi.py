@@ -26,8 +26,10 @@ def test_header_symbols_exported_and_bound():
     assert lib.pg_version() >= 100
     assert nat.query("pg_sort_pairs_ws_bytes", 10_000) > 0
     assert nat.query("pg_graph_extract_ws_bytes", 3, 21) > 21 ** 4 * 8
-    assert nat.query("pg_ngram_count_ws_bytes", 3, 21) >= 256 + 21 ** 4 * 8   # 8-bit lanes: scratch table
-    assert nat.query("pg_ngram_count_ws_bytes", 1, 21) == 256                 # strict variants: status word only
+    tables = 148 * 224 * 1024                                                   # one packed table per CTA
+    assert nat.query("pg_ngram_count_ws_bytes", 3, 21) >= 256 + 21 ** 4 * 8 + tables   # 8-bit lanes: + drain scratch
+    assert nat.query("pg_ngram_count_ws_bytes", 1, 21) == 256 + tables          # strict lanes: status word + tables
+    assert nat.query("pg_ngram_count_ws_bytes", 5, 21) == 256                   # 85.8 M bins: L2 REDs, no workspace
 
 
 def test_argument_errors_are_reported_not_crashed():
