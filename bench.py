@@ -505,13 +505,17 @@ def run_b200(args):
     }
     if count_ms:
         alg = pipe.nbytes
-        line["roofline"] = {"kernel": f"ngram_count_smem_kernel<{N_LEVEL + 1}>", "bound": "hbm", "achieved": alg / (count_ms * 1e-3) / 1e9,
+        line["roofline"] = {"kernel": f"ngram_count_smem_kernel<M={N_LEVEL + 1}, 8-bit lanes> (+ memset, reduce_partials_kernel<8>, 2 gated no-op launches: "
+                                      "everything pg_ngram_count enqueues, timed as one)",
+                            "bound": "hbm", "achieved": alg / (count_ms * 1e-3) / 1e9,
                             "peak": peak_gbs, "unit": "GB/s", "frac": alg / (count_ms * 1e-3) / 1e9 / peak_gbs,
-                            "traffic": 181_936_896,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_ncu_count_smem_v2.txt)
+                            "traffic": 181_280_000,  # dram__bytes_read+write of the count kernel, ncu --set full (profiles/r01_ncu_count_smem8_v3.txt)
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": count_ms,
                             "share_of_step": count_ms / ms_step,
-                            "note": "1 B/residue read (DRAM traffic == algorithmic bytes); the kernel is bound by the 175 M shared-memory "
-                                    "table updates + key arithmetic (issue-bound, IPC 0.7), not by HBM: see DESIGN.md section 4"}
+                            "note": "1 B/residue read (DRAM traffic == algorithmic bytes).  A 194,481-bin histogram cannot run at the HBM "
+                                    "roofline: the count kernel alone takes 147 us under ncu, 88% issue-active (about 400 instructions per "
+                                    "16 residues: rank lookup, rolling key, validity mask, packed 8-bit shared-memory add, overflow check); "
+                                    "see DESIGN.md section 4.  The HBM-bound kernel of this system is the SpMM: spmm_large / spmm_partitioned."}
         line["build"] = {"count_residues_per_s": NSEQ * SEQ_LEN / (count_ms * 1e-3)}
     if rank == 0:
         line["phases_ms"] = phase_breakdown(pipe)

@@ -320,30 +320,47 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const unsigned *__
     if (run_if >= 0 && (*status != 0) != (run_if != 0)) return;
     constexpr uint32_t PER_WORD = 32 / LB;
     constexpr uint32_t LANE_MASK = LB == 32 ? 0xFFFFFFFFu : ((1u << (LB % 32)) - 1u);
+    constexpr int SLICES = 8;  // a CTA = 32 consecutive words x 8 slices of the CTA tables (coalesced 128 B rows)
+    __shared__ unsigned long long sub[SLICES][32][PER_WORD];
     const uint32_t words = lanes_per_split / PER_WORD;
     const int64_t total = (int64_t)splits * words;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
-        const int split = (int)(w / words);
-        const uint32_t wi = (uint32_t)(w - (int64_t)split * words);
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    for (int64_t w0 = (int64_t)blockIdx.x * 32; w0 < total; w0 += (int64_t)gridDim.x * 32) {
+        const int64_t w = w0 + lane;
         unsigned long long acc[PER_WORD];
 #pragma unroll
         for (uint32_t j = 0; j < PER_WORD; ++j) acc[j] = 0ull;
-        const unsigned *src = partials + (size_t)split * words + wi;
+        int split = 0;
+        uint32_t wi = 0;
+        if (w < total) {
+            split = (int)(w / words);
+            wi = (uint32_t)(w - (int64_t)split * words);
+            const unsigned *src = partials + (size_t)split * words + wi;
 #pragma unroll 4
-        for (int g = 0; g < groups; ++g) {
-            const unsigned v = src[(size_t)g * splits * words];
+            for (int g = slice; g < groups; g += SLICES) {
+                const unsigned v = src[(size_t)g * splits * words];
 #pragma unroll
-            for (uint32_t j = 0; j < PER_WORD; ++j) acc[j] += LB == 32 ? v : ((v >> ((j * LB) % 32)) & LANE_MASK);
-        }
-        const uint32_t k0 = (uint32_t)split * lanes_per_split + wi * PER_WORD;
-#pragma unroll
-        for (uint32_t j = 0; j < PER_WORD; ++j) {
-            const uint32_t k = k0 + j;
-            if (k < sigma_pow_m) {
-                const unsigned long long c = acc[j] + (scratch != nullptr ? scratch[k] : 0ull);
-                if (c) bins[k] += c;
+                for (uint32_t j = 0; j < PER_WORD; ++j) acc[j] += LB == 32 ? v : ((v >> ((j * LB) % 32)) & LANE_MASK);
             }
         }
+#pragma unroll
+        for (uint32_t j = 0; j < PER_WORD; ++j) sub[slice][lane][j] = acc[j];
+        __syncthreads();
+        if (slice == 0 && w < total) {
+            const uint32_t k0 = (uint32_t)split * lanes_per_split + wi * PER_WORD;
+#pragma unroll
+            for (uint32_t j = 0; j < PER_WORD; ++j) {
+                unsigned long long c = 0ull;
+#pragma unroll
+                for (int sl = 0; sl < SLICES; ++sl) c += sub[sl][lane][j];
+                const uint32_t k = k0 + j;
+                if (k < sigma_pow_m) {
+                    if (scratch != nullptr) c += scratch[k];
+                    if (c) bins[k] += c;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -505,7 +522,7 @@ int launch_smem_count(int m, const CountArgs &a, unsigned long long *bins, unsig
 #undef PG_LAUNCH_SMEM
     PG_CUDA_LAUNCH_CHECK("ngram_count_smem_kernel");
     const int64_t total_words = (int64_t)splits * words;
-    reduce_partials_kernel<LB><<<grid_for(total_words, 256, 4), 256, 0, a.st>>>(
+    reduce_partials_kernel<LB><<<grid_for(total_words * 8, 256, 16), 256, 0, a.st>>>(
         ws.partials, (int)groups, splits, lanes, a.pow_m, LB == 8 ? ws.scratch : nullptr, ws.status, run_if, bins);
     PG_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return PG_OK;
