@@ -377,6 +377,45 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     return out
 
 
+def pooling_leg(pipe, emb, graph, iters=5, cpu_sample=400):
+    """Row f2: protein-level pooling of the level's embeddings over the whole corpus (reference
+    models_utils.py:210-262: a Python loop over every residue).  Device-resident raw sequences (the bench corpus
+    without its padding bytes), n = N_LEVEL, F = DIMS[-1]; the oracle is timed on `cpu_sample` proteins."""
+    from oracle import next_oracle, ngram_oracle
+    nat, dev = pipe.nat, pipe.dev
+    lead = 1 if pipe.rank == 0 else 0
+    raw = pipe.d_buf[lead:lead + NSEQ * (SEQ_LEN + 2)].view(NSEQ, SEQ_LEN + 2)[:, :SEQ_LEN].contiguous().view(-1)
+    offsets = torch.arange(NSEQ + 1, dtype=torch.int64, device=dev) * SEQ_LEN
+    nodes = graph.node_sequences
+    symbols = np.array(sorted({ord(c) for s in nodes for c in s}), dtype=np.uint8)
+    rank = np.full(256, 255, dtype=np.uint8)
+    rank[symbols] = np.arange(symbols.size, dtype=np.uint8)
+    codes = np.zeros(len(nodes), dtype=np.int64)
+    chars = np.frombuffer("".join(nodes).encode("ascii"), dtype=np.uint8).reshape(len(nodes), N_LEVEL)
+    for k in range(N_LEVEL):
+        codes = codes * symbols.size + rank[chars[:, k]]
+    table = np.full(int(symbols.size) ** N_LEVEL, -1, dtype=np.int32)
+    table[codes] = np.arange(len(nodes), dtype=np.int32)
+    d_rank, d_tab = torch.from_numpy(rank).to(dev), torch.from_numpy(table).to(dev)
+    emb = emb.detach().contiguous()
+    F = int(emb.shape[1])
+    out = torch.empty((NSEQ, F), dtype=torch.float32, device=dev)
+    valid = torch.empty(NSEQ, dtype=torch.uint8, device=dev)
+    fn = lambda: nat.call("pg_pool_proteins", nat.ptr(raw), nat.ptr(offsets), NSEQ, N_LEVEL, nat.ptr(d_rank), int(symbols.size),
+                          nat.ptr(d_tab), nat.ptr(emb), emb.stride(0), F, nat.ptr(out), out.stride(0), nat.ptr(valid), nat.stream_ptr())
+    ms = _time_ms(fn, iters)
+    seqs = [(str(i), s) for i, s in enumerate(ngram_oracle.synth_sequences(pipe.rank * NSEQ, cpu_sample, SEQ_LEN, SEED))]
+    emb_h = emb.cpu().numpy()
+    t0 = time.perf_counter()
+    _, pooled, ok = next_oracle.pool_proteins(seqs, N_LEVEL, {s: i for i, s in enumerate(nodes)}, emb_h)
+    t_cpu = time.perf_counter() - t0
+    exact = bool(np.array_equal(out[:cpu_sample].cpu().numpy()[ok], pooled[ok]))
+    return {"what": f"pool_ngram_embeddings_for_protein_fast over {NSEQ} proteins x {SEQ_LEN} residues, n={N_LEVEL}, F={F}",
+            "ms": ms, "residues_per_s": NSEQ * SEQ_LEN / (ms * 1e-3), "proteins_per_s": NSEQ / (ms * 1e-3),
+            "cpu_oracle": {"proteins": cpu_sample, "seconds": t_cpu, "residues_per_s": cpu_sample * SEQ_LEN / t_cpu, "cores": 1},
+            "bit_exact_vs_oracle_on_sample": exact}
+
+
 def phase_breakdown(pipe, reps=5):
     """Untimed diagnostic: wall-clock per phase of the resident step with a device sync after each phase."""
     import collections
@@ -542,6 +581,11 @@ def run_b200(args):
             leg = {"error": repr(exc)}
         if rank == 0:
             line["spmm_partitioned"] = leg
+    if rank == 0 and world == 1 and not args.no_large:
+        try:
+            line["pooling_f2"] = pooling_leg(pipe, emb, graph)
+        except Exception as exc:  # noqa: BLE001
+            line["pooling_f2"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(sample_seqs=6000, procs=1)
     if rank == 0:

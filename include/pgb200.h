@@ -288,6 +288,36 @@ int pg_softmax_nll(float *d_logits, int64_t ld, int64_t n, int64_t c, const int6
                    float grad_scale, float *d_row_loss, float *d_colsum, float *d_loss, void *d_ws,
                    size_t ws_bytes, pg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rows f2 / f4: the callers on either side of the two hot paths
+ * ---------------------------------------------------------------------------------------- */
+
+/* f4, replaces _generate_next_node_labels (protgram_directgcn_trainer.py:222-237): labels[i] = the
+ * successor of node i with the largest A_out_w weight (rows of the coalesced matrix given as
+ * d_rowptr[n+1] over d_dst / d_weight); ties -> the first in (src, dst) order (the reference draws
+ * one of the maximal successors at random: every one of them is admissible); no successor -> i. */
+int pg_next_node_labels(const int64_t *d_rowptr, const int64_t *d_dst, const float *d_weight,
+                        int64_t num_nodes, int64_t *d_labels, pg_stream_t stream);
+
+/* f2a, replaces the feature hand-off between levels (protgram_directgcn_trainer.py:312-330):
+ * x[i] = mean of the level-(n-1) embeddings of node i's prefix and suffix (n-1)-grams (those that
+ * exist; zeros if neither).  d_code / d_prev_code: packed base-sigma node codes of level n / n-1
+ * (ascending = node-id order, as pg_graph_extract_fill emits them), same alphabet. */
+int pg_ngram_feature_init(const int64_t *d_code, int64_t num_nodes, const int64_t *d_prev_code,
+                          int64_t num_prev, int sigma, int n, const float *d_prev_emb, int64_t ld,
+                          int F, float *d_x, int64_t ldx, pg_stream_t stream);
+
+/* f2b, replaces EmbeddingProcessor.pool_ngram_embeddings_for_protein_fast (models_utils.py:210-262):
+ * d_out[p] = mean over the DISTINCT known n-grams of protein p of their embedding rows, summed in
+ * ascending code order in fp32 (the reference's order when ids are ranks of the sorted n-grams),
+ * d_valid[p] = 0 (and a zero row) when the protein holds no known n-gram.  d_seqs: the raw sequence
+ * bytes back to back, d_offsets[P+1] their bounds; d_rank_of_byte[256]: symbol rank or 255 for bytes
+ * outside the alphabet; d_code_to_id[sigma^n]: node id of a packed code or -1.  F <= 512. */
+int pg_pool_proteins(const uint8_t *d_seqs, const int64_t *d_offsets, int64_t num_proteins, int n,
+                     const uint8_t *d_rank_of_byte, int sigma, const int32_t *d_code_to_id,
+                     const float *d_emb, int64_t ld, int F, float *d_out, int64_t ldout,
+                     uint8_t *d_valid, pg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,6 +315,41 @@ def pg_unpack_layer_param_grads(p, dw_ext, dga, dgb, dgc, num_gate, F_in, F_out,
     d.c_dir.reshape(-1).copy_(s * call); d.c_und.reshape(-1).copy_(dgc * call); d.c_all.reshape(-1).copy_(s * cdir + dgc * cund)
 
 
+def pg_next_node_labels(rowptr, dst, w, n, labels, stream=None):
+    for i in range(n):
+        lo, hi = int(rowptr[i]), int(rowptr[i + 1])
+        labels[i] = i if lo == hi else int(dst[lo:hi][torch.argmax((w[lo:hi] == w[lo:hi].max()).to(torch.int8))])
+
+
+def pg_ngram_feature_init(code, num, prev_code, num_prev, sigma, n, prev_emb, ld, F, x, ldx, stream=None):
+    pos = {int(c): i for i, c in enumerate(prev_code.tolist())}
+    for i, c in enumerate(code.tolist()):
+        rows = [pos.get(c // sigma), pos.get(c % sigma ** (n - 1))]
+        rows = [r for r in rows if r is not None]
+        x[i, :F] = torch.stack([prev_emb[r, :F] for r in rows]).mean(0) if rows else 0.0
+
+
+def pg_pool_proteins(seqs, offsets, P, n, rank_of_byte, sigma, code_to_id, emb, ld, F, out, ldout, valid, stream=None):
+    rank = rank_of_byte.tolist()
+    for p in range(P):
+        b, e = int(offsets[p]), int(offsets[p + 1])
+        ids = set()
+        for i in range(b, e - n + 1):
+            rs = [rank[int(seqs[i + k])] for k in range(n)]
+            if 255 in rs:
+                continue
+            code = 0
+            for r in rs:
+                code = code * sigma + r
+            if int(code_to_id[code]) >= 0:
+                ids.add(code)
+        acc = torch.zeros(F, dtype=torch.float32)
+        for code in sorted(ids):
+            acc = acc + emb[int(code_to_id[code]), :F]
+        out[p, :F] = acc / float(len(ids)) if ids else 0.0
+        valid[p] = 1 if ids else 0
+
+
 def pg_softmax_nll_ws_bytes(n, c):
     return 256
 
