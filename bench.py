@@ -416,6 +416,32 @@ def pooling_leg(pipe, emb, graph, iters=5, cpu_sample=400):
             "bit_exact_vs_oracle_on_sample": exact}
 
 
+def layer_gemm_leg(pipe, n=160_000, f_in=256, f_out=256, iters=10):
+    """The dense transform of one DirectGCN layer at config C3's shape (N = 160k, hidden 256, K_ext = 771): the
+    tcgen05 kernel (3 x TF32 split, fp32-level accuracy) against the SIMT fp32 kernel.  flops = 2 N K_ext F_out;
+    the tensor-pipe figure counts the 3 MMAs per product (what the hardware executes)."""
+    nat, dev = pipe.nat, pipe.dev
+    k_ext = 3 * f_in + 3
+    z, x = torch.randn(n, 3 * f_in, device=dev), torch.randn(n, f_in, device=dev)
+    g = [torch.rand(n, device=dev) + 0.5 for _ in range(3)]
+    w = torch.randn(k_ext, f_out, device=dev) * 0.1
+    c = torch.randn(n, f_out, device=dev)
+    h = torch.empty(n, f_out, device=dev)
+    ws = torch.empty(nat.query("pg_layer_gemm_fwd_tc_ws_bytes", f_in, f_out, 0), dtype=torch.uint8, device=dev)
+    st = nat.stream_ptr()
+    simt = lambda: nat.call("pg_layer_gemm_fwd", nat.ptr(z), 3 * f_in, nat.ptr(x), f_in, nat.ptr(g[0]), nat.ptr(g[1]), nat.ptr(g[2]), 1,
+                            nat.ptr(w), nat.ptr(c), f_out, n, f_in, f_out, 0, 1, 0.01, nat.ptr(h), f_out, st)
+    tc = lambda: nat.call("pg_layer_gemm_fwd_tc", nat.ptr(z), 3 * f_in, nat.ptr(x), f_in, nat.ptr(g[0]), nat.ptr(g[1]), nat.ptr(g[2]), 1,
+                          nat.ptr(w), nat.ptr(c), f_out, n, f_in, f_out, 0, 1, 0.01, nat.ptr(h), f_out, nat.ptr(ws), ws.numel(), st)
+    ms_simt, ms_tc = _time_ms(simt, iters, warm=3), _time_ms(tc, iters, warm=3)
+    nat.call("pg_layer_gemm_fwd_tc_check", nat.ptr(ws), f_in, f_out, 0, st)
+    flops = 2.0 * n * k_ext * f_out
+    return {"shape": f"N={n} F_in={f_in} F_out={f_out} K_ext={k_ext} (C3 layer)", "simt_fp32_ms": ms_simt,
+            "simt_fp32_tflops": flops / ms_simt / 1e9, "tcgen05_3xtf32_ms": ms_tc, "tcgen05_effective_tflops": flops / ms_tc / 1e9,
+            "tcgen05_tensor_pipe_tflops_tf32": 3 * flops / ms_tc / 1e9,
+            "note": "tf32 dense peak is half the bf16 one (MEASURED_PEAKS bf16_tflops / 2); every product costs 3 tf32 MMAs"}
+
+
 def phase_breakdown(pipe, reps=5):
     """Untimed diagnostic: wall-clock per phase of the resident step with a device sync after each phase."""
     import collections
@@ -582,6 +608,10 @@ def run_b200(args):
         if rank == 0:
             line["spmm_partitioned"] = leg
     if rank == 0 and world == 1 and not args.no_large:
+        try:
+            line["layer_gemm_c3"] = layer_gemm_leg(pipe)
+        except Exception as exc:  # noqa: BLE001
+            line["layer_gemm_c3"] = {"error": repr(exc)}
         try:
             line["pooling_f2"] = pooling_leg(pipe, emb, graph)
         except Exception as exc:  # noqa: BLE001
