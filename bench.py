@@ -442,6 +442,128 @@ def layer_gemm_leg(pipe, n=160_000, f_in=256, f_out=256, iters=10):
             "note": "tf32 dense peak is half the bf16 one (MEASURED_PEAKS bf16_tflops / 2); every product costs 3 tf32 MMAs"}
 
 
+def _max_over_ranks(dist, dev, v):
+    if dist is None:
+        return float(v)
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def build_scale_leg(pipe, dist, n_level, total_seqs, iters=2, normalise=True):
+    """Graph build of one n level at BASELINE configs C3 (n=4) / C4 (n=5, 50 M sequences = 17.5 G residues):
+    `total_seqs` 350-residue sequences split over the ranks by contiguous ranges (STRONG scaling: the corpus is
+    fixed), each shard generated on its GPU (counter-based, shard independent); timed = count -> NCCL sum of the
+    dense (n+1)-gram tables -> node ids / edge table.  Times are device times, max over ranks."""
+    nat, db, dev, rank, world = pipe.nat, pipe.db, pipe.dev, pipe.rank, pipe.world
+    per = total_seqs // world
+    nbytes = per * (SEQ_LEN + 2) + (1 if rank == 0 else 0)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    nat.call("pg_synth_corpus", nat.ptr(buf), rank * per, per, SEQ_LEN, SEED, int(rank == 0), nat.stream_ptr())
+    symbols, d_rank = pipe.corpus.discover_alphabet(buf, pipe.group)
+    sigma = int(symbols.size)
+    pow_n, pow_m = db.table_sizes(n_level, sigma)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ws = db.count_workspace(n_level, sigma, nbytes, dev)     # allocated once, like GraphBuilder does per level
+    t_count, t_merge, t_extract = [], [], []
+    res = None
+    for it in range(iters + 1):
+        bins = torch.zeros(pow_m, dtype=torch.int64, device=dev)
+        short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        db.count_level(buf, n_level, d_rank, sigma, bins, short, ws)
+        ev[1].record()
+        if dist is not None:
+            dist.all_reduce(bins, op=dist.ReduceOp.SUM)
+            s32 = short.to(torch.int32)
+            dist.all_reduce(s32, op=dist.ReduceOp.MAX)
+            short = s32.to(torch.uint8)
+        ev[2].record()
+        res = db.extract_level(bins, short, n_level, sigma)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it > 0:      # first pass = warm-up
+            t_count.append(ev[0].elapsed_time(ev[1])); t_merge.append(ev[1].elapsed_time(ev[2])); t_extract.append(ev[2].elapsed_time(ev[3]))
+        del bins, short
+    node_code, src, dst, cnt = res
+    mc, mm, me = (_max_over_ranks(dist, dev, statistics.mean(t)) for t in (t_count, t_merge, t_extract))
+    residues = per * world * SEQ_LEN
+    nodes, edges = int(node_code.numel()), int(src.numel())
+    out = {"n": n_level, "sequences": per * world, "residues": residues, "sigma": sigma, "table_bins": pow_m, "nodes": nodes,
+           "unique_edges": edges, "transitions_counted": int(cnt.sum().item()), "scaling": "strong (fixed corpus split over ranks)",
+           "count_ms": mc, "merge_allreduce_ms": mm, "extract_ms": me, "build_ms": mc + mm + me,
+           "build_residues_per_s": residues / ((mc + mm + me) * 1e-3), "count_residues_per_s": residues / (mc * 1e-3),
+           "count_variant": ("partition by 2-symbol prefix + shared-memory count per bucket (variant P)"
+                             if nat.query("pg_ngram_count_ws_bytes_for", n_level, sigma, nbytes) > nat.query("pg_ngram_count_ws_bytes", n_level, sigma)
+                             and nbytes >= 32 << 20 else "L2 RED.ADD.u64 on the dense table"),
+           "count_frac_of_1B_per_residue_hbm_bound": nbytes / (mc * 1e-3) / 1e9 / peaks()[0]}
+    if dist is not None:
+        out["merge_bytes_per_gpu"] = pow_m * 8
+    del buf, ws
+    if normalise and rank == 0:
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        w = cnt.to(torch.float32)
+        resn = pipe.gu.device_normalize(src, dst, w, nodes, 1e-9)
+        b.record()
+        torch.cuda.synchronize()
+        out["normalise_ms"] = a.elapsed_time(b)
+        out["pattern_nnz"] = int(resn["pattern_nnz"])
+        out["_graph"] = (nodes, resn)
+    torch.cuda.empty_cache()
+    return out
+
+
+def c3_directgcn_leg(pipe, nodes, res, dims=(64, 256, 256, 256), classes=21, iters=5):
+    """Config C3's DirectGCN: 3 layers of hidden 256 on the n=4 graph (full batch, fused loss, `classes` labels as
+    in the closest_aa task).  One step = train forward + nll + backward + Adam + eval-mode embedding extraction.
+    edge unit: one stored nonzero of one propagation matrix per layer pass; a step makes 3 passes
+    (train fwd, bwd, eval fwd) over 3 matrices x L layers."""
+    from protgram_directgcn_b200.host.protgram_directgcn import Data, register_symmetric_structure
+    from protgram_directgcn_b200.host.models_utils import EmbeddingProcessor
+    dev = pipe.dev
+    torch.manual_seed(SEED)
+    model = pipe.pg.ProtGramDirectGCN(list(dims), nodes, classes, 4, 0, 512, DROPOUT, True).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=LR, fused=True)
+    x = torch.randn(nodes, dims[0], device=dev)
+    y = torch.randint(0, classes, (nodes,), device=dev)
+    ei = torch.zeros((2, 1), dtype=torch.int64, device=dev)
+    vals = (res["val_in"], res["val_out"], res["val_und"])
+    register_symmetric_structure(ei, vals, nodes, res["rowptr"], res["col"])
+    data = Data(x=x, edge_index_in=ei, edge_weight_in=vals[0], edge_index_out=ei, edge_weight_out=vals[1],
+                edge_index_undirected_norm=ei, edge_weight_undirected_norm=vals[2], num_nodes=nodes)
+    P, L = int(res["pattern_nnz"]), len(dims) - 1
+
+    def train():
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        loss = model.nll_loss(data, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def fwd_only():
+        model.eval()
+        with torch.no_grad():
+            return EmbeddingProcessor.l2_normalize_torch(model.embed(data), eps=model.l2_eps)
+
+    def step():
+        train()
+        return fwd_only()
+
+    ms_step = _time_ms(step, iters, warm=2)
+    ms_fwd = _time_ms(fwd_only, iters, warm=1)
+    return {"dims": list(dims), "nodes": nodes, "pattern_nnz": P, "classes": classes, "ms_per_step": ms_step,
+            "ms_eval_forward": ms_fwd, "ms_train_fwd_bwd_adam": ms_step - ms_fwd,
+            "edges_per_s_step": 3 * P * L * 3 / (ms_step * 1e-3), "edges_per_s_forward": 3 * P * L / (ms_fwd * 1e-3),
+            "dense_flops_per_layer_fwd": [2.0 * nodes * (3 * a + 3 + (a + 1 if a != b else 0)) * b for a, b in zip(dims[:-1], dims[1:])],
+            "mode": "eager (autograd over libpgb200 kernels), tcgen05 forward transform, SIMT backward GEMMs"}
+
+
 def phase_breakdown(pipe, reps=5):
     """Untimed diagnostic: wall-clock per phase of the resident step with a device sync after each phase."""
     import collections
@@ -607,6 +729,26 @@ def run_b200(args):
             leg = {"error": repr(exc)}
         if rank == 0:
             line["spmm_partitioned"] = leg
+    if not args.no_scale:
+        # BASELINE configs C3 (n=4) and C4 (n=5, 50 M sequences): every rank takes part (sharded corpus, NCCL merge)
+        for key, n_level, seqs in (("build_c3_n4", 4, args.c3_seqs), ("build_c4_n5", 5, args.c4_seqs)):
+            g = None
+            try:
+                leg = build_scale_leg(pipe, dist, n_level, seqs, normalise=(n_level == 4 or world == 1))
+                g = leg.pop("_graph", None)
+            except Exception as exc:  # noqa: BLE001 - the headline must still print
+                leg = {"error": repr(exc)}
+            if rank == 0:
+                line[key] = leg
+            if rank == 0 and n_level == 4 and g is not None:
+                try:
+                    line["directgcn_c3"] = c3_directgcn_leg(pipe, *g)
+                except Exception as exc:  # noqa: BLE001
+                    line["directgcn_c3"] = {"error": repr(exc)}
+            del g
+            torch.cuda.empty_cache()
+            if dist is not None:
+                dist.barrier()
     if rank == 0 and world == 1 and not args.no_large:
         try:
             line["layer_gemm_c3"] = layer_gemm_leg(pipe)
@@ -740,6 +882,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the DirectGCN step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--large-log2-nodes", type=int, default=21)
+    ap.add_argument("--no-scale", action="store_true", help="skip the C3 (n=4) / C4 (n=5) build legs and the C3 DirectGCN leg")
+    ap.add_argument("--c3-seqs", type=int, default=2_000_000, help="sequences of the n=4 build leg (whole job)")
+    ap.add_argument("--c4-seqs", type=int, default=50_000_000, help="sequences of the n=5 build leg (whole job; 17.5 G residues)")
     ap.add_argument("--profile-host", default=None, help="write a cProfile of 10 resident steps to this file")
     ap.add_argument("--profile-e2e", action="store_true", help="profile e2e steps instead of resident ones")
     args = ap.parse_args()

@@ -79,12 +79,21 @@ int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d
  * strictly exact variant recounts (all on the stream, no host round trip).
  * d_ws may be NULL: every window is then one L2 atomic on d_bins (slower, same result). */
 size_t pg_ngram_count_ws_bytes(int n, int sigma);
+/* Same, sized for a corpus buffer of `nbytes`: tables too large for one CTA's shared memory (n >= 4 at
+ * sigma = 21) are counted by a partition pass (windows appended to sigma^2 buckets keyed by their first two
+ * symbols, 4 B per window) followed by shared-memory counting per bucket; the workspace then also holds the
+ * bucket entries of one corpus chunk (<= 2^30 windows = 4 GiB) and, for 8-bit lanes, the scratch table.
+ * pg_ngram_count picks that variant when the workspace it is given is large enough, else falls back to
+ * L2 atomics on d_bins (same result). */
+size_t pg_ngram_count_ws_bytes_for(int n, int sigma, int64_t nbytes);
 
 /* Test hook: pins the variant of pg_ngram_count so parity tests can cover every kernel.
  * AUTO: widest shared-memory lanes that fit one CTA (32/16 bit: strict; 8 bit: scratch + hazard
  * check + gated strict recount), L2 REDs for tables beyond 4 key-range splits or tiny corpora.
  * STRICT: the 32/16-bit variants even for tiny corpora; FAST8*: the 8-bit variant where it applies. */
-enum { PG_COUNT_AUTO = 0, PG_COUNT_GLOBAL = 1, PG_COUNT_STRICT = 2, PG_COUNT_FAST8 = 3, PG_COUNT_FAST8_FORCE_HAZARD = 4 };
+enum { PG_COUNT_AUTO = 0, PG_COUNT_GLOBAL = 1, PG_COUNT_STRICT = 2, PG_COUNT_FAST8 = 3, PG_COUNT_FAST8_FORCE_HAZARD = 4,
+       PG_COUNT_PARTITIONED = 5 /* partition + shared-memory count even for tiny corpora (needs the _for workspace) */,
+       PG_COUNT_PARTITIONED_FORCE_HAZARD = 6 };
 void pg_debug_count_variant(int variant);
 
 /* Replaces data_builder.py:151-177 (distinct + sorted ids) and :281-286 (edge table).

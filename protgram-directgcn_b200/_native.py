@@ -26,6 +26,7 @@ _SIGS = {
     "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
     "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "pg_ngram_count_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pg_ngram_count_ws_bytes_for": (c_size_t, [c_int, c_int, c_int64]),
     "pg_debug_count_variant": (None, [c_int]),
     "pg_graph_extract_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_graph_extract_sizes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),

@@ -117,10 +117,13 @@ __device__ __forceinline__ void load_vector(const uint8_t *__restrict__ buf, int
     }
 }
 
-template <int M>
+// SPLIT2 (partitioned variant below): codes[k] = (code of the first two symbols) << 18 | code of the other M-2
+// symbols, i.e. (key / sub_bins) << 18 | key % sub_bins with sub_bins = sigma^(M-2) <= 2^18.
+template <int M, bool SPLIT2 = false>
 __device__ __forceinline__ uint32_t scan_words(const uint32_t (&w)[6], int64_t nbytes, int64_t p0, const uint8_t *lut,
                                                uint32_t sigma, uint32_t sigma_pow_m, uint32_t sigma_pow_n,
-                                               uint8_t *__restrict__ short_present, uint32_t (&codes)[16]) {
+                                               uint8_t *__restrict__ short_present, uint32_t (&codes)[16],
+                                               uint32_t sub_bins = 0) {
     constexpr int LB = M - 1;  // look-back bytes (= n)
     uint32_t sep = 0;
 #pragma unroll
@@ -140,7 +143,14 @@ __device__ __forceinline__ uint32_t scan_words(const uint32_t (&w)[6], int64_t n
         code = code * sigma + r;
         if (i >= M) code += r_hist[i % M] * neg_pow_m;  // - r_old * sigma^M (mod 2^32)
         r_hist[i % M] = r;
-        if (i >= LB) codes[i - LB] = code;
+        if (i >= LB) {
+            if (SPLIT2) {  // the window's oldest two ranks sit at (i+1) % M and (i+2) % M of the ring
+                const uint32_t pre = r_hist[(i + 1) % M] * sigma + r_hist[(i + 2) % M];
+                codes[i - LB] = (pre << 18) | (code - pre * sub_bins);
+            } else {
+                codes[i - LB] = code;
+            }
+        }
     }
     if (short_present != nullptr) {
         // a padded sequence of exactly n bytes: separator at s (inside this vector), n clean bytes
@@ -185,13 +195,14 @@ __global__ void __launch_bounds__(256) ngram_count_kernel(const uint8_t *__restr
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = rank_of_byte[threadIdx.x];
     __syncthreads();
-    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (p0 >= nbytes) return;
-    uint32_t codes[16];
-    const uint32_t valid = scan_vector<M>(buf, nbytes, p0, lut, sigma, sigma_pow_m, sigma_pow_n, short_present, codes);
+    const int64_t nvec = (nbytes + 15) / 16;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t codes[16];
+        const uint32_t valid = scan_vector<M>(buf, nbytes, v * 16, lut, sigma, sigma_pow_m, sigma_pow_n, short_present, codes);
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if ((valid >> k) & 1u) atomicAdd(&bins[codes[k]], 1ull);
+        for (int k = 0; k < 16; ++k)
+            if ((valid >> k) & 1u) atomicAdd(&bins[codes[k]], 1ull);
+    }
 }
 
 // Variant S: privatised table in shared memory, persistent CTAs (one per SM, 1024 threads).
@@ -364,6 +375,296 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const unsigned *__
     }
 }
 
+// ------------------------------------------------------------------ Variant P: partition + shared-memory count
+// Tables that do not fit one CTA (n >= 4 at sigma = 21: 4 M / 86 M bins).  L2 REDs cap at ~200 G
+// updates/s while the table sits in L2 (n = 4) and drop to ~30 G/s once it does not (n = 5, 686 MB).
+// Here the corpus is cut into chunks; per chunk
+//   P1  every CTA scans a contiguous range of vectors and histograms its windows by the code of their
+//       first two symbols ("bucket", nb = sigma^2 <= 1024),
+//   P2  one CTA turns the [CTA][bucket] histogram into exact write cursors (bucket-major) and a work list,
+//   P3  the same CTAs rescan their ranges tile by tile (1024 vectors), counting-sort the tile's windows by
+//       bucket in shared memory and append the remaining (M-2)-symbol codes to their buckets: runs of one
+//       bucket are contiguous in the tile AND continue where the CTA's previous tile stopped, so the
+//       4 B/window stores coalesce,
+//   P4  persistent CTAs take (bucket, slice) items from the work list and count the slice's codes in a
+//       shared-memory table of sub_bins = sigma^(M-2) lanes (32/16/8 bit as above), then add the non-zero
+//       lanes to the dense table (one RED per lane and item).
+// Traffic: 2 B/residue read + 4 B written + 4 B read; every table update is a shared-memory atomic.
+// This is the north star's "radix pass + segmented reduce" with the reduce done by a histogram.
+constexpr int kPartThreads = 1024;                         // P2, P4
+constexpr int kPartScanThreads = 512;                      // P1, P3: two CTAs per SM, so one's barriers hide under the other's work
+constexpr int kPartScanCtasPerSm = 2;
+constexpr uint32_t kPartTileVecs = kPartScanThreads;       // one 16-byte vector (16 windows) per thread and tile
+constexpr uint32_t kPartSuffixBits = 18;
+constexpr uint32_t kPartSuffixMask = (1u << kPartSuffixBits) - 1u;
+constexpr uint32_t kPartMaxBuckets = 1024;
+
+struct PartRange {  // the vectors [lo, hi) of this chunk are split evenly over the CTAs of P1 / P3
+    int64_t lo, hi;
+    __device__ __forceinline__ void mine(int64_t &a, int64_t &b) const {
+        const int64_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+        a = lo + (int64_t)blockIdx.x * per;
+        b = a + per < hi ? a + per : hi;
+    }
+};
+
+template <int M>
+__global__ void __launch_bounds__(kPartScanThreads, kPartScanCtasPerSm) part_hist_kernel(
+    const uint8_t *__restrict__ buf, int64_t nbytes, PartRange range, const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
+    uint32_t sigma_pow_m, uint32_t sigma_pow_n, uint32_t sub_bins, uint32_t nb, uint8_t *__restrict__ short_present,
+    uint32_t *__restrict__ hist) {
+    __shared__ uint32_t cnt[kPartMaxBuckets];
+    __shared__ uint8_t lut[256];
+    if (threadIdx.x < 256) lut[threadIdx.x] = rank_of_byte[threadIdx.x];
+    for (uint32_t b = threadIdx.x; b < kPartMaxBuckets; b += kPartScanThreads) cnt[b] = 0;
+    __syncthreads();
+    int64_t lo, hi;
+    range.mine(lo, hi);
+    int64_t vec = lo + threadIdx.x;
+    uint32_t wn[6];
+    if (vec < hi) load_vector(buf, nbytes, vec * 16, wn);
+    for (; vec < hi; vec += kPartScanThreads) {
+        uint32_t wc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wc[k] = wn[k];
+        if (vec + kPartScanThreads < hi) load_vector(buf, nbytes, (vec + kPartScanThreads) * 16, wn);
+        uint32_t codes[16];
+        const uint32_t valid = scan_words<M, true>(wc, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, short_present, codes, sub_bins);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) atomicAdd(&cnt[codes[k] >> kPartSuffixBits], (valid >> k) & 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += kPartScanThreads) hist[(size_t)blockIdx.x * nb + b] = cnt[b];
+}
+
+// block-wide exclusive scan of one value per thread (blockDim.x a multiple of 32, <= 1024); *total gets the sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t x, uint32_t *wsum /*[33] shared*/, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = lane < (blockDim.x >> 5) ? wsum[lane] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+            if (lane >= d) s += y;
+        }
+        wsum[lane] = s - v;
+        if (lane == 31) wsum[32] = s;
+    }
+    __syncthreads();
+    const uint32_t r = incl - x + wsum[warp];
+    if (total != nullptr) *total = wsum[32];
+    __syncthreads();  // wsum may be reused by the caller's next scan
+    return r;
+}
+
+// ctrl[0] = number of work items, ctrl[1] = next item (P4's fetch counter).
+// offs[c][b] = first entry slot of CTA c's bucket-b run; items = (bucket, begin, end) triples, slices of
+// `slice` entries; bucket regions start at multiples of 4 entries (16-byte loads in P4).
+__global__ void __launch_bounds__(kPartThreads, 1) part_offsets_kernel(const uint32_t *__restrict__ hist, int ctas, uint32_t nb,
+                                                                       uint32_t slice, uint32_t *__restrict__ offs,
+                                                                       uint32_t *__restrict__ items, uint32_t *__restrict__ ctrl) {
+    __shared__ uint32_t wsum[33];
+    const uint32_t b = threadIdx.x;
+    uint32_t total = 0;
+    if (b < nb)
+        for (int c = 0; c < ctas; ++c) {
+            const uint32_t h = hist[(size_t)c * nb + b];
+            offs[(size_t)c * nb + b] = total;
+            total += h;
+        }
+    const uint32_t padded = (total + 3u) & ~3u;
+    const uint32_t start = block_excl_scan(padded, wsum, nullptr);
+    const uint32_t n_items = (total + slice - 1) / slice;
+    uint32_t all_items;
+    const uint32_t item0 = block_excl_scan(n_items, wsum, &all_items);
+    if (b < nb) {
+        for (int c = 0; c < ctas; ++c) offs[(size_t)c * nb + b] += start;
+        for (uint32_t j = 0; j < n_items; ++j) {
+            uint32_t *it = items + 3 * (size_t)(item0 + j);
+            it[0] = b;
+            it[1] = start + j * slice;
+            it[2] = start + min(total, (j + 1) * slice);
+        }
+    }
+    if (b == 0) {
+        ctrl[0] = all_items;
+        ctrl[1] = 0;
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kPartScanThreads, kPartScanCtasPerSm) part_scatter_kernel(
+    const uint8_t *__restrict__ buf, int64_t nbytes, PartRange range, const uint8_t *__restrict__ rank_of_byte, uint32_t sigma,
+    uint32_t sigma_pow_m, uint32_t sigma_pow_n, uint32_t sub_bins, uint32_t nb, const uint32_t *__restrict__ offs,
+    uint32_t *__restrict__ entries) {
+    extern __shared__ uint32_t staging[];           // kPartTileVecs * 16 entries (dynamic: static + this exceeds 48 KB)
+    __shared__ uint32_t cnt[kPartMaxBuckets];       // windows of this tile per bucket
+    __shared__ uint32_t base[kPartMaxBuckets];      // first staging slot of the bucket's run
+    __shared__ uint32_t gdelta[kPartMaxBuckets];    // entries index = staging slot + gdelta[bucket]  (mod 2^32)
+    __shared__ uint32_t cursor[kPartMaxBuckets];    // next free slot of this CTA's run in the bucket
+    __shared__ uint32_t wsum[33];
+    __shared__ uint8_t lut[256];
+    const uint32_t tid = threadIdx.x;
+    static_assert(kPartMaxBuckets == 2 * kPartScanThreads, "thread t owns buckets 2t and 2t+1");
+    if (tid < 256) lut[tid] = rank_of_byte[tid];
+#pragma unroll
+    for (uint32_t j = 0; j < 2; ++j) {
+        const uint32_t b = 2 * tid + j;
+        cursor[b] = b < nb ? offs[(size_t)blockIdx.x * nb + b] : 0u;
+        cnt[b] = 0;
+    }
+    __syncthreads();
+    int64_t lo, hi;
+    range.mine(lo, hi);
+    uint32_t wn[6];
+    if (lo + tid < hi) load_vector(buf, nbytes, (lo + tid) * 16, wn);
+    for (int64_t tile = lo; tile < hi; tile += kPartTileVecs) {
+        const int64_t vec = tile + tid;
+        uint32_t codes[16];
+        unsigned short slot[16];
+        uint32_t valid = 0;
+        if (vec < hi) {
+            uint32_t wc[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wc[k] = wn[k];
+            if (vec + kPartTileVecs < hi) load_vector(buf, nbytes, (vec + kPartTileVecs) * 16, wn);
+            valid = scan_words<M, true>(wc, nbytes, vec * 16, lut, sigma, sigma_pow_m, sigma_pow_n, nullptr, codes, sub_bins);
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if ((valid >> k) & 1u) slot[k] = (unsigned short)atomicAdd(&cnt[codes[k] >> kPartSuffixBits], 1u);
+        }
+        __syncthreads();
+        uint32_t total;
+        const uint32_t c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+        const uint32_t excl = block_excl_scan(c0 + c1, wsum, &total);
+        base[2 * tid] = excl;
+        base[2 * tid + 1] = excl + c0;
+        gdelta[2 * tid] = cursor[2 * tid] - excl;
+        gdelta[2 * tid + 1] = cursor[2 * tid + 1] - (excl + c0);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if ((valid >> k) & 1u) staging[base[codes[k] >> kPartSuffixBits] + slot[k]] = codes[k];
+        __syncthreads();
+        for (uint32_t i = tid; i < total; i += kPartScanThreads) {
+            const uint32_t c = staging[i];
+            entries[gdelta[c >> kPartSuffixBits] + i] = c & kPartSuffixMask;
+        }
+        cursor[2 * tid] += c0;
+        cursor[2 * tid + 1] += c1;
+        cnt[2 * tid] = 0;
+        cnt[2 * tid + 1] = 0;
+        __syncthreads();
+    }
+}
+
+// P4.  LB as in the shared-memory variant: 32 = plain adds; 16 = strict drain at 32767; 8 = drain at 127 into `out`
+// (a zeroed scratch table) + *status on a lane observed >= 192 (result then discarded, see pg_ngram_count).
+template <int LB>
+__global__ void __launch_bounds__(kPartThreads, 1) part_count_kernel(const uint32_t *__restrict__ entries,
+                                                                     const uint32_t *__restrict__ items, uint32_t *__restrict__ ctrl,
+                                                                     uint32_t sub_bins, unsigned long long *__restrict__ out,
+                                                                     int *__restrict__ status) {
+    constexpr uint32_t PER_WORD = 32 / LB;
+    constexpr uint32_t LSH = LB == 32 ? 0 : (LB == 16 ? 1 : 2);
+    constexpr uint32_t LANE_MASK = LB == 32 ? 0xFFFFFFFFu : ((1u << (LB % 32)) - 1u);
+    constexpr uint32_t HALF = LB == 32 ? 0u : (1u << ((LB - 1) % 32));
+    extern __shared__ unsigned tbl[];
+    __shared__ uint32_t s_item;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t words = (sub_bins + PER_WORD - 1) / PER_WORD;
+    const uint32_t n_items = ctrl[0];
+    bool hazard = false;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(&ctrl[1], 1u);
+        for (uint32_t i = tid; i < words; i += kPartThreads) tbl[i] = 0;
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint32_t bucket = items[3 * (size_t)item], begin = items[3 * (size_t)item + 1], end = items[3 * (size_t)item + 2];
+        unsigned long long *dst = out + (size_t)bucket * sub_bins;
+        for (uint32_t b0 = begin; b0 < end; b0 += 16u * kPartThreads) {
+            uint32_t e[16];
+            uint32_t vm = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t idx = b0 + ((uint32_t)j * kPartThreads + tid) * 4u;
+                if (idx + 4u <= end) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(entries + idx);
+                    e[4 * j] = q.x; e[4 * j + 1] = q.y; e[4 * j + 2] = q.z; e[4 * j + 3] = q.w;
+                    vm |= 0xFu << (4 * j);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const bool in = idx + (uint32_t)t < end;
+                        e[4 * j + t] = in ? entries[idx + t] : 0u;
+                        vm |= (in ? 1u : 0u) << (4 * j + t);
+                    }
+                }
+            }
+            if (LB == 32) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) atomicAdd(&tbl[e[k]], (vm >> k) & 1u);
+            } else {
+                unsigned old[16];
+                uint32_t att = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t sh = (e[k] * LB) & 31u;
+                    const uint32_t inc = ((vm >> k) & 1u) << sh;
+                    old[k] = atomicAdd(&tbl[e[k] >> LSH], inc);
+                    att |= (old[k] + inc) & (inc << (LB - 1));
+                }
+                if (att) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        if (!((vm >> k) & 1u)) continue;
+                        const uint32_t sh = (e[k] * LB) & 31u;
+                        const uint32_t lane = (old[k] >> sh) & LANE_MASK;
+                        if (lane == HALF - 1u) {
+                            atomicSub(&tbl[e[k] >> LSH], HALF << sh);
+                            atomicAdd(&dst[e[k]], (unsigned long long)HALF);
+                        }
+                        if (LB == 8 && lane >= 192u) hazard = true;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < words; i += kPartThreads) {
+            const unsigned v = tbl[i];
+            if (v == 0u) continue;
+#pragma unroll
+            for (uint32_t j = 0; j < PER_WORD; ++j) {
+                const unsigned c = LB == 32 ? v : ((v >> ((j * LB) % 32)) & LANE_MASK);
+                const uint32_t k = i * PER_WORD + j;
+                if (c != 0u && k < sub_bins) atomicAdd(&dst[k], (unsigned long long)c);
+            }
+        }
+        __syncthreads();  // table is re-zeroed at the top; s_item is rewritten by thread 0 only after this barrier
+    }
+    if (LB == 8 && hazard) *status = 1;
+}
+
+// bins[k] += scratch[k] if the 8-bit result was proven exact (*status == 0)
+__global__ void __launch_bounds__(256) merge_scratch_kernel(const unsigned long long *__restrict__ scratch, int64_t nbins,
+                                                            const int *__restrict__ status, unsigned long long *__restrict__ bins) {
+    if (*status != 0) return;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = scratch[k];
+        if (c) bins[k] += c;
+    }
+}
+
 __global__ void set_flag_kernel(int *flag, int v) { *flag = v; }
 
 // ------------------------------------------------------------------ table -> ids / edges
@@ -529,7 +830,7 @@ int launch_smem_count(int m, const CountArgs &a, unsigned long long *bins, unsig
 }
 
 int launch_global_count(int m, const CountArgs &a, unsigned long long *bins, const int *gate) {
-    const unsigned grid = (unsigned)pg_ceil_div(pg_ceil_div(a.nbytes, 16), 256);
+    const unsigned grid = grid_for(pg_ceil_div(a.nbytes, 16), 256, 8);   // grid-stride: a gated (no-op) launch costs ~1200 CTAs, not one per 4 KB
 #define PG_LAUNCH_COUNT(MM) \
     ngram_count_kernel<MM><<<grid, 256, 0, a.st>>>(a.buf, a.nbytes, a.rank, a.sigma, a.pow_m, a.pow_n, bins, a.short_present, gate)
     switch (m) {
@@ -556,6 +857,130 @@ int launch_strict_count(int m, const CountArgs &a, unsigned long long *bins, con
     if (allow_smem && s16 <= kMaxSplits) return launch_smem_count<16, true>(m, a, bins, bins, s16, *ws, run_if);
     return launch_global_count(m, a, bins, run_if == 1 ? ws->status : nullptr);
 }
+
+// ---- variant P (partition + shared-memory count)
+constexpr int64_t kPartMinChunk = 16 * (int64_t)kPartTileVecs;   // one tile of windows
+constexpr int64_t kPartMaxChunk = 1ll << 30;                     // entry indices stay 32-bit
+constexpr int64_t kPartAutoMinBytes = 32ll << 20;                // AUTO: smaller corpora stay on the L2 REDs
+
+struct PartPlan {
+    bool ok;
+    int lane_bits;
+    uint32_t nb, sub_bins;
+    size_t fixed_bytes;  // everything but the entries
+    size_t scratch_off, hist_off, offs_off, items_off, entries_off;
+    int64_t max_items_cap;
+};
+
+// lane_bits = widest of 32/16/8 whose sub-table (sigma^(m-2) lanes) fits one CTA; ok = false if none does
+PartPlan part_plan(int m, int sigma, int64_t pow_m) {
+    PartPlan p{};
+    if (m < 5 || sigma * sigma > (int)kPartMaxBuckets) return p;
+    p.nb = (uint32_t)(sigma * sigma);
+    const int64_t sub = pow_m / p.nb;
+    if (sub > (int64_t)kPartSuffixMask + 1) return p;
+    p.sub_bins = (uint32_t)sub;
+    p.lane_bits = sub * 4 <= kSmemTableBytes ? 32 : (sub * 2 <= kSmemTableBytes ? 16 : (sub <= kSmemTableBytes ? 8 : 0));
+    if (p.lane_bits == 0) return p;
+    p.max_items_cap = kPartMaxChunk / (64 * kPartMinChunk) + p.nb + 8;   // slices are never smaller than 64 tiles at the largest chunk
+    size_t off = 512;  // [status 256 B][ctrl 256 B]
+    p.scratch_off = off;
+    if (p.lane_bits == 8) off += pg_align_up((size_t)pow_m * 8, 256);
+    p.hist_off = off;
+    off += pg_align_up((size_t)PG_NUM_SMS * kPartScanCtasPerSm * p.nb * 4, 256);
+    p.offs_off = off;
+    off += pg_align_up((size_t)PG_NUM_SMS * kPartScanCtasPerSm * p.nb * 4, 256);
+    p.items_off = off;
+    off += pg_align_up((size_t)p.max_items_cap * 12, 256);
+    p.entries_off = off;
+    p.fixed_bytes = off;
+    p.ok = true;
+    return p;
+}
+
+inline size_t part_entry_bytes(const PartPlan &p, int64_t chunk_windows) { return pg_align_up((size_t)(chunk_windows + 4 * p.nb + 64) * 4, 256); }
+
+// windows per chunk the workspace allows (0 = variant P cannot run with this workspace)
+int64_t part_chunk_windows(const PartPlan &p, size_t ws_bytes, int64_t nbytes) {
+    if (!p.ok || ws_bytes <= p.fixed_bytes + part_entry_bytes(p, kPartMinChunk)) return 0;
+    int64_t cap = (int64_t)((ws_bytes - p.fixed_bytes) / 4) - 4 * p.nb - 128;
+    if (cap > kPartMaxChunk) cap = kPartMaxChunk;
+    const int64_t need = pg_ceil_div(nbytes, kPartMinChunk) * kPartMinChunk;
+    if (cap > need) cap = need;
+    return cap / kPartMinChunk * kPartMinChunk;
+}
+
+int launch_partitioned_count(int m, const CountArgs &a, unsigned long long *bins, void *d_ws, const PartPlan &p, int64_t chunk_windows) {
+    char *ws = (char *)d_ws;
+    int *status = (int *)ws;
+    uint32_t *ctrl = (uint32_t *)(ws + 256);
+    unsigned long long *scratch = p.lane_bits == 8 ? (unsigned long long *)(ws + p.scratch_off) : nullptr;
+    uint32_t *hist = (uint32_t *)(ws + p.hist_off), *offs = (uint32_t *)(ws + p.offs_off), *items = (uint32_t *)(ws + p.items_off);
+    uint32_t *entries = (uint32_t *)(ws + p.entries_off);
+    unsigned long long *out = p.lane_bits == 8 ? scratch : bins;
+    PG_CUDA_CALL(cudaMemsetAsync(ws, 0, p.lane_bits == 8 ? p.hist_off : 512, a.st));   // status, ctrl (+ scratch)
+    if (g_count_variant == PG_COUNT_PARTITIONED_FORCE_HAZARD) {
+        set_flag_kernel<<<1, 1, 0, a.st>>>(status, 1);
+        PG_CUDA_LAUNCH_CHECK("set_flag_kernel");
+    }
+    const int64_t nvec = pg_ceil_div(a.nbytes, 16);
+    const int64_t chunk_vecs = chunk_windows / 16;
+    // slices: large enough that zero + flush of the sub-table (sub_bins lanes) stays a small part of an item
+    int64_t slice = pg_ceil_div(chunk_windows, 256 * kPartMinChunk) * kPartMinChunk;
+    if (slice < 4 * kPartMinChunk) slice = 4 * kPartMinChunk;
+    if (slice > 64 * kPartMinChunk * 8) slice = 64 * kPartMinChunk * 8;   // 4 M entries
+    if (chunk_windows / slice + p.nb + 1 > p.max_items_cap) {
+        pg_set_error("pg_ngram_count: internal error (work list capacity)");
+        return PG_EINVAL;
+    }
+    const size_t stage_bytes = (size_t)kPartTileVecs * 16 * 4;
+    const uint32_t words = (p.sub_bins + 32 / p.lane_bits - 1) / (32 / p.lane_bits);
+    const size_t tbl_bytes = (size_t)words * 4;
+    for (int64_t v0 = 0; v0 < nvec; v0 += chunk_vecs) {
+        PartRange r{v0, v0 + chunk_vecs < nvec ? v0 + chunk_vecs : nvec};
+        int64_t ctas = pg_ceil_div(r.hi - r.lo, kPartTileVecs);
+        if (ctas > PG_NUM_SMS * kPartScanCtasPerSm) ctas = PG_NUM_SMS * kPartScanCtasPerSm;
+#define PG_PART_SCAN(MM)                                                                                                          \
+    do {                                                                                                                          \
+        part_hist_kernel<MM><<<(unsigned)ctas, kPartScanThreads, 0, a.st>>>(a.buf, a.nbytes, r, a.rank, a.sigma, a.pow_m, a.pow_n, \
+                                                                       p.sub_bins, p.nb, a.short_present, hist);                  \
+        PG_CUDA_LAUNCH_CHECK("part_hist_kernel");                                                                                 \
+        part_offsets_kernel<<<1, kPartThreads, 0, a.st>>>(hist, (int)ctas, p.nb, (uint32_t)slice, offs, items, ctrl);              \
+        PG_CUDA_LAUNCH_CHECK("part_offsets_kernel");                                                                              \
+        PG_CUDA_CALL(cudaFuncSetAttribute(part_scatter_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes)); \
+        part_scatter_kernel<MM><<<(unsigned)ctas, kPartScanThreads, stage_bytes, a.st>>>(a.buf, a.nbytes, r, a.rank, a.sigma,     \
+                                                                                        a.pow_m, a.pow_n, p.sub_bins, p.nb, offs, \
+                                                                                        entries);                                 \
+        PG_CUDA_LAUNCH_CHECK("part_scatter_kernel");                                                                              \
+    } while (0)
+        switch (m) {
+            case 5: PG_PART_SCAN(5); break;
+            case 6: PG_PART_SCAN(6); break;
+            case 7: PG_PART_SCAN(7); break;
+            default: pg_set_error("pg_ngram_count: variant P needs n >= 4"); return PG_EINVAL;
+        }
+#undef PG_PART_SCAN
+        const unsigned grid4 = (unsigned)(PG_NUM_SMS * (tbl_bytes <= 96 * 1024 ? 2 : 1));
+#define PG_PART_COUNT(LL)                                                                                                     \
+    do {                                                                                                                      \
+        PG_CUDA_CALL(cudaFuncSetAttribute(part_count_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_bytes)); \
+        part_count_kernel<LL><<<grid4, kPartThreads, tbl_bytes, a.st>>>(entries, items, ctrl, p.sub_bins, out, status);         \
+    } while (0)
+        if (p.lane_bits == 32) PG_PART_COUNT(32);
+        else if (p.lane_bits == 16) PG_PART_COUNT(16);
+        else PG_PART_COUNT(8);
+#undef PG_PART_COUNT
+        PG_CUDA_LAUNCH_CHECK("part_count_kernel");
+    }
+    if (p.lane_bits == 8) {
+        merge_scratch_kernel<<<grid_for(a.pow_m), 256, 0, a.st>>>(scratch, (int64_t)a.pow_m, status, bins);
+        PG_CUDA_LAUNCH_CHECK("merge_scratch_kernel");
+        CountArgs strict = a;
+        strict.short_present = a.short_present;   // idempotent flags
+        return launch_global_count(m, strict, bins, status);   // no-op unless a hazard was flagged
+    }
+    return PG_OK;
+}
 }  // namespace
 
 extern "C" size_t pg_ngram_count_ws_bytes(int n, int sigma) {
@@ -563,6 +988,18 @@ extern "C" size_t pg_ngram_count_ws_bytes(int n, int sigma) {
     if (!table_sizes(n, sigma, &pow_n, &pow_m)) return 0;
     if (splits_for(pow_m, 8) > kMaxSplits) return 256;  // L2 REDs only: no workspace needed
     return 256 + scratch_bytes(pow_m) + kPartialBytes;
+}
+
+extern "C" size_t pg_ngram_count_ws_bytes_for(int n, int sigma, int64_t nbytes) {
+    int64_t pow_n, pow_m;
+    if (!table_sizes(n, sigma, &pow_n, &pow_m)) return 0;
+    const size_t base = pg_ngram_count_ws_bytes(n, sigma);
+    const PartPlan p = part_plan(n + 1, sigma, pow_m);
+    if (!p.ok || splits_for(pow_m, 8) <= kMaxSplits || nbytes <= 0) return base;
+    int64_t chunk = pg_ceil_div(nbytes, kPartMinChunk) * kPartMinChunk;
+    if (chunk > kPartMaxChunk) chunk = kPartMaxChunk;
+    const size_t want = p.fixed_bytes + part_entry_bytes(p, chunk) + 1024;
+    return want > base ? want : base;
 }
 
 extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const uint8_t *d_rank_of_byte, int sigma,
@@ -583,9 +1020,17 @@ extern "C" int pg_ngram_count(const uint8_t *d_buf, int64_t nbytes, int n, const
     const int variant = g_count_variant;
     // tiny corpora: zeroing and reducing 148 tables costs more than the L2 REDs
     const bool big_enough = nvec >= 4 * kSmemCountThreads;
-    const bool have_ws = d_ws != nullptr && ((uintptr_t)d_ws & 255) == 0 && ws_bytes >= pg_ngram_count_ws_bytes(n, sigma) &&
-                         splits_for(pow_m, 8) <= kMaxSplits;
-    if (variant == PG_COUNT_GLOBAL || !have_ws) return launch_global_count(m, a, d_bins, nullptr);
+    const bool ws_usable = d_ws != nullptr && ((uintptr_t)d_ws & 255) == 0;
+    const bool part_forced = variant == PG_COUNT_PARTITIONED || variant == PG_COUNT_PARTITIONED_FORCE_HAZARD;
+    if (ws_usable && splits_for(pow_m, 8) > kMaxSplits && (part_forced || (variant == PG_COUNT_AUTO && nbytes >= kPartAutoMinBytes))) {
+        const PartPlan p = part_plan(m, sigma, pow_m);
+        const int64_t chunk = part_chunk_windows(p, ws_bytes, nbytes);
+        // AUTO wants chunks of >= 1/16 of the corpus or 64 M windows (the dense-table flush per chunk and bucket must amortise)
+        if (chunk > 0 && (part_forced || chunk >= (nbytes < (64ll << 20) * 16 ? nbytes / 16 : (64ll << 20))))
+            return launch_partitioned_count(m, a, d_bins, d_ws, p, chunk);
+    }
+    const bool have_ws = ws_usable && ws_bytes >= pg_ngram_count_ws_bytes(n, sigma) && splits_for(pow_m, 8) <= kMaxSplits;
+    if (variant == PG_COUNT_GLOBAL || part_forced || !have_ws) return launch_global_count(m, a, d_bins, nullptr);
     CountWs ws;
     ws.status = (int *)d_ws;
     ws.scratch = uses_fast8(pow_m) ? (unsigned long long *)((char *)d_ws + 256) : nullptr;

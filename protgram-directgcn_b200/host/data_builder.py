@@ -30,10 +30,17 @@ def table_sizes(n: int, sigma: int) -> Tuple[int, int]:
     return sigma ** n, sigma ** (n + 1)
 
 
+def count_workspace(n: int, sigma: int, nbytes: int, device) -> torch.Tensor:
+    """Workspace of pg_ngram_count for corpus buffers of up to `nbytes` (reusable across chunks and calls)."""
+    return nat.workspace(nat.query("pg_ngram_count_ws_bytes_for", n, sigma, int(nbytes)), device)
+
+
 def count_level(d_buf: torch.Tensor, n: int, d_rank: torch.Tensor, sigma: int,
-                bins: Optional[torch.Tensor] = None, short: Optional[torch.Tensor] = None):
+                bins: Optional[torch.Tensor] = None, short: Optional[torch.Tensor] = None,
+                ws: Optional[torch.Tensor] = None):
     """Accumulate the (n+1)-gram table of one corpus buffer.  -> (bins int64[sigma^(n+1)],
-    short_present uint8[sigma^n]).  Replaces reference data_builder.py:45-54,203-220,267-273."""
+    short_present uint8[sigma^n]).  Replaces reference data_builder.py:45-54,203-220,267-273.
+    ws: optional workspace from count_workspace() (multi-GB for n >= 4: allocate it once per level)."""
     nat.require_cuda()
     pow_n, pow_m = table_sizes(n, sigma)
     dev = d_buf.device
@@ -41,7 +48,8 @@ def count_level(d_buf: torch.Tensor, n: int, d_rank: torch.Tensor, sigma: int,
         bins = torch.zeros(pow_m, dtype=torch.int64, device=dev)
     if short is None:
         short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
-    ws = nat.workspace(nat.query("pg_ngram_count_ws_bytes", n, sigma), dev)
+    if ws is None:
+        ws = count_workspace(n, sigma, d_buf.numel(), dev)
     nat.call("pg_ngram_count", nat.ptr(d_buf), d_buf.numel(), n, nat.ptr(d_rank), sigma, nat.ptr(bins), nat.ptr(short),
              nat.ptr(ws), ws.numel(), nat.stream_ptr())
     return bins, short
@@ -73,18 +81,20 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
     sigma = int(symbols.size)
     chunks = list(d_buf) if isinstance(d_buf, (list, tuple)) else [d_buf]
     bins = short = None
+    biggest = max((int(c.numel()) if torch.is_tensor(c) else int(c.size) for c in chunks), default=0)
+    ws = count_workspace(n, sigma, biggest, d_rank.device) if chunks else None   # one workspace for all chunks of the level
     host_idx = [i for i, c in enumerate(chunks) if not (torch.is_tensor(c) and c.is_cuda)]
     up = corpus.CorpusUploader(d_rank.device) if host_idx else None
     if up is not None:
         up.submit(chunks[host_idx[0]])
     for i, c in enumerate(chunks):
         if torch.is_tensor(c) and c.is_cuda:
-            bins, short = count_level(c, n, d_rank, sigma, bins, short)
+            bins, short = count_level(c, n, d_rank, sigma, bins, short, ws)
             continue
         nxt = host_idx.index(i) + 1
         if nxt < len(host_idx):
             up.submit(chunks[host_idx[nxt]])            # upload of the next chunk runs under this chunk's count
-        bins, short = count_level(up.acquire(), n, d_rank, sigma, bins, short)
+        bins, short = count_level(up.acquire(), n, d_rank, sigma, bins, short, ws)
         up.release()
     if bins is None:
         bins, short = count_level(torch.empty(0, dtype=torch.uint8, device=d_rank.device), n, d_rank, sigma)

@@ -31,6 +31,10 @@ def pg_ngram_count_ws_bytes(n, sigma):
     return 256
 
 
+def pg_ngram_count_ws_bytes_for(n, sigma, nbytes):
+    return 256
+
+
 def pg_ngram_count(buf, nbytes, n, rank_of_byte, sigma, bins, short_present, ws=None, ws_bytes=0, stream=None):
     b = buf[:nbytes].cpu().numpy()
     rank = rank_of_byte.cpu().numpy().astype(np.int64)

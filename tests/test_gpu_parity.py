@@ -297,7 +297,7 @@ def test_synth_corpus_matches_cpu_twin_and_is_shard_independent():
     assert np.array_equal(a, ref[1 + 600 * 52:])
 
 
-COUNT_VARIANTS = {"auto": 0, "global": 1, "strict": 2, "fast8_forced_hazard": 4}
+COUNT_VARIANTS = {"auto": 0, "global": 1, "strict": 2, "fast8_forced_hazard": 4, "partitioned": 5}
 
 
 @pytest.fixture(params=sorted(COUNT_VARIANTS))
@@ -347,6 +347,62 @@ def test_count_lane_overflow_homopolymer(count_variant, extra):
         bins, _ = data_builder.count_level(d_buf, n, d_rank, symbols.size)
         assert np.array_equal(bins.cpu().numpy().astype(np.uint64), ref)
         assert int(bins.max()) > 2_900_000
+
+
+@pytest.mark.parametrize("n", [4, 5])
+@pytest.mark.parametrize("tiles_per_chunk", [1, 5, 1000])
+def test_count_partitioned_chunks_vs_c_oracle(n, tiles_per_chunk):
+    """Variant P of pg_ngram_count (tables too large for shared memory: windows partitioned by their first two
+    symbols, then counted per bucket in shared memory) with a workspace that forces 1-tile, 5-tile and
+    single chunks; ragged buffer length; bit-exact vs oracle/ngram_count.c."""
+    from oracle import c_oracle
+    d_buf = _device_corpus(3001, 347)
+    h_buf = d_buf.cpu().numpy()
+    symbols, rank = c_oracle.alphabet(h_buf)
+    sigma = int(symbols.size)
+    d_rank = torch.from_numpy(rank).to(DEV)
+    bins_ref, present_ref = c_oracle.count_level(h_buf, n, rank, sigma)
+    lib = nat.load()
+    lib.pg_debug_count_variant(COUNT_VARIANTS["partitioned"])
+    try:
+        bins = torch.zeros(sigma ** (n + 1), dtype=torch.int64, device=DEV)
+        short = torch.zeros(sigma ** n, dtype=torch.uint8, device=DEV)
+        ws = nat.workspace(nat.query("pg_ngram_count_ws_bytes_for", n, sigma, tiles_per_chunk * 16384), DEV)
+        before = nat.kernel_launches()
+        for _ in range(2):   # accumulates: two passes = twice the table
+            nat.call("pg_ngram_count", nat.ptr(d_buf), d_buf.numel(), n, nat.ptr(d_rank), sigma, nat.ptr(bins), nat.ptr(short),
+                     nat.ptr(ws), ws.numel(), nat.stream_ptr())
+        chunks = -(-d_buf.numel() // (min(tiles_per_chunk, 65) * 16384))
+        assert nat.kernel_launches() - before >= 2 * 4 * chunks   # the partitioned kernels ran (4 per chunk), not the fallback
+    finally:
+        lib.pg_debug_count_variant(0)
+    assert np.array_equal(bins.cpu().numpy().astype(np.uint64), 2 * bins_ref)
+    node_code, *_ = data_builder.extract_level(bins, short, n, sigma)
+    assert np.array_equal(node_code.cpu().numpy(), np.nonzero(present_ref)[0])
+
+
+@pytest.mark.parametrize("variant", [5, 6])
+def test_count_partitioned_lane_overflow_homopolymer(variant):
+    """3 M identical 6-grams land in ONE bucket and one 8-bit lane of variant P's shared-memory table (n = 5,
+    sigma = 21: sub-table 21^4): the hazard check must fire and the gated strict recount take over; n = 4 uses
+    32-bit lanes (no overflow possible).  variant 6 forces the hazard flag."""
+    from oracle import c_oracle
+    seqs = ["A" * 3000] * 1000 + ["AC" * 700] * 300 + ["DEFGHIKLMNPQRSTVWY"]
+    buf = c_oracle.pack_corpus(seqs)
+    symbols, rank = c_oracle.alphabet(buf)
+    assert symbols.size == 21
+    d_buf = corpus.to_device(buf, DEV)
+    d_rank = torch.from_numpy(rank).to(DEV)
+    lib = nat.load()
+    lib.pg_debug_count_variant(variant)
+    try:
+        for n in (4, 5):
+            ref, _ = c_oracle.count_level(buf, n, rank, symbols.size)
+            bins, _ = data_builder.count_level(d_buf, n, d_rank, symbols.size)
+            assert np.array_equal(bins.cpu().numpy().astype(np.uint64), ref)
+            assert int(bins.max()) > 2_900_000
+    finally:
+        lib.pg_debug_count_variant(0)
 
 
 def test_count_ragged_tail_and_chunked_accumulation():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs the two dominant kernels a few times at benchmark size, for `ncu --set full` captures:
    ngram_count (C2 corpus, n=3) and the nv=3 fan-out / fan-in SpMM on the R-MAT graph of bench.py.
-usage: python tools/run_kernels.py [count] [spmm] [--log2 N]"""
+usage: python tools/run_kernels.py [count] [count4] [count5] [spmm] [--log2 N] [--seqs S]"""
 import os
 import sys
 
@@ -23,6 +23,11 @@ def main():
             bins, short = pipe.db.count_level(pipe.d_buf, bench.N_LEVEL, d_rank, int(symbols.size))
         torch.cuda.synchronize()
         print("count ok", int(bins.sum()))
+    for key, n_level in (("count4", 4), ("count5", 5)):   # variant P (partition + shared-memory count) at C3 / C4 shape
+        if key in which:
+            seqs = int(sys.argv[sys.argv.index("--seqs") + 1]) if "--seqs" in sys.argv else 2_000_000
+            out = bench.build_scale_leg(pipe, None, n_level, seqs, iters=1, normalise=False)
+            print({k: v for k, v in out.items() if not k.startswith("_")})
     if "spmm" in which:
         out = bench.spmm_large_leg(pipe, 6548.5, log2, iters=2)
         print({k: (v if not isinstance(v, dict) else {a: round(b, 3) for a, b in v.items()}) for k, v in out.items()})
