@@ -66,4 +66,9 @@ size_t pg_scan_ws_bytes(int64_t n);
 int pg_exclusive_scan_i64(const int64_t *d_in, int64_t *d_out, int64_t n, int64_t *d_total, void *d_ws,
                           size_t ws_bytes, cudaStream_t stream);
 
+// gating of dZ + gate gradients after a data-gradient GEMM (gemm.cu; also used by gemm_tc.cu)
+int pg_launch_gate_grad(float *d_dz, int64_t lddz, const float *d_z, int64_t ldz, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                        const float *d_gate_a, const float *d_gate_b, const float *d_gate_c, int gate_stride, int64_t num_rows, int F_in,
+                        int F_out, int k_data, float *d_dgate, cudaStream_t st);
+
 static inline cudaStream_t pg_cu(pg_stream_t s) { return (cudaStream_t)s; }

@@ -391,6 +391,16 @@ int split_count(int64_t M, int k_ext, int F_out) {
 }
 }  // namespace
 
+// shared with the tensor-core data gradient (gemm_tc.cu): gating of dZ + gate gradients
+int pg_launch_gate_grad(float *d_dz, int64_t lddz, const float *d_z, int64_t ldz, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                        const float *d_gate_a, const float *d_gate_b, const float *d_gate_c, int gate_stride, int64_t num_rows, int F_in,
+                        int F_out, int k_data, float *d_dgate, cudaStream_t st) {
+    gate_grad_kernel<<<grid_for(num_rows * 32), 256, 0, st>>>(d_dz, lddz, d_z, ldz, d_dy, lddy, d_w_ext, d_gate_a, d_gate_b, d_gate_c,
+                                                              gate_stride, num_rows, F_in, F_out, k_data, d_dgate);
+    PG_CUDA_LAUNCH_CHECK("gate_grad_kernel");
+    return PG_OK;
+}
+
 extern "C" int pg_layer_gemm_fwd(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx, const float *d_gate_a,
                                  const float *d_gate_b, const float *d_gate_c, int gate_stride, const float *d_w_ext,
                                  const float *d_constant, int64_t ldconst, int64_t num_rows, int F_in, int F_out, int has_res,
@@ -441,10 +451,8 @@ extern "C" int pg_layer_gemm_bwd_data(const float *d_dy, int64_t lddy, const flo
         int rc = launch_gemm(opa, opb, epi, num_rows, k_data, F_out, F_out, 1, st);
         if (rc != PG_OK) return rc;
     }
-    gate_grad_kernel<<<grid_for(num_rows * 32), 256, 0, st>>>(d_dz, lddz, d_z, ldz, d_dy, lddy, d_w_ext, d_gate_a, d_gate_b, d_gate_c,
-                                                              gate_stride, num_rows, F_in, F_out, k_data, d_dgate);
-    PG_CUDA_LAUNCH_CHECK("gate_grad_kernel");
-    return PG_OK;
+    return pg_launch_gate_grad(d_dz, lddz, d_z, ldz, d_dy, lddy, d_w_ext, d_gate_a, d_gate_b, d_gate_c, gate_stride, num_rows, F_in, F_out,
+                               k_data, d_dgate, st);
 }
 
 extern "C" size_t pg_layer_gemm_bwd_weight_ws_bytes(int64_t num_rows, int F_in, int F_out, int has_res) {

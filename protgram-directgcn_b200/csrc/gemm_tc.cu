@@ -20,9 +20,10 @@
 //     tcgen05.commit's them to the stage's mbarrier, so the loads of tile k+1 overlap the MMAs of
 //     tile k.  Epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> +X, +constant, leaky_relu.
 //   * every mbarrier wait is bounded (watchdog): a wrong descriptor must fail a test, not hang a GPU.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+using namespace pgtc;
 
 // ---- the same virtual A operand as gemm.cu (kept in sync by tests/test_gpu_parity.py) ----
 struct AExtTc {
@@ -60,49 +61,6 @@ constexpr int TC_BM = 128;      // rows per CTA = UMMA M
 // The smaller stage lets 2 CTAs share an SM, so one CTA's prologue / epilogue hides under the other's mainloop.
 constexpr uint32_t TC_LBO_A = (TC_BM + 1) * 16;
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // cute::UMMA::SmemDescriptor: start [0,14) | LBO [16,30) | SBO [32,46) | version=1 [46,48) | layout NONE [61,64)
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-// bounded wait: returns false when the watchdog expires (caller flags the error and bails out)
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return true;
-    }
-    return false;
-}
-
 // W_ext [k_ext, F_out] -> per k-tile image [kt][half(hi,lo)][chunk 0..7][n 0..F_out-1] of float4 (4 consecutive k)
 __global__ void __launch_bounds__(256) wprep_kernel(const float *__restrict__ w_ext, int k_ext, int F_out, int k_tiles, int TC_CHUNKS,
                                                     float4 *__restrict__ wp) {
@@ -126,31 +84,58 @@ __global__ void __launch_bounds__(256) wprep_kernel(const float *__restrict__ w_
     }
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // Warp roles: warps 0..7 (256 threads) build the A tiles (and run the epilogue), warp 8 lane 0 streams
 // the B tiles with 1-D bulk copies (TMA engine, no register staging) and issues the MMAs.
-//   full[s]  : 256 producer arrivals + 1 expect_tx arrival + the B bytes  -> stage s is ready
+//   full[s]  : 8 producer-warp arrivals + 1 expect_tx arrival + the B bytes -> stage s is ready
 //   empty[s] : tcgen05.commit of the MMAs that read stage s               -> stage s may be refilled
 constexpr int TC_PRODUCERS = 256;
 constexpr int TC_THREADS2 = TC_PRODUCERS + 32;
 
-template <int TC_CHUNKS>
-__global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_gemm_fwd_tc_kernel(AExtTc A, const float4 *__restrict__ wp, int F_out, int k_tiles,
-                                                                           const float *__restrict__ constant, int64_t ldconst,
-                                                                           int add_identity, float slope, float *__restrict__ h,
-                                                                           int64_t ldh, int *__restrict__ error_flag) {
+// Epilogue of the forward transform: H = leaky_relu(acc (+X) + constant); the side operands of the NEXT 16 columns are
+// loaded while this chunk's accumulators come out of TMEM.
+struct EpiFwdTc {
+    const float *constant, *x;
+    int64_t ldconst, ldx;
+    int add_identity;
+    float slope;
+    float *h;
+    int64_t ldh;
+    static constexpr bool kHasSide = true;
+    __device__ __forceinline__ void load_side(int64_t row, int c, float4 (&dst)[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (constant) acc4 = __ldg(reinterpret_cast<const float4 *>(constant + row * ldconst + c + q * 4));
+            if (add_identity) {
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + row * ldx + c + q * 4));
+                acc4.x += xv.x; acc4.y += xv.y; acc4.z += xv.z; acc4.w += xv.w;
+            }
+            dst[q] = acc4;
+        }
+    }
+    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&side)[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 sd = side[q];
+            float y[4] = {__uint_as_float(r[q * 4 + 0]) + sd.x, __uint_as_float(r[q * 4 + 1]) + sd.y,
+                          __uint_as_float(r[q * 4 + 2]) + sd.z, __uint_as_float(r[q * 4 + 3]) + sd.w};
+            if (slope != 1.f) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
+            }
+            *reinterpret_cast<float4 *>(h + row * ldh + c + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+};
+
+// D[rows m0..m0+127, columns n0..n0+n_blk) = A[rows, K] @ B[K, columns]:  one CTA per (row tile, column block).
+// AOp: the A operand, built by the producer warps (at4(row, k0) = 4 consecutive k; zero outside the matrix).
+// wp : pre-split B image per column block [block][kt][hi|lo][chunk][n] (wprep kernels), streamed with bulk copies;
+//      every block but the last is n_full columns wide.  Epi: what happens to the accumulators.
+template <int TC_CHUNKS, class AOp, class Epi>
+__global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) tc_rows_gemm_kernel(AOp A, Epi epi, const float4 *__restrict__ wp_all,
+                                                                                           int n_full, int n_total, int k_tiles,
+                                                                                           int *__restrict__ error_flag) {
     constexpr int TC_BK = TC_CHUNKS * 4;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[2], empty[2], done;
@@ -158,31 +143,30 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
     __shared__ volatile int bail;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
-    const uint32_t lbo_b = (uint32_t)F_out * 16u;              // B chunks are written by the copy engine: no padding needed
+    const int n0 = (int)blockIdx.y * n_full;
+    const int n_blk = min(n_full, ((n_total - n0 + 15) / 16) * 16);   // columns of this CTA (multiple of 16; the image is zero-padded)
+    const float4 *wp = wp_all + (int64_t)blockIdx.y * k_tiles * 2 * TC_CHUNKS * n_full;
+    const uint32_t lbo_b = (uint32_t)n_blk * 16u;              // B chunks are written by the copy engine: no padding needed
     const uint32_t a_bytes = TC_CHUNKS * TC_LBO_A, b_bytes = TC_CHUNKS * lbo_b;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;  // A_hi | A_lo | B_hi | B_lo
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * (uint32_t)TC_CHUNKS * (uint32_t)n_full * 16u;  // A_hi | A_lo | B_hi | B_lo
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < F_out) tmem_cols <<= 1;
+    while ((int)tmem_cols < n_blk) tmem_cols <<= 1;
 
     if (tid == 0) {
-        mbar_init(&full[0], TC_PRODUCERS + 1);
-        mbar_init(&full[1], TC_PRODUCERS + 1);
+        mbar_init(&full[0], TC_PRODUCERS / 32 + 1);
+        mbar_init(&full[1], TC_PRODUCERS / 32 + 1);
         mbar_init(&empty[0], 1);
         mbar_init(&empty[1], 1);
         mbar_init(&done, 1);
         bail = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 0) tmem_alloc(&tmem_base_slot, tmem_cols);
+    fence_before_sync();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fence_after_sync();
     const uint32_t tmem_d = tmem_base_slot;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F_out >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_blk >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
     if (warp < TC_PRODUCERS / 32) {
         // ------------------------------------------------------------------ A producers
@@ -216,8 +200,9 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
                         *reinterpret_cast<float4 *>(st + kc * TC_LBO_A + r * 16) = hi;
                         *reinterpret_cast<float4 *>(st + a_bytes + kc * TC_LBO_A + r * 16) = lo;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-                    mbar_arrive(&full[sg]);
+                    fence_async_smem();  // generic-proxy stores -> visible to the tensor core
+                    __syncwarp();        // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise
+                    if (lane == 0) mbar_arrive(&full[sg]);
                     if (t + PF < k_tiles) {  // refill the register slot with the tile PF steps ahead
                         const int k0 = (t + PF) * TC_BK;
 #pragma unroll
@@ -240,11 +225,11 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
             if (bail) break;
             const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
             mbar_arrive_expect_tx(&full[s], 2 * b_bytes);
-            const float4 *src = wp + (int64_t)kt * 2 * TC_CHUNKS * F_out;  // [half][chunk][n] contiguous == B_hi | B_lo image
+            const float4 *src = wp + (int64_t)kt * 2 * TC_CHUNKS * n_blk;  // [half][chunk][n] contiguous == B_hi | B_lo image
             bulk_g2s(b_hi, src, b_bytes, &full[s]);
-            bulk_g2s(b_lo, src + (int64_t)TC_CHUNKS * F_out, b_bytes, &full[s]);
+            bulk_g2s(b_lo, src + (int64_t)TC_CHUNKS * n_blk, b_bytes, &full[s]);
             if (!mbar_wait(&full[s], (uint32_t)((kt >> 1) & 1))) { bail = 1; break; }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            fence_after_sync();
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {  // one MMA consumes 2 chunks (K = 8 tf32)
                 const uint64_t dah = umma_desc(a_hi + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
@@ -255,58 +240,29 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
                 umma_tf32(tmem_d, dah, dbl, idesc, 1);
                 umma_tf32(tmem_d, dal, dbh, idesc, 1);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+            umma_commit(&empty[s]);
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done)) : "memory");
+        umma_commit(&done);
     }
     // ---------------------------------------------------------------------- epilogue (warps 0..7)
     if (warp < TC_PRODUCERS / 32) {
         if (!bail && !mbar_wait(&done, 0)) bail = 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        fence_after_sync();
         if (!bail) {
             // TMEM lanes are owned per warp quadrant (warp % 4); warps 4..7 take the upper half of the columns
             const int quad = warp & 3;
             const int64_t row = m0 + quad * 32 + lane;
-            const int half_cols = ((F_out / 16 + 1) / 2) * 16;
-            const int c_begin = (warp < 4) ? 0 : half_cols, c_end = (warp < 4) ? half_cols : F_out;
+            const int half_cols = ((n_blk / 16 + 1) / 2) * 16;
+            const int c_begin = (warp < 4) ? 0 : half_cols, c_end = (warp < 4) ? half_cols : n_blk;
             const bool in_range = row < A.M;
             auto load_side = [&](int c0, float4 (&dst)[4]) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in_range && c0 < c_end) {
-                        if (constant) acc4 = __ldg(reinterpret_cast<const float4 *>(constant + row * ldconst + c0 + q * 4));
-                        if (add_identity) {
-                            const float4 xv = __ldg(reinterpret_cast<const float4 *>(A.x + row * A.ldx + c0 + q * 4));
-                            acc4.x += xv.x; acc4.y += xv.y; acc4.z += xv.z; acc4.w += xv.w;
-                        }
-                    }
-                    dst[q] = acc4;
-                }
+                if (Epi::kHasSide && in_range && c0 < c_end) epi.load_side(row, n0 + c0, dst);
             };
             auto process = [&](int c0, const float4 (&cur)[4], float4 (&nxt)[4]) {
                 load_side(c0 + 16, nxt);  // next chunk's side loads fly under this chunk's TMEM read + stores
                 uint32_t r[16];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (in_range) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 sd = cur[q];
-                        float y[4] = {__uint_as_float(r[q * 4 + 0]) + sd.x, __uint_as_float(r[q * 4 + 1]) + sd.y,
-                                      __uint_as_float(r[q * 4 + 2]) + sd.z, __uint_as_float(r[q * 4 + 3]) + sd.w};
-                        if (slope != 1.f) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
-                        }
-                        *reinterpret_cast<float4 *>(h + row * ldh + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                    }
-                }
+                tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+                if (in_range) epi.store(row, n0 + c0, r, cur);
             };
             float4 side_a[4], side_b[4];
             load_side(c_begin, side_a);
@@ -316,12 +272,314 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) layer_g
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    fence_before_sync();
     __syncthreads();
     if (bail && tid == 0) atomicExch(error_flag, 1);
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, data gradient:  dA[:, :k_data] = dY @ W_ext[:k_data, :]^T   (gating + gate gradients: gate_grad_kernel, gemm.cu)
+// Same kernel: A = rows of dY, B image = W_ext^T cut into column blocks of <= 256 (TMEM columns), epilogue = plain stores.
+// ------------------------------------------------------------------------------------------------
+struct APlainTc {
+    const float *p;
+    int64_t ld, M;
+    int K;
+    __device__ __forceinline__ float4 at4(int64_t i, int k0) const {  // K % 4 == 0, 16 B aligned rows
+        if (i < M && k0 + 3 < K) return __ldg(reinterpret_cast<const float4 *>(p + i * ld + k0));
+        return make_float4(0.f, 0.f, 0.f, 0.f);
     }
+};
+
+struct EpiBwdDataTc {  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in, k_data) -> dXres
+    float *dz, *dxres;
+    int64_t lddz, lddxres;
+    int f3, k_data;
+    static constexpr bool kHasSide = false;
+    __device__ __forceinline__ void load_side(int64_t, int, float4 (&)[4]) const {}
+    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&)[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = c + 4 * q;   // f3 and k_data are multiples of 4: a float4 never straddles a boundary
+            if (cc >= k_data) continue;
+            const float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                         __uint_as_float(r[q * 4 + 3]));
+            if (cc < f3) *reinterpret_cast<float4 *>(dz + row * lddz + cc) = v;
+            else *reinterpret_cast<float4 *>(dxres + row * lddxres + (cc - f3)) = v;
+        }
+    }
+};
+
+// W_ext [k_ext, F_out] -> images of W_ext[:k_data]^T per column block: [block][kt][half][chunk][n] float4 over 4 consecutive f
+__global__ void __launch_bounds__(256) wprep_t_kernel(const float *__restrict__ w_ext, int k_data, int F_out, int k_tiles, int n_full,
+                                                      int blocks, float4 *__restrict__ wp) {
+    constexpr int CH = 4;
+    const int64_t per_block = (int64_t)k_tiles * 2 * CH * n_full;
+    const int64_t total = (int64_t)blocks * k_tiles * CH * n_full;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / ((int64_t)k_tiles * CH * n_full));
+        const int64_t u = t - (int64_t)b * k_tiles * CH * n_full;
+        const int n0 = b * n_full;
+        const int n_blk = min(n_full, ((k_data - n0 + 15) / 16) * 16);
+        // enumerate (kt, kc, n) over the block's own width so that the image is dense in n_blk
+        const int64_t dense = (int64_t)k_tiles * CH * n_blk;
+        if (u >= dense) continue;
+        const int n = (int)(u % n_blk);
+        const int kc = (int)((u / n_blk) % CH);
+        const int kt = (int)(u / ((int64_t)n_blk * CH));
+        const int c = n0 + n;
+        const int f0 = kt * 16 + kc * 4;
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = (c < k_data && f0 + j < F_out) ? w_ext[(int64_t)c * F_out + f0 + j] : 0.f;
+            h[j] = tf32_hi(v[j]);
+            l[j] = v[j] - h[j];
+        }
+        float4 *img = wp + (int64_t)b * per_block + (int64_t)kt * 2 * CH * n_blk;
+        img[(int64_t)kc * n_blk + n] = make_float4(h[0], h[1], h[2], h[3]);
+        img[(int64_t)(CH + kc) * n_blk + n] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, weight gradient:  dW_ext = A_ext^T @ dY  -- the reduction runs over the graph rows.
+// Both operands are contiguous along their M / N dimension in memory (A_ext rows hold the ext columns, dY rows the
+// output features), so they go to shared memory MN-major: core matrix = 8 k (rows of 16 B) x 4 consecutive m/n,
+// cores of one k-group TCW_SBO apart along M/N (128 B + 16 B pad: the producers' 16-byte stores of consecutive
+// cores hit disjoint banks), k-groups LBO apart; one MMA (K = 8 tf32) consumes exactly one k-group.  The
+// producers therefore load float4 along M/N (coalesced) and never transpose.  Grid = (ext-column tiles of 128) x
+// (row splits); every CTA writes its 128 x F_out partial, a second kernel sums the splits in fixed order.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t TCW_SBO = 144;
+constexpr int TCW_BK = 16;   // graph rows per stage = 2 k-groups
+
+// `mode` (MN_MAJOR only; experiments behind pg_debug_tcw_layout): 1 = no swizzle, cores TCW_SBO apart; 2 = same with the
+// descriptor's LBO / SBO fields swapped; 3 = no swizzle, dense cores (128 B); 4 = 128-byte swizzle (atoms of 32 m/n x 8 k).
+template <bool MN_MAJOR>
+__global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A, const float *__restrict__ dy, int64_t lddy, int F_out,
+                                                                       int64_t rows_per_split, float *__restrict__ partial,
+                                                                       int *__restrict__ error_flag, int mode) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned (swizzle atoms)
+    __shared__ __align__(8) uint64_t full[2], empty[2], done;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ volatile int bail;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = (int)blockIdx.x * TC_BM;                         // first ext column of this tile
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_end = min(r_begin + rows_per_split, A.M);
+    const int k_tiles = (int)((r_end - r_begin + TCW_BK - 1) / TCW_BK);
+    const int nb4 = F_out / 4;                                       // 16-byte cores along N
+    const uint32_t core = mode == 3 ? 128u : TCW_SBO;               // stride of the 16-byte-wide cores along M / N (modes 1-3)
+    const uint32_t a_lbo = mode == 4 ? (TC_BM / 32) * 1024u : (TC_BM / 4) * core;        // stride of the k-groups
+    const uint32_t b_lbo = mode == 4 ? (uint32_t)(F_out / 32) * 1024u : (uint32_t)nb4 * core;
+    const uint32_t a_bytes = 2 * a_lbo, b_bytes = 2 * b_lbo;
+    auto mn_off = [&](int k, int c4, uint32_t kg_stride) -> uint32_t {   // byte offset of (row k, columns 4 c4 .. 4 c4 + 3) in an operand tile
+        const uint32_t kg = (uint32_t)k >> 3, kr = (uint32_t)k & 7u;
+        if (mode == 4) return kg * kg_stride + ((uint32_t)c4 >> 3) * 1024u + kr * 128u + ((((uint32_t)c4 & 7u) ^ kr) << 4);
+        return kg * kg_stride + (uint32_t)c4 * core + kr * 16u;
+    };
+    auto mn_desc = [&](uint32_t saddr, uint32_t kg_stride) -> uint64_t {
+        if (mode == 4) return umma_desc(saddr, 1024u, kg_stride) | (2ull << 61);   // SWIZZLE_128B: LBO = atom stride along M/N, SBO = k-group stride
+        if (mode == 2) return umma_desc(saddr, core, kg_stride);
+        return umma_desc(saddr, kg_stride, core);
+    };
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;          // A_hi | A_lo | B_hi | B_lo
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < F_out) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        mbar_init(&full[0], TC_PRODUCERS / 32);
+        mbar_init(&full[1], TC_PRODUCERS / 32);
+        mbar_init(&empty[0], 1);
+        mbar_init(&empty[1], 1);
+        mbar_init(&done, 1);
+        bail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = tmem_base_slot;
+    // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), N = F_out, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MN_MAJOR ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(F_out >> 3) << 17) |
+                           ((uint32_t)(TC_BM >> 4) << 24);
+    // K-major alternative (MN_MAJOR = false): the producers transpose instead -- a thread gathers 4 consecutive graph rows of one
+    // column (scalar loads, coalesced across the warp) into one 16-byte chunk of the layout gemm_tc's forward uses.
+    const uint32_t kb_lbo = (uint32_t)(F_out + 1) * 16u;
+
+    if (warp < TC_PRODUCERS / 32) {
+        // ------------------------------------------------------------------ producers: A (2 float4) and B (<= 4 float4) per thread and k-tile
+        int a_k[2], a_col[2], b_k[4], b_col[4];
+        uint32_t a_off[2], b_off[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = j * TC_PRODUCERS + tid;
+            a_k[j] = idx >> 5;
+            const int c4 = idx & 31;
+            a_col[j] = m0 + 4 * c4;
+            a_off[j] = mn_off(a_k[j], c4, a_lbo);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = j * TC_PRODUCERS + tid;
+            b_k[j] = idx < TCW_BK * nb4 ? idx / nb4 : -1;
+            const int c4 = idx < TCW_BK * nb4 ? idx % nb4 : 0;
+            b_col[j] = 4 * c4;
+            b_off[j] = mn_off(max(b_k[j], 0), c4, b_lbo);
+        }
+        if (!MN_MAJOR) {   // (column, chunk of 4 rows) slots instead of (row, 4 columns)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int idx = j * TC_PRODUCERS + tid;
+                a_k[j] = 4 * (idx >> 7);
+                a_col[j] = m0 + (idx & 127);
+                a_off[j] = (uint32_t)(idx >> 7) * TC_LBO_A + (uint32_t)(idx & 127) * 16u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = j * TC_PRODUCERS + tid;
+                const bool on = idx < 4 * F_out;
+                b_k[j] = on ? 4 * (idx / F_out) : -1;
+                b_col[j] = on ? idx % F_out : 0;
+                b_off[j] = (uint32_t)(on ? idx / F_out : 0) * kb_lbo + (uint32_t)b_col[j] * 16u;
+            }
+        }
+        auto load_tile = [&](int t, float4 (&va)[2], float4 (&vb)[4]) {
+            const int64_t r0 = r_begin + (int64_t)t * TCW_BK;
+            if (MN_MAJOR) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) va[j] = A.at4(r0 + a_k[j], a_col[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = r0 + b_k[j];
+                    vb[j] = (b_k[j] >= 0 && r < A.M) ? __ldg(reinterpret_cast<const float4 *>(dy + r * lddy + b_col[j]))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t r = r0 + a_k[j];
+                    va[j] = make_float4(A.at(r, a_col[j]), A.at(r + 1, a_col[j]), A.at(r + 2, a_col[j]), A.at(r + 3, a_col[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = r0 + b_k[j];
+                    float e[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) e[q] = (b_k[j] >= 0 && r + q < A.M) ? __ldg(dy + (r + q) * lddy + b_col[j]) : 0.f;
+                    vb[j] = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+        };
+        auto split_store = [&](uint8_t *hi_base, uint8_t *lo_base, uint32_t off, const float4 &x4) {
+            const float4 hi = make_float4(tf32_hi(x4.x), tf32_hi(x4.y), tf32_hi(x4.z), tf32_hi(x4.w));
+            const float4 lo = make_float4(x4.x - hi.x, x4.y - hi.y, x4.z - hi.z, x4.w - hi.w);
+            *reinterpret_cast<float4 *>(hi_base + off) = hi;
+            *reinterpret_cast<float4 *>(lo_base + off) = lo;
+        };
+        float4 va[2][2], vb[2][4];   // two k-tiles of global loads in flight
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            if (d < k_tiles) load_tile(d, va[d], vb[d]);
+        }
+        for (int kt = 0; kt < k_tiles; kt += 2) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int t = kt + d;
+                if (t < k_tiles) {
+                    uint8_t *st = smem + (size_t)d * stage_bytes;     // stage == t & 1 == d
+                    if (t >= 2 && !bail) {
+                        if (!mbar_wait(&empty[d], (uint32_t)(((t >> 1) - 1) & 1))) bail = 1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) split_store(st, st + a_bytes, a_off[j], va[d][j]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (b_k[j] >= 0) split_store(st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, b_off[j], vb[d][j]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[d]);
+                    if (t + 2 < k_tiles) load_tile(t + 2, va[d], vb[d]);
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issue (one thread)
+        for (int kt = 0; kt < k_tiles; ++kt) {
+            const int s = kt & 1;
+            if (bail) break;
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+            if (!mbar_wait(&full[s], (uint32_t)((kt >> 1) & 1))) { bail = 1; break; }
+            fence_after_sync();
+#pragma unroll
+            for (int ks = 0; ks < TCW_BK / 8; ++ks) {  // one MMA = one k-group of 8 graph rows
+                const uint64_t dah = MN_MAJOR ? mn_desc(a_hi + ks * a_lbo, a_lbo) : umma_desc(a_hi + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
+                const uint64_t dal = MN_MAJOR ? mn_desc(a_lo + ks * a_lbo, a_lbo) : umma_desc(a_lo + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
+                const uint64_t dbh = MN_MAJOR ? mn_desc(b_hi + ks * b_lbo, b_lbo) : umma_desc(b_hi + ks * 2 * kb_lbo, kb_lbo, 128);
+                const uint64_t dbl = MN_MAJOR ? mn_desc(b_lo + ks * b_lbo, b_lbo) : umma_desc(b_lo + ks * 2 * kb_lbo, kb_lbo, 128);
+                umma_tf32(tmem_d, dah, dbh, idesc, (kt | ks) != 0);
+                umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                umma_tf32(tmem_d, dal, dbh, idesc, 1);
+            }
+            umma_commit(&empty[s]);
+        }
+        umma_commit(&done);
+    }
+    // ---------------------------------------------------------------------- epilogue: TMEM -> this split's partial
+    if (warp < TC_PRODUCERS / 32) {
+        if (!bail && !mbar_wait(&done, 0)) bail = 1;
+        fence_after_sync();
+        if (!bail) {
+            const int quad = warp & 3;
+            const int m = m0 + quad * 32 + lane;
+            const int half_cols = ((F_out / 16 + 1) / 2) * 16;
+            const int c_begin = (warp < 4) ? 0 : half_cols, c_end = (warp < 4) ? half_cols : F_out;
+            float *out = partial + ((int64_t)blockIdx.y * A.k_ext + m) * F_out;
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+                if (m < A.k_ext) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4 *>(out + c0 + q * 4) = k_tiles > 0
+                            ? make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (bail && tid == 0) atomicExch(error_flag, 1);
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+__global__ void __launch_bounds__(256) tc_reduce_splits_kernel(const float *__restrict__ partial, int splits, int64_t numel,
+                                                               float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * numel + i];  // fixed order
+        out[i] = s;
+    }
+}
+
+template <int CHUNKS, class AOp, class Epi>
+int launch_rows_gemm(const AOp &A, const Epi &epi, const float4 *wp, int n_full, int n_total, int k_tiles, int *err, dim3 grid,
+                     size_t smem, cudaStream_t st) {
+    static bool attr_set = false;   // one flag per instantiation
+    if (!attr_set) {
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_rows_gemm_kernel<CHUNKS, AOp, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          CHUNKS == 4 ? 110 * 1024 : 200 * 1024));
+        if (CHUNKS == 4)
+            PG_CUDA_CALL(cudaFuncSetAttribute(tc_rows_gemm_kernel<CHUNKS, AOp, Epi>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    tc_rows_gemm_kernel<CHUNKS, AOp, Epi><<<grid, TC_THREADS2, smem, st>>>(A, epi, wp, n_full, n_total, k_tiles, err);
+    return PG_OK;
 }
 
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
@@ -383,19 +641,12 @@ extern "C" int pg_layer_gemm_fwd_tc(const float *d_z, int64_t ldz, const float *
     }
     const size_t stage = 2 * (size_t)chunks * TC_LBO_A + 2 * (size_t)chunks * F_out * 16;
     const size_t smem = 2 * stage;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PG_CUDA_CALL(cudaFuncSetAttribute(layer_gemm_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        PG_CUDA_CALL(cudaFuncSetAttribute(layer_gemm_fwd_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        PG_CUDA_CALL(cudaFuncSetAttribute(layer_gemm_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    const unsigned grid = (unsigned)pg_ceil_div(num_rows, TC_BM);
-    if (chunks == 4)
-        layer_gemm_fwd_tc_kernel<4><<<grid, TC_THREADS2, smem, st>>>(A, wp, F_out, kt, d_constant, ldconst, add_identity, slope, d_h, ldh, err);
-    else
-        layer_gemm_fwd_tc_kernel<8><<<grid, TC_THREADS2, smem, st>>>(A, wp, F_out, kt, d_constant, ldconst, add_identity, slope, d_h, ldh, err);
-    PG_CUDA_LAUNCH_CHECK("layer_gemm_fwd_tc_kernel");
+    EpiFwdTc epi{d_constant, d_x, ldconst, ldx, add_identity, slope, d_h, ldh};
+    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), 1, 1);
+    int rc = chunks == 4 ? launch_rows_gemm<4>(A, epi, wp, F_out, F_out, kt, err, grid, smem, st)
+                         : launch_rows_gemm<8>(A, epi, wp, F_out, F_out, kt, err, grid, smem, st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (forward)");
     return PG_OK;
 }
 
@@ -407,6 +658,152 @@ extern "C" int pg_layer_gemm_fwd_tc_check(const void *d_ws, int F_in, int F_out,
     PG_CUDA_CALL(cudaStreamSynchronize(pg_cu(stream)));
     if (flag) {
         pg_set_error("pg_layer_gemm_fwd_tc: tensor-core pipeline watchdog expired (MMA never signalled completion)");
+        return PG_ECUDA;
+    }
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- backward on tensor cores
+namespace {
+struct BwdDataPlan { int k_data, k_tiles, n_full, blocks; size_t image_bytes; };
+inline BwdDataPlan bwd_data_plan(int F_in, int F_out, int has_res) {
+    BwdDataPlan p;
+    p.k_data = 3 * F_in + (has_res ? F_in : 0);
+    p.k_tiles = (F_out + 15) / 16;
+    const int padded = (p.k_data + 15) / 16 * 16;
+    p.n_full = padded < 256 ? padded : 256;
+    p.blocks = (p.k_data + p.n_full - 1) / p.n_full;
+    p.image_bytes = (size_t)p.blocks * p.k_tiles * 2 * 4 * p.n_full * sizeof(float4);
+    return p;
+}
+struct BwdWeightPlan { int k_ext, m_tiles, splits; int64_t rows_per_split; };
+inline BwdWeightPlan bwd_weight_plan(int64_t num_rows, int F_in, int has_res) {
+    BwdWeightPlan p;
+    p.k_ext = k_ext_of(F_in, has_res);
+    p.m_tiles = (p.k_ext + TC_BM - 1) / TC_BM;
+    int64_t s = (2 * PG_NUM_SMS) / p.m_tiles;                 // two CTAs per SM
+    const int64_t max_s = pg_ceil_div(num_rows, 512);         // >= 32 k-tiles per CTA so the epilogue amortises
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    p.rows_per_split = pg_ceil_div(pg_ceil_div(num_rows, s), TCW_BK) * TCW_BK;
+    p.splits = (int)pg_ceil_div(num_rows, p.rows_per_split);
+    if (p.splits < 1) p.splits = 1;
+    return p;
+}
+}  // namespace
+
+extern "C" size_t pg_layer_gemm_bwd_data_tc_ws_bytes(int F_in, int F_out, int has_res) {
+    return bwd_data_plan(F_in, F_out, has_res).image_bytes + 256;
+}
+
+extern "C" int pg_layer_gemm_bwd_data_tc(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z, int64_t ldz,
+                                         const float *d_gate_a, const float *d_gate_b, const float *d_gate_c, int gate_stride,
+                                         int64_t num_rows, int F_in, int F_out, int has_res, float *d_dz, int64_t lddz, float *d_dxres,
+                                         int64_t lddxres, float *d_dgate, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 1 && F_out >= 1 && (gate_stride == 0 || gate_stride == 1), "pg_layer_gemm_bwd_data_tc: bad shape");
+    PG_CHECK_ARG(pg_layer_gemm_fwd_tc_supported(F_in, F_out), "pg_layer_gemm_bwd_data_tc: needs F_in %% 4 == 0, F_out %% 16 == 0, F_out <= 256");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_dy && d_w_ext && d_z && d_gate_a && d_gate_b && d_gate_c && d_dz && d_dgate && d_ws, "pg_layer_gemm_bwd_data_tc: null buffer");
+    PG_CHECK_ARG(!has_res || d_dxres, "pg_layer_gemm_bwd_data_tc: has_res needs d_dxres");
+    PG_CHECK_ARG(lddy >= F_out && ldz >= 3 * (int64_t)F_in && lddz >= 3 * (int64_t)F_in && (!has_res || lddxres >= F_in),
+                 "pg_layer_gemm_bwd_data_tc: bad stride");
+    PG_CHECK_ARG(al16(d_dy) && lddy % 4 == 0 && al16(d_dz) && lddz % 4 == 0 && (!has_res || (al16(d_dxres) && lddxres % 4 == 0)) && al16(d_ws),
+                 "pg_layer_gemm_bwd_data_tc: operands must be 16-byte aligned with row strides %% 4 == 0");
+    const BwdDataPlan p = bwd_data_plan(F_in, F_out, has_res);
+    const size_t need = p.image_bytes + 256;
+    if (ws_bytes < need) {
+        pg_set_error("pg_layer_gemm_bwd_data_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    float4 *wp = reinterpret_cast<float4 *>(d_ws);
+    int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
+    PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    {
+        const int64_t total = (int64_t)p.blocks * p.k_tiles * 4 * p.n_full;
+        wprep_t_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w_ext, p.k_data, F_out, p.k_tiles, p.n_full, p.blocks, wp);
+        PG_CUDA_LAUNCH_CHECK("wprep_t_kernel");
+    }
+    APlainTc A{d_dy, lddy, num_rows, F_out};
+    EpiBwdDataTc epi{d_dz, d_dxres, lddz, lddxres, 3 * F_in, p.k_data};
+    const size_t stage = 2 * (size_t)4 * TC_LBO_A + 2 * (size_t)4 * p.n_full * 16;
+    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), (unsigned)p.blocks, 1);
+    int rc = launch_rows_gemm<4>(A, epi, wp, p.n_full, p.k_data, p.k_tiles, err, grid, 2 * stage, st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (data gradient)");
+    return pg_launch_gate_grad(d_dz, lddz, d_z, ldz, d_dy, lddy, d_w_ext, d_gate_a, d_gate_b, d_gate_c, gate_stride, num_rows, F_in, F_out,
+                               p.k_data, d_dgate, st);
+}
+
+// operand layout of the weight-gradient kernel: 0 = K-major (transposing producers), 1..4 = MN-major variants (see the kernel)
+static int g_tcw_layout = 0;
+extern "C" void pg_debug_tcw_layout(int mode) { g_tcw_layout = mode; }
+
+extern "C" size_t pg_layer_gemm_bwd_weight_tc_ws_bytes(int64_t num_rows, int F_in, int F_out, int has_res) {
+    const BwdWeightPlan p = bwd_weight_plan(num_rows, F_in, has_res);
+    return pg_align_up((size_t)p.splits * p.k_ext * F_out * sizeof(float), 256) + 256;
+}
+
+extern "C" int pg_layer_gemm_bwd_weight_tc(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx, const float *d_gate_a,
+                                           const float *d_gate_b, const float *d_gate_c, int gate_stride, const float *d_dy,
+                                           int64_t lddy, int64_t num_rows, int F_in, int F_out, int has_res, float *d_dw_ext,
+                                           void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 1 && F_out >= 1 && (gate_stride == 0 || gate_stride == 1), "pg_layer_gemm_bwd_weight_tc: bad shape");
+    PG_CHECK_ARG(pg_layer_gemm_fwd_tc_supported(F_in, F_out), "pg_layer_gemm_bwd_weight_tc: needs F_in %% 4 == 0, F_out %% 16 == 0, F_out <= 256");
+    PG_CHECK_ARG(d_dw_ext, "pg_layer_gemm_bwd_weight_tc: null output");
+    cudaStream_t st = pg_cu(stream);
+    const BwdWeightPlan p = bwd_weight_plan(num_rows, F_in, has_res);
+    const int64_t numel = (int64_t)p.k_ext * F_out;
+    if (num_rows == 0) {
+        PG_CUDA_CALL(cudaMemsetAsync(d_dw_ext, 0, (size_t)numel * sizeof(float), st));
+        return PG_OK;
+    }
+    PG_CHECK_ARG(d_z && d_gate_a && d_gate_b && d_gate_c && d_dy && d_ws && (!has_res || d_x), "pg_layer_gemm_bwd_weight_tc: null buffer");
+    PG_CHECK_ARG(al16(d_z) && ldz % 4 == 0 && (!has_res || (al16(d_x) && ldx % 4 == 0)) && al16(d_dy) && lddy % 4 == 0 && al16(d_ws),
+                 "pg_layer_gemm_bwd_weight_tc: operands must be 16-byte aligned with row strides %% 4 == 0");
+    PG_CHECK_ARG(ldz >= 3 * (int64_t)F_in && lddy >= F_out, "pg_layer_gemm_bwd_weight_tc: bad stride");
+    const size_t need = pg_layer_gemm_bwd_weight_tc_ws_bytes(num_rows, F_in, F_out, has_res);
+    if (ws_bytes < need) {
+        pg_set_error("pg_layer_gemm_bwd_weight_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+        return PG_EWORKSPACE;
+    }
+    AExtTc A;
+    A.z = d_z; A.x = d_x; A.ga = d_gate_a; A.gb = d_gate_b; A.gc = d_gate_c; A.gate_stride = gate_stride;
+    A.ldz = ldz; A.ldx = ldx; A.M = num_rows; A.F_in = F_in; A.has_res = has_res;
+    A.k_data = 3 * F_in + (has_res ? F_in : 0);
+    A.k_ext = p.k_ext;
+    float *partial = reinterpret_cast<float *>(d_ws);
+    int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
+    PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    const size_t stage = 2 * (size_t)2 * (TC_BM / 4) * TCW_SBO + 2 * (size_t)2 * (F_out / 4) * TCW_SBO;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)p.m_tiles, (unsigned)p.splits, 1);
+    int mode = g_tcw_layout;
+    if (mode == 4 && F_out % 32 != 0) mode = 0;   // swizzle atoms are 32 columns wide
+    if (mode != 0)
+        tc_bwd_weight_kernel<true><<<grid, TC_THREADS2, 2 * stage + 1024, st>>>(A, d_dy, lddy, F_out, p.rows_per_split, partial, err, mode);
+    else
+        tc_bwd_weight_kernel<false><<<grid, TC_THREADS2, 2 * stage + 1024, st>>>(A, d_dy, lddy, F_out, p.rows_per_split, partial, err, 0);
+    PG_CUDA_LAUNCH_CHECK("tc_bwd_weight_kernel");
+    tc_reduce_splits_kernel<<<(unsigned)pg_ceil_div(numel, 256), 256, 0, st>>>(partial, p.splits, numel, d_dw_ext);
+    PG_CUDA_LAUNCH_CHECK("tc_reduce_splits_kernel");
+    return PG_OK;
+}
+
+// watchdog flag of the last tensor-core call that used this workspace; `need` = the ws_bytes query of that call (host sync; tests only)
+extern "C" int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream) {
+    int flag = 0;
+    PG_CUDA_CALL(cudaMemcpyAsync(&flag, reinterpret_cast<const char *>(d_ws) + need - 256, sizeof(int), cudaMemcpyDeviceToHost, pg_cu(stream)));
+    PG_CUDA_CALL(cudaStreamSynchronize(pg_cu(stream)));
+    if (flag) {
+        pg_set_error("tensor-core pipeline watchdog expired (an MMA never signalled completion)");
         return PG_ECUDA;
     }
     return PG_OK;

@@ -195,6 +195,7 @@ import os as _os
 
 TC_MODE = _os.environ.get("PGB200_TC", "auto")
 TC_MIN_WIDTH, TC_MIN_ROWS = 128, 4096
+TC_BWD_WEIGHT_MIN_ROWS = 65536   # the weight gradient splits the ROWS over CTAs: below this the SIMT kernel (more, smaller tiles) is faster
 
 
 def _use_tensor_cores(n: int, f_in: int, f_out: int) -> bool:
@@ -222,7 +223,8 @@ class _DirectGCNFused(torch.autograd.Function):
         if const_rows is not None:
             const_rows = const_rows.contiguous().float()
         ldc = const_rows.stride(0) if const_rows is not None else 0
-        if _use_tensor_cores(n, f_in, f_out) and ldc % 4 == 0:
+        use_tc = _use_tensor_cores(n, f_in, f_out) and ldc % 4 == 0
+        if use_tc:
             ws = nat.workspace(nat.query("pg_layer_gemm_fwd_tc_ws_bytes", f_in, f_out, int(has_res)), x.device)
             nat.call("pg_layer_gemm_fwd_tc", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
                      gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), ldc, n, f_in, f_out, int(has_res), int(add_identity),
@@ -232,6 +234,7 @@ class _DirectGCNFused(torch.autograd.Function):
                      gate_stride, nat.ptr(w_ext), nat.ptr(const_rows), ldc, n, f_in, f_out, int(has_res), int(add_identity),
                      float(slope), nat.ptr(h), h.stride(0), nat.stream_ptr())
         ctx.save_for_backward(x, ga, gb, gc, w_ext, z, h)
+        ctx.use_tc = use_tc
         ctx.struct, ctx.has_res, ctx.add_identity, ctx.slope = struct, bool(has_res), bool(add_identity), float(slope)
         ctx.gate_stride, ctx.has_const = gate_stride, const_rows is not None
         return h
@@ -251,17 +254,23 @@ class _DirectGCNFused(torch.autograd.Function):
         has_res = int(ctx.has_res)
         # dW_ext = A_ext^T dY
         dw = torch.empty_like(w_ext)
-        ws = nat.workspace(nat.query("pg_layer_gemm_bwd_weight_ws_bytes", n, f_in, f_out, has_res), x.device)
-        nat.call("pg_layer_gemm_bwd_weight", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb),
+        tc = "_tc" if ctx.use_tc and (n >= TC_BWD_WEIGHT_MIN_ROWS or TC_MODE == "force") else ""
+        ws = nat.workspace(nat.query(f"pg_layer_gemm_bwd_weight{tc}_ws_bytes", n, f_in, f_out, has_res), x.device)
+        nat.call(f"pg_layer_gemm_bwd_weight{tc}", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb),
                  nat.ptr(gc), ctx.gate_stride, nat.ptr(dy), dy.stride(0), n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws),
                  ws.numel(), st)
         # dA = dY W_ext^T  -> dZ (gated), dXres, dgates
         dz = torch.empty_like(z)
         dxres = torch.empty_like(x) if ctx.has_res else None
         dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
-        nat.call("pg_layer_gemm_bwd_data", nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), nat.ptr(ga),
-                 nat.ptr(gb), nat.ptr(gc), ctx.gate_stride, n, f_in, f_out, has_res, nat.ptr(dz), dz.stride(0),
-                 nat.ptr(dxres), dxres.stride(0) if dxres is not None else 0, nat.ptr(dgate), st)
+        args = (nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
+                ctx.gate_stride, n, f_in, f_out, has_res, nat.ptr(dz), dz.stride(0), nat.ptr(dxres),
+                dxres.stride(0) if dxres is not None else 0, nat.ptr(dgate))
+        if ctx.use_tc:
+            ws2 = nat.workspace(nat.query("pg_layer_gemm_bwd_data_tc_ws_bytes", f_in, f_out, has_res), x.device)
+            nat.call("pg_layer_gemm_bwd_data_tc", *args, nat.ptr(ws2), ws2.numel(), st)
+        else:
+            nat.call("pg_layer_gemm_bwd_data", *args, st)
         dx = None
         if ctx.needs_input_grad[0]:
             init = dxres if ctx.has_res else (dy if ctx.add_identity else None)

@@ -591,6 +591,61 @@ def test_layer_gemm_fwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
     assert rel_err(h.cpu().numpy(), h2.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("n,f_in,f_out,has_res,vec_gate", [(1000, 64, 256, 1, 1), (4096, 256, 256, 0, 1), (777, 128, 128, 1, 1),
+                                                           (5000, 128, 64, 1, 0), (300, 32, 16, 1, 1), (129, 4, 32, 0, 1),
+                                                           (20000, 64, 128, 1, 1)])
+def test_layer_gemm_bwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
+    """tcgen05 (3 x TF32 split) data and weight gradients against the fp64 spec and the SIMT kernels
+    (same contracts): K-major dY rows x pre-split W_ext^T image in column blocks (data), MN-major
+    producer-built operands with row splits (weights)."""
+    g = torch.Generator().manual_seed(7 * n + f_in)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    z, x, dy = rnd(n, 3 * f_in), rnd(n, f_in), rnd(n, f_out)
+    gates = [rnd(n) if vec_gate else rnd(1) for _ in range(3)]
+    k_ext = 3 * f_in + (f_in if has_res else 0) + 3 + (1 if has_res else 0)
+    w_ext = rnd(k_ext, f_out) * 0.2
+    gs = 1 if vec_gate else 0
+    D = lambda t: t.double()
+    dz_ref, dxres_ref, dgate_ref = (torch.empty(n, 3 * f_in, dtype=torch.float64), torch.empty(n, f_in, dtype=torch.float64),
+                                    torch.empty(3, n, dtype=torch.float64))
+    spec.pg_layer_gemm_bwd_data(D(dy), f_out, D(w_ext), D(z), 3 * f_in, *[D(t) for t in gates], gs, n, f_in, f_out, has_res, dz_ref,
+                                3 * f_in, dxres_ref, f_in, dgate_ref)
+    dw_ref = torch.empty(k_ext, f_out, dtype=torch.float64)
+    spec.pg_layer_gemm_bwd_weight(D(z), 3 * f_in, D(x), f_in, *[D(t) for t in gates], gs, D(dy), f_out, n, f_in, f_out, has_res, dw_ref, None, 0)
+    d = lambda t: t.to(DEV).contiguous()
+    zd, xd, wd, dyd = d(z), d(x), d(w_ext), d(dy)
+    gd = [d(t) for t in gates]
+    st = nat.stream_ptr()
+    nan = lambda *s: torch.full(s, float("nan"), device=DEV)
+    # data gradient
+    dz, dxres, dgate = nan(n, 3 * f_in), nan(n, f_in), nan(3, n)
+    need = nat.query("pg_layer_gemm_bwd_data_tc_ws_bytes", f_in, f_out, has_res)
+    ws = _ws(need)
+    nat.call("pg_layer_gemm_bwd_data_tc", nat.ptr(dyd), f_out, nat.ptr(wd), nat.ptr(zd), 3 * f_in, nat.ptr(gd[0]), nat.ptr(gd[1]),
+             nat.ptr(gd[2]), gs, n, f_in, f_out, has_res, nat.ptr(dz), 3 * f_in, nat.ptr(dxres), f_in, nat.ptr(dgate), nat.ptr(ws), ws.numel(), st)
+    nat.call("pg_tc_check", nat.ptr(ws), need, st)
+    assert rel_err(dz.cpu().numpy(), dz_ref.numpy()) <= 2e-5
+    assert rel_err(dgate.cpu().numpy(), dgate_ref.numpy()) <= 2e-5
+    if has_res:
+        assert rel_err(dxres.cpu().numpy(), dxres_ref.numpy()) <= 2e-5
+    # weight gradient
+    dw = nan(k_ext, f_out)
+    need = nat.query("pg_layer_gemm_bwd_weight_tc_ws_bytes", n, f_in, f_out, has_res)
+    ws = _ws(need)
+    nat.call("pg_layer_gemm_bwd_weight_tc", nat.ptr(zd), 3 * f_in, nat.ptr(xd), f_in, nat.ptr(gd[0]), nat.ptr(gd[1]), nat.ptr(gd[2]), gs,
+             nat.ptr(dyd), f_out, n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws), ws.numel(), st)
+    nat.call("pg_tc_check", nat.ptr(ws), need, st)
+    assert rel_err(dw.cpu().numpy(), dw_ref.numpy()) <= 2e-5
+    # and against the SIMT kernels
+    dz2, dxres2, dgate2, dw2 = nan(n, 3 * f_in), nan(n, f_in), nan(3, n), nan(k_ext, f_out)
+    nat.call("pg_layer_gemm_bwd_data", nat.ptr(dyd), f_out, nat.ptr(wd), nat.ptr(zd), 3 * f_in, nat.ptr(gd[0]), nat.ptr(gd[1]),
+             nat.ptr(gd[2]), gs, n, f_in, f_out, has_res, nat.ptr(dz2), 3 * f_in, nat.ptr(dxres2), f_in, nat.ptr(dgate2), st)
+    ws = _ws(nat.query("pg_layer_gemm_bwd_weight_ws_bytes", n, f_in, f_out, has_res))
+    nat.call("pg_layer_gemm_bwd_weight", nat.ptr(zd), 3 * f_in, nat.ptr(xd), f_in, nat.ptr(gd[0]), nat.ptr(gd[1]), nat.ptr(gd[2]), gs,
+             nat.ptr(dyd), f_out, n, f_in, f_out, has_res, nat.ptr(dw2), nat.ptr(ws), ws.numel(), st)
+    assert rel_err(dz.cpu().numpy(), dz2.cpu().numpy()) <= 2e-5 and rel_err(dw.cpu().numpy(), dw2.cpu().numpy()) <= 2e-5
+
+
 def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     """Force the tcgen05 dense transform inside the model and re-check the reference goldens
     (model_refgraph has widths 24/40/16/8 -> only the 16-wide layer qualifies; the C2-shaped oracle

@@ -28,6 +28,10 @@ def main():
             seqs = int(sys.argv[sys.argv.index("--seqs") + 1]) if "--seqs" in sys.argv else 2_000_000
             out = bench.build_scale_leg(pipe, None, n_level, seqs, iters=1, normalise=False)
             print({k: v for k, v in out.items() if not k.startswith("_")})
+    if "c3step" in which:   # config C3's DirectGCN step (3 layers, hidden 256) on the n=4 graph
+        out = bench.build_scale_leg(pipe, None, 4, 2_000_000, iters=1, normalise=True)
+        nodes, res = out.pop("_graph")
+        print(bench.c3_directgcn_leg(pipe, nodes, res, iters=1))
     if "spmm" in which:
         out = bench.spmm_large_leg(pipe, 6548.5, log2, iters=2)
         print({k: (v if not isinstance(v, dict) else {a: round(b, 3) for a, b in v.items()}) for k, v in out.items()})
