@@ -561,7 +561,7 @@ def c3_directgcn_leg(pipe, nodes, res, dims=(64, 256, 256, 256), classes=21, ite
             "ms_eval_forward": ms_fwd, "ms_train_fwd_bwd_adam": ms_step - ms_fwd,
             "edges_per_s_step": 3 * P * L * 3 / (ms_step * 1e-3), "edges_per_s_forward": 3 * P * L / (ms_fwd * 1e-3),
             "dense_flops_per_layer_fwd": [2.0 * nodes * (3 * a + 3 + (a + 1 if a != b else 0)) * b for a, b in zip(dims[:-1], dims[1:])],
-            "mode": "eager (autograd over libpgb200 kernels), tcgen05 forward transform, SIMT backward GEMMs"}
+            "mode": "eager (autograd over libpgb200 kernels); dense transform, data gradient and weight gradient on tcgen05 (3 x TF32)"}
 
 
 def phase_breakdown(pipe, reps=5):

@@ -30,6 +30,11 @@ def test_header_symbols_exported_and_bound():
     assert nat.query("pg_ngram_count_ws_bytes", 3, 21) >= 256 + 21 ** 4 * 8 + tables   # 8-bit lanes: + drain scratch
     assert nat.query("pg_ngram_count_ws_bytes", 1, 21) == 256 + tables          # strict lanes: status word + tables
     assert nat.query("pg_ngram_count_ws_bytes", 5, 21) == 256                   # 85.8 M bins: L2 REDs, no workspace
+    # ... unless the caller sizes it for the partitioned variant: bucket entries (4 B / window) + scratch table + lists
+    assert nat.query("pg_ngram_count_ws_bytes_for", 5, 21, 1 << 28) > 4 * (1 << 28) + 21 ** 6 * 8
+    assert nat.query("pg_ngram_count_ws_bytes_for", 3, 21, 1 << 28) == nat.query("pg_ngram_count_ws_bytes", 3, 21)
+    assert nat.query("pg_layer_gemm_bwd_data_tc_ws_bytes", 256, 256, 0) >= 3 * 16 * 2 * 4 * 256 * 16
+    assert nat.query("pg_layer_gemm_bwd_weight_tc_ws_bytes", 168_000, 256, 256, 0) >= 771 * 256 * 4
 
 
 def test_argument_errors_are_reported_not_crashed():
