@@ -49,6 +49,25 @@ const char *pg_last_error(void);
 unsigned long long pg_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Row f3: FASTA text -> corpus buffer on the HOST (no CUDA call; replaces the Python line loop of
+ * data_utils.py:182-213 fused with the padding rule of data_builder.py:29-35,97-102).
+ * pg_fasta_open mmaps the file (NULL + pg_last_error() on failure).  pg_fasta_next_chunk packs whole records
+ * "[' ' before global sequence #0] SEQUENCE ' ' 0xFF" into out[0, cap) until the next record would not fit and
+ * returns the bytes written (0 = end of file) or a negative code; records are dealt to `world` ranks in blocks
+ * of `block` records (rank 0 of 1 = everything).  Same record rules as the reference parser, including its
+ * early stop at a bare ">" header (pg_fasta_stopped_early); sequence bytes >= 0x80 are refused.
+ * ---------------------------------------------------------------------------------------- */
+#define PG_FASTA_ETOOSMALL (-10) /* not even one record fits the caller's buffer */
+#define PG_FASTA_ENONASCII (-11) /* non-ASCII byte in sequence text */
+typedef struct pg_fasta_reader pg_fasta_reader;
+pg_fasta_reader *pg_fasta_open(const char *path);
+void pg_fasta_close(pg_fasta_reader *reader);
+int64_t pg_fasta_file_bytes(const pg_fasta_reader *reader);
+int64_t pg_fasta_records(const pg_fasta_reader *reader); /* records emitted so far, all ranks */
+int pg_fasta_stopped_early(const pg_fasta_reader *reader);
+int64_t pg_fasta_next_chunk(pg_fasta_reader *reader, uint8_t *out, int64_t cap, int rank, int world, int block);
+
+/* ------------------------------------------------------------------------------------------
  * Hot path A, part 1: n-gram transition counting
  * ---------------------------------------------------------------------------------------- */
 

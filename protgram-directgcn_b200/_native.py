@@ -17,6 +17,9 @@ class NativeError(RuntimeError):
     pass
 
 
+PG_FASTA_ETOOSMALL, PG_FASTA_ENONASCII = -10, -11   # include/pgb200.h
+
+
 _P = c_void_p
 _SIGS = {
     "pg_version": (c_int, []),
@@ -24,6 +27,12 @@ _SIGS = {
     "pg_launch_count": (ctypes.c_uint64, []),
     "pg_byte_presence": (c_int, [_P, c_int64, _P, _P]),
     "pg_synth_corpus": (c_int, [_P, c_int64, c_int64, c_int, c_uint32, c_int, _P]),
+    "pg_fasta_open": (_P, [ctypes.c_char_p]),
+    "pg_fasta_close": (None, [_P]),
+    "pg_fasta_file_bytes": (c_int64, [_P]),
+    "pg_fasta_records": (c_int64, [_P]),
+    "pg_fasta_stopped_early": (c_int, [_P]),
+    "pg_fasta_next_chunk": (c_int64, [_P, _P, c_int64, c_int, c_int, c_int]),
     "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "pg_ngram_count_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_ngram_count_ws_bytes_for": (c_size_t, [c_int, c_int, c_int64]),

@@ -72,6 +72,66 @@ __global__ void __launch_bounds__(kThreads) softmax_nll_kernel(float *__restrict
     for (int j = threadIdx.x; j < c; j += kThreads) out[j] = colsum[j];
 }
 
+// Few classes (c <= 128: the community / closest_aa tasks, 21 classes at config C3): one WARP per row, the row lives in
+// registers (4 columns per lane), 8 rows per CTA in flight.  Same outputs, same fixed summation orders.
+constexpr int kSmallC = 128, kSmallThreads = 256;
+__global__ void __launch_bounds__(kSmallThreads) softmax_nll_small_kernel(float *__restrict__ logits, int64_t ld, int64_t n, int c,
+                                                                          const int64_t *__restrict__ labels, float grad_scale,
+                                                                          float *__restrict__ row_loss, float *__restrict__ colsum_partial) {
+    __shared__ float cs[kSmallThreads / 32][kSmallC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t warps = (int64_t)gridDim.x * (kSmallThreads / 32);
+    for (int64_t r = (int64_t)blockIdx.x * (kSmallThreads / 32) + warp; r < n; r += warps) {
+        float *x = logits + r * ld;
+        const int64_t y = labels[r];
+        if (y < 0 || y >= c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (lane + 32 * k < c) x[lane + 32 * k] = 0.f;
+            if (lane == 0) row_loss[r] = 0.f;
+            continue;
+        }
+        float v[4], m = -INFINITY, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = lane + 32 * k < c ? x[lane + 32 * k] : -INFINITY;
+            m = fmaxf(m, v[k]);
+            if (lane + 32 * k == (int)y) xy = v[k];  // only the lane that owns column y keeps it
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = lane + 32 * k < c ? expf(v[k] - m) : 0.f;
+            sum += v[k];
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            if (j < c) {
+                const float g = (v[k] * inv - (j == (int)y ? 1.f : 0.f)) * grad_scale;
+                x[j] = g;
+                acc[k] += g;
+            }
+        }
+        if (lane == (int)(y & 31)) row_loss[r] = (m - xy) + logf(sum);  // -log_softmax(x)[y]
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cs[warp][lane + 32 * k] = acc[k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < c; j += kSmallThreads) {
+        float t = cs[0][j];
+#pragma unroll
+        for (int w = 1; w < kSmallThreads / 32; ++w) t += cs[w][j];  // fixed order
+        colsum_partial[(int64_t)blockIdx.x * c + j] = t;
+    }
+}
+
 // colsum[j] = sum_p partial[p][j]: a CTA owns 32 columns, its 8 warps take every 8th partial (coalesced 128 B
 // rows), the 8 sub-sums are combined in warp order -> fixed summation order
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float *__restrict__ partial, int parts, int c,
@@ -103,6 +163,10 @@ __global__ void __launch_bounds__(kThreads) loss_reduce_kernel(const float *__re
 }
 
 int nll_grid(int64_t n, int c) {
+    if (c <= kSmallC) {  // warp per row
+        const int64_t g = pg_ceil_div(n, kSmallThreads / 32);
+        return (int)(g < (int64_t)PG_NUM_SMS * 8 ? g : (int64_t)PG_NUM_SMS * 8);
+    }
     const size_t smem = (size_t)c * 8;
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     if (per_sm > 4) per_sm = 4;
@@ -140,10 +204,15 @@ extern "C" int pg_softmax_nll(float *d_logits, int64_t ld, int64_t n, int64_t c,
         pg_set_error("pg_softmax_nll: workspace too small (%zu < %zu)", ws_bytes, pg_softmax_nll_ws_bytes(n, c));
         return PG_EWORKSPACE;
     }
-    const size_t smem = (size_t)c * 8;
-    PG_CUDA_CALL(cudaFuncSetAttribute(softmax_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    softmax_nll_kernel<<<grid, kThreads, smem, st>>>(d_logits, ld, n, (int)c, d_labels, grad_scale, d_row_loss, (float *)d_ws);
-    PG_CUDA_LAUNCH_CHECK("softmax_nll_kernel");
+    if (c <= kSmallC) {
+        softmax_nll_small_kernel<<<grid, kSmallThreads, 0, st>>>(d_logits, ld, n, (int)c, d_labels, grad_scale, d_row_loss, (float *)d_ws);
+        PG_CUDA_LAUNCH_CHECK("softmax_nll_small_kernel");
+    } else {
+        const size_t smem = (size_t)c * 8;
+        PG_CUDA_CALL(cudaFuncSetAttribute(softmax_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        softmax_nll_kernel<<<grid, kThreads, smem, st>>>(d_logits, ld, n, (int)c, d_labels, grad_scale, d_row_loss, (float *)d_ws);
+        PG_CUDA_LAUNCH_CHECK("softmax_nll_kernel");
+    }
     const int g2 = (int)pg_ceil_div(c, 32);
     colsum_reduce_kernel<<<g2, 256, 0, st>>>((const float *)d_ws, grid, (int)c, d_colsum);
     PG_CUDA_LAUNCH_CHECK("colsum_reduce_kernel");

@@ -1,0 +1,211 @@
+// Row f3 of SURVEY.md section 8: FASTA text -> corpus buffer, natively (host code only).
+//
+// Replaces the Python line loop of reference src/utils/data_utils.py:182-213 (DataLoader.parse_sequences)
+// fused with the padding rule of src/pipeline/data_builder.py:29-35,97-102: the file is mmap'ed and
+// every record goes straight into the byte layout the count kernel reads,
+//     [' ' before global sequence #0] SEQUENCE ' ' 0xFF
+// so no Python string is ever created (UniRef50: 17.5 GB of residues).  Record rules, restated from the
+// reference (the parity tests compare against its Python twin, host/data_utils.py):
+//   * lines end at \n, \r\n or a lone \r (Python text mode, universal newlines); each line is stripped of
+//     leading / trailing white space (str.strip(): \t \n \v \f \r, \x1c-\x1f, space); blank lines are skipped
+//   * a line starting with '>' opens a record and closes the previous one; the previous one is emitted only
+//     if it collected at least one sequence line (`if protein_id and sequence_parts`)
+//   * a header that is exactly ">" makes the reference raise inside `header.split()[0]`; its generator
+//     prints and STOPS there (everything before it was already yielded) -- so does this parser
+//   * text before the first header is ignored; sequence lines are upper-cased, interior bytes kept as is
+//   * bytes >= 0x80 inside sequence text are refused (PG_FASTA_ENONASCII): the reference windows per code
+//     point, the byte kernels cannot, and the Python path already refuses them
+// Multi-GPU: sequences are dealt to ranks in blocks of `block` records, like host/corpus.py:stream_chunks.
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <new>
+
+#include "common.cuh"
+
+struct pg_fasta_reader {
+    const uint8_t *data;
+    int64_t size;
+    int fd;
+    int64_t pos;          // next unread byte: the start of a header line, or of text that belongs to no record
+    int64_t records;      // records emitted so far (all ranks) = global index of the next one
+    bool stopped;         // the reference's generator died on a bare ">" header
+    bool done;
+};
+
+namespace {
+inline bool is_space(uint8_t c) { return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
+
+// [b, e) = the next line without its terminator, stripped; returns the position after the terminator.
+// memchr finds the '\n'; a '\r' before it (CRLF, or a lone CR that ends a line by itself) is looked for inside that span.
+inline int64_t next_line(const uint8_t *d, int64_t pos, int64_t size, int64_t *b, int64_t *e) {
+    const uint8_t *nl = (const uint8_t *)memchr(d + pos, '\n', (size_t)(size - pos));
+    int64_t end = nl ? (int64_t)(nl - d) : size;
+    const uint8_t *cr = (const uint8_t *)memchr(d + pos, '\r', (size_t)(end - pos));
+    int64_t next;
+    if (cr) {
+        end = (int64_t)(cr - d);
+        next = (end + 1 < size && d[end + 1] == '\n') ? end + 2 : end + 1;
+    } else {
+        next = end < size ? end + 1 : size;
+    }
+    int64_t lo = pos, hi = end;
+    while (lo < hi && is_space(d[lo])) ++lo;
+    while (hi > lo && is_space(d[hi - 1])) --hi;
+    *b = lo;
+    *e = hi;
+    return next;
+}
+
+// dst[i] = upper(src[i]); returns the OR of all bytes (top bit set = some byte was not ASCII).  Branch-free: vectorises.
+inline uint8_t copy_upper(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n) {
+    uint8_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t c = src[i];
+        acc |= c;
+        dst[i] = (uint8_t)(c - (((uint8_t)(c - 'a') < 26u) << 5));
+    }
+    return acc;
+}
+inline uint8_t or_bytes(const uint8_t *src, int64_t n) {
+    uint8_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) acc |= src[i];
+    return acc;
+}
+}  // namespace
+
+extern "C" pg_fasta_reader *pg_fasta_open(const char *path) {
+    if (path == nullptr) {
+        pg_set_error("pg_fasta_open: null path");
+        return nullptr;
+    }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) {
+        pg_set_error("pg_fasta_open: cannot open '%s'", path);
+        return nullptr;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        pg_set_error("pg_fasta_open: cannot stat '%s'", path);
+        return nullptr;
+    }
+    const uint8_t *data = nullptr;
+    if (st.st_size > 0) {
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) {
+            close(fd);
+            pg_set_error("pg_fasta_open: mmap of '%s' failed", path);
+            return nullptr;
+        }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        data = (const uint8_t *)m;
+    }
+    pg_fasta_reader *r = new (std::nothrow) pg_fasta_reader{data, (int64_t)st.st_size, fd, 0, 0, false, st.st_size == 0};
+    if (r == nullptr) {
+        if (data) munmap((void *)data, (size_t)st.st_size);
+        close(fd);
+        pg_set_error("pg_fasta_open: out of memory");
+    }
+    return r;
+}
+
+extern "C" void pg_fasta_close(pg_fasta_reader *r) {
+    if (r == nullptr) return;
+    if (r->data) munmap((void *)r->data, (size_t)r->size);
+    close(r->fd);
+    delete r;
+}
+
+extern "C" int64_t pg_fasta_file_bytes(const pg_fasta_reader *r) { return r ? r->size : -1; }
+extern "C" int64_t pg_fasta_records(const pg_fasta_reader *r) { return r ? r->records : -1; }
+extern "C" int pg_fasta_stopped_early(const pg_fasta_reader *r) { return r && r->stopped ? 1 : 0; }
+
+// Packs whole records into out[0, cap) until the next one would not fit or the file ends.
+// Returns the bytes written (0 = end of file), PG_FASTA_ETOOSMALL if not even one record fits, PG_FASTA_ENONASCII.
+extern "C" int64_t pg_fasta_next_chunk(pg_fasta_reader *r, uint8_t *out, int64_t cap, int rank, int world, int block) {
+    if (r == nullptr || out == nullptr || cap < 4 || world < 1 || rank < 0 || rank >= world || block < 1) {
+        pg_set_error("pg_fasta_next_chunk: bad arguments");
+        return PG_EINVAL;
+    }
+    const uint8_t *d = r->data;
+    int64_t w = 0;             // bytes written and committed (whole records)
+    bool open_rec = false;            // a header has been consumed and its record is being collected
+    int64_t rec_start_pos = r->pos;   // file position of that header: where the next call resumes if the record does not fit
+    int64_t rec_w = w;                // where the open record's bytes start in `out`
+    int64_t rec_len = 0;              // sequence bytes of the open record so far
+    auto mine = [&](int64_t idx) { return (idx / block) % world == rank; };
+    auto begin_record = [&](int64_t pos_of_header) {
+        open_rec = true;
+        rec_start_pos = pos_of_header;
+        rec_w = w;
+        rec_len = 0;
+    };
+    // returns false if the record did not fit
+    auto finish_record = [&]() -> bool {
+        if (open_rec && rec_len > 0) {
+            if (mine(r->records)) {
+                if (rec_w + (r->records == 0 ? 1 : 0) + rec_len + 2 > cap) return false;
+                out[rec_w + (r->records == 0 ? 1 : 0) + rec_len] = ' ';
+                out[rec_w + (r->records == 0 ? 1 : 0) + rec_len + 1] = PG_SEP;
+                w = rec_w + (r->records == 0 ? 1 : 0) + rec_len + 2;
+            }
+            r->records += 1;
+        }
+        open_rec = false;
+        return true;
+    };
+    if (r->done || r->stopped) return 0;
+    int64_t pos = r->pos;
+    while (pos < r->size) {
+        int64_t b, e;
+        const int64_t line_pos = pos;
+        const int64_t next = next_line(d, pos, r->size, &b, &e);
+        if (b == e) {
+            pos = next;
+            continue;
+        }
+        if (d[b] == '>') {
+            if (!finish_record()) goto no_room;
+            // the committed prefix is safe; from here on a failure must come back to THIS header
+            if (e - b == 1) {  // bare ">": the reference's generator raises and stops here
+                r->stopped = true;
+                r->pos = r->size;
+                return w;
+            }
+            begin_record(line_pos);
+            pos = next;
+            continue;
+        }
+        if (open_rec) {
+            const bool take = mine(r->records);
+            const int64_t lead = r->records == 0 ? 1 : 0;
+            if (take && rec_w + lead + rec_len + (e - b) + 2 > cap) goto no_room;
+            if (take && rec_len == 0 && lead) out[rec_w] = ' ';
+            const uint8_t any = take ? copy_upper(out + rec_w + lead + rec_len, d + b, e - b) : or_bytes(d + b, e - b);
+            if (any & 0x80u) {
+                int64_t i = b;
+                while (d[i] < 0x80) ++i;
+                pg_set_error("pg_fasta_next_chunk: non-ASCII byte 0x%02x in sequence text at file offset %lld", d[i], (long long)i);
+                return PG_FASTA_ENONASCII;
+            }
+            rec_len += e - b;
+        }
+        pos = next;
+    }
+    if (!finish_record()) goto no_room;
+    r->pos = r->size;
+    r->done = true;
+    return w;
+
+no_room:
+    if (w == 0) {
+        pg_set_error("pg_fasta_next_chunk: a single record does not fit %lld bytes", (long long)cap);
+        return PG_FASTA_ETOOSMALL;
+    }
+    r->pos = rec_start_pos;
+    return w;
+}

@@ -51,6 +51,47 @@ def stream_chunks(seqs: Iterable[str], chunk_bytes: int = 1 << 28, rank: int = 0
         yield np.frombuffer(b"".join(parts), dtype=np.uint8)
 
 
+class NonAsciiSequence(ValueError):
+    pass
+
+
+def stream_chunks_native(fasta_path: str, chunk_bytes: int = 1 << 28, rank: int = 0, world: int = 1, block: int = 4096,
+                         pinned: bool = False, stats: dict = None):
+    """FASTA file -> corpus-buffer chunks without a Python string per sequence (row f3 of SURVEY.md 8): the native
+    reader (csrc/fasta.cu) applies the record rules of DataLoader.parse_sequences and the padding rule of
+    pack_sequences while copying out of the mmap'ed file.  Same chunks as
+    `stream_chunks((s for _, s in DataLoader.parse_sequences(path)), ...)` up to where the cuts fall.
+    Yields uint8 torch tensors (pinned when asked: they go to the GPU with one async copy).
+    stats (optional dict) receives 'sequences' (all ranks) and 'stopped_early'."""
+    import ctypes
+    import os
+    lib = nat.load()
+    reader = lib.pg_fasta_open(os.path.normpath(fasta_path).encode())
+    if not reader:
+        raise FileNotFoundError(lib.pg_last_error().decode())
+    try:
+        # a packed record never takes more bytes than its text (header >= 2 bytes pay for the ' ' 0xFF): file size + 1 bounds it
+        cap = max(min(int(chunk_bytes), int(lib.pg_fasta_file_bytes(reader)) + 64), 1 << 12)
+        while True:
+            buf = torch.empty(cap, dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
+            got = int(lib.pg_fasta_next_chunk(reader, ctypes.c_void_p(buf.data_ptr()), cap, rank, world, block))
+            if got == nat.PG_FASTA_ETOOSMALL:
+                cap *= 4          # one record longer than the chunk: grow and retry (the reader did not advance)
+                continue
+            if got == nat.PG_FASTA_ENONASCII:
+                raise NonAsciiSequence(lib.pg_last_error().decode())
+            if got < 0:
+                raise nat.NativeError(f"pg_fasta_next_chunk failed ({got}): {lib.pg_last_error().decode()}")
+            if got == 0:
+                break
+            yield buf[:got]
+        if stats is not None:
+            stats["sequences"] = int(lib.pg_fasta_records(reader))
+            stats["stopped_early"] = bool(lib.pg_fasta_stopped_early(reader))
+    finally:
+        lib.pg_fasta_close(reader)
+
+
 def to_device(buf: np.ndarray, device) -> torch.Tensor:
     """Pinned staging + async H2D of the corpus buffer (16 B aligned by the allocator)."""
     host = torch.from_numpy(np.ascontiguousarray(buf).copy()) if not isinstance(buf, torch.Tensor) else buf

@@ -148,12 +148,29 @@ class GraphBuilder:
                 n_seqs[0] += 1
                 yield s
 
+        def host_chunks():
+            # FASTA -> corpus buffer natively (csrc/fasta.cu: mmap, no Python string per sequence; row f3).  Non-ASCII
+            # sequence text takes the Python parser, which reproduces the reference's utf-8 'ignore' decoding first.
+            stats = {}
+            try:
+                for buf in corpus.stream_chunks_native(self.protein_sequence_file, chunk_bytes, rank, world, pinned=True, stats=stats):
+                    yield buf
+                n_seqs[0] = stats.get("sequences", 0)
+                if stats.get("stopped_early"):
+                    print(f"Error parsing FASTA file {self.protein_sequence_file}: list index out of range")  # the reference's message
+                return
+            except corpus.NonAsciiSequence:
+                if chunks:
+                    raise ValueError("FASTA holds non-ASCII sequence text; unsupported on the CUDA path")
+            yield from corpus.stream_chunks(sequences(), chunk_bytes, rank, world)
+
         chunks, resident = [], 0
         try:
-            for buf in corpus.stream_chunks(sequences(), chunk_bytes, rank, world):
-                if resident + buf.size <= hbm_budget:      # keep the corpus in HBM across the n levels
+            for buf in host_chunks():
+                size = int(buf.numel()) if torch.is_tensor(buf) else int(buf.size)
+                if resident + size <= hbm_budget:          # keep the corpus in HBM across the n levels
                     chunks.append(corpus.to_device(buf, dev))
-                    resident += buf.size
+                    resident += size
                 else:                                       # larger than the budget: re-streamed per level
                     chunks.append(buf)
         except ValueError as exc:

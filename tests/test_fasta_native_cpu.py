@@ -1,0 +1,105 @@
+"""Row f3: the native FASTA -> corpus-buffer reader (csrc/fasta.cu, host code, no GPU needed)
+against the Python twin of the reference parser (host/data_utils.py:DataLoader.parse_sequences, itself checked
+against the reference's own parse_sequences in tests/golden) + host/corpus.py:stream_chunks."""
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from protgram_directgcn_b200 import _native as nat
+from protgram_directgcn_b200.host import corpus
+from protgram_directgcn_b200.host.data_utils import DataLoader
+
+
+def _python_chunks(path, chunk_bytes=1 << 20, rank=0, world=1, block=4096):
+    return [bytes(c) for c in corpus.stream_chunks((s for _, s in DataLoader.parse_sequences(path)), chunk_bytes, rank, world, block)]
+
+
+def _native_chunks(path, chunk_bytes=1 << 20, rank=0, world=1, block=4096, stats=None):
+    return [bytes(c.numpy()) for c in corpus.stream_chunks_native(path, chunk_bytes, rank, world, block, stats=stats)]
+
+
+def _write(tmp_path, data: bytes, name="x.fasta"):
+    p = tmp_path / name
+    p.write_bytes(data)
+    return str(p)
+
+
+CASES = {
+    "ka1": b">seq1\nACGTACT\n>seq2\nTTACGTT\n>seq3\nAGATAGA\n",                       # run_graph_builder.py:24-28
+    "ka2": b">p1\nACGT\n>p2\nTTAC\n>p3\nAGA",                                            # unit_tests.py:41, no trailing newline
+    "crlf_lower_multiline": b">sp|P12345|NAME_HUMAN desc\r\nacde\r\nfghi\r\n\r\n>tr|Q9|x\r\n  klmn  \r\n",
+    "lone_cr": b">a\rACD\rEF\r>b\rGG\r",
+    "junk_before_header": b"ACGT\n\n  \nXX\n>a\nAC\n",
+    "empty_records": b">a\n>b\n\n\n>c\nAC\n>d\n   \n>e",
+    "interior_space_tab": b">a\nAC DE\tFG\n>b\n\tAC\x0b\n",
+    "bare_header_stops": b">a\nAC\n>b\nDE\n>\nFG\n>c\nHI\n",                            # '>' alone: the reference's generator raises there
+    "bare_header_first": b">   \nAC\n>c\nHI\n",
+    "pipes": b">||x\nAC\n>|id|\nDE\n>a|\nFG\n",
+    "control_ws": b">a\n\x1cAC\x1f\n\x1d\n>b\n\x0cDE\x0c\n",
+    "only_text": b"no header at all\nACGT\n",
+    "empty": b"",
+    "header_with_gt": b">a>b\nAC>DE\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_native_reader_matches_python_parser(name, tmp_path):
+    path = _write(tmp_path, CASES[name])
+    stats = {}
+    assert b"".join(_native_chunks(path, stats=stats)) == b"".join(_python_chunks(path))
+    assert stats["sequences"] == sum(1 for _ in DataLoader.parse_sequences(path))
+    assert stats["stopped_early"] == name.startswith("bare_header")
+
+
+def test_native_reader_small_chunks_and_rank_dealing(tmp_path):
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(1500):
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYacd"), size=int(rng.integers(1, 200))))
+        lines = [seq[j:j + 60] for j in range(0, len(seq), 60)]
+        recs.append(f">id{i} x\n" + "\n".join(lines) + "\n")
+    path = _write(tmp_path, "".join(recs).encode())
+    whole = b"".join(_python_chunks(path))
+    for cap in (1 << 16, 70_000, 1 << 20):
+        assert b"".join(_native_chunks(path, cap)) == whole
+    for world in (2, 3):
+        for rank in range(world):
+            assert b"".join(_native_chunks(path, 1 << 16, rank, world, block=64)) == b"".join(_python_chunks(path, 1 << 16, rank, world, block=64))
+    # chunks are cut at record boundaries
+    for c in _native_chunks(path, 1 << 16):
+        assert c.endswith(b" \xff")
+
+
+def test_native_reader_long_record_grows_the_chunk(tmp_path):
+    path = _write(tmp_path, b">a\n" + b"ACDE" * 100_000 + b"\n>b\nAC\n")
+    assert b"".join(_native_chunks(path, 1 << 16)) == b"".join(_python_chunks(path))
+
+
+def test_native_reader_refuses_non_ascii_and_missing_file(tmp_path):
+    path = _write(tmp_path, ">a\nAC\xc3\xa9DE\n".encode("latin-1"))
+    with pytest.raises(corpus.NonAsciiSequence):
+        _native_chunks(path)
+    ok = _write(tmp_path, ">a \xc3\xa9\nACDE\n".encode("latin-1"), "hdr.fasta")     # non-ASCII in a HEADER is fine (ids are not used)
+    assert b"".join(_native_chunks(ok)) == b" ACDE \xff"
+    with pytest.raises(FileNotFoundError):
+        _native_chunks(str(tmp_path / "missing.fasta"))
+
+
+LINE = st.one_of(st.just(b""), st.just(b">"), st.binary(max_size=12).map(lambda b: bytes(c & 0x7F for c in b)),
+                 st.text(alphabet="ACDEFGacdefg >|\t ", max_size=20).map(str.encode),
+                 st.text(alphabet="abcXYZ|_ ", min_size=1, max_size=10).map(lambda s: b">" + s.encode()))
+EOL = st.sampled_from([b"\n", b"\r\n", b"\r"])
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.tuples(LINE, EOL), max_size=25), st.booleans())
+def test_native_reader_fuzz(tmp_path_factory, lines, final_eol):
+    data = b"".join(l + e for l, e in lines)
+    if not final_eol and lines:
+        data = data[:-len(lines[-1][1])]
+    path = str(tmp_path_factory.mktemp("fz") / "f.fasta")
+    with open(path, "wb") as fh:
+        fh.write(data)
+    assert b"".join(_native_chunks(path)) == b"".join(_python_chunks(path)), data

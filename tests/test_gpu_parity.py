@@ -187,6 +187,7 @@ def test_pack_layer_params_matches_tensor_ops(f_in, f_out, n_gate, has_res):
 
 
 @pytest.mark.parametrize("n,c,ld,ignored", [(1, 1, 1, False), (7, 5, 8, False), (300, 1000, 1000, True), (513, 513, 520, False),
+                                            (20001, 21, 24, True), (3000, 128, 128, False), (999, 129, 132, False),
                                             (2000, 8401, 8401, False), (64, 28672, 28672, True)])
 def test_softmax_nll_fused_vs_fp64(n, c, ld, ignored):
     """pg_softmax_nll (row f1) against log_softmax + nll_loss + autograd in fp64: loss, dlogits, bias gradient;
