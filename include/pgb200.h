@@ -271,8 +271,8 @@ int pg_layer_gemm_bwd_weight(const float *d_z, int64_t ldz, const float *d_x, in
 /* The two backward GEMMs on the tcgen05 tensor cores (3 x TF32 operand split like the forward; same contracts,
  * shapes as pg_layer_gemm_fwd_tc_supported, 16-byte aligned operands).  Data gradient: rows of dY against the
  * pre-split image of W_ext[:K_data]^T, output columns cut into blocks of <= 256 TMEM columns, then the same
- * gating / gate-gradient pass as the SIMT path.  Weight gradient: both operands MN-major in shared memory
- * (no transposition), rows split over CTAs, partials summed in fixed order.  pg_tc_check (host-synchronising,
+ * gating / gate-gradient pass as the SIMT path.  Weight gradient: producers transpose both operands into the
+ * K-major layout (kind::tf32 takes no MN-major operands), rows split over CTAs, partials summed in fixed order.  pg_tc_check (host-synchronising,
  * tests only) reads the watchdog flag a call leaves at d_ws + need - 256, need = that call's *_ws_bytes. */
 size_t pg_layer_gemm_bwd_data_tc_ws_bytes(int F_in, int F_out, int has_res);
 int pg_layer_gemm_bwd_data_tc(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z,
@@ -288,9 +288,6 @@ int pg_layer_gemm_bwd_weight_tc(const float *d_z, int64_t ldz, const float *d_x,
                                 int F_in, int F_out, int has_res, float *d_dw_ext, void *d_ws,
                                 size_t ws_bytes, pg_stream_t stream);
 int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream);
-/* Test hook: operand layout of pg_layer_gemm_bwd_weight_tc in shared memory (0 = K-major, transposing producers;
- * 1..4 = MN-major variants, see csrc/gemm_tc.cu). */
-void pg_debug_tcw_layout(int mode);
 
 /* Row-wise L2 normalisation  out = h / (||h||_2 + eps)   (models_utils.py:139-147). */
 int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_rows, int F, float eps,

@@ -346,23 +346,20 @@ __global__ void __launch_bounds__(256) wprep_t_kernel(const float *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // backward, weight gradient:  dW_ext = A_ext^T @ dY  -- the reduction runs over the graph rows.
 // Both operands are contiguous along their M / N dimension in memory (A_ext rows hold the ext columns, dY rows the
-// output features), so they go to shared memory MN-major: core matrix = 8 k (rows of 16 B) x 4 consecutive m/n,
-// cores of one k-group TCW_SBO apart along M/N (128 B + 16 B pad: the producers' 16-byte stores of consecutive
-// cores hit disjoint banks), k-groups LBO apart; one MMA (K = 8 tf32) consumes exactly one k-group.  The
-// producers therefore load float4 along M/N (coalesced) and never transpose.  Grid = (ext-column tiles of 128) x
-// (row splits); every CTA writes its 128 x F_out partial, a second kernel sums the splits in fixed order.
+// output features), i.e. MN-major for the MMA.  kind::tf32 does not take MN-major operands on this part: with bit 15
+// or 16 of the instruction descriptor set, every shared-memory layout (no swizzle / 32 / 64 / 128-byte swizzle, LBO and
+// SBO either way round) returns exact zeros while the K-major forms of the same probe are correct (tools/probe_umma.cu,
+// profiles/r01_probe_umma_tf32_major.txt).  So the producers transpose: a thread gathers 4 consecutive graph rows of ONE
+// column (scalar loads, coalesced across the warp) into one 16-byte chunk of the K-major layout the forward uses.
+// Grid = (ext-column tiles of 128) x (row splits, ~2 CTAs per SM); every CTA writes its 128 x F_out partial, a second
+// kernel sums the splits in fixed order.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t TCW_SBO = 144;
-constexpr int TCW_BK = 16;   // graph rows per stage = 2 k-groups
+constexpr int TCW_BK = 16;   // graph rows per stage = 4 chunks of 4
 
-// `mode` (MN_MAJOR only; experiments behind pg_debug_tcw_layout): 1 = no swizzle, cores TCW_SBO apart; 2 = same with the
-// descriptor's LBO / SBO fields swapped; 3 = no swizzle, dense cores (128 B); 4 = 128-byte swizzle (atoms of 32 m/n x 8 k).
-template <bool MN_MAJOR>
 __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A, const float *__restrict__ dy, int64_t lddy, int F_out,
                                                                        int64_t rows_per_split, float *__restrict__ partial,
-                                                                       int *__restrict__ error_flag, int mode) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned (swizzle atoms)
+                                                                       int *__restrict__ error_flag) {
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[2], empty[2], done;
     __shared__ uint32_t tmem_base_slot;
     __shared__ volatile int bail;
@@ -371,22 +368,9 @@ __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A,
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_end = min(r_begin + rows_per_split, A.M);
     const int k_tiles = (int)((r_end - r_begin + TCW_BK - 1) / TCW_BK);
-    const int nb4 = F_out / 4;                                       // 16-byte cores along N
-    const uint32_t core = mode == 3 ? 128u : TCW_SBO;               // stride of the 16-byte-wide cores along M / N (modes 1-3)
-    const uint32_t a_lbo = mode == 4 ? (TC_BM / 32) * 1024u : (TC_BM / 4) * core;        // stride of the k-groups
-    const uint32_t b_lbo = mode == 4 ? (uint32_t)(F_out / 32) * 1024u : (uint32_t)nb4 * core;
-    const uint32_t a_bytes = 2 * a_lbo, b_bytes = 2 * b_lbo;
-    auto mn_off = [&](int k, int c4, uint32_t kg_stride) -> uint32_t {   // byte offset of (row k, columns 4 c4 .. 4 c4 + 3) in an operand tile
-        const uint32_t kg = (uint32_t)k >> 3, kr = (uint32_t)k & 7u;
-        if (mode == 4) return kg * kg_stride + ((uint32_t)c4 >> 3) * 1024u + kr * 128u + ((((uint32_t)c4 & 7u) ^ kr) << 4);
-        return kg * kg_stride + (uint32_t)c4 * core + kr * 16u;
-    };
-    auto mn_desc = [&](uint32_t saddr, uint32_t kg_stride) -> uint64_t {
-        if (mode == 4) return umma_desc(saddr, 1024u, kg_stride) | (2ull << 61);   // SWIZZLE_128B: LBO = atom stride along M/N, SBO = k-group stride
-        if (mode == 2) return umma_desc(saddr, core, kg_stride);
-        return umma_desc(saddr, kg_stride, core);
-    };
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;          // A_hi | A_lo | B_hi | B_lo
+    const uint32_t b_lbo = (uint32_t)(F_out + 1) * 16u;             // +1 row of padding like TC_LBO_A
+    const uint32_t a_bytes = 4 * TC_LBO_A, b_bytes = 4 * b_lbo;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;         // A_hi | A_lo | B_hi | B_lo
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < F_out) tmem_cols <<= 1;
 
@@ -404,75 +388,41 @@ __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A,
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_d = tmem_base_slot;
-    // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), N = F_out, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MN_MAJOR ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(F_out >> 3) << 17) |
-                           ((uint32_t)(TC_BM >> 4) << 24);
-    // K-major alternative (MN_MAJOR = false): the producers transpose instead -- a thread gathers 4 consecutive graph rows of one
-    // column (scalar loads, coalesced across the warp) into one 16-byte chunk of the layout gemm_tc's forward uses.
-    const uint32_t kb_lbo = (uint32_t)(F_out + 1) * 16u;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F_out >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
     if (warp < TC_PRODUCERS / 32) {
-        // ------------------------------------------------------------------ producers: A (2 float4) and B (<= 4 float4) per thread and k-tile
-        int a_k[2], a_col[2], b_k[4], b_col[4];
+        // ------------------------------------------------------------------ producers: 2 A chunks and <= 4 B chunks per thread and k-tile
+        int a_row[2], a_col[2], b_row[4], b_col[4];   // slot = (first of 4 graph rows inside the tile, column)
         uint32_t a_off[2], b_off[4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int idx = j * TC_PRODUCERS + tid;
-            a_k[j] = idx >> 5;
-            const int c4 = idx & 31;
-            a_col[j] = m0 + 4 * c4;
-            a_off[j] = mn_off(a_k[j], c4, a_lbo);
+            a_row[j] = 4 * (idx >> 7);
+            a_col[j] = m0 + (idx & 127);
+            a_off[j] = (uint32_t)(idx >> 7) * TC_LBO_A + (uint32_t)(idx & 127) * 16u;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int idx = j * TC_PRODUCERS + tid;
-            b_k[j] = idx < TCW_BK * nb4 ? idx / nb4 : -1;
-            const int c4 = idx < TCW_BK * nb4 ? idx % nb4 : 0;
-            b_col[j] = 4 * c4;
-            b_off[j] = mn_off(max(b_k[j], 0), c4, b_lbo);
-        }
-        if (!MN_MAJOR) {   // (column, chunk of 4 rows) slots instead of (row, 4 columns)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int idx = j * TC_PRODUCERS + tid;
-                a_k[j] = 4 * (idx >> 7);
-                a_col[j] = m0 + (idx & 127);
-                a_off[j] = (uint32_t)(idx >> 7) * TC_LBO_A + (uint32_t)(idx & 127) * 16u;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = j * TC_PRODUCERS + tid;
-                const bool on = idx < 4 * F_out;
-                b_k[j] = on ? 4 * (idx / F_out) : -1;
-                b_col[j] = on ? idx % F_out : 0;
-                b_off[j] = (uint32_t)(on ? idx / F_out : 0) * kb_lbo + (uint32_t)b_col[j] * 16u;
-            }
+            const bool on = idx < 4 * F_out;
+            b_row[j] = on ? 4 * (idx / F_out) : -1;
+            b_col[j] = on ? idx % F_out : 0;
+            b_off[j] = (uint32_t)(on ? idx / F_out : 0) * b_lbo + (uint32_t)b_col[j] * 16u;
         }
         auto load_tile = [&](int t, float4 (&va)[2], float4 (&vb)[4]) {
             const int64_t r0 = r_begin + (int64_t)t * TCW_BK;
-            if (MN_MAJOR) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) va[j] = A.at4(r0 + a_k[j], a_col[j]);
+            for (int j = 0; j < 2; ++j) {
+                const int64_t r = r0 + a_row[j];
+                va[j] = make_float4(A.at(r, a_col[j]), A.at(r + 1, a_col[j]), A.at(r + 2, a_col[j]), A.at(r + 3, a_col[j]));
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t r = r0 + b_k[j];
-                    vb[j] = (b_k[j] >= 0 && r < A.M) ? __ldg(reinterpret_cast<const float4 *>(dy + r * lddy + b_col[j]))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {
+            for (int j = 0; j < 4; ++j) {
+                const int64_t r = r0 + b_row[j];
+                float e[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int64_t r = r0 + a_k[j];
-                    va[j] = make_float4(A.at(r, a_col[j]), A.at(r + 1, a_col[j]), A.at(r + 2, a_col[j]), A.at(r + 3, a_col[j]));
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t r = r0 + b_k[j];
-                    float e[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) e[q] = (b_k[j] >= 0 && r + q < A.M) ? __ldg(dy + (r + q) * lddy + b_col[j]) : 0.f;
-                    vb[j] = make_float4(e[0], e[1], e[2], e[3]);
-                }
+                for (int q = 0; q < 4; ++q) e[q] = (b_row[j] >= 0 && r + q < A.M) ? __ldg(dy + (r + q) * lddy + b_col[j]) : 0.f;
+                vb[j] = make_float4(e[0], e[1], e[2], e[3]);
             }
         };
         auto split_store = [&](uint8_t *hi_base, uint8_t *lo_base, uint32_t off, const float4 &x4) {
@@ -499,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A,
                     for (int j = 0; j < 2; ++j) split_store(st, st + a_bytes, a_off[j], va[d][j]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (b_k[j] >= 0) split_store(st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, b_off[j], vb[d][j]);
+                        if (b_row[j] >= 0) split_store(st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, b_off[j], vb[d][j]);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[d]);
@@ -516,11 +466,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A,
             if (!mbar_wait(&full[s], (uint32_t)((kt >> 1) & 1))) { bail = 1; break; }
             fence_after_sync();
 #pragma unroll
-            for (int ks = 0; ks < TCW_BK / 8; ++ks) {  // one MMA = one k-group of 8 graph rows
-                const uint64_t dah = MN_MAJOR ? mn_desc(a_hi + ks * a_lbo, a_lbo) : umma_desc(a_hi + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
-                const uint64_t dal = MN_MAJOR ? mn_desc(a_lo + ks * a_lbo, a_lbo) : umma_desc(a_lo + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
-                const uint64_t dbh = MN_MAJOR ? mn_desc(b_hi + ks * b_lbo, b_lbo) : umma_desc(b_hi + ks * 2 * kb_lbo, kb_lbo, 128);
-                const uint64_t dbl = MN_MAJOR ? mn_desc(b_lo + ks * b_lbo, b_lbo) : umma_desc(b_lo + ks * 2 * kb_lbo, kb_lbo, 128);
+            for (int ks = 0; ks < TCW_BK / 8; ++ks) {  // one MMA consumes 2 chunks (K = 8 tf32)
+                const uint64_t dah = umma_desc(a_hi + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
+                const uint64_t dal = umma_desc(a_lo + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
+                const uint64_t dbh = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
+                const uint64_t dbl = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
                 umma_tf32(tmem_d, dah, dbh, idesc, (kt | ks) != 0);
                 umma_tf32(tmem_d, dah, dbl, idesc, 1);
                 umma_tf32(tmem_d, dal, dbh, idesc, 1);
@@ -735,10 +685,6 @@ extern "C" int pg_layer_gemm_bwd_data_tc(const float *d_dy, int64_t lddy, const 
                                p.k_data, d_dgate, st);
 }
 
-// operand layout of the weight-gradient kernel: 0 = K-major (transposing producers), 1..4 = MN-major variants (see the kernel)
-static int g_tcw_layout = 0;
-extern "C" void pg_debug_tcw_layout(int mode) { g_tcw_layout = mode; }
-
 extern "C" size_t pg_layer_gemm_bwd_weight_tc_ws_bytes(int64_t num_rows, int F_in, int F_out, int has_res) {
     const BwdWeightPlan p = bwd_weight_plan(num_rows, F_in, has_res);
     return pg_align_up((size_t)p.splits * p.k_ext * F_out * sizeof(float), 256) + 256;
@@ -775,22 +721,15 @@ extern "C" int pg_layer_gemm_bwd_weight_tc(const float *d_z, int64_t ldz, const 
     float *partial = reinterpret_cast<float *>(d_ws);
     int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
     PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
-    const size_t stage = 2 * (size_t)2 * (TC_BM / 4) * TCW_SBO + 2 * (size_t)2 * (F_out / 4) * TCW_SBO;
+    const size_t stage = 2 * (size_t)4 * TC_LBO_A + 2 * (size_t)4 * (F_out + 1) * 16;
     static bool attr_set = false;
     if (!attr_set) {
-        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        PG_CUDA_CALL(cudaFuncSetAttribute(tc_bwd_weight_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     const dim3 grid((unsigned)p.m_tiles, (unsigned)p.splits, 1);
-    int mode = g_tcw_layout;
-    if (mode == 4 && F_out % 32 != 0) mode = 0;   // swizzle atoms are 32 columns wide
-    if (mode != 0)
-        tc_bwd_weight_kernel<true><<<grid, TC_THREADS2, 2 * stage + 1024, st>>>(A, d_dy, lddy, F_out, p.rows_per_split, partial, err, mode);
-    else
-        tc_bwd_weight_kernel<false><<<grid, TC_THREADS2, 2 * stage + 1024, st>>>(A, d_dy, lddy, F_out, p.rows_per_split, partial, err, 0);
+    tc_bwd_weight_kernel<<<grid, TC_THREADS2, 2 * stage, st>>>(A, d_dy, lddy, F_out, p.rows_per_split, partial, err);
     PG_CUDA_LAUNCH_CHECK("tc_bwd_weight_kernel");
     tc_reduce_splits_kernel<<<(unsigned)pg_ceil_div(numel, 256), 256, 0, st>>>(partial, p.splits, numel, d_dw_ext);
     PG_CUDA_LAUNCH_CHECK("tc_reduce_splits_kernel");
