@@ -426,6 +426,47 @@ def test_count_ragged_tail_and_chunked_accumulation():
         assert np.array_equal(node_code.cpu().numpy(), np.nonzero(pres_ref)[0])
 
 
+def test_c4_full_size_properties():
+    """BASELINE config C4 at FULL size on one GPU: n = 5 from 50 M x 350-residue sequences (17.5 G residues, 18 chunks of
+    variant P).  No oracle runs at this size; properties instead: every window counted once; summing out the last
+    symbol of the 6-gram table gives the 5-gram table (counted independently, 32-bit-lane sub-tables) up to one
+    boundary window per sequence; the partitioned count equals the one-RED-per-window count bit for bit on a 2 M
+    sequence prefix; the extracted graph is sorted with dense ids."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~30 GB of free HBM")
+    nseq, L, n = 50_000_000, 350, 5
+    d_buf = _device_corpus(nseq, L)
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    sigma = int(symbols.size)
+    assert sigma == 21
+    before = nat.kernel_launches()
+    bins6, short = data_builder.count_level(d_buf, n, d_rank, sigma)
+    assert nat.kernel_launches() - before >= 4 * 17                       # variant P ran (4 kernels per chunk), not the RED fallback
+    assert int(bins6.sum()) == nseq * (L + 1 - n) + 1
+    bins5, _ = data_builder.count_level(d_buf, n - 1, d_rank, sigma)
+    assert int(bins5.sum()) == nseq * (L + 1 - (n - 1)) + 1
+    diff = bins5 - bins6.view(sigma ** n, sigma).sum(1)                    # 5-gram occurrences that no byte follows
+    assert int(diff.min()) >= 0 and int(diff.sum()) == nseq
+    del bins5, diff
+    # bit-exact against the RED variant on a prefix (cut at a sequence boundary)
+    sub = d_buf[:1 + 2_000_000 * (L + 2)]
+    part, _ = data_builder.count_level(sub, n, d_rank, sigma)
+    lib = nat.load()
+    lib.pg_debug_count_variant(COUNT_VARIANTS["global"])
+    try:
+        ref, _ = data_builder.count_level(sub, n, d_rank, sigma)
+    finally:
+        lib.pg_debug_count_variant(0)
+    assert torch.equal(part, ref)
+    del part, ref, sub, d_buf
+    node_code, src, dst, cnt = data_builder.extract_level(bins6, short, n, sigma)
+    assert 3_300_000 <= node_code.numel() <= 21 ** 5 and 60_000_000 <= src.numel() <= 21 ** 6
+    assert torch.all(node_code[1:] > node_code[:-1])
+    key = src * node_code.numel() + dst
+    assert torch.all(key[1:] > key[:-1]) and int(cnt.sum()) == nseq * (L + 1 - n) + 1
+
+
 def test_c2_full_size_properties():
     """BASELINE config C2: 500 k x 350 residues, n = 3.  Properties that need no oracle at this size:
     every window counted once; lower-order tables are marginals of the 4-gram table up to the
