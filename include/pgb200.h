@@ -367,6 +367,23 @@ int pg_pool_proteins(const uint8_t *d_seqs, const int64_t *d_offsets, int64_t nu
                      const float *d_emb, int64_t ld, int F, float *d_out, int64_t ldout,
                      uint8_t *d_valid, pg_stream_t stream);
 
+/* f4b, replaces the three torch_geometric.utils.subgraph(..., relabel_nodes=True) calls per cluster of
+ * _create_clustered_subgraphs (protgram_directgcn_trainer.py:179-197) by ONE pass over the shared-pattern CSR:
+ * keeps the stored entries whose row AND column are in `subset`, relabelled by position in `subset`
+ * (node_idx[subset] = arange(len(subset))), rows in subset order, columns in stored order -- for an ascending
+ * subset that is exactly the reference's edge order, and the result is again a sorted symmetric CSR.
+ * Step 1 fills d_new_id[num_nodes] (-1 = outside) and d_sub_rowptr[n_sub + 1]; step 2 (after the caller read
+ * d_sub_rowptr[n_sub] = kept entries and allocated) writes int32 columns, up to three value arrays and,
+ * optionally, the int64 COO rows / columns of the reference layout. */
+size_t pg_subgraph_ws_bytes(int64_t n_sub);
+int pg_subgraph_sizes(const int64_t *d_rowptr, const int32_t *d_col, int64_t num_nodes, const int64_t *d_subset,
+                      int64_t n_sub, int32_t *d_new_id, int64_t *d_sub_rowptr, void *d_ws, size_t ws_bytes,
+                      pg_stream_t stream);
+int pg_subgraph_fill(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val_a, const float *d_val_b,
+                     const float *d_val_c, int64_t num_nodes, const int64_t *d_subset, int64_t n_sub,
+                     const int32_t *d_new_id, const int64_t *d_sub_rowptr, int32_t *d_sub_col, float *d_sub_a,
+                     float *d_sub_b, float *d_sub_c, int64_t *d_coo_row, int64_t *d_coo_col, pg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,18 @@ def next_node_label_sets(indices: np.ndarray, values: np.ndarray, num_nodes: int
             w = values[lo:hi]
             out.append(np.sort(dst[lo:hi][w == w.max()]).astype(np.int64))
     return out
+
+
+def subgraph(subset, edge_index, edge_attr, num_nodes):
+    """torch_geometric.utils.subgraph(subset, edge_index, edge_attr, relabel_nodes=True, num_nodes=N) restated from its
+    published semantics (PyG is not installed here; call site protgram_directgcn_trainer.py:183-186): keep the edges
+    whose two end points are in `subset`, in their original order, relabelled by node_idx[subset] = arange(len(subset))."""
+    import numpy as np
+    subset = np.asarray(subset, dtype=np.int64)
+    edge_index = np.asarray(edge_index)
+    node_mask = np.zeros(num_nodes, dtype=bool)
+    node_mask[subset] = True
+    edge_mask = node_mask[edge_index[0]] & node_mask[edge_index[1]]
+    node_idx = np.zeros(num_nodes, dtype=np.int64)
+    node_idx[subset] = np.arange(subset.size)
+    return node_idx[edge_index[:, edge_mask]], np.asarray(edge_attr)[edge_mask]

@@ -13,7 +13,8 @@ from .host.graph_utils import DirectedNgramGraph, Graph  # noqa: F401
 from .host.data_builder import GraphBuilder  # noqa: F401
 from .host.protgram_directgcn import Data, DirectGCNLayer, ProtGramDirectGCN  # noqa: F401
 from .host.models_utils import EmbeddingProcessor  # noqa: F401
-from .host.trainer_utils import generate_next_node_labels, init_level_features  # noqa: F401
+from .host.trainer_utils import create_clustered_subgraphs, generate_next_node_labels, init_level_features  # noqa: F401
 
 __all__ = ["Config", "DataLoader", "DataUtils", "Graph", "DirectedNgramGraph", "GraphBuilder", "Data",
-           "DirectGCNLayer", "ProtGramDirectGCN", "EmbeddingProcessor", "generate_next_node_labels", "init_level_features"]
+           "DirectGCNLayer", "ProtGramDirectGCN", "EmbeddingProcessor", "generate_next_node_labels", "init_level_features",
+           "create_clustered_subgraphs"]

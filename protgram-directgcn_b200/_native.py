@@ -80,6 +80,9 @@ _SIGS = {
     "pg_unpack_layer_param_grads": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "pg_next_node_labels": (c_int, [_P, _P, _P, c_int64, _P, _P]),
     "pg_ngram_feature_init": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
+    "pg_subgraph_ws_bytes": (c_size_t, [c_int64]),
+    "pg_subgraph_sizes": (c_int, [_P, _P, c_int64, _P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "pg_subgraph_fill": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pg_pool_proteins": (c_int, [_P, _P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, _P, c_int64, _P, _P]),
     "pg_softmax_nll_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "pg_softmax_nll": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),

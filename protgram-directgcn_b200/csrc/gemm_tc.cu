@@ -409,8 +409,26 @@ __global__ void __launch_bounds__(TC_THREADS2, 2) tc_bwd_weight_kernel(AExtTc A,
             b_col[j] = on ? idx % F_out : 0;
             b_off[j] = (uint32_t)(on ? idx / F_out : 0) * b_lbo + (uint32_t)b_col[j] * 16u;
         }
+        // The loads below are latency-bound (ncu: 6.6 long-scoreboard stall cycles per issued instruction with two k-tiles
+        // in flight); more register prefetch costs the second CTA per SM, so tiles further ahead are pulled into L2
+        // instead: 64 threads touch the 128-byte lines of an A tile (Z columns only), 128 threads those of a dY tile.
+        constexpr int kL2Ahead = 8;
+        auto prefetch_l2 = [&](int t) {
+            const int64_t r0 = r_begin + (int64_t)(t + kL2Ahead) * TCW_BK;
+            if (tid < 64) {
+                const int64_t r = r0 + (tid >> 2);
+                const int col = m0 + (tid & 3) * 32;
+                if (r < r_end && col + 31 < 3 * A.F_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.z + r * A.ldz + col));
+            } else if (tid < 192) {
+                const int u = tid - 64;
+                const int64_t r = r0 + (u >> 3);
+                const int col = (u & 7) * 32;
+                if (r < r_end && col < F_out) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + r * lddy + col));
+            }
+        };
         auto load_tile = [&](int t, float4 (&va)[2], float4 (&vb)[4]) {
             const int64_t r0 = r_begin + (int64_t)t * TCW_BK;
+            prefetch_l2(t);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int64_t r = r0 + a_row[j];

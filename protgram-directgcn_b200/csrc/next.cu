@@ -2,7 +2,8 @@
 //   f4  next_node labels      reference src/pipeline/protgram_directgcn_trainer.py:222-237  (O(N*E) Python masks)
 //   f2a feature hand-off      reference protgram_directgcn_trainer.py:312-330  (Python loop over all nodes, dict lookups)
 //   f2b protein pooling       reference src/utils/models_utils.py:210-262      (Python loop over all residues)
-// All three are gather kernels over the packed base-sigma n-gram codes hot path A already computes.
+//   f4b cluster mini-batches  reference protgram_directgcn_trainer.py:179-197  (3 x torch_geometric.utils.subgraph per cluster)
+// The first three are gather kernels over the packed base-sigma n-gram codes hot path A already computes.
 #include "common.cuh"
 
 namespace {
@@ -154,6 +155,49 @@ __global__ void __launch_bounds__(kPoolThreads) pool_proteins_kernel(const uint8
     }
 }
 
+// ------------------------------------------------------------------ f4b: cluster mini-batch = induced subgraph of the shared-pattern CSR
+__global__ void __launch_bounds__(256) subgraph_mark_kernel(const int64_t *__restrict__ subset, int64_t n_sub, int64_t num_nodes,
+                                                            int32_t *__restrict__ new_id, int *__restrict__ bad) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sub; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = subset[s];
+        if (r < 0 || r >= num_nodes) *bad = 1;
+        else new_id[r] = (int32_t)s;   // duplicates in `subset`: the last position wins, like node_idx[subset] = arange(...)
+    }
+}
+
+// FILL = false: kept[s] = stored entries of row subset[s] whose column is in the subset;  FILL = true: write them
+template <bool FILL>
+__global__ void __launch_bounds__(256) subgraph_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                            const float *__restrict__ va, const float *__restrict__ vb,
+                                                            const float *__restrict__ vc, const int64_t *__restrict__ subset, int64_t n_sub,
+                                                            int64_t num_nodes, const int32_t *__restrict__ new_id,
+                                                            int64_t *__restrict__ kept, const int64_t *__restrict__ sub_rowptr,
+                                                            int32_t *__restrict__ sub_col, float *__restrict__ sa, float *__restrict__ sb,
+                                                            float *__restrict__ sc, int64_t *__restrict__ coo_row, int64_t *__restrict__ coo_col) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sub; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = subset[s];
+        int64_t out = FILL ? sub_rowptr[s] : 0;
+        if (r >= 0 && r < num_nodes && new_id[r] == (int32_t)s) {   // a duplicated node keeps its edges at its last position only
+            for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+                const int32_t c = new_id[col[e]];
+                if (c < 0) continue;
+                if (FILL) {
+                    sub_col[out] = c;
+                    sa[out] = va[e];
+                    if (vb) sb[out] = vb[e];
+                    if (vc) sc[out] = vc[e];
+                    if (coo_row) {
+                        coo_row[out] = s;
+                        coo_col[out] = c;
+                    }
+                }
+                ++out;
+            }
+        }
+        if (!FILL) kept[s] = out;
+    }
+}
+
 inline unsigned grid_for(int64_t n, int threads = 256, int per_sm = 8) {
     int64_t want = pg_ceil_div(n, threads);
     const int64_t cap = (int64_t)PG_NUM_SMS * per_sm;
@@ -210,5 +254,53 @@ extern "C" int pg_pool_proteins(const uint8_t *d_seqs, const int64_t *d_offsets,
                                                                                 (uint32_t)sigma, (uint32_t)pow_n, d_code_to_id, d_emb, ld,
                                                                                 F, d_out, ldout, d_valid);
     PG_CUDA_LAUNCH_CHECK("pool_proteins_kernel");
+    return PG_OK;
+}
+
+extern "C" size_t pg_subgraph_ws_bytes(int64_t n_sub) {
+    return pg_align_up((size_t)(n_sub > 0 ? n_sub : 1) * sizeof(int64_t), 256) + pg_scan_ws_bytes(n_sub > 0 ? n_sub : 1) + 512;
+}
+
+extern "C" int pg_subgraph_sizes(const int64_t *d_rowptr, const int32_t *d_col, int64_t num_nodes, const int64_t *d_subset, int64_t n_sub,
+                                 int32_t *d_new_id, int64_t *d_sub_rowptr, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_nodes >= 0 && n_sub >= 0 && num_nodes < (1ll << 31), "pg_subgraph_sizes: bad shape");
+    PG_CHECK_ARG(d_sub_rowptr && (num_nodes == 0 || d_new_id), "pg_subgraph_sizes: null output");
+    cudaStream_t st = pg_cu(stream);
+    if (num_nodes > 0) PG_CUDA_CALL(cudaMemsetAsync(d_new_id, 0xFF, (size_t)num_nodes * sizeof(int32_t), st));   // -1
+    if (n_sub == 0) {
+        PG_CUDA_CALL(cudaMemsetAsync(d_sub_rowptr, 0, sizeof(int64_t), st));
+        return PG_OK;
+    }
+    PG_CHECK_ARG(d_rowptr && d_col && d_subset && d_ws, "pg_subgraph_sizes: null buffer");
+    if (ws_bytes < pg_subgraph_ws_bytes(n_sub)) {
+        pg_set_error("pg_subgraph_sizes: workspace too small (%zu < %zu)", ws_bytes, pg_subgraph_ws_bytes(n_sub));
+        return PG_EWORKSPACE;
+    }
+    PgArena a(d_ws, ws_bytes);
+    int *bad = a.take<int>(64);
+    int64_t *kept = a.take<int64_t>((size_t)n_sub);
+    const size_t scan_bytes = pg_scan_ws_bytes(n_sub);
+    void *scan_ws = a.take<char>(scan_bytes);
+    PG_CUDA_CALL(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    subgraph_mark_kernel<<<grid_for(n_sub), 256, 0, st>>>(d_subset, n_sub, num_nodes, d_new_id, bad);
+    PG_CUDA_LAUNCH_CHECK("subgraph_mark_kernel");
+    subgraph_rows_kernel<false><<<grid_for(n_sub), 256, 0, st>>>(d_rowptr, d_col, nullptr, nullptr, nullptr, d_subset, n_sub, num_nodes, d_new_id,
+                                                                 kept, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    PG_CUDA_LAUNCH_CHECK("subgraph_rows_kernel<count>");
+    return pg_exclusive_scan_i64(kept, d_sub_rowptr, n_sub, d_sub_rowptr + n_sub, scan_ws, scan_bytes, st);
+}
+
+extern "C" int pg_subgraph_fill(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val_a, const float *d_val_b,
+                                const float *d_val_c, int64_t num_nodes, const int64_t *d_subset, int64_t n_sub, const int32_t *d_new_id,
+                                const int64_t *d_sub_rowptr, int32_t *d_sub_col, float *d_sub_a, float *d_sub_b, float *d_sub_c,
+                                int64_t *d_coo_row, int64_t *d_coo_col, pg_stream_t stream) {
+    PG_CHECK_ARG(num_nodes >= 0 && n_sub >= 0, "pg_subgraph_fill: bad shape");
+    if (n_sub == 0 || num_nodes == 0) return PG_OK;
+    PG_CHECK_ARG(d_rowptr && d_col && d_val_a && d_subset && d_new_id && d_sub_rowptr && d_sub_col && d_sub_a, "pg_subgraph_fill: null buffer");
+    PG_CHECK_ARG((!d_val_b || d_sub_b) && (!d_val_c || d_sub_c) && (!d_coo_row == !d_coo_col), "pg_subgraph_fill: inconsistent optional outputs");
+    subgraph_rows_kernel<true><<<grid_for(n_sub), 256, 0, pg_cu(stream)>>>(d_rowptr, d_col, d_val_a, d_val_b, d_val_c, d_subset, n_sub, num_nodes,
+                                                                           d_new_id, nullptr, d_sub_rowptr, d_sub_col, d_sub_a, d_sub_b,
+                                                                           d_sub_c, d_coo_row, d_coo_col);
+    PG_CUDA_LAUNCH_CHECK("subgraph_rows_kernel<fill>");
     return PG_OK;
 }

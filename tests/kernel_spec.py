@@ -406,3 +406,41 @@ def install(monkeypatch, nat):
     monkeypatch.setattr(nat, "check_tensor", lambda t, what="input": None)
     monkeypatch.setattr(nat, "current_device", lambda: torch.device("cpu"))
     monkeypatch.setattr(nat, "workspace", lambda nbytes, device: torch.empty(8, dtype=torch.uint8))
+
+
+# --------------------------------------------------------------------------- f4b: cluster mini-batch extraction
+def pg_subgraph_ws_bytes(n_sub):
+    return 256
+
+
+def pg_subgraph_sizes(rowptr, col, num_nodes, subset, n_sub, new_id, sub_rowptr, ws=None, ws_bytes=0, stream=None):
+    new_id[:num_nodes] = -1
+    new_id[subset[:n_sub]] = torch.arange(n_sub, dtype=new_id.dtype)
+    kept = torch.zeros(n_sub, dtype=torch.int64)
+    for s in range(n_sub):
+        r = int(subset[s])
+        if int(new_id[r]) == s:
+            c = col[int(rowptr[r]):int(rowptr[r + 1])].long()
+            kept[s] = int((new_id[c] >= 0).sum())
+    sub_rowptr[0] = 0
+    sub_rowptr[1:n_sub + 1] = torch.cumsum(kept, 0)
+
+
+def pg_subgraph_fill(rowptr, col, va, vb, vc, num_nodes, subset, n_sub, new_id, sub_rowptr, sub_col, sa, sb, sc, coo_row, coo_col,
+                     stream=None):
+    for s in range(n_sub):
+        r = int(subset[s])
+        if int(new_id[r]) != s:
+            continue
+        lo, hi = int(rowptr[r]), int(rowptr[r + 1])
+        c = new_id[col[lo:hi].long()]
+        keep = c >= 0
+        o = int(sub_rowptr[s])
+        m = int(keep.sum())
+        sub_col[o:o + m] = c[keep]
+        for src, dst in ((va, sa), (vb, sb), (vc, sc)):
+            if src is not None:
+                dst[o:o + m] = src[lo:hi][keep]
+        if coo_row is not None:
+            coo_row[o:o + m] = s
+            coo_col[o:o + m] = c[keep].long()

@@ -83,3 +83,67 @@ def test_pooling_long_and_repetitive_proteins_gpu():
     ids, pooled, valid = next_oracle.pool_proteins(seqs, n, ngram_map, emb)
     assert list(got.keys()) == [p for p, v in zip(ids, valid) if v] and "short" not in got
     assert np.array_equal(np.stack(list(got.values())), pooled[valid])
+
+
+class _PatternGraph:
+    """Three value-symmetric matrices on one symmetric pattern with self loops (what a reference-built graph carries)."""
+
+    def __init__(self, n, density, seed):
+        rng = np.random.default_rng(seed)
+        a = rng.random((n, n)) < density
+        a = a | a.T | np.eye(n, dtype=bool)
+        r, c = np.nonzero(a)
+        idx = torch.from_numpy(np.stack([r, c]).astype(np.int64))
+        self.number_of_nodes = n
+        mats = []
+        for _ in range(3):
+            v = rng.standard_normal((n, n)).astype(np.float32)
+            v = (v + v.T) / 2
+            mats.append(torch.sparse_coo_tensor(idx, torch.from_numpy(v[r, c]), (n, n)).coalesce())
+        self.mathcal_A_in, self.mathcal_A_out, self.A_undirected_norm_sparse = mats
+
+
+def check_clusters(device):
+    n = 300
+    graph = _PatternGraph(n, 0.03, 1)
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(n)
+    clusters = [sorted(perm[:120].tolist()), sorted(perm[120:299].tolist()), [int(perm[299])], perm[:50].tolist(), []]
+    full = pg.Data(x=torch.randn(n, 6), y=torch.arange(n))
+    subs = pg.create_clustered_subgraphs(graph, clusters, full, device=device)
+    assert len(subs) == len(clusters)
+    for cl, d in zip(clusters, subs):
+        assert torch.equal(d.original_indices.cpu(), torch.tensor(cl, dtype=torch.long))
+        assert torch.equal(d.x.cpu(), full.x[cl]) and torch.equal(d.y.cpu(), full.y[cl])
+        for name, m in (("in", graph.mathcal_A_in), ("out", graph.mathcal_A_out), ("undirected_norm", graph.A_undirected_norm_sparse)):
+            ei_ref, w_ref = next_oracle.subgraph(cl, m.indices().numpy(), m.values().numpy(), n)
+            ei = getattr(d, f"edge_index_{name}").cpu().numpy()
+            w = getattr(d, f"edge_weight_{name}").cpu().numpy()
+            assert ei.dtype == np.int64 and ei.shape == ei_ref.shape
+            if cl == sorted(cl):                       # ascending cluster: the reference's edge order, bit for bit
+                assert np.array_equal(ei, ei_ref) and np.array_equal(w, w_ref)
+            else:                                      # same edge set, rows in cluster order
+                key = lambda e: np.lexsort((e[1], e[0]))
+                assert np.array_equal(ei[:, key(ei)], ei_ref[:, key(ei_ref)]) and np.array_equal(w[key(ei)], w_ref[key(ei_ref)])
+    return graph, clusters, subs
+
+
+def test_cluster_subgraphs_host_logic_cpu(monkeypatch):
+    kernel_spec.install(monkeypatch, nat)
+    check_clusters("cpu")
+
+
+@pytest.mark.gpu
+def test_cluster_subgraphs_gpu():
+    graph, clusters, subs = check_clusters("cuda")
+    # the layer on a cluster batch: the sub-CSR handed over by the extraction == the general path on cloned edge tensors
+    from protgram_directgcn_b200.host import protgram_directgcn as model_mod
+    torch.manual_seed(0)
+    model = pg.ProtGramDirectGCN([6, 16, 8], graph.number_of_nodes, 4, 2, 0, 512, 0.0, True).cuda().eval()
+    d = subs[0]
+    with torch.no_grad():
+        a, _ = model(data=d)
+        model_mod._STRUCT_CACHE.clear()
+        clone = pg.Data(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in vars(d).items()})
+        b, _ = model(data=clone)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
