@@ -289,6 +289,13 @@ int pg_layer_gemm_bwd_weight_tc(const float *d_z, int64_t ldz, const float *d_x,
                                 size_t ws_bytes, pg_stream_t stream);
 int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream);
 
+/* Plain Linear on the same tensor-core kernel: out[N, C] = x[N, K] @ W[C, K]^T + bias (torch.nn.Linear layout, bias may be
+ * NULL).  Used for the decoder's output layer (protgram_directgcn.py:177-180 with C = N classes, row f1).  K % 4 == 0,
+ * x / out 16-byte aligned with row strides % 4 == 0 (pad the output rows to a multiple of 4 columns). */
+size_t pg_linear_tc_ws_bytes(int K, int C);
+int pg_linear_tc(const float *d_x, int64_t ldx, int64_t num_rows, int K, const float *d_w, const float *d_bias, int C,
+                 float *d_out, int64_t ldo, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
 /* Row-wise L2 normalisation  out = h / (||h||_2 + eps)   (models_utils.py:139-147). */
 int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_rows, int F, float eps,
                          float *d_out, int64_t ldout, pg_stream_t stream);

@@ -75,6 +75,8 @@ _SIGS = {
     "pg_layer_gemm_bwd_weight_tc": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int,
                                             c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_tc_check": (c_int, [_P, c_size_t, _P]),
+    "pg_linear_tc_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pg_linear_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
     "pg_pack_layer_params": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pg_unpack_layer_param_grads": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),

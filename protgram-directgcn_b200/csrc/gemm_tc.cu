@@ -61,26 +61,33 @@ constexpr int TC_BM = 128;      // rows per CTA = UMMA M
 // The smaller stage lets 2 CTAs share an SM, so one CTA's prologue / epilogue hides under the other's mainloop.
 constexpr uint32_t TC_LBO_A = (TC_BM + 1) * 16;
 
-// W_ext [k_ext, F_out] -> per k-tile image [kt][half(hi,lo)][chunk 0..7][n 0..F_out-1] of float4 (4 consecutive k)
+// W_ext [k_ext, F_out] -> per column block (n_full columns, the last one narrower) and k-tile the image
+// [block][kt][half(hi,lo)][chunk][n] of float4 (4 consecutive k), dense in the block's own width
 __global__ void __launch_bounds__(256) wprep_kernel(const float *__restrict__ w_ext, int k_ext, int F_out, int k_tiles, int TC_CHUNKS,
-                                                    float4 *__restrict__ wp) {
+                                                    int n_full, int blocks, float4 *__restrict__ wp) {
     const int TC_BK = TC_CHUNKS * 4;
-    const int64_t total = (int64_t)k_tiles * TC_CHUNKS * F_out;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(t % F_out);
-        const int kc = (int)((t / F_out) % TC_CHUNKS);
-        const int kt = (int)(t / ((int64_t)F_out * TC_CHUNKS));
+    const int64_t per_block = (int64_t)k_tiles * 2 * TC_CHUNKS * n_full;
+    const int64_t slots = (int64_t)k_tiles * TC_CHUNKS * n_full;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots * blocks; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / slots);
+        const int64_t u = t - (int64_t)b * slots;
+        const int n0 = b * n_full;
+        const int n_blk = min(n_full, ((F_out - n0 + 15) / 16) * 16);
+        if (u >= (int64_t)k_tiles * TC_CHUNKS * n_blk) continue;
+        const int n = (int)(u % n_blk);
+        const int kc = (int)((u / n_blk) % TC_CHUNKS);
+        const int kt = (int)(u / ((int64_t)n_blk * TC_CHUNKS));
         float v[4], h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = kt * TC_BK + kc * 4 + j;
-            v[j] = k < k_ext ? w_ext[(int64_t)k * F_out + n] : 0.f;
+            v[j] = (k < k_ext && n0 + n < F_out) ? w_ext[(int64_t)k * F_out + n0 + n] : 0.f;
             h[j] = tf32_hi(v[j]);
             l[j] = v[j] - h[j];
         }
-        const int64_t base = (int64_t)kt * 2 * TC_CHUNKS * F_out;
-        wp[base + (int64_t)kc * F_out + n] = make_float4(h[0], h[1], h[2], h[3]);
-        wp[base + (int64_t)(TC_CHUNKS + kc) * F_out + n] = make_float4(l[0], l[1], l[2], l[3]);
+        float4 *img = wp + (int64_t)b * per_block + (int64_t)kt * 2 * TC_CHUNKS * n_blk;
+        img[(int64_t)kc * n_blk + n] = make_float4(h[0], h[1], h[2], h[3]);
+        img[(int64_t)(TC_CHUNKS + kc) * n_blk + n] = make_float4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -307,6 +314,32 @@ struct EpiBwdDataTc {  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in,
                                          __uint_as_float(r[q * 4 + 3]));
             if (cc < f3) *reinterpret_cast<float4 *>(dz + row * lddz + cc) = v;
             else *reinterpret_cast<float4 *>(dxres + row * lddxres + (cc - f3)) = v;
+        }
+    }
+};
+
+struct EpiLinearTc {  // out[row, c] = acc + bias[c]   (plain Linear; c < n_total, rows padded to ldo % 4 == 0)
+    float *out;
+    int64_t ldo;
+    const float *bias;
+    int n_total;
+    static constexpr bool kHasSide = false;
+    __device__ __forceinline__ void load_side(int64_t, int, float4 (&)[4]) const {}
+    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&)[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = c + 4 * q;
+            if (cc >= n_total) continue;
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = __uint_as_float(r[q * 4 + j]) + ((bias && cc + j < n_total) ? __ldg(bias + cc + j) : 0.f);
+            if (cc + 3 < n_total) {
+                *reinterpret_cast<float4 *>(out + row * ldo + cc) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cc + j < n_total) out[row * ldo + cc + j] = y[j];
+            }
         }
     }
 };
@@ -568,7 +601,8 @@ extern "C" int pg_layer_gemm_fwd_tc_supported(int F_in, int F_out) {
 }
 
 extern "C" size_t pg_layer_gemm_fwd_tc_ws_bytes(int F_in, int F_out, int has_res) {
-    return (size_t)k_tiles_of(F_in, F_out, has_res) * 2 * chunks_for(F_in, F_out, has_res) * F_out * sizeof(float4) + 256;
+    // + 16 columns: the output may be cut into two column blocks whose widths are rounded up to 16 (few row tiles, see below)
+    return (size_t)k_tiles_of(F_in, F_out, has_res) * 2 * chunks_for(F_in, F_out, has_res) * (F_out + 16) * sizeof(float4) + 256;
 }
 
 extern "C" int pg_layer_gemm_fwd_tc(const float *d_z, int64_t ldz, const float *d_x, int64_t ldx, const float *d_gate_a,
@@ -602,17 +636,25 @@ extern "C" int pg_layer_gemm_fwd_tc(const float *d_z, int64_t ldz, const float *
     float4 *wp = reinterpret_cast<float4 *>(d_ws);
     int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
     PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    // Few row tiles (n-gram graphs of n <= 3: 66 tiles at config C2) leave most SMs idle and the kernel latency-bound:
+    // cut the output into two column blocks so that twice as many CTAs run (each rebuilds the A tile, from L2).
+    const int64_t row_tiles = pg_ceil_div(num_rows, TC_BM);
+    int n_full = F_out, blocks = 1;
+    if (row_tiles < PG_NUM_SMS && F_out >= 64) {
+        n_full = ((F_out + 1) / 2 + 15) / 16 * 16;
+        blocks = (F_out + n_full - 1) / n_full;
+    }
     {
-        const int64_t total = (int64_t)kt * chunks * F_out;
-        wprep_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w_ext, A.k_ext, F_out, kt, chunks, wp);
+        const int64_t total = (int64_t)blocks * kt * chunks * n_full;
+        wprep_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w_ext, A.k_ext, F_out, kt, chunks, n_full, blocks, wp);
         PG_CUDA_LAUNCH_CHECK("wprep_kernel");
     }
-    const size_t stage = 2 * (size_t)chunks * TC_LBO_A + 2 * (size_t)chunks * F_out * 16;
+    const size_t stage = 2 * (size_t)chunks * TC_LBO_A + 2 * (size_t)chunks * n_full * 16;
     const size_t smem = 2 * stage;
     EpiFwdTc epi{d_constant, d_x, ldconst, ldx, add_identity, slope, d_h, ldh};
-    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), 1, 1);
-    int rc = chunks == 4 ? launch_rows_gemm<4>(A, epi, wp, F_out, F_out, kt, err, grid, smem, st)
-                         : launch_rows_gemm<8>(A, epi, wp, F_out, F_out, kt, err, grid, smem, st);
+    const dim3 grid((unsigned)row_tiles, (unsigned)blocks, 1);
+    int rc = chunks == 4 ? launch_rows_gemm<4>(A, epi, wp, n_full, F_out, kt, err, grid, smem, st)
+                         : launch_rows_gemm<8>(A, epi, wp, n_full, F_out, kt, err, grid, smem, st);
     if (rc != PG_OK) return rc;
     PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (forward)");
     return PG_OK;
@@ -634,10 +676,13 @@ extern "C" int pg_layer_gemm_fwd_tc_check(const void *d_ws, int F_in, int F_out,
 // ---------------------------------------------------------------------------------------------- backward on tensor cores
 namespace {
 struct BwdDataPlan { int k_data, k_tiles, n_full, blocks; size_t image_bytes; };
-inline BwdDataPlan bwd_data_plan(int F_in, int F_out, int has_res) {
+// output columns `cols` (the B image's n), reduction length K: column blocks of <= 256, k-tiles of 16
+inline BwdDataPlan bwd_data_plan_raw(int cols, int K);
+inline BwdDataPlan bwd_data_plan(int F_in, int F_out, int has_res) { return bwd_data_plan_raw(3 * F_in + (has_res ? F_in : 0), F_out); }
+inline BwdDataPlan bwd_data_plan_raw(int cols, int K) {
     BwdDataPlan p;
-    p.k_data = 3 * F_in + (has_res ? F_in : 0);
-    p.k_tiles = (F_out + 15) / 16;
+    p.k_data = cols;
+    p.k_tiles = (K + 15) / 16;
     const int padded = (p.k_data + 15) / 16 * 16;
     p.n_full = padded < 256 ? padded : 256;
     p.blocks = (p.k_data + p.n_full - 1) / p.n_full;
@@ -763,5 +808,45 @@ extern "C" int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream) {
         pg_set_error("tensor-core pipeline watchdog expired (an MMA never signalled completion)");
         return PG_ECUDA;
     }
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plain Linear on tensor cores
+// out[N, C] = x[N, K] @ W[C, K]^T + bias  (torch.nn.Linear layout) -- the decoder's output layer with C = N classes
+// (row f1: 8401 x 8401 logits from K = 32 at config C2).  Same kernel as the data gradient: rows of x against the
+// pre-split image of W^T in column blocks of 256.
+extern "C" size_t pg_linear_tc_ws_bytes(int K, int C) {
+    if (K < 1 || C < 1) return 0;
+    const BwdDataPlan p = bwd_data_plan_raw(C, K);
+    return p.image_bytes + 256;
+}
+
+extern "C" int pg_linear_tc(const float *d_x, int64_t ldx, int64_t num_rows, int K, const float *d_w, const float *d_bias, int C,
+                            float *d_out, int64_t ldo, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && K >= 4 && K % 4 == 0 && C >= 1, "pg_linear_tc: needs K %% 4 == 0");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_x && d_w && d_out && d_ws, "pg_linear_tc: null buffer");
+    PG_CHECK_ARG(al16(d_x) && ldx % 4 == 0 && ldx >= K && al16(d_out) && ldo % 4 == 0 && ldo >= C && al16(d_ws),
+                 "pg_linear_tc: x / out must be 16-byte aligned with row strides %% 4 == 0 (pad the output rows)");
+    const BwdDataPlan p = bwd_data_plan_raw(C, K);
+    const size_t need = p.image_bytes + 256;
+    if (ws_bytes < need) {
+        pg_set_error("pg_linear_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    float4 *wp = reinterpret_cast<float4 *>(d_ws);
+    int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
+    PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    const int64_t total = (int64_t)p.blocks * p.k_tiles * 4 * p.n_full;
+    wprep_t_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w, C, K, p.k_tiles, p.n_full, p.blocks, wp);
+    PG_CUDA_LAUNCH_CHECK("wprep_t_kernel");
+    APlainTc A{d_x, ldx, num_rows, K};
+    EpiLinearTc epi{d_out, ldo, d_bias, C};
+    const size_t stage = 2 * (size_t)4 * TC_LBO_A + 2 * (size_t)4 * p.n_full * 16;
+    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), (unsigned)p.blocks, 1);
+    int rc = launch_rows_gemm<4>(A, epi, wp, p.n_full, C, p.k_tiles, err, grid, 2 * stage, st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (linear)");
     return PG_OK;
 }

@@ -340,7 +340,18 @@ class _LinearLogSoftmaxNLL(torch.autograd.Function):
         nat.check_tensor(d, "decoder input")
         n, c = d.shape[0], weight.shape[0]
         dev = d.device
-        logits = torch.addmm(bias, d, weight.t()) if bias is not None else d @ weight.t()
+        k = d.shape[1]
+        if TC_MODE != "off" and d.is_cuda and k % 4 == 0 and (TC_MODE == "force" or (n >= TC_MIN_ROWS and c >= TC_MIN_WIDTH)):
+            # output layer on the tensor cores (3 x TF32): rows padded to a multiple of 4 columns, logits = a view of the buffer
+            ld = (c + 3) // 4 * 4
+            buf = torch.empty((n, ld), dtype=torch.float32, device=dev)
+            ws_tc = nat.workspace(nat.query("pg_linear_tc_ws_bytes", k, c), dev)
+            d32, w32 = d.contiguous().float(), weight.contiguous().float()
+            nat.call("pg_linear_tc", nat.ptr(d32), d32.stride(0), n, k, nat.ptr(w32), nat.ptr(bias.contiguous().float()) if bias is not None else None,
+                     c, nat.ptr(buf), ld, nat.ptr(ws_tc), ws_tc.numel(), nat.stream_ptr())
+            logits = buf[:, :c]
+        else:
+            logits = torch.addmm(bias, d, weight.t()) if bias is not None else d @ weight.t()
         # grad_scale is a host scalar of the C ABI: with every row counted (the trainer's case) it is 1/n and no
         # device->host read is needed; masked labels take the exact count from the device
         scale = 1.0 / max(n, 1)

@@ -688,6 +688,44 @@ def test_layer_gemm_bwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
     assert rel_err(dz.cpu().numpy(), dz2.cpu().numpy()) <= 2e-5 and rel_err(dw.cpu().numpy(), dw2.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("n,k,c,with_bias", [(8401, 32, 8401, True), (300, 4, 17, True), (1000, 64, 256, False), (129, 32, 1000, True)])
+def test_linear_tensor_core_vs_fp64(n, k, c, with_bias):
+    """pg_linear_tc (decoder output layer, row f1): out = x W^T + b on tcgen05 with the 3 x TF32 split, odd class counts
+    (rows padded to a multiple of 4 columns, partial last column block)."""
+    g = torch.Generator().manual_seed(n + c)
+    x, w, b = torch.randn(n, k, generator=g), torch.randn(c, k, generator=g) * 0.3, torch.randn(c, generator=g)
+    ref = x.double() @ w.double().t() + (b.double() if with_bias else 0)
+    ld = (c + 3) // 4 * 4
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    out = torch.full((n, ld), float("nan"), device=DEV)
+    need = nat.query("pg_linear_tc_ws_bytes", k, c)
+    ws = _ws(need)
+    st = nat.stream_ptr()
+    nat.call("pg_linear_tc", nat.ptr(xd), k, n, k, nat.ptr(wd), nat.ptr(bd) if with_bias else None, c, nat.ptr(out), ld, nat.ptr(ws), ws.numel(), st)
+    nat.call("pg_tc_check", nat.ptr(ws), need, st)
+    assert rel_err(out[:, :c].cpu().numpy(), ref.numpy()) <= 2e-5
+    assert bool(torch.isnan(out[:, c:]).all())        # the padding columns are never written
+
+
+def test_fused_loss_with_tensor_core_logits_matches_torch(monkeypatch):
+    """linear_log_softmax_nll with the output layer on tensor cores (forced) against torch's Linear + log_softmax + nll_loss:
+    loss and all three gradients."""
+    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    torch.manual_seed(1)
+    n, k, c = 2000, 32, 1999
+    d = torch.randn(n, k, device=DEV, requires_grad=True)
+    w = (torch.randn(c, k, device=DEV) * 0.2).requires_grad_()
+    b = torch.randn(c, device=DEV, requires_grad=True)
+    y = torch.randint(0, c, (n,), device=DEV)
+    loss = model_mod.linear_log_softmax_nll(d, w, b, y)
+    grads = torch.autograd.grad(loss, (d, w, b))
+    ref = torch.nn.functional.nll_loss(torch.log_softmax(torch.nn.functional.linear(d.double(), w.double(), b.double()), -1), y)
+    ref_grads = torch.autograd.grad(ref, (d, w, b))
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    for a, r in zip(grads, ref_grads):
+        assert rel_err(a.cpu().numpy(), r.cpu().numpy()) <= 5e-5
+
+
 def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     """Force the tcgen05 dense transform inside the model and re-check the reference goldens
     (model_refgraph has widths 24/40/16/8 -> only the 16-wide layer qualifies; the C2-shaped oracle
