@@ -131,6 +131,13 @@ class B200Pipeline:
         self.count_ms = []
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.model = self.opt = self.x = self.labels = self.graphed = None
+        # Two-stage software pipeline over consecutive batches: the graph build of batch k+1 (its own stream; its three small
+        # host reads -- alphabet, node / edge counts, pattern size -- only wait for THAT stream) runs under the DirectGCN replay
+        # of batch k on the main stream.  pipelined = False restores the strictly sequential step.
+        self.pipelined = True
+        self.build_stream = torch.cuda.Stream(device=device)
+        self.pending = None
+        self._build_stream_primed = False
 
     # ---- hot path A on a device-resident corpus; returns the device edge table + matrices
     def build(self, d_buf, materialise_host: bool, after_count=None):
@@ -170,7 +177,7 @@ class B200Pipeline:
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         g = torch.Generator().manual_seed(SEED)
         self.x = torch.randn(n, DIMS[0], generator=g).to(self.dev)
-        self.labels = next_node_labels(graph.A_out_w.coalesce().cpu(), n).to(self.dev)
+        self.labels = self.pg.generate_next_node_labels(graph)[0].to(self.dev)    # row f4 kernel (deterministic: first maximal successor)
         self.graphed = None
         if self.use_cuda_graph:
             from protgram_directgcn_b200.host.graphed_step import GraphedDirectGCNStep
@@ -207,11 +214,39 @@ class B200Pipeline:
             _, emb = self.model(data=data)
         return loss, emb
 
+    def _build_on_side_stream(self, get_buf, **kw):
+        """build() on the build stream; the main stream then waits for it (and takes co-ownership of the device CSR)."""
+        main = torch.cuda.current_stream(self.dev)
+        if not self.pipelined:
+            return self.build(get_buf(), **kw)
+        if not self._build_stream_primed:          # the corpus buffer was generated on the main stream
+            self.build_stream.wait_stream(main)
+            self._build_stream_primed = True
+        with torch.cuda.stream(self.build_stream):
+            graph = self.build(get_buf(), **kw)
+            ready = torch.cuda.Event()
+            ready.record()
+        main.wait_event(ready)
+        for t in (getattr(graph, "_pg_device", None) or {}).values():
+            t.record_stream(main)
+        return graph
+
     def step_resident(self):
-        graph = self.build(self.d_buf, materialise_host=False)
+        graph = self._build_on_side_stream(lambda: self.d_buf, materialise_host=False)
         out = self.train_and_extract(graph)
         graph.node_sequences                       # the node names are part of the step: decoded here, under the GPU work
         return out + (graph,)
+
+    def _finish_e2e(self):
+        """Host-side results of the step whose DirectGCN replay is in flight on the main stream."""
+        if self.pending is None:
+            return None
+        loss, emb, graph = self.pending
+        self.pending = None
+        graph.node_sequences                                                      # node names decoded under the GPU work
+        graph.wait_ready()                                                        # D2H of the five matrices (side stream) has landed
+        emb_host = emb.cpu().numpy()                                              # D2H: embeddings (models_utils.py:265-273)
+        return float(loss.item()), emb_host, graph
 
     def step_e2e(self):
         if self.h_buf is None:
@@ -223,13 +258,18 @@ class B200Pipeline:
             self.up.release()                                                    # step: it runs on the copy stream under this
             self.up.submit(self.h_buf)                                           # step's extract/normalise/DirectGCN kernels
 
-        d_buf = self.up.acquire()                                                # H2D of this step's bytes (waits for the copy)
-        graph = self.build(d_buf, materialise_host=True, after_count=prefetch_next)  # graph object on the host (reference contract)
-        loss, emb = self.train_and_extract(graph)
-        graph.node_sequences                                                      # node names decoded under the GPU work
-        graph.wait_ready()                                                        # D2H of the five matrices (side stream) has landed
-        emb_host = emb.cpu().numpy()                                              # D2H: embeddings (models_utils.py:265-273)
-        return float(loss.item()), emb_host, graph
+        # H2D of this step's bytes (the building stream waits for the copy); graph object on the host (reference contract)
+        graph = self._build_on_side_stream(self.up.acquire, materialise_host=True, after_count=prefetch_next)
+        if not self.pipelined:
+            self.pending = self.train_and_extract(graph) + (graph,)
+            return self._finish_e2e()
+        prev = self._finish_e2e()        # batch k-1: its replay ran on the main stream while batch k was being built
+        self.pending = self.train_and_extract(graph) + (graph,)
+        return prev
+
+    def flush(self):
+        """Results of the last pipelined e2e step (inside the timed region: every batch's outputs reach the host)."""
+        return self._finish_e2e()
 
     def collect_count_ms(self):
         if getattr(self, "_pending_count_event", False):
@@ -612,6 +652,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     pipe = B200Pipeline(rank, world, dev)
     pipe.use_cuda_graph = not args.no_cuda_graph
+    pipe.pipelined = not args.no_pipeline
     nat = pipe.nat
     peak_gbs, peak_src = peaks()
 
@@ -625,6 +666,7 @@ def run_b200(args):
         for _ in range(warmup):
             last = fn()         # keep the previous result alive exactly like the timed loop does (same allocator pattern)
             pipe.collect_count_ms()
+        pipe.flush()
         pipe.count_ms.clear()
         gc.collect()
         gc.disable()            # timing hygiene (as timeit does): a gen-2 collection is a 50 ms host stall with torch loaded
@@ -642,6 +684,8 @@ def run_b200(args):
             pipe.collect_count_ms()
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
+        tail = pipe.flush()                          # pipelined e2e: the last batch's outputs are read inside the timed region
+        last = tail if tail is not None else last
         if getattr(pipe, "up", None) is not None:   # the prefetch issued by the last step belongs to the timed region
             torch.cuda.current_stream().wait_stream(pipe.up.copy_stream)
         t1.record()
@@ -683,7 +727,9 @@ def run_b200(args):
                    "nodes": graph.number_of_nodes, "unique_edges": graph.number_of_edges, "pattern_nnz": int(graph.mathcal_A_out._nnz()),
                    "l2_handling": "inputs larger than L2 (corpus 176 MB per GPU > 126 MB L2)",
                    "multi_gpu": "corpus sharded by sequence range, tables merged by NCCL all-reduce, n=3 DirectGCN replicated",
-                   "directgcn_step": "eager" if args.no_cuda_graph else "CUDA graph replay (fwd+loss+bwd+Adam+eval fwd captured once)"},
+                   "directgcn_step": "eager" if args.no_cuda_graph else "CUDA graph replay (fwd+loss+bwd+Adam+eval fwd captured once)",
+                   "pipelining": ("graph build of batch k+1 on its own stream under the DirectGCN replay of batch k (two-stage software pipeline; "
+                                  "e2e reads batch k's outputs while batch k+1 is built)") if pipe.pipelined else "none (sequential step)"},
         "clocks": clocks, "gpu_launches": int(launches / max(1, args.steps)),
         "e2e": {"value": residues / (e2e_ms * 1e-3), "unit": "residues/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
@@ -880,6 +926,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-large", action="store_true", help="skip the large-graph SpMM leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="strictly sequential steps (no overlap of batch k+1's build with batch k's DirectGCN step)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the DirectGCN step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--large-log2-nodes", type=int, default=21)
     ap.add_argument("--no-scale", action="store_true", help="skip the C3 (n=4) / C4 (n=5) build legs and the C3 DirectGCN leg")
