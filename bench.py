@@ -508,6 +508,7 @@ def build_scale_leg(pipe, dist, n_level, total_seqs, iters=2, normalise=True):
     t_count, t_merge, t_extract = [], [], []
     res = None
     for it in range(iters + 1):
+        res = None                                   # release the previous pass's outputs first: the allocator then reuses their blocks
         bins = torch.zeros(pow_m, dtype=torch.int64, device=dev)
         short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
         if dist is not None:
@@ -738,6 +739,12 @@ def run_b200(args):
     }
     if count_ms:
         alg = pipe.nbytes
+        # the same call timed alone (no DirectGCN replay of the previous batch sharing the SMs)
+        symbols_, d_rank_ = pipe.corpus.discover_alphabet(pipe.d_buf, None)
+        ws_ = pipe.db.count_workspace(N_LEVEL, int(symbols_.size), pipe.nbytes, dev)
+        pn_, pm_ = pipe.db.table_sizes(N_LEVEL, int(symbols_.size))
+        bins_, short_ = torch.zeros(pm_, dtype=torch.int64, device=dev), torch.zeros(pn_, dtype=torch.uint8, device=dev)
+        alone_ms = _time_ms(lambda: pipe.db.count_level(pipe.d_buf, N_LEVEL, d_rank_, int(symbols_.size), bins_, short_, ws_), 10, warm=3)
         line["roofline"] = {"kernel": f"ngram_count_smem_kernel<M={N_LEVEL + 1}, 8-bit lanes> (+ memset, reduce_partials_kernel<8>, 2 gated no-op launches: "
                                       "everything pg_ngram_count enqueues, timed as one)",
                             "bound": "hbm", "achieved": alg / (count_ms * 1e-3) / 1e9,
@@ -745,7 +752,13 @@ def run_b200(args):
                             "traffic": 181_280_000,  # dram__bytes_read+write of the count kernel, ncu --set full (profiles/r01_ncu_count_smem8_v3.txt)
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": count_ms,
                             "share_of_step": count_ms / ms_step,
-                            "note": "1 B/residue read (DRAM traffic == algorithmic bytes).  A 194,481-bin histogram cannot run at the HBM "
+                            "ms_per_launch_alone": alone_ms, "frac_alone": alg / (alone_ms * 1e-3) / 1e9 / peak_gbs,
+                            "shared_atomic_bound": {"achieved_Gupdates_per_s": NSEQ * SEQ_LEN / (alone_ms * 1e-3) / 1e9, "peak_Gupdates_per_s": 1300.0,
+                                                    "peak_source": "tools/microbench_atomics.cu (shared-memory atomicAdd, 148 SMs)",
+                                                    "note": "one shared-memory atomic per window is the floor of this kernel; includes memset + reduce + gated launches"},
+                            "note": "ms_per_launch is measured inside the timed region, where the count kernel shares the SMs with the previous batch's "
+                                    "DirectGCN replay (pipelining); ms_per_launch_alone is the same call without that overlap.  "
+                                    "1 B/residue read (DRAM traffic == algorithmic bytes).  A 194,481-bin histogram cannot run at the HBM "
                                     "roofline: the count kernel alone takes 147 us under ncu, 88% issue-active (about 400 instructions per "
                                     "16 residues: rank lookup, rolling key, validity mask, packed 8-bit shared-memory add, overflow check); "
                                     "see DESIGN.md section 4.  The HBM-bound kernel of this system is the SpMM: spmm_large / spmm_partitioned."}
