@@ -138,6 +138,8 @@ class B200Pipeline:
         self.build_stream = torch.cuda.Stream(device=device)
         self.pending = None
         self._build_stream_primed = False
+        self.host_bytes = False
+        self.h_packed = None
 
     # ---- hot path A on a device-resident corpus; returns the device edge table + matrices
     def build(self, d_buf, materialise_host: bool, after_count=None):
@@ -250,7 +252,13 @@ class B200Pipeline:
 
     def step_e2e(self):
         if self.h_buf is None:
-            self.h_buf = self.d_buf.cpu().pin_memory()
+            # host format of the corpus: 5 bits per symbol (8 symbols in 5 bytes; what the ingest keeps in host memory for corpora
+            # that are streamed to the GPU), unpacked on the device right after the copy; --host-bytes keeps 1 byte per symbol
+            host = self.d_buf.cpu()
+            packed = None if self.host_bytes else self.corpus.pack5(host)
+            self.h_packed = packed
+            self.h_buf = packed.packed if packed is not None else host.pin_memory()
+            self.d_unpacked = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev) if packed is not None else None
             self.up = self.corpus.CorpusUploader(self.dev)
             self.up.submit(self.h_buf)
 
@@ -258,8 +266,12 @@ class B200Pipeline:
             self.up.release()                                                    # step: it runs on the copy stream under this
             self.up.submit(self.h_buf)                                           # step's extract/normalise/DirectGCN kernels
 
-        # H2D of this step's bytes (the building stream waits for the copy); graph object on the host (reference contract)
-        graph = self._build_on_side_stream(self.up.acquire, materialise_host=True, after_count=prefetch_next)
+        def acquire():
+            d = self.up.acquire()                                                # the building stream waits for the copy
+            return d if self.h_packed is None else self.corpus.unpack5(d, self.h_packed.n_symbols, self.d_unpacked)
+
+        # H2D of this step's bytes; graph object on the host (reference contract)
+        graph = self._build_on_side_stream(acquire, materialise_host=True, after_count=prefetch_next)
         if not self.pipelined:
             self.pending = self.train_and_extract(graph) + (graph,)
             return self._finish_e2e()
@@ -654,6 +666,7 @@ def run_b200(args):
     pipe = B200Pipeline(rank, world, dev)
     pipe.use_cuda_graph = not args.no_cuda_graph
     pipe.pipelined = not args.no_pipeline
+    pipe.host_bytes = args.host_bytes
     nat = pipe.nat
     peak_gbs, peak_src = peaks()
 
@@ -715,7 +728,7 @@ def run_b200(args):
     # end to end: host bytes in, embeddings out
     e2e_ms, e2e_wall, _, last_e2e = timed(pipe.step_e2e, max(1, args.steps), max(args.warmup, 6))  # the e2e path warms its own allocations
     graph_h = last_e2e[2]
-    h2d = pipe.nbytes + 256 + 256
+    h2d = int(pipe.h_buf.numel()) + 256 + 256      # the corpus as it crosses PCIe (5-bit symbols unless --host-bytes) + alphabet tables
     pat = graph_h.mathcal_A_out._nnz()
     d2h = (graph_h.number_of_nodes * 8 + 3 * graph_h.number_of_edges * 8 + 16  # node codes, edge table, sizes
            + graph_h.number_of_edges * (16 + 4) * 2 + pat * (16 + 12)          # A_out/A_in COO + pattern + 3 value arrays
@@ -733,7 +746,8 @@ def run_b200(args):
                                   "e2e reads batch k's outputs while batch k+1 is built)") if pipe.pipelined else "none (sequential step)"},
         "clocks": clocks, "gpu_launches": int(launches / max(1, args.steps)),
         "e2e": {"value": residues / (e2e_ms * 1e-3), "unit": "residues/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+                "d2h_bytes_per_step": int(d2h),
+                "host_format": "1 byte per symbol" if pipe.h_packed is None else "5-bit symbols (8 per 5 bytes, pg_pack5_host), unpacked on the device (pg_unpack5)"},
         "wall_ms_per_step": wall_step * 1e3,
         "per_step_ms": {"resident": step_ms_resident, "e2e": pipe.step_ms},
     }
@@ -939,6 +953,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-large", action="store_true", help="skip the large-graph SpMM leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-bytes", action="store_true", help="e2e: upload 1 byte per symbol instead of the 5-bit host format")
     ap.add_argument("--no-pipeline", action="store_true", help="strictly sequential steps (no overlap of batch k+1's build with batch k's DirectGCN step)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the DirectGCN step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--large-log2-nodes", type=int, default=21)

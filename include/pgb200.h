@@ -67,6 +67,15 @@ int64_t pg_fasta_records(const pg_fasta_reader *reader); /* records emitted so f
 int pg_fasta_stopped_early(const pg_fasta_reader *reader);
 int64_t pg_fasta_next_chunk(pg_fasta_reader *reader, uint8_t *out, int64_t cap, int rank, int world, int block);
 
+/* 5-bit host format of the corpus buffer (what crosses PCIe when a corpus is streamed from host memory): 8 symbols in
+ * 5 bytes, fixed code ' ' = 0, 'A'..'Z' = 1..26, '*' = 27, '-' = 28, '.' = 29, separator = 31 (also the tail padding).
+ * pg_pack5_host (host code) returns the packed size = pg_pack5_bytes(n) or PG_EPACK when a byte has no code (keep the
+ * byte format then); pg_unpack5 restores the n_symbols corpus bytes on the device (d_out 16-byte aligned). */
+#define PG_EPACK (-12)
+int64_t pg_pack5_bytes(int64_t n_symbols);
+int64_t pg_pack5_host(const uint8_t *bytes, int64_t n_symbols, uint8_t *out);
+int pg_unpack5(const uint8_t *d_packed, int64_t n_symbols, uint8_t *d_out, pg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Hot path A, part 1: n-gram transition counting
  * ---------------------------------------------------------------------------------------- */

@@ -17,7 +17,7 @@ class NativeError(RuntimeError):
     pass
 
 
-PG_FASTA_ETOOSMALL, PG_FASTA_ENONASCII = -10, -11   # include/pgb200.h
+PG_FASTA_ETOOSMALL, PG_FASTA_ENONASCII, PG_EPACK = -10, -11, -12   # include/pgb200.h
 
 
 _P = c_void_p
@@ -33,6 +33,9 @@ _SIGS = {
     "pg_fasta_records": (c_int64, [_P]),
     "pg_fasta_stopped_early": (c_int, [_P]),
     "pg_fasta_next_chunk": (c_int64, [_P, _P, c_int64, c_int, c_int, c_int]),
+    "pg_pack5_bytes": (c_int64, [c_int64]),
+    "pg_pack5_host": (c_int64, [_P, c_int64, _P]),
+    "pg_unpack5": (c_int, [_P, c_int64, _P, _P]),
     "pg_ngram_count": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "pg_ngram_count_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_ngram_count_ws_bytes_for": (c_size_t, [c_int, c_int, c_int64]),

@@ -209,3 +209,48 @@ no_room:
     r->pos = rec_start_pos;
     return w;
 }
+
+// ------------------------------------------------------------------------------------------------
+// 5-bit host format of the corpus buffer: what crosses PCIe when a corpus is streamed from host memory
+// (end-to-end step; corpora larger than HBM that are re-uploaded per n level).  Protein text needs 5 bits
+// per symbol, so 8 symbols travel in 5 bytes (0.625 B/symbol instead of 1): symbol i of a group sits in bits
+// [5i, 5i+5) of the group's 40-bit little-endian word.  Fixed code (no alphabet pass needed on the host):
+//   0 = ' ', 1..26 = 'A'..'Z', 27 = '*', 28 = '-', 29 = '.', 31 = 0xFF (sequence separator; also the tail padding,
+//   which adds no window).  Any other byte is refused (PG_EPACK): the caller keeps the byte format.
+// pg_unpack5 (device) restores the byte buffer the kernels read; csrc/ngram.cu holds its kernel.
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline int code5(uint8_t c) {
+    if (c == ' ') return 0;
+    if (c >= 'A' && c <= 'Z') return c - 'A' + 1;
+    if (c == '*') return 27;
+    if (c == '-') return 28;
+    if (c == '.') return 29;
+    if (c == PG_SEP) return 31;
+    return -1;
+}
+}  // namespace
+
+extern "C" int64_t pg_pack5_bytes(int64_t n_symbols) { return n_symbols < 0 ? -1 : (n_symbols + 7) / 8 * 5; }
+
+extern "C" int64_t pg_pack5_host(const uint8_t *bytes, int64_t n_symbols, uint8_t *out) {
+    if (n_symbols < 0 || (n_symbols > 0 && (bytes == nullptr || out == nullptr))) {
+        pg_set_error("pg_pack5_host: bad arguments");
+        return PG_EINVAL;
+    }
+    const int64_t groups = (n_symbols + 7) / 8;
+    for (int64_t g = 0; g < groups; ++g) {
+        uint64_t word = 0;
+        for (int i = 0; i < 8; ++i) {
+            const int64_t p = g * 8 + i;
+            const int c = p < n_symbols ? code5(bytes[p]) : 31;
+            if (c < 0) {
+                pg_set_error("pg_pack5_host: byte 0x%02x at offset %lld has no 5-bit code", bytes[p], (long long)p);
+                return PG_EPACK;
+            }
+            word |= (uint64_t)c << (5 * i);
+        }
+        for (int b = 0; b < 5; ++b) out[g * 5 + b] = (uint8_t)(word >> (8 * b));
+    }
+    return groups * 5;
+}

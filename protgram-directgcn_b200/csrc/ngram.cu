@@ -37,6 +37,40 @@ __global__ void __launch_bounds__(256) byte_presence_kernel(const uint8_t *__res
     if (seen[threadIdx.x] && threadIdx.x != PG_SEP) present256[threadIdx.x] = 1;
 }
 
+// ------------------------------------------------------------------ 5-bit host format -> corpus bytes (see csrc/fasta.cu)
+__constant__ uint8_t kCode5ToByte[32] = {' ', 'A', 'B', 'C', 'D', 'E', 'F', 'G', 'H', 'I', 'J', 'K', 'L', 'M', 'N', 'O',
+                                         'P', 'Q', 'R', 'S', 'T', 'U', 'V', 'W', 'X', 'Y', 'Z', '*', '-', '.', PG_SEP, PG_SEP};
+
+// one thread = two 40-bit groups = 10 packed bytes -> 16 corpus bytes (one 16-byte store)
+__global__ void __launch_bounds__(256) unpack5_kernel(const uint8_t *__restrict__ packed, int64_t n_symbols, uint8_t *__restrict__ out) {
+    __shared__ uint8_t lut[32];
+    if (threadIdx.x < 32) lut[threadIdx.x] = kCode5ToByte[threadIdx.x];
+    __syncthreads();
+    const int64_t pairs = (n_symbols + 15) / 16;
+    const int64_t groups = (n_symbols + 7) / 8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t g = 2 * t + h;
+            unsigned long long word = ~0ull;   // a missing second group decodes to separators (never stored)
+            if (g < groups) {
+                const uint8_t *src = packed + g * 5;
+                word = (unsigned long long)src[0] | ((unsigned long long)src[1] << 8) | ((unsigned long long)src[2] << 16) |
+                       ((unsigned long long)src[3] << 24) | ((unsigned long long)src[4] << 32);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[2 * h + i / 4] |= (uint32_t)lut[(word >> (5 * i)) & 31u] << (8 * (i % 4));
+        }
+        const int64_t p0 = t * 16;
+        if (p0 + 16 <= n_symbols) {
+            *reinterpret_cast<uint4 *>(out + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int i = 0; i < 16 && p0 + i < n_symbols; ++i) out[p0 + i] = (uint8_t)(w[i / 4] >> (8 * (i % 4)));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ synthetic corpus
 __constant__ uint32_t kAaCum16[20] = {5408,  6308,  9885,  14308, 16838, 21473, 22961, 26847, 30662, 37140,
                                       38723, 41383, 44486, 47063, 50689, 54995, 58502, 63002, 63720, 65536};
@@ -745,6 +779,15 @@ extern "C" int pg_byte_presence(const uint8_t *d_buf, int64_t nbytes, uint32_t *
     if (nbytes == 0) return PG_OK;
     byte_presence_kernel<<<grid_for(nbytes / 16 + 1), 256, 0, pg_cu(stream)>>>(d_buf, nbytes, d_present256);
     PG_CUDA_LAUNCH_CHECK("byte_presence_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_unpack5(const uint8_t *d_packed, int64_t n_symbols, uint8_t *d_out, pg_stream_t stream) {
+    PG_CHECK_ARG(n_symbols >= 0, "pg_unpack5: bad size");
+    if (n_symbols == 0) return PG_OK;
+    PG_CHECK_ARG(d_packed && d_out && ((uintptr_t)d_out & 15) == 0, "pg_unpack5: null buffer or output not 16-byte aligned");
+    unpack5_kernel<<<grid_for((n_symbols + 15) / 16, 256, 16), 256, 0, pg_cu(stream)>>>(d_packed, n_symbols, d_out);
+    PG_CUDA_LAUNCH_CHECK("unpack5_kernel");
     return PG_OK;
 }
 

@@ -92,6 +92,50 @@ def stream_chunks_native(fasta_path: str, chunk_bytes: int = 1 << 28, rank: int 
         lib.pg_fasta_close(reader)
 
 
+class PackedChunk:
+    """A corpus chunk kept in HOST memory in the 5-bit format (8 symbols in 5 bytes, include/pgb200.h): what crosses
+    PCIe when a corpus is streamed from the host (chunks beyond the HBM budget are uploaded once per n level)."""
+
+    def __init__(self, packed: torch.Tensor, n_symbols: int):
+        self.packed, self.n_symbols = packed, int(n_symbols)
+
+    @property
+    def size(self) -> int:               # logical corpus bytes
+        return self.n_symbols
+
+
+def pack5(host_buf, pinned: bool = True):
+    """Corpus buffer (host bytes) -> PackedChunk, or None when some byte has no 5-bit code (keep the byte format)."""
+    import ctypes
+    host = torch.from_numpy(np.ascontiguousarray(host_buf)) if not torch.is_tensor(host_buf) else host_buf.contiguous()
+    n = int(host.numel())
+    lib = nat.load()
+    out = torch.empty(int(lib.pg_pack5_bytes(n)), dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
+    got = int(lib.pg_pack5_host(ctypes.c_void_p(host.data_ptr()), n, ctypes.c_void_p(out.data_ptr())))
+    if got == nat.PG_EPACK:
+        return None
+    if got < 0:
+        raise nat.NativeError(f"pg_pack5_host failed ({got}): {lib.pg_last_error().decode()}")
+    return PackedChunk(out[:got], n)
+
+
+def unpack5(d_packed: torch.Tensor, n_symbols: int, out: torch.Tensor = None) -> torch.Tensor:
+    """Packed bytes on the device -> the corpus buffer the kernels read (a view of `out` when it is large enough)."""
+    if out is None or out.numel() < n_symbols:
+        out = torch.empty(max(int(n_symbols), 16), dtype=torch.uint8, device=d_packed.device)
+    nat.call("pg_unpack5", nat.ptr(d_packed), int(n_symbols), nat.ptr(out), nat.stream_ptr())
+    return out[:n_symbols]
+
+
+def chunk_to_device(c, device) -> torch.Tensor:
+    """Device tensor / host byte array / PackedChunk -> corpus buffer on `device`."""
+    if isinstance(c, PackedChunk):
+        return unpack5(to_device(c.packed, device), c.n_symbols)
+    if torch.is_tensor(c) and c.is_cuda:
+        return c
+    return to_device(c, device)
+
+
 def to_device(buf: np.ndarray, device) -> torch.Tensor:
     """Pinned staging + async H2D of the corpus buffer (16 B aligned by the allocator)."""
     host = torch.from_numpy(np.ascontiguousarray(buf).copy()) if not isinstance(buf, torch.Tensor) else buf
@@ -179,7 +223,7 @@ def discover_alphabet(d_buf, group=None) -> Tuple[np.ndarray, torch.Tensor]:
     dev = next((c.device for c in chunks if torch.is_tensor(c) and c.is_cuda), None) or nat.current_device()
     pres = torch.zeros(256, dtype=torch.int32, device=dev)
     for c in chunks:
-        c_dev = c if torch.is_tensor(c) and c.is_cuda else to_device(c, dev)   # host chunks stream through one at a time
+        c_dev = chunk_to_device(c, dev)                                         # host chunks stream through one at a time
         nat.call("pg_byte_presence", nat.ptr(c_dev), c_dev.numel(), nat.ptr(pres), nat.stream_ptr())
     if group is not None:
         import torch.distributed as dist

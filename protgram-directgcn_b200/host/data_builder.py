@@ -81,20 +81,27 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
     sigma = int(symbols.size)
     chunks = list(d_buf) if isinstance(d_buf, (list, tuple)) else [d_buf]
     bins = short = None
-    biggest = max((int(c.numel()) if torch.is_tensor(c) else int(c.size) for c in chunks), default=0)
+    biggest = max((int(c.numel()) if torch.is_tensor(c) else int(c.size) for c in chunks), default=0)   # PackedChunk.size = logical bytes
     ws = count_workspace(n, sigma, biggest, d_rank.device) if chunks else None   # one workspace for all chunks of the level
     host_idx = [i for i, c in enumerate(chunks) if not (torch.is_tensor(c) and c.is_cuda)]
     up = corpus.CorpusUploader(d_rank.device) if host_idx else None
+    wire = lambda c: c.packed if isinstance(c, corpus.PackedChunk) else c     # what crosses PCIe: 5-bit symbols when the chunk was packed
+    scratch = None
     if up is not None:
-        up.submit(chunks[host_idx[0]])
+        up.submit(wire(chunks[host_idx[0]]))
     for i, c in enumerate(chunks):
         if torch.is_tensor(c) and c.is_cuda:
             bins, short = count_level(c, n, d_rank, sigma, bins, short, ws)
             continue
         nxt = host_idx.index(i) + 1
         if nxt < len(host_idx):
-            up.submit(chunks[host_idx[nxt]])            # upload of the next chunk runs under this chunk's count
-        bins, short = count_level(up.acquire(), n, d_rank, sigma, bins, short, ws)
+            up.submit(wire(chunks[host_idx[nxt]]))      # upload of the next chunk runs under this chunk's count
+        d_chunk = up.acquire()
+        if isinstance(c, corpus.PackedChunk):
+            if scratch is None or scratch.numel() < c.n_symbols:
+                scratch = torch.empty(max(c.n_symbols, 16), dtype=torch.uint8, device=d_rank.device)
+            d_chunk = corpus.unpack5(d_chunk, c.n_symbols, scratch)
+        bins, short = count_level(d_chunk, n, d_rank, sigma, bins, short, ws)
         up.release()
     if bins is None:
         bins, short = count_level(torch.empty(0, dtype=torch.uint8, device=d_rank.device), n, d_rank, sigma)
@@ -171,8 +178,8 @@ class GraphBuilder:
                 if resident + size <= hbm_budget:          # keep the corpus in HBM across the n levels
                     chunks.append(corpus.to_device(buf, dev))
                     resident += size
-                else:                                       # larger than the budget: re-streamed per level
-                    chunks.append(buf)
+                else:                                       # larger than the budget: re-streamed per level, 5 bits per symbol on the wire
+                    chunks.append(corpus.pack5(buf) or buf)
         except ValueError as exc:
             print(f"ERROR: {exc}")
             return

@@ -444,3 +444,17 @@ def pg_subgraph_fill(rowptr, col, va, vb, vc, num_nodes, subset, n_sub, new_id, 
         if coo_row is not None:
             coo_row[o:o + m] = s
             coo_col[o:o + m] = c[keep].long()
+
+
+# --------------------------------------------------------------------------- 5-bit host format
+_CODE5 = [ord(" ")] + [ord("A") + i for i in range(26)] + [ord("*"), ord("-"), ord("."), SEP, SEP]
+
+
+def pg_unpack5(packed, n_symbols, out, stream=None):
+    p = packed.cpu().numpy().astype(np.uint64)
+    groups = (n_symbols + 7) // 8
+    w = np.zeros(groups, dtype=np.uint64)
+    for b in range(5):
+        w |= p[b:groups * 5:5] << np.uint64(8 * b)
+    sym = np.stack([(w >> np.uint64(5 * i)) & np.uint64(31) for i in range(8)], 1).reshape(-1)[:n_symbols]
+    out[:n_symbols] = torch.from_numpy(np.array(_CODE5, dtype=np.uint8)[sym.astype(np.int64)])

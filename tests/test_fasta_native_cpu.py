@@ -103,3 +103,53 @@ def test_native_reader_fuzz(tmp_path_factory, lines, final_eol):
     with open(path, "wb") as fh:
         fh.write(data)
     assert b"".join(_native_chunks(path)) == b"".join(_python_chunks(path)), data
+
+
+# ------------------------------------------------------------------------------------------------ 5-bit host format
+def test_pack5_roundtrip_against_spec_and_refusal():
+    import torch
+    from tests import kernel_spec
+    rng = np.random.default_rng(9)
+    alphabet = np.frombuffer(b" ABCDEFGHIJKLMNOPQRSTUVWXYZ*-.\xff", dtype=np.uint8)
+    for n in (0, 1, 7, 8, 9, 15, 16, 17, 1000, 4099):
+        buf = alphabet[rng.integers(0, alphabet.size, n)]
+        chunk = corpus.pack5(buf, pinned=False)
+        assert chunk is not None and chunk.n_symbols == n and chunk.packed.numel() == (n + 7) // 8 * 5
+        out = torch.zeros(max(n, 1), dtype=torch.uint8)
+        kernel_spec.pg_unpack5(chunk.packed, n, out)
+        assert np.array_equal(out[:n].numpy(), buf)
+    assert corpus.pack5(np.frombuffer(b"ACD1EF", dtype=np.uint8), pinned=False) is None      # '1' has no code: keep bytes
+    assert corpus.pack5(np.frombuffer(b"acd", dtype=np.uint8), pinned=False) is None          # the reader upper-cases first
+
+
+def test_graph_builder_streams_packed_host_chunks(monkeypatch, tmp_path):
+    """Corpus beyond the HBM budget: chunks stay on the host in the 5-bit format and are re-uploaded + unpacked per level;
+    the graphs equal the all-resident run."""
+    import pickle
+    from tests import kernel_spec
+    from protgram_directgcn_b200.host import data_builder
+    from protgram_directgcn_b200.host.config import Config
+    kernel_spec.install(monkeypatch, nat)
+    rng = np.random.default_rng(4)
+    recs = "".join(f">p{i}\n" + "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=int(rng.integers(5, 90)))) + "\n" for i in range(400))
+    fasta = _write(tmp_path, recs.encode())
+    graphs = {}
+    real_unpack5 = corpus.unpack5
+    for name, resident in (("resident", 1 << 40), ("streamed", 0)):
+        cfg = Config()
+        cfg.GCN_INPUT_FASTA_PATH = fasta
+        cfg.BASE_OUTPUT_DIR = str(tmp_path / name)
+        cfg.GRAPH_OBJECTS_DIR = str(tmp_path / name / "graphs")
+        cfg.GCN_NGRAM_MAX_N = 2
+        cfg.GRAPH_BUILDER_CHUNK_BYTES = 1 << 12                  # several chunks
+        cfg.GRAPH_BUILDER_RESIDENT_BYTES = resident
+        seen = []
+        monkeypatch.setattr(corpus, "unpack5", lambda *a, _seen=seen, **k: (_seen.append(1), real_unpack5(*a, **k))[1])
+        data_builder.GraphBuilder(cfg).run()
+        assert bool(seen) == (name == "streamed")
+        graphs[name] = [pickle.load(open(os.path.join(cfg.GRAPH_OBJECTS_DIR, f"ngram_graph_n{n}.pkl"), "rb")) for n in (1, 2)]
+    for a, b in zip(graphs["resident"], graphs["streamed"]):
+        assert a.node_sequences == b.node_sequences and a.number_of_edges == b.number_of_edges
+        assert np.array_equal(a.A_out_w.coalesce().indices().numpy(), b.A_out_w.coalesce().indices().numpy())
+        assert np.array_equal(a.A_out_w.coalesce().values().numpy(), b.A_out_w.coalesce().values().numpy())
+        assert np.array_equal(a.mathcal_A_in.coalesce().values().numpy(), b.mathcal_A_in.coalesce().values().numpy())

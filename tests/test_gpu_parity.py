@@ -298,6 +298,18 @@ def test_synth_corpus_matches_cpu_twin_and_is_shard_independent():
     assert np.array_equal(a, ref[1 + 600 * 52:])
 
 
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4096, 1_000_003])
+def test_unpack5_matches_host_packing(n):
+    """5-bit host format (pg_pack5_host) -> pg_unpack5 on the device restores the corpus bytes, any length."""
+    rng = np.random.default_rng(n)
+    alphabet = np.frombuffer(b" ABCDEFGHIJKLMNOPQRSTUVWXYZ*-.\xff", dtype=np.uint8)
+    buf = alphabet[rng.integers(0, alphabet.size, n)]
+    chunk = corpus.pack5(buf)
+    assert chunk is not None and chunk.n_symbols == n
+    out = corpus.unpack5(corpus.to_device(chunk.packed, DEV), n) if n else torch.empty(0, dtype=torch.uint8)
+    assert np.array_equal(out.cpu().numpy(), buf)
+
+
 COUNT_VARIANTS = {"auto": 0, "global": 1, "strict": 2, "fast8_forced_hazard": 4, "partitioned": 5}
 
 
