@@ -238,19 +238,35 @@ extern "C" int64_t pg_pack5_host(const uint8_t *bytes, int64_t n_symbols, uint8_
         pg_set_error("pg_pack5_host: bad arguments");
         return PG_EINVAL;
     }
-    const int64_t groups = (n_symbols + 7) / 8;
-    for (int64_t g = 0; g < groups; ++g) {
+    uint8_t lut[256];
+    for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)(code5((uint8_t)c) < 0 ? 0x80 : code5((uint8_t)c));
+    const int64_t groups = (n_symbols + 7) / 8, full = n_symbols / 8;
+    uint8_t bad = 0;
+    for (int64_t g = 0; g < full; ++g) {   // branch-free: invalid bytes only raise the top bit of `bad`
+        const uint8_t *src = bytes + g * 8;
         uint64_t word = 0;
         for (int i = 0; i < 8; ++i) {
-            const int64_t p = g * 8 + i;
-            const int c = p < n_symbols ? code5(bytes[p]) : 31;
-            if (c < 0) {
-                pg_set_error("pg_pack5_host: byte 0x%02x at offset %lld has no 5-bit code", bytes[p], (long long)p);
-                return PG_EPACK;
-            }
-            word |= (uint64_t)c << (5 * i);
+            const uint8_t c = lut[src[i]];
+            bad |= c;
+            word |= (uint64_t)(c & 31u) << (5 * i);
         }
         for (int b = 0; b < 5; ++b) out[g * 5 + b] = (uint8_t)(word >> (8 * b));
+    }
+    if (full < groups) {                   // tail group, padded with separators
+        uint64_t word = 0;
+        for (int i = 0; i < 8; ++i) {
+            const int64_t p = full * 8 + i;
+            const uint8_t c = p < n_symbols ? lut[bytes[p]] : (uint8_t)31;
+            bad |= c;
+            word |= (uint64_t)(c & 31u) << (5 * i);
+        }
+        for (int b = 0; b < 5; ++b) out[full * 5 + b] = (uint8_t)(word >> (8 * b));
+    }
+    if (bad & 0x80u) {
+        int64_t p = 0;
+        while (p < n_symbols && !(lut[bytes[p]] & 0x80u)) ++p;
+        pg_set_error("pg_pack5_host: byte 0x%02x at offset %lld has no 5-bit code", bytes[p], (long long)p);
+        return PG_EPACK;
     }
     return groups * 5;
 }
