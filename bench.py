@@ -680,6 +680,15 @@ def run_b200(args):
         for _ in range(warmup):
             last = fn()         # keep the previous result alive exactly like the timed loop does (same allocator pattern)
             pipe.collect_count_ms()
+        # a cudaMalloc inside the timed region is a device-wide stall (seen as one 4-5 ms step): keep warming up, untimed, until the
+        # caching allocator (two streams = two pools) has stopped growing for three steps in a row
+        quiet, extra = 0, 0
+        while quiet < 3 and extra < 16:
+            before = torch.cuda.memory_stats(dev)["num_device_alloc"]
+            last = fn()
+            pipe.collect_count_ms()
+            quiet = quiet + 1 if torch.cuda.memory_stats(dev)["num_device_alloc"] == before else 0
+            extra += 1
         pipe.flush()
         pipe.count_ms.clear()
         gc.collect()

@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(256) wprep_kernel(const float *__restrict__ w_
 constexpr int TC_PRODUCERS = 256;
 constexpr int TC_THREADS2 = TC_PRODUCERS + 32;
 
-// Epilogue of the forward transform: H = leaky_relu(acc (+X) + constant); the side operands of the NEXT 16 columns are
-// loaded while this chunk's accumulators come out of TMEM.
+// Epilogue of the forward transform: H = leaky_relu(acc (+X) + constant).  The kernel hands the epilogues float4s of one row
+// in an order that makes a warp's stores cover whole 128-byte lines (see the staging in tc_rows_gemm_kernel).
 struct EpiFwdTc {
     const float *constant, *x;
     int64_t ldconst, ldx;
@@ -107,31 +107,23 @@ struct EpiFwdTc {
     float slope;
     float *h;
     int64_t ldh;
-    static constexpr bool kHasSide = true;
-    __device__ __forceinline__ void load_side(int64_t row, int c, float4 (&dst)[4]) const {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (constant) acc4 = __ldg(reinterpret_cast<const float4 *>(constant + row * ldconst + c + q * 4));
-            if (add_identity) {
-                const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + row * ldx + c + q * 4));
-                acc4.x += xv.x; acc4.y += xv.y; acc4.z += xv.z; acc4.w += xv.w;
-            }
-            dst[q] = acc4;
+    // 4 consecutive columns c..c+3 of one row (c % 4 == 0, inside the matrix)
+    __device__ __forceinline__ void store4(int64_t row, int c, float4 v) const {
+        if (constant) {
+            const float4 cv = __ldg(reinterpret_cast<const float4 *>(constant + row * ldconst + c));
+            v.x += cv.x; v.y += cv.y; v.z += cv.z; v.w += cv.w;
         }
-    }
-    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&side)[4]) const {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 sd = side[q];
-            float y[4] = {__uint_as_float(r[q * 4 + 0]) + sd.x, __uint_as_float(r[q * 4 + 1]) + sd.y,
-                          __uint_as_float(r[q * 4 + 2]) + sd.z, __uint_as_float(r[q * 4 + 3]) + sd.w};
-            if (slope != 1.f) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
-            }
-            *reinterpret_cast<float4 *>(h + row * ldh + c + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+        if (add_identity) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + row * ldx + c));
+            v.x += xv.x; v.y += xv.y; v.z += xv.z; v.w += xv.w;
         }
+        if (slope != 1.f) {
+            v.x = v.x > 0.f ? v.x : v.x * slope;
+            v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope;
+            v.w = v.w > 0.f ? v.w : v.w * slope;
+        }
+        *reinterpret_cast<float4 *>(h + row * ldh + c) = v;
     }
 };
 
@@ -256,26 +248,39 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) tc_rows
         if (!bail && !mbar_wait(&done, 0)) bail = 1;
         fence_after_sync();
         if (!bail) {
-            // TMEM lanes are owned per warp quadrant (warp % 4); warps 4..7 take the upper half of the columns
+            // TMEM lanes are owned per warp quadrant (warp % 4); warps 4..7 take the upper half of the columns.  tcgen05.ld
+            // gives every lane 32 consecutive columns of ITS row; written out like that, one store instruction would touch 32
+            // different rows (32 lines, 16 bytes each).  Each warp therefore transposes through its own 32 x 32 patch of the
+            // (now idle) pipeline stages: rows padded to 36 floats (conflict-free float4 rows), read back as 8 lanes per row,
+            // so a store instruction covers 4 rows x 128 contiguous bytes.
             const int quad = warp & 3;
-            const int64_t row = m0 + quad * 32 + lane;
+            float *stg = reinterpret_cast<float *>(smem) + warp * (32 * 36);
             const int half_cols = ((n_blk / 16 + 1) / 2) * 16;
             const int c_begin = (warp < 4) ? 0 : half_cols, c_end = (warp < 4) ? half_cols : n_blk;
-            const bool in_range = row < A.M;
-            auto load_side = [&](int c0, float4 (&dst)[4]) {
-                if (Epi::kHasSide && in_range && c0 < c_end) epi.load_side(row, n0 + c0, dst);
-            };
-            auto process = [&](int c0, const float4 (&cur)[4], float4 (&nxt)[4]) {
-                load_side(c0 + 16, nxt);  // next chunk's side loads fly under this chunk's TMEM read + stores
-                uint32_t r[16];
-                tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-                if (in_range) epi.store(row, n0 + c0, r, cur);
-            };
-            float4 side_a[4], side_b[4];
-            load_side(c_begin, side_a);
+            const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                process(c0, side_a, side_b);
-                if (c0 + 16 < c_end) process(c0 + 16, side_b, side_a);
+                uint32_t r[32];
+                tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                if (c0 + 16 < c_end) {
+                    tmem_ld16(taddr + (uint32_t)(c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+                } else {
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(stg + lane * 36 + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + (lane >> 3);
+                    const int cc = c0 + 4 * (lane & 7);
+                    const int64_t row = m0 + quad * 32 + rl;
+                    const float4 v = *reinterpret_cast<const float4 *>(stg + rl * 36 + 4 * (lane & 7));
+                    if (row < A.M && cc < c_end) epi.store4(row, n0 + cc, v);
+                }
+                __syncwarp();
             }
         }
     }
@@ -303,18 +308,10 @@ struct EpiBwdDataTc {  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in,
     float *dz, *dxres;
     int64_t lddz, lddxres;
     int f3, k_data;
-    static constexpr bool kHasSide = false;
-    __device__ __forceinline__ void load_side(int64_t, int, float4 (&)[4]) const {}
-    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&)[4]) const {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int cc = c + 4 * q;   // f3 and k_data are multiples of 4: a float4 never straddles a boundary
-            if (cc >= k_data) continue;
-            const float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                         __uint_as_float(r[q * 4 + 3]));
-            if (cc < f3) *reinterpret_cast<float4 *>(dz + row * lddz + cc) = v;
-            else *reinterpret_cast<float4 *>(dxres + row * lddxres + (cc - f3)) = v;
-        }
+    __device__ __forceinline__ void store4(int64_t row, int c, float4 v) const {
+        if (c >= k_data) return;   // f3 and k_data are multiples of 4: a float4 never straddles a boundary
+        if (c < f3) *reinterpret_cast<float4 *>(dz + row * lddz + c) = v;
+        else *reinterpret_cast<float4 *>(dxres + row * lddxres + (c - f3)) = v;
     }
 };
 
@@ -323,23 +320,20 @@ struct EpiLinearTc {  // out[row, c] = acc + bias[c]   (plain Linear; c < n_tota
     int64_t ldo;
     const float *bias;
     int n_total;
-    static constexpr bool kHasSide = false;
-    __device__ __forceinline__ void load_side(int64_t, int, float4 (&)[4]) const {}
-    __device__ __forceinline__ void store(int64_t row, int c, const uint32_t (&r)[16], const float4 (&)[4]) const {
+    __device__ __forceinline__ void store4(int64_t row, int c, float4 v) const {
+        if (c >= n_total) return;
+        float y[4] = {v.x, v.y, v.z, v.w};
+        if (bias) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int cc = c + 4 * q;
-            if (cc >= n_total) continue;
-            float y[4];
+            for (int j = 0; j < 4; ++j)
+                if (c + j < n_total) y[j] += __ldg(bias + c + j);
+        }
+        if (c + 3 < n_total) {
+            *reinterpret_cast<float4 *>(out + row * ldo + c) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = __uint_as_float(r[q * 4 + j]) + ((bias && cc + j < n_total) ? __ldg(bias + cc + j) : 0.f);
-            if (cc + 3 < n_total) {
-                *reinterpret_cast<float4 *>(out + row * ldo + cc) = make_float4(y[0], y[1], y[2], y[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (cc + j < n_total) out[row * ldo + cc + j] = y[j];
-            }
+            for (int j = 0; j < 4; ++j)
+                if (c + j < n_total) out[row * ldo + c + j] = y[j];
         }
     }
 };
@@ -579,6 +573,7 @@ int launch_rows_gemm(const AOp &A, const Epi &epi, const float4 *wp, int n_full,
             PG_CUDA_CALL(cudaFuncSetAttribute(tc_rows_gemm_kernel<CHUNKS, AOp, Epi>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
+    if (smem < (size_t)8 * 32 * 36 * sizeof(float)) smem = (size_t)8 * 32 * 36 * sizeof(float);   // the epilogue's staging patches
     tc_rows_gemm_kernel<CHUNKS, AOp, Epi><<<grid, TC_THREADS2, smem, st>>>(A, epi, wp, n_full, n_total, k_tiles, err);
     return PG_OK;
 }
