@@ -502,7 +502,7 @@ def _max_over_ranks(dist, dev, v):
     return float(t.item())
 
 
-def build_scale_leg(pipe, dist, n_level, total_seqs, iters=2, normalise=True):
+def build_scale_leg(pipe, dist, n_level, total_seqs, iters=3, normalise=True):
     """Graph build of one n level at BASELINE configs C3 (n=4) / C4 (n=5, 50 M sequences = 17.5 G residues):
     `total_seqs` 350-residue sequences split over the ranks by contiguous ranges (STRONG scaling: the corpus is
     fixed), each shard generated on its GPU (counter-based, shard independent); timed = count -> NCCL sum of the
@@ -542,7 +542,9 @@ def build_scale_leg(pipe, dist, n_level, total_seqs, iters=2, normalise=True):
             t_count.append(ev[0].elapsed_time(ev[1])); t_merge.append(ev[1].elapsed_time(ev[2])); t_extract.append(ev[2].elapsed_time(ev[3]))
         del bins, short
     node_code, src, dst, cnt = res
-    mc, mm, me = (_max_over_ranks(dist, dev, statistics.mean(t)) for t in (t_count, t_merge, t_extract))
+    # median over the passes: the extraction allocates ~3 GB of outputs + workspace per pass and an occasional cudaMalloc
+    # (allocator growth, not kernel time) would otherwise dominate a 2 ms phase
+    mc, mm, me = (_max_over_ranks(dist, dev, statistics.median(t)) for t in (t_count, t_merge, t_extract))
     residues = per * world * SEQ_LEN
     nodes, edges = int(node_code.numel()), int(src.numel())
     out = {"n": n_level, "sequences": per * world, "residues": residues, "sigma": sigma, "table_bins": pow_m, "nodes": nodes,
