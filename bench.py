@@ -661,6 +661,18 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run it (and first-touch its pinned upload buffers) on the CPUs / NUMA node next to that GPU --
+    # with 8 ranks the end-to-end step is bound by host memory and PCIe traffic, not by the GPUs
+    affinity = None
+    if world > 1:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            affinity = f"nvml ideal cpus ({len(os.sched_getaffinity(0))} cores)"
+            torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)) // 8)))    # the ranks of one socket share its cores
+        except Exception as exc:  # noqa: BLE001 - best effort
+            affinity = f"unchanged ({type(exc).__name__})"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -750,7 +762,7 @@ def run_b200(args):
         "dtype": "u8 keys / u64 counts / f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "residues_per_step_per_gpu": NSEQ * SEQ_LEN, "n": N_LEVEL, "layer_dims": DIMS,
                    "nodes": graph.number_of_nodes, "unique_edges": graph.number_of_edges, "pattern_nnz": int(graph.mathcal_A_out._nnz()),
-                   "l2_handling": "inputs larger than L2 (corpus 176 MB per GPU > 126 MB L2)",
+                   "l2_handling": "inputs larger than L2 (corpus 176 MB per GPU > 126 MB L2)", "cpu_affinity": affinity,
                    "multi_gpu": "corpus sharded by sequence range, tables merged by NCCL all-reduce, n=3 DirectGCN replicated",
                    "directgcn_step": "eager" if args.no_cuda_graph else "CUDA graph replay (fwd+loss+bwd+Adam+eval fwd captured once)",
                    "pipelining": ("graph build of batch k+1 on its own stream under the DirectGCN replay of batch k (two-stage software pipeline; "
