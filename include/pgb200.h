@@ -66,6 +66,11 @@ int64_t pg_fasta_file_bytes(const pg_fasta_reader *reader);
 int64_t pg_fasta_records(const pg_fasta_reader *reader); /* records emitted so far, all ranks */
 int pg_fasta_stopped_early(const pg_fasta_reader *reader);
 int64_t pg_fasta_next_chunk(pg_fasta_reader *reader, uint8_t *out, int64_t cap, int rank, int world, int block);
+/* The whole file (this rank's records) in one call, parsed by `threads` host threads over file ranges cut at header
+ * lines; out needs file size + 16 bytes at most.  Returns the bytes written (same bytes as draining pg_fasta_next_chunk)
+ * or a negative code; *n_records = records of all ranks, *stopped_early as above. */
+int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_t cap, int threads, int rank, int world, int block,
+                               int64_t *n_records, int *stopped_early);
 
 /* 5-bit host format of the corpus buffer (what crosses PCIe when a corpus is streamed from host memory): 8 symbols in
  * 5 bytes, fixed code ' ' = 0, 'A'..'Z' = 1..26, '*' = 27, '-' = 28, '.' = 29, separator = 31 (also the tail padding).

@@ -270,3 +270,171 @@ extern "C" int64_t pg_pack5_host(const uint8_t *bytes, int64_t n_symbols, uint8_
     }
     return groups * 5;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Whole-file variant on several host threads.  The file is cut into ranges that start at header lines ('>' right after
+// a line break), so no record spans two ranges; pass 1 counts the records of every range, a prefix sum gives every
+// range its first global record index (rank dealing and the leading space of record #0 depend on it), pass 2 sizes
+// this rank's bytes per range, pass 3 writes them -- all three passes in parallel over the ranges.  Same output as
+// draining pg_fasta_next_chunk into one buffer.
+// ------------------------------------------------------------------------------------------------
+#include <thread>
+#include <vector>
+
+namespace {
+struct RangeStat {
+    int64_t lo, hi;         // file range
+    int64_t records;        // records emitted in this range
+    int64_t stop_at;        // file offset of a bare ">" header inside the range, or -1
+    int64_t first_index;    // global index of the range's first record
+    int64_t bytes;          // packed bytes of this rank's records
+    int64_t out_off;        // where they go
+    int bad;                // non-ASCII sequence byte seen
+};
+
+// mode 0: count records (+ find the stop);  1: size this rank's bytes;  2: write them
+template <int MODE>
+void parse_range(const uint8_t *d, RangeStat &r, uint8_t *out, int rank, int world, int block) {
+    int64_t pos = r.lo;
+    const int64_t end = r.stop_at >= 0 ? r.stop_at : r.hi;
+    bool open_rec = false;
+    int64_t rec_len = 0, idx = r.first_index, w = r.out_off, bytes = 0, records = 0;
+    auto mine = [&](int64_t i) { return (i / block) % world == rank; };
+    auto finish = [&]() {
+        if (open_rec && rec_len > 0) {
+            if (MODE == 0) bytes += rec_len + 2;   // world == 1 needs no sizing pass: every record is this rank's
+            if (MODE >= 1 && mine(idx)) {
+                const int64_t lead = idx == 0 ? 1 : 0;
+                if (MODE == 2) {
+                    out[w + lead + rec_len] = ' ';
+                    out[w + lead + rec_len + 1] = PG_SEP;
+                    w += lead + rec_len + 2;
+                }
+                bytes += lead + rec_len + 2;
+            }
+            ++idx;
+            ++records;
+        }
+        open_rec = false;
+    };
+    while (pos < end) {
+        int64_t b, e;
+        const int64_t line_pos = pos;
+        const int64_t next = next_line(d, pos, r.hi, &b, &e);
+        pos = next;
+        if (b == e) continue;
+        if (d[b] == '>') {
+            finish();
+            if (e - b == 1) {   // the reference's generator stops here
+                if (MODE == 0) r.stop_at = line_pos;
+                break;
+            }
+            open_rec = true;
+            rec_len = 0;
+            continue;
+        }
+        if (!open_rec) continue;
+        if (MODE == 2 && mine(idx)) {
+            const int64_t lead = idx == 0 ? 1 : 0;
+            if (rec_len == 0 && lead) out[w] = ' ';
+            if (copy_upper(out + w + lead + rec_len, d + b, e - b) & 0x80u) r.bad = 1;
+        } else if (MODE == 0) {
+            if (or_bytes(d + b, e - b) & 0x80u) r.bad = 1;
+        }
+        rec_len += e - b;
+    }
+    finish();
+    if (MODE == 0) r.records = records;
+    if (MODE <= 1) r.bytes = bytes;
+}
+
+template <class F>
+void run_parallel(int n, int threads, F f) {
+    if (threads <= 1 || n <= 1) {
+        for (int i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=] { for (int i = t; i < n; i += threads) f(i); });
+    for (auto &th : pool) th.join();
+}
+}  // namespace
+
+extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_t cap, int threads, int rank, int world, int block,
+                                          int64_t *n_records, int *stopped_early) {
+    if (out == nullptr || cap < 4 || world < 1 || rank < 0 || rank >= world || block < 1 || threads < 1) {
+        pg_set_error("pg_fasta_pack_parallel: bad arguments");
+        return PG_EINVAL;
+    }
+    pg_fasta_reader *rd = pg_fasta_open(path);
+    if (rd == nullptr) return PG_EINVAL;
+    const uint8_t *d = rd->data;
+    const int64_t size = rd->size;
+    // ranges: nominal cuts moved forward to the next header line
+    const int n_ranges = (int)(size < (1 << 20) ? 1 : (threads * 4 < 256 ? threads * 4 : 256));
+    std::vector<RangeStat> rs;
+    auto next_header = [&](int64_t from) -> int64_t {   // first '>' at or after `from` that directly follows a line break
+        int64_t p = from;
+        while (p < size) {
+            const uint8_t *q = (const uint8_t *)memchr(d + p, '>', (size_t)(size - p));
+            if (q == nullptr) return size;
+            p = (int64_t)(q - d);
+            if (p > 0 && (d[p - 1] == '\n' || d[p - 1] == '\r')) return p;
+            ++p;
+        }
+        return size;
+    };
+    int64_t lo = 0;
+    for (int i = 1; i <= n_ranges && lo < size; ++i) {
+        const int64_t nominal = size / n_ranges * i;
+        const int64_t cut = i == n_ranges ? size : next_header(nominal > lo ? nominal : lo + 1);
+        if (cut > lo) {
+            rs.push_back(RangeStat{lo, cut, 0, -1, 0, 0, 0, 0});
+            lo = cut;
+        }
+    }
+    const int n = (int)rs.size();
+    run_parallel(n, threads, [&](int i) { parse_range<0>(d, rs[i], nullptr, rank, world, block); });
+    int stop_range = -1;
+    int64_t total_records = 0;
+    for (int i = 0; i < n; ++i) {
+        if (stop_range >= 0) {      // everything after the stop is ignored
+            rs[i].hi = rs[i].lo;
+            rs[i].records = 0;
+            continue;
+        }
+        rs[i].first_index = total_records;
+        total_records += rs[i].records;
+        if (rs[i].stop_at >= 0) stop_range = i;
+    }
+    int64_t rcode = 0;
+    for (int i = 0; i < n; ++i)
+        if (rs[i].bad && rs[i].hi > rs[i].lo) rcode = PG_FASTA_ENONASCII;
+    if (rcode == 0) {
+        if (world > 1) {
+            run_parallel(n, threads, [&](int i) { if (rs[i].hi > rs[i].lo) parse_range<1>(d, rs[i], nullptr, rank, world, block); });
+        } else {
+            for (int i = 0; i < n; ++i)   // pass 1 sized every record; the leading space goes to the range that holds record #0
+                if (rs[i].hi > rs[i].lo && rs[i].records > 0 && rs[i].first_index == 0) rs[i].bytes += 1;
+        }
+        int64_t off = 0;
+        for (int i = 0; i < n; ++i) {
+            rs[i].out_off = off;
+            off += rs[i].hi > rs[i].lo ? rs[i].bytes : 0;
+        }
+        if (off > cap) {
+            pg_set_error("pg_fasta_pack_parallel: %lld bytes do not fit the buffer (%lld)", (long long)off, (long long)cap);
+            rcode = PG_FASTA_ETOOSMALL;
+        } else {
+            run_parallel(n, threads, [&](int i) { if (rs[i].hi > rs[i].lo) parse_range<2>(d, rs[i], out, rank, world, block); });
+            rcode = off;
+        }
+    } else {
+        pg_set_error("pg_fasta_pack_parallel: non-ASCII byte in sequence text");
+    }
+    if (n_records) *n_records = total_records;
+    if (stopped_early) *stopped_early = stop_range >= 0 ? 1 : 0;
+    pg_fasta_close(rd);
+    return rcode;
+}

@@ -136,6 +136,50 @@ def chunk_to_device(c, device) -> torch.Tensor:
     return to_device(c, device)
 
 
+def read_fasta_parallel(fasta_path: str, threads: int = 0, rank: int = 0, world: int = 1, block: int = 4096,
+                        pinned: bool = False, stats: dict = None) -> torch.Tensor:
+    """Whole FASTA file -> ONE corpus buffer (this rank's records), parsed by several host threads over file ranges cut at
+    header lines (csrc/fasta.cu:pg_fasta_pack_parallel).  Same bytes as concatenating stream_chunks_native()."""
+    import ctypes
+    import os
+    lib = nat.load()
+    path = os.path.normpath(fasta_path)
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    threads = int(threads) if threads else max(1, min(32, len(os.sched_getaffinity(0))))
+    cap = os.path.getsize(path) + 64
+    buf = torch.empty(cap, dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
+    n_rec, stopped = ctypes.c_int64(0), ctypes.c_int(0)
+    got = int(lib.pg_fasta_pack_parallel(path.encode(), ctypes.c_void_p(buf.data_ptr()), cap, threads, rank, world, block,
+                                         ctypes.byref(n_rec), ctypes.byref(stopped)))
+    if got == nat.PG_FASTA_ENONASCII:
+        raise NonAsciiSequence(lib.pg_last_error().decode())
+    if got < 0:
+        raise nat.NativeError(f"pg_fasta_pack_parallel failed ({got}): {lib.pg_last_error().decode()}")
+    if stats is not None:
+        stats["sequences"], stats["stopped_early"] = int(n_rec.value), bool(stopped.value)
+    return buf[:got]
+
+
+def split_at_separators(buf: torch.Tensor, chunk_bytes: int):
+    """Views of a host corpus buffer of about chunk_bytes each, cut right after a sequence separator."""
+    n = int(buf.numel())
+    out, lo = [], 0
+    arr = buf.numpy()
+    while lo < n:
+        hi = min(n, lo + max(int(chunk_bytes), 1))
+        if hi < n:
+            back = np.flatnonzero(arr[lo:hi] == SEP)
+            if back.size:
+                hi = lo + int(back[-1]) + 1
+            else:                                   # one sequence longer than the chunk: extend to its separator
+                fwd = np.flatnonzero(arr[hi:] == SEP)
+                hi = hi + int(fwd[0]) + 1 if fwd.size else n
+        out.append(buf[lo:hi])
+        lo = hi
+    return out
+
+
 def to_device(buf: np.ndarray, device) -> torch.Tensor:
     """Pinned staging + async H2D of the corpus buffer (16 B aligned by the allocator)."""
     host = torch.from_numpy(np.ascontiguousarray(buf).copy()) if not isinstance(buf, torch.Tensor) else buf

@@ -160,8 +160,19 @@ class GraphBuilder:
             # sequence text takes the Python parser, which reproduces the reference's utf-8 'ignore' decoding first.
             stats = {}
             try:
-                for buf in corpus.stream_chunks_native(self.protein_sequence_file, chunk_bytes, rank, world, pinned=True, stats=stats):
-                    yield buf
+                path = os.path.normpath(self.protein_sequence_file)
+                try:
+                    ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+                except (ValueError, OSError):
+                    ram = 0
+                if os.path.getsize(path) <= ram // 4:
+                    # fits host memory comfortably: parse it with all host threads in one call, then cut at sequence boundaries
+                    whole = corpus.read_fasta_parallel(path, rank=rank, world=world, pinned=True, stats=stats)
+                    for buf in corpus.split_at_separators(whole, chunk_bytes):
+                        yield buf
+                else:
+                    for buf in corpus.stream_chunks_native(path, chunk_bytes, rank, world, pinned=True, stats=stats):
+                        yield buf
                 n_seqs[0] = stats.get("sequences", 0)
                 if stats.get("stopped_early"):
                     print(f"Error parsing FASTA file {self.protein_sequence_file}: list index out of range")  # the reference's message

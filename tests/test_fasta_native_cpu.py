@@ -153,3 +153,45 @@ def test_graph_builder_streams_packed_host_chunks(monkeypatch, tmp_path):
         assert np.array_equal(a.A_out_w.coalesce().indices().numpy(), b.A_out_w.coalesce().indices().numpy())
         assert np.array_equal(a.A_out_w.coalesce().values().numpy(), b.A_out_w.coalesce().values().numpy())
         assert np.array_equal(a.mathcal_A_in.coalesce().values().numpy(), b.mathcal_A_in.coalesce().values().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ parallel whole-file reader
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_parallel_reader_matches_streaming_reader_on_edge_files(name, tmp_path):
+    path = _write(tmp_path, CASES[name])
+    ref_stats, stats = {}, {}
+    ref = b"".join(_native_chunks(path, stats=ref_stats))
+    for threads in (1, 3):
+        got = bytes(corpus.read_fasta_parallel(path, threads=threads, stats=stats).numpy())
+        assert got == ref and stats == ref_stats
+
+
+def test_parallel_reader_large_file_threads_and_ranks(tmp_path):
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(30_000):
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYacd"), size=int(rng.integers(1, 120))))
+        recs.append(f">id{i} x\n" + "\n".join(seq[j:j + 60] for j in range(0, len(seq), 60)) + ("\r\n" if i % 7 == 0 else "\n"))
+        if i == 17_000:
+            recs.append(">emptyrecord\n\n")
+    data = "".join(recs).encode()
+    assert len(data) > (1 << 20)                    # several ranges
+    path = _write(tmp_path, data)
+    ref_stats = {}
+    ref = b"".join(_native_chunks(path, 1 << 22, stats=ref_stats))
+    for threads in (1, 2, 8):
+        stats = {}
+        assert bytes(corpus.read_fasta_parallel(path, threads=threads, stats=stats).numpy()) == ref and stats == ref_stats
+    for rank in range(3):
+        assert bytes(corpus.read_fasta_parallel(path, threads=4, rank=rank, world=3, block=64).numpy()) == \
+            b"".join(_native_chunks(path, 1 << 22, rank, 3, 64))
+    # a bare '>' in the middle stops every later range as well
+    stop = data[:len(data) // 2].rsplit(b"\n>", 1)[0] + b"\n>\n" + data[len(data) // 2:]
+    path2 = _write(tmp_path, stop, "stop.fasta")
+    s1, s2 = {}, {}
+    assert bytes(corpus.read_fasta_parallel(path2, threads=8, stats=s1).numpy()) == b"".join(_native_chunks(path2, 1 << 22, stats=s2))
+    assert s1 == s2 and s1["stopped_early"]
+    # chunking of a whole buffer at separators
+    whole = corpus.read_fasta_parallel(path, threads=4)
+    parts = corpus.split_at_separators(whole, 1 << 18)
+    assert b"".join(bytes(p.numpy()) for p in parts) == ref and all(bytes(p.numpy()).endswith(b"\xff") for p in parts)
