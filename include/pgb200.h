@@ -223,6 +223,14 @@ int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d
                    const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
                    const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
                    const pg_spmm_plan *plan, pg_stream_t stream);
+/* Same with per-SOURCE-row scales: Z_v[i] = sum_j val_v[i,j] * s_v[j] * X[j] (d_s0 NULL = unscaled; scale_stride 1 = one
+ * scale per row, 0 = a scalar).  The layer's backward uses it with X = dY and s_v = gate_v on the symmetric structure:
+ * dX = sum_v (A_v (g_v * dY)) W_v^T gathers F_out-wide rows once instead of the 3 F_in-wide gated gradient. */
+int pg_spmm_fanout_scaled(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
+                          const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
+                          const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
+                          const float *d_s0, const float *d_s1, const float *d_s2, int scale_stride,
+                          const pg_spmm_plan *plan, pg_stream_t stream);
 
 /* Fan-in SpMM (backward of the above over the transposed structure; forward of nothing else):
  *     Y[i, :] = (d_init ? init[i, :] : 0) + sum_v sum_k val_v[k] * G[col[k], g_off + v*F : +F]
@@ -301,6 +309,13 @@ int pg_layer_gemm_bwd_weight_tc(const float *d_z, int64_t ldz, const float *d_x,
                                 int gate_stride, const float *d_dy, int64_t lddy, int64_t num_rows,
                                 int F_in, int F_out, int has_res, float *d_dw_ext, void *d_ws,
                                 size_t ws_bytes, pg_stream_t stream);
+/* Input gradient through the transposed structure (symmetric shared pattern): with d_t = [T_in | T_out | T_und],
+ * T_v = A_v (gate_v * dY) from pg_spmm_fanout_scaled,  dX = d_t @ [W'_in^T; W'_out^T; W'_und^T] (+ dY @ W_res^T | + dY).
+ * Replaces gathering the 3 F_in-wide gated gradient (pg_spmm_fanin) by gathering F_out-wide rows of dY. */
+size_t pg_layer_gemm_bwd_dx_tc_ws_bytes(int F_in, int F_out, int has_res);
+int pg_layer_gemm_bwd_dx_tc(const float *d_t, int64_t ldt, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                            int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx,
+                            int64_t lddx, void *d_ws, size_t ws_bytes, pg_stream_t stream);
 int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream);
 
 /* Plain Linear on the same tensor-core kernel: out[N, C] = x[N, K] @ W[C, K]^T + bias (torch.nn.Linear layout, bias may be

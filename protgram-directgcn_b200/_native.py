@@ -57,6 +57,8 @@ _SIGS = {
     "pg_edges_to_csr_ws_bytes": (c_size_t, [c_int64]),
     "pg_edges_to_csr": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "pg_spmm_fanout": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P, _P]),
+    "pg_spmm_fanout_scaled": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
+                                      _P, _P]),
     "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
                               c_int64, c_int, _P, _P]),
     "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
@@ -78,6 +80,8 @@ _SIGS = {
     "pg_layer_gemm_bwd_weight_tc_ws_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "pg_layer_gemm_bwd_weight_tc": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int,
                                             c_int, c_int, _P, _P, c_size_t, _P]),
+    "pg_layer_gemm_bwd_dx_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pg_layer_gemm_bwd_dx_tc": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_size_t, _P]),
     "pg_tc_check": (c_int, [_P, c_size_t, _P]),
     "pg_linear_tc_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_linear_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),

@@ -315,6 +315,64 @@ struct EpiBwdDataTc {  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in,
     }
 };
 
+// ---- input gradient through the transposed structure:  dX = [T_in | T_out | T_und | dY?] @ Wcat (+ dY),  T_v = A_v (g_v * dY)
+struct ACat2Tc {   // A(i, k) = k < K1 ? t[i, k] : dy[i, k - K1]     (K1 and K multiples of 4, 16 B aligned rows)
+    const float *t, *dy;
+    int64_t ldt, lddy, M;
+    int K1, K;
+    __device__ __forceinline__ float4 at4(int64_t i, int k0) const {
+        if (i >= M || k0 + 3 >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < K1) return __ldg(reinterpret_cast<const float4 *>(t + i * ldt + k0));
+        return __ldg(reinterpret_cast<const float4 *>(dy + i * lddy + (k0 - K1)));
+    }
+};
+
+struct EpiDxTc {   // dX[row, c] = acc (+ dY[row, c] for the identity residual); c < F_in
+    float *dx;
+    const float *dy;   // null unless add_identity
+    int64_t lddx, lddy;
+    int F_in;
+    __device__ __forceinline__ void store4(int64_t row, int c, float4 v) const {
+        if (c >= F_in) return;
+        if (dy) {
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(dy + row * lddy + c));
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *reinterpret_cast<float4 *>(dx + row * lddx + c) = v;
+    }
+};
+
+// B image of the dX GEMM: B(k, n = c) = W_ext[(k / F_out) * F_in + c][k % F_out] for the three propagation blocks and, with a
+// residual projection, W_ext[3 F_in + c][k - 3 F_out] for k >= 3 F_out; [block][kt][half][chunk][n] like wprep_kernel
+__global__ void __launch_bounds__(256) wprep_dx_kernel(const float *__restrict__ w_ext, int F_in, int F_out, int K, int k_tiles, int n_full,
+                                                       int blocks, float4 *__restrict__ wp) {
+    constexpr int CH = 4;
+    const int64_t per_block = (int64_t)k_tiles * 2 * CH * n_full;
+    const int64_t slots = (int64_t)k_tiles * CH * n_full;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots * blocks; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / slots);
+        const int64_t u = t - (int64_t)b * slots;
+        const int n0 = b * n_full;
+        const int n_blk = min(n_full, ((F_in - n0 + 15) / 16) * 16);
+        if (u >= (int64_t)k_tiles * CH * n_blk) continue;
+        const int n = (int)(u % n_blk);
+        const int kc = (int)((u / n_blk) % CH);
+        const int kt = (int)(u / ((int64_t)n_blk * CH));
+        const int c = n0 + n;
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = kt * 16 + kc * 4 + j;
+            v[j] = (k < K && c < F_in) ? w_ext[((int64_t)(k / F_out) * F_in + c) * F_out + (k % F_out)] : 0.f;
+            h[j] = tf32_hi(v[j]);
+            l[j] = v[j] - h[j];
+        }
+        float4 *img = wp + (int64_t)b * per_block + (int64_t)kt * 2 * CH * n_blk;
+        img[(int64_t)kc * n_blk + n] = make_float4(h[0], h[1], h[2], h[3]);
+        img[(int64_t)(CH + kc) * n_blk + n] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 struct EpiLinearTc {  // out[row, c] = acc + bias[c]   (plain Linear; c < n_total, rows padded to ldo % 4 == 0)
     float *out;
     int64_t ldo;
@@ -843,5 +901,47 @@ extern "C" int pg_linear_tc(const float *d_x, int64_t ldx, int64_t num_rows, int
     int rc = launch_rows_gemm<4>(A, epi, wp, p.n_full, C, p.k_tiles, err, grid, 2 * stage, st);
     if (rc != PG_OK) return rc;
     PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (linear)");
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- dX through the fan-out kernel
+// dX = sum_v (A_v (g_v * dY)) W'_v^T (+ dY W_res^T | + dY): d_t = [T_in | T_out | T_und] from pg_spmm_fanout_scaled on dY
+// (symmetric structure), then this GEMM with K = 3 F_out (+ F_out for a residual projection).
+extern "C" size_t pg_layer_gemm_bwd_dx_tc_ws_bytes(int F_in, int F_out, int has_res) {
+    const BwdDataPlan p = bwd_data_plan_raw(F_in, (3 + (has_res ? 1 : 0)) * F_out);
+    return p.image_bytes + 256;
+}
+
+extern "C" int pg_layer_gemm_bwd_dx_tc(const float *d_t, int64_t ldt, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                                       int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx, int64_t lddx,
+                                       void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 4 && F_in % 4 == 0 && F_out >= 4 && F_out % 4 == 0, "pg_layer_gemm_bwd_dx_tc: needs F_in, F_out %% 4 == 0");
+    PG_CHECK_ARG(!(has_res && add_identity) && (!add_identity || F_in == F_out), "pg_layer_gemm_bwd_dx_tc: bad residual mode");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_t && d_dy && d_w_ext && d_dx && d_ws, "pg_layer_gemm_bwd_dx_tc: null buffer");
+    PG_CHECK_ARG(al16(d_t) && ldt % 4 == 0 && ldt >= 3 * (int64_t)F_out && al16(d_dy) && lddy % 4 == 0 && lddy >= F_out && al16(d_dx) &&
+                     lddx % 4 == 0 && lddx >= F_in && al16(d_ws),
+                 "pg_layer_gemm_bwd_dx_tc: operands must be 16-byte aligned with row strides %% 4 == 0");
+    const int K = (3 + (has_res ? 1 : 0)) * F_out;
+    const BwdDataPlan p = bwd_data_plan_raw(F_in, K);
+    const size_t need = p.image_bytes + 256;
+    if (ws_bytes < need) {
+        pg_set_error("pg_layer_gemm_bwd_dx_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    float4 *wp = reinterpret_cast<float4 *>(d_ws);
+    int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + need - 256);
+    PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    const int64_t total = (int64_t)p.blocks * p.k_tiles * 4 * p.n_full;
+    wprep_dx_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w_ext, F_in, F_out, K, p.k_tiles, p.n_full, p.blocks, wp);
+    PG_CUDA_LAUNCH_CHECK("wprep_dx_kernel");
+    ACat2Tc A{d_t, d_dy, ldt, lddy, num_rows, 3 * F_out, K};
+    EpiDxTc epi{d_dx, add_identity ? d_dy : nullptr, lddx, lddy, F_in};
+    const size_t stage = 2 * (size_t)4 * TC_LBO_A + 2 * (size_t)4 * p.n_full * 16;
+    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), (unsigned)p.blocks, 1);
+    int rc = launch_rows_gemm<4>(A, epi, wp, p.n_full, F_in, p.k_tiles, err, grid, 2 * stage, st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (input gradient)");
     return PG_OK;
 }

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restr
                                                           const float *__restrict__ val0, const float *__restrict__ val1,
                                                           const float *__restrict__ val2, RowMap map, int F,
                                                           const float *__restrict__ x, int64_t ldx, float *__restrict__ z,
-                                                          int64_t ldz, int64_t z_off) {
+                                                          int64_t ldz, int64_t z_off, const float *__restrict__ s0,
+                                                          const float *__restrict__ s1, const float *__restrict__ s2, int sstride) {
+    // s0..s2 (optional): per-SOURCE-row scales, z_v[i] = sum_j val_v[i,j] * s_v[j] * x[j]  (backward of the gated layer:
+    // x = dY, s_v = gate_v, so that the 3F-wide gated gradient never has to be gathered)
     constexpr int UNROLL = (CHUNKS == 1) ? 4 : 2;
     const int lane = threadIdx.x & 31;
     const int lg = lane & (LPR - 1);                       // lane inside the row group
@@ -86,6 +89,12 @@ __global__ void __launch_bounds__(256) spmm_fanout_kernel(const int64_t *__restr
             my_v[0] = val0[base + lg];
             if (NV > 1) my_v[1] = val1[base + lg];
             if (NV > 2) my_v[NV - 1] = val2[base + lg];
+            if (s0 != nullptr) {
+                const int64_t so = (int64_t)my_col * sstride;
+                my_v[0] *= __ldg(s0 + so);
+                if (NV > 1) my_v[1] *= __ldg(s1 + so);
+                if (NV > 2) my_v[NV - 1] *= __ldg(s2 + so);
+            }
         }
         int t = 0;
         for (; t + UNROLL <= cnt; t += UNROLL) {
@@ -239,7 +248,8 @@ __global__ void __launch_bounds__(256) spmm_fanout_scalar_kernel(const int64_t *
                                                                  const float *__restrict__ val0, const float *__restrict__ val1,
                                                                  const float *__restrict__ val2, int64_t num_rows, int F,
                                                                  const float *__restrict__ x, int64_t ldx, float *__restrict__ z,
-                                                                 int64_t ldz, int64_t z_off) {
+                                                                 int64_t ldz, int64_t z_off, const float *__restrict__ s0,
+                                                                 const float *__restrict__ s1, const float *__restrict__ s2, int sstride) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= num_rows) return;
@@ -249,10 +259,11 @@ __global__ void __launch_bounds__(256) spmm_fanout_scalar_kernel(const int64_t *
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = 0.f;
         for (int64_t k = rb; k < re; ++k) {
-            const float xv = x[(int64_t)col[k] * ldx + f];
-            acc[0] = fmaf(val0[k], xv, acc[0]);
-            if (NV > 1) acc[1] = fmaf(val1[k], xv, acc[1]);
-            if (NV > 2) acc[NV - 1] = fmaf(val2[k], xv, acc[NV - 1]);
+            const int64_t c = col[k];
+            const float xv = x[c * ldx + f];
+            acc[0] = fmaf(s0 ? val0[k] * s0[c * sstride] : val0[k], xv, acc[0]);
+            if (NV > 1) acc[1] = fmaf(s0 ? val1[k] * s1[c * sstride] : val1[k], xv, acc[1]);
+            if (NV > 2) acc[NV - 1] = fmaf(s0 ? val2[k] * s2[c * sstride] : val2[k], xv, acc[NV - 1]);
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) z[row * ldz + z_off + (int64_t)v * F + f] = acc[v];
@@ -349,7 +360,17 @@ inline bool plan_ok(const pg_spmm_plan *plan) {
 extern "C" int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
                               const float *d_val2, int nv, int64_t num_rows, int F, const float *d_x, int64_t ldx, float *d_z,
                               int64_t ldz, int64_t z_off, const pg_spmm_plan *plan, pg_stream_t stream) {
+    return pg_spmm_fanout_scaled(d_rowptr, d_col, d_val0, d_val1, d_val2, nv, num_rows, F, d_x, ldx, d_z, ldz, z_off, nullptr, nullptr,
+                                 nullptr, 0, plan, stream);
+}
+
+extern "C" int pg_spmm_fanout_scaled(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
+                                     const float *d_val2, int nv, int64_t num_rows, int F, const float *d_x, int64_t ldx, float *d_z,
+                                     int64_t ldz, int64_t z_off, const float *d_s0, const float *d_s1, const float *d_s2,
+                                     int scale_stride, const pg_spmm_plan *plan, pg_stream_t stream) {
     cudaStream_t st = pg_cu(stream);
+    PG_CHECK_ARG(!d_s0 || ((nv == 1 || (d_s1 && d_s2)) && (scale_stride == 0 || scale_stride == 1)), "pg_spmm_fanout_scaled: bad scales");
+    const float *s1 = nv == 3 ? d_s1 : d_s0, *s2 = nv == 3 ? d_s2 : d_s0;
     PG_CHECK_ARG(nv == 1 || nv == 3, "pg_spmm_fanout: nv must be 1 or 3 (got %d)", nv);
     PG_CHECK_ARG(num_rows >= 0 && F >= 1 && ldx >= F && ldz >= z_off + (int64_t)nv * F && z_off >= 0, "pg_spmm_fanout: bad shape");
     PG_CHECK_ARG(plan_ok(plan), "pg_spmm_fanout: malformed plan");
@@ -360,14 +381,14 @@ extern "C" int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, con
     const bool vec = pick_shape(F, &lpr, &chunks) && aligned16(d_x) && aligned16(d_z) && ldx % 4 == 0 && ldz % 4 == 0 && z_off % 4 == 0;
     if (vec) {
         const RowMap rm = rows_map(num_rows, plan);
-        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off);
-        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off);
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off, d_s0, s1, s2, scale_stride);
+        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, d_x, ldx, d_z, ldz, z_off, d_s0, s1, s2, scale_stride);
         PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel");
         if (plan && plan->n_long > 0) {
             const RowMap im = items_map(plan);
             const int64_t w = (int64_t)nv * F;
-            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0);
-            else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0);
+            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0, d_s0, s1, s2, scale_stride);
+            else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, d_x, ldx, plan->d_partials, w, 0, d_s0, s1, s2, scale_stride);
             PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel(long rows)");
             spmm_reduce_long_kernel<<<(unsigned)plan->n_long, 256, 0, st>>>(plan->d_long_rows, plan->d_item_ptr, plan->n_long, (int)w,
                                                                             plan->d_partials, d_z, ldz, z_off, nullptr, 0, 0);
@@ -375,8 +396,8 @@ extern "C" int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, con
         }
     } else {
         const unsigned grid = (unsigned)pg_ceil_div(num_rows * 32, 256);
-        if (nv == 3) spmm_fanout_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
-        else spmm_fanout_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off);
+        if (nv == 3) spmm_fanout_scalar_kernel<3><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off, d_s0, s1, s2, scale_stride);
+        else spmm_fanout_scalar_kernel<1><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val0, v1, v2, num_rows, F, d_x, ldx, d_z, ldz, z_off, d_s0, s1, s2, scale_stride);
         PG_CUDA_LAUNCH_CHECK("spmm_fanout_scalar_kernel");
     }
     return PG_OK;

@@ -155,11 +155,17 @@ def get_structure(eis, ews, n: int) -> EdgeStructure:
 # ------------------------------------------------------------------------------------------------
 # kernels as autograd function
 # ------------------------------------------------------------------------------------------------
-def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int) -> torch.Tensor:
+def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
+    """Z = [A_in X | A_out X | U X]; with `scales` = (s_in, s_out, s_und) per SOURCE row: A_v diag(s_v) X (shared structures only)."""
     n = x.shape[0]
     z = torch.empty((n, 3 * f_in), dtype=torch.float32, device=x.device)
     st = nat.stream_ptr()
-    if struct.shared:
+    if struct.shared and scales is not None:
+        c = struct.by_dst[0]
+        nat.call("pg_spmm_fanout_scaled", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
+                 3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, nat.ptr(scales[0]), nat.ptr(scales[1]),
+                 nat.ptr(scales[2]), int(scale_stride), c.plan(3 * f_in), st)
+    elif struct.shared:
         c = struct.by_dst[0]
         nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
                  3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, c.plan(3 * f_in), st)
@@ -195,6 +201,7 @@ import os as _os
 
 TC_MODE = _os.environ.get("PGB200_TC", "auto")
 TC_MIN_WIDTH, TC_MIN_ROWS = 128, 4096
+BWD_DX_MODE = _os.environ.get("PGB200_BWD_DX", "fanout")   # "fanin": gather the gated gradient (the SIMT path's way) also on the TC path
 TC_BWD_WEIGHT_MIN_ROWS = 65536   # the weight gradient splits the ROWS over CTAs: below this the SIMT kernel (more, smaller tiles) is faster
 
 
@@ -273,8 +280,17 @@ class _DirectGCNFused(torch.autograd.Function):
             nat.call("pg_layer_gemm_bwd_data", *args, st)
         dx = None
         if ctx.needs_input_grad[0]:
-            init = dxres if ctx.has_res else (dy if ctx.add_identity else None)
-            dx = _fanin(ctx.struct, dz, f_in, init)
+            if ctx.use_tc and ctx.struct.shared and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0:
+                # dX = sum_v (A_v (g_v * dY)) W'_v^T (+ residual): the symmetric structure lets the fan-out kernel gather F_out-wide
+                # rows of dY once for all three matrices instead of the fan-in kernel gathering the 3 F_in-wide gated gradient
+                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride)
+                dx = torch.empty((n, f_in), dtype=torch.float32, device=x.device)
+                ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
+                nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
+                         has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), nat.ptr(ws3), ws3.numel(), st)
+            else:
+                init = dxres if ctx.has_res else (dy if ctx.add_identity else None)
+                dx = _fanin(ctx.struct, dz, f_in, init)
         if ctx.gate_stride == 1:
             dga, dgb, dgc = (dgate[v].reshape(ga.shape) for v in range(3))
         else:

@@ -738,6 +738,42 @@ def test_fused_loss_with_tensor_core_logits_matches_torch(monkeypatch):
         assert rel_err(a.cpu().numpy(), r.cpu().numpy()) <= 5e-5
 
 
+@pytest.mark.parametrize("dims,vec", [([32, 64, 48, 16], True), ([16, 16, 16], True), ([24, 32, 64], False)])
+def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec):
+    """Backward on the tensor-core path: dX = sum_v (A_v (g_v * dY)) W_v^T via the scaled fan-out kernel + one GEMM must equal
+    the fan-in formulation (gather of the gated 3 F_in-wide gradient) in every gradient: residual projection, identity
+    residual, vector and scalar gates."""
+    from oracle import ngram_oracle
+    seqs = ngram_oracle.synth_sequences(0, 400, 80)
+    d_buf = corpus.to_device(corpus.pack_sequences(seqs), DEV)
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    graph = data_builder.build_level_graph(d_buf, 2, symbols, d_rank, 1e-9)
+    n = graph.number_of_nodes
+    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    torch.manual_seed(3)
+    x = torch.randn(n, dims[0], device=DEV, requires_grad=True)
+    y = torch.randint(0, 5, (n,), device=DEV)
+    grads = {}
+    for mode in ("fanin", "fanout"):
+        monkeypatch.setattr(model_mod, "BWD_DX_MODE", mode)
+        model_mod._STRUCT_CACHE.clear()
+        torch.manual_seed(5)
+        model = pg.ProtGramDirectGCN(dims, n if vec else None, 5, 2, 0, 16, 0.0, vec).to(DEV)
+        with torch.no_grad():
+            for p_ in model.parameters():
+                if p_.ndim == 1 or p_.shape[-1] == 1:
+                    p_.add_(0.3 * torch.randn_like(p_))
+        data = graph.gcn_data(x, DEV)
+        before = nat.kernel_launches()
+        loss = model.nll_loss(data, y)
+        g = torch.autograd.grad(loss, [x] + list(model.parameters()), allow_unused=True)
+        grads[mode] = [t for t in g if t is not None]
+        grads[mode + "_launches"] = nat.kernel_launches() - before
+    assert len(grads["fanin"]) == len(grads["fanout"])
+    for a, b in zip(grads["fanin"], grads["fanout"]):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 2e-5
+
+
 def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     """Force the tcgen05 dense transform inside the model and re-check the reference goldens
     (model_refgraph has widths 24/40/16/8 -> only the 16-wide layer qualifies; the C2-shaped oracle
