@@ -316,6 +316,13 @@ size_t pg_layer_gemm_bwd_dx_tc_ws_bytes(int F_in, int F_out, int has_res);
 int pg_layer_gemm_bwd_dx_tc(const float *d_t, int64_t ldt, const float *d_dy, int64_t lddy, const float *d_w_ext,
                             int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx,
                             int64_t lddx, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+/* Gate gradients alone (the input gradient going through pg_spmm_fanout_scaled + pg_layer_gemm_bwd_dx_tc needs no dZ):
+ * d_dgate[v][i] = <dY[i] W_v^T, Z_v[i]> + <dY[i], beta_v>, the data-gradient GEMM with a dot-product epilogue -- dZ is
+ * never written.  Same values as pg_layer_gemm_bwd_data(_tc)'s d_dgate. */
+size_t pg_layer_gate_grad_tc_ws_bytes(int64_t num_rows, int F_in, int F_out);
+int pg_layer_gate_grad_tc(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z, int64_t ldz,
+                          int64_t num_rows, int F_in, int F_out, int has_res, float *d_dgate /* [3 x num_rows] */,
+                          void *d_ws, size_t ws_bytes, pg_stream_t stream);
 int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream);
 
 /* Plain Linear on the same tensor-core kernel: out[N, C] = x[N, K] @ W[C, K]^T + bias (torch.nn.Linear layout, bias may be

@@ -82,6 +82,8 @@ _SIGS = {
                                             c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_layer_gemm_bwd_dx_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pg_layer_gemm_bwd_dx_tc": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_size_t, _P]),
+    "pg_layer_gate_grad_tc_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "pg_layer_gate_grad_tc": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_tc_check": (c_int, [_P, c_size_t, _P]),
     "pg_linear_tc_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_linear_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),

@@ -101,6 +101,7 @@ constexpr int TC_THREADS2 = TC_PRODUCERS + 32;
 // Epilogue of the forward transform: H = leaky_relu(acc (+X) + constant).  The kernel hands the epilogues float4s of one row
 // in an order that makes a warp's stores cover whole 128-byte lines (see the staging in tc_rows_gemm_kernel).
 struct EpiFwdTc {
+    static constexpr bool kRowDots = false;
     const float *constant, *x;
     int64_t ldconst, ldx;
     int add_identity;
@@ -258,6 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) tc_rows
             const int half_cols = ((n_blk / 16 + 1) / 2) * 16;
             const int c_begin = (warp < 4) ? 0 : half_cols, c_end = (warp < 4) ? half_cols : n_blk;
             const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
+            float dots[Epi::kRowDots ? 8 : 1][3];
+#pragma unroll
+            for (int i = 0; i < (Epi::kRowDots ? 8 : 1); ++i) dots[i][0] = dots[i][1] = dots[i][2] = 0.f;
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
@@ -278,9 +282,27 @@ __global__ void __launch_bounds__(TC_THREADS2, (TC_CHUNKS == 4) ? 2 : 1) tc_rows
                     const int cc = c0 + 4 * (lane & 7);
                     const int64_t row = m0 + quad * 32 + rl;
                     const float4 v = *reinterpret_cast<const float4 *>(stg + rl * 36 + 4 * (lane & 7));
-                    if (row < A.M && cc < c_end) epi.store4(row, n0 + cc, v);
+                    if (row < A.M && cc < c_end) {
+                        if constexpr (Epi::kRowDots) epi.dot4(row, n0 + cc, v, dots[i]);
+                        else epi.store4(row, n0 + cc, v);
+                    }
                 }
                 __syncwarp();
+            }
+            if constexpr (Epi::kRowDots) {   // 8 lanes share a row: sum their parts, lane 0 of the group writes
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        float d = dots[i][v];
+                        d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2);
+                        d += __shfl_xor_sync(0xffffffffu, d, 4);
+                        dots[i][v] = d;
+                    }
+                    const int64_t row = m0 + quad * 32 + 4 * i + (lane >> 3);
+                    if ((lane & 7) == 0 && row < A.M) epi.write_dots(row, (int)blockIdx.y * 2 + (warp >= 4 ? 1 : 0), dots[i]);
+                }
             }
         }
     }
@@ -304,7 +326,8 @@ struct APlainTc {
     }
 };
 
-struct EpiBwdDataTc {  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in, k_data) -> dXres
+struct EpiBwdDataTc {
+    static constexpr bool kRowDots = false;  // columns [0, 3 F_in) -> dZ (raw, gated later), [3 F_in, k_data) -> dXres
     float *dz, *dxres;
     int64_t lddz, lddxres;
     int f3, k_data;
@@ -327,7 +350,8 @@ struct ACat2Tc {   // A(i, k) = k < K1 ? t[i, k] : dy[i, k - K1]     (K1 and K m
     }
 };
 
-struct EpiDxTc {   // dX[row, c] = acc (+ dY[row, c] for the identity residual); c < F_in
+struct EpiDxTc {
+    static constexpr bool kRowDots = false;   // dX[row, c] = acc (+ dY[row, c] for the identity residual); c < F_in
     float *dx;
     const float *dy;   // null unless add_identity
     int64_t lddx, lddy;
@@ -373,7 +397,80 @@ __global__ void __launch_bounds__(256) wprep_dx_kernel(const float *__restrict__
     }
 }
 
-struct EpiLinearTc {  // out[row, c] = acc + bias[c]   (plain Linear; c < n_total, rows padded to ldo % 4 == 0)
+// ---- gate gradients without materialising dZ:  dgate_v[i] = <dY[i] W_v^T, Z_v[i]> + <dY[i], beta_v>
+// GEMM columns [0, 3 F_in) are the rows of dA = dY W_ext[:3 F_in]^T, columns 3 F_in + v the bias rows; the epilogue only forms
+// per-row dot products with Z (kRowDots: the kernel keeps 3 sums per row group, reduces them over the 8 lanes that share a row
+// and hands them to write_dots; a second kernel sums the column-block parts in fixed order).
+struct EpiGateDotTc {
+    static constexpr bool kRowDots = true;
+    const float *z;
+    int64_t ldz, M;
+    int F_in, f3;
+    float *partial;   // [parts][3][M]
+    __device__ __forceinline__ void store4(int64_t, int, float4) const {}
+    __device__ __forceinline__ void dot4(int64_t row, int c, float4 v, float (&acc)[3]) const {
+        if (c < f3) {
+            const float4 zv = __ldg(reinterpret_cast<const float4 *>(z + row * ldz + c));
+            const float d = fmaf(v.x, zv.x, fmaf(v.y, zv.y, fmaf(v.z, zv.z, v.w * zv.w)));
+            const int seg = c / F_in;    // F_in % 4 == 0: a float4 lies in one segment
+            acc[0] += seg == 0 ? d : 0.f;
+            acc[1] += seg == 1 ? d : 0.f;
+            acc[2] += seg == 2 ? d : 0.f;
+        } else if (c == f3) {            // the three bias-row columns share one float4
+            acc[0] += v.x;
+            acc[1] += v.y;
+            acc[2] += v.z;
+        }
+    }
+    __device__ __forceinline__ void write_dots(int64_t row, int part, const float (&acc)[3]) const {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) partial[((int64_t)part * 3 + v) * M + row] = acc[v];
+    }
+};
+
+// images of [W_ext[:3 F_in]; W_ext[k_data .. k_data+2]]^T per column block (columns 3 F_in + 3 .. are zero padding)
+__global__ void __launch_bounds__(256) wprep_gate_kernel(const float *__restrict__ w_ext, int f3, int k_data, int F_out, int k_tiles,
+                                                         int n_full, int blocks, float4 *__restrict__ wp) {
+    constexpr int CH = 4;
+    const int cols = f3 + 3;
+    const int64_t per_block = (int64_t)k_tiles * 2 * CH * n_full;
+    const int64_t slots = (int64_t)k_tiles * CH * n_full;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots * blocks; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / slots);
+        const int64_t u = t - (int64_t)b * slots;
+        const int n0 = b * n_full;
+        const int n_blk = min(n_full, ((cols - n0 + 15) / 16) * 16);
+        if (u >= (int64_t)k_tiles * CH * n_blk) continue;
+        const int n = (int)(u % n_blk);
+        const int kc = (int)((u / n_blk) % CH);
+        const int kt = (int)(u / ((int64_t)n_blk * CH));
+        const int c = n0 + n;
+        const int64_t src_row = c < f3 ? c : (c < cols ? k_data + (c - f3) : -1);
+        const int f0 = kt * 16 + kc * 4;
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = (src_row >= 0 && f0 + j < F_out) ? w_ext[src_row * F_out + f0 + j] : 0.f;
+            h[j] = tf32_hi(v[j]);
+            l[j] = v[j] - h[j];
+        }
+        float4 *img = wp + (int64_t)b * per_block + (int64_t)kt * 2 * CH * n_blk;
+        img[(int64_t)kc * n_blk + n] = make_float4(h[0], h[1], h[2], h[3]);
+        img[(int64_t)(CH + kc) * n_blk + n] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gate_parts_reduce_kernel(const float *__restrict__ partial, int parts, int64_t numel,
+                                                                float *__restrict__ dgate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < parts; ++p) acc += partial[(int64_t)p * numel + i];   // fixed order
+        dgate[i] = acc;
+    }
+}
+
+struct EpiLinearTc {
+    static constexpr bool kRowDots = false;  // out[row, c] = acc + bias[c]   (plain Linear; c < n_total, rows padded to ldo % 4 == 0)
     float *out;
     int64_t ldo;
     const float *bias;
@@ -943,5 +1040,54 @@ extern "C" int pg_layer_gemm_bwd_dx_tc(const float *d_t, int64_t ldt, const floa
     int rc = launch_rows_gemm<4>(A, epi, wp, p.n_full, F_in, p.k_tiles, err, grid, 2 * stage, st);
     if (rc != PG_OK) return rc;
     PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (input gradient)");
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- gate gradients, dZ never stored
+namespace {
+struct GatePlan { BwdDataPlan g; int parts; size_t partial_off, need; };
+inline GatePlan gate_plan(int64_t num_rows, int F_in, int F_out) {
+    GatePlan p;
+    p.g = bwd_data_plan_raw(3 * F_in + 3, F_out);
+    p.parts = 2 * p.g.blocks;
+    p.partial_off = pg_align_up(p.g.image_bytes, 256);
+    p.need = p.partial_off + pg_align_up((size_t)p.parts * 3 * (size_t)num_rows * sizeof(float), 256) + 256;
+    return p;
+}
+}  // namespace
+
+extern "C" size_t pg_layer_gate_grad_tc_ws_bytes(int64_t num_rows, int F_in, int F_out) { return gate_plan(num_rows, F_in, F_out).need; }
+
+extern "C" int pg_layer_gate_grad_tc(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z, int64_t ldz, int64_t num_rows,
+                                     int F_in, int F_out, int has_res, float *d_dgate, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 4 && F_in % 4 == 0 && F_out >= 4 && F_out % 4 == 0, "pg_layer_gate_grad_tc: needs F_in, F_out %% 4 == 0");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_dy && d_w_ext && d_z && d_dgate && d_ws, "pg_layer_gate_grad_tc: null buffer");
+    PG_CHECK_ARG(al16(d_dy) && lddy % 4 == 0 && lddy >= F_out && al16(d_z) && ldz % 4 == 0 && ldz >= 3 * (int64_t)F_in && al16(d_ws),
+                 "pg_layer_gate_grad_tc: operands must be 16-byte aligned with row strides %% 4 == 0");
+    const GatePlan p = gate_plan(num_rows, F_in, F_out);
+    if (ws_bytes < p.need) {
+        pg_set_error("pg_layer_gate_grad_tc: workspace too small (%zu < %zu)", ws_bytes, p.need);
+        return PG_EWORKSPACE;
+    }
+    cudaStream_t st = pg_cu(stream);
+    float4 *wp = reinterpret_cast<float4 *>(d_ws);
+    float *partial = reinterpret_cast<float *>(reinterpret_cast<char *>(d_ws) + p.partial_off);
+    int *err = reinterpret_cast<int *>(reinterpret_cast<char *>(d_ws) + p.need - 256);
+    PG_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(int), st));
+    const int k_data = 3 * F_in + (has_res ? F_in : 0);
+    const int64_t total = (int64_t)p.g.blocks * p.g.k_tiles * 4 * p.g.n_full;
+    wprep_gate_kernel<<<(unsigned)pg_ceil_div(total, 256), 256, 0, st>>>(d_w_ext, 3 * F_in, k_data, F_out, p.g.k_tiles, p.g.n_full, p.g.blocks, wp);
+    PG_CUDA_LAUNCH_CHECK("wprep_gate_kernel");
+    APlainTc A{d_dy, lddy, num_rows, F_out};
+    EpiGateDotTc epi{d_z, ldz, num_rows, F_in, 3 * F_in, partial};
+    const size_t stage = 2 * (size_t)4 * TC_LBO_A + 2 * (size_t)4 * p.g.n_full * 16;
+    const dim3 grid((unsigned)pg_ceil_div(num_rows, TC_BM), (unsigned)p.g.blocks, 1);
+    int rc = launch_rows_gemm<4>(A, epi, wp, p.g.n_full, 3 * F_in + 3, p.g.k_tiles, err, grid, 2 * stage, st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA_LAUNCH_CHECK("tc_rows_gemm_kernel (gate gradients)");
+    const int64_t numel = 3 * num_rows;
+    gate_parts_reduce_kernel<<<(unsigned)pg_ceil_div(numel, 256), 256, 0, st>>>(partial, p.parts, numel, d_dgate);
+    PG_CUDA_LAUNCH_CHECK("gate_parts_reduce_kernel");
     return PG_OK;
 }

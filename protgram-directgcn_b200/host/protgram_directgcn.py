@@ -211,6 +211,16 @@ def _use_tensor_cores(n: int, f_in: int, f_out: int) -> bool:
     return TC_MODE == "force" or (f_out >= TC_MIN_WIDTH and n >= TC_MIN_ROWS)
 
 
+def _finish_backward(ctx, ga, dgate, dx, dw, dy):
+    """Common tail of _DirectGCNFused.backward: per-row gate gradients -> the gates' shapes, constant's gradient = dY."""
+    if ctx.gate_stride == 1:
+        dga, dgb, dgc = (dgate[v].reshape(ga.shape) for v in range(3))
+    else:
+        dga, dgb, dgc = (dgate[v].sum().reshape(ga.shape) for v in range(3))
+    dconst = dy if ctx.has_const else None
+    return dx, dga, dgb, dgc, dw, dconst, None, None, None, None
+
+
 class _DirectGCNFused(torch.autograd.Function):
     """H = act( [aZ_in | bZ_out | cZ_und | X? | a b c | 1?] @ W_ext (+X) + constant )."""
 
@@ -266,10 +276,26 @@ class _DirectGCNFused(torch.autograd.Function):
         nat.call(f"pg_layer_gemm_bwd_weight{tc}", nat.ptr(z), z.stride(0), nat.ptr(x), x.stride(0), nat.ptr(ga), nat.ptr(gb),
                  nat.ptr(gc), ctx.gate_stride, nat.ptr(dy), dy.stride(0), n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws),
                  ws.numel(), st)
+        dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
+        fanout_bwd = ctx.use_tc and ctx.struct.shared and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0
+        if fanout_bwd:
+            # gate gradients from the data-gradient GEMM with a dot-product epilogue (dZ is never written); the input gradient
+            # regrouped as dX = sum_v (A_v (g_v * dY)) W'_v^T (+ residual): the symmetric structure lets the fan-out kernel gather
+            # F_out-wide rows of dY once for all three matrices instead of the fan-in kernel gathering the 3 F_in-wide gated gradient
+            wsg = nat.workspace(nat.query("pg_layer_gate_grad_tc_ws_bytes", n, f_in, f_out), x.device)
+            nat.call("pg_layer_gate_grad_tc", nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), n, f_in, f_out, has_res,
+                     nat.ptr(dgate), nat.ptr(wsg), wsg.numel(), st)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride)
+                dx = torch.empty((n, f_in), dtype=torch.float32, device=x.device)
+                ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
+                nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
+                         has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), nat.ptr(ws3), ws3.numel(), st)
+            return _finish_backward(ctx, ga, dgate, dx, dw, dy)
         # dA = dY W_ext^T  -> dZ (gated), dXres, dgates
         dz = torch.empty_like(z)
         dxres = torch.empty_like(x) if ctx.has_res else None
-        dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
         args = (nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), nat.ptr(ga), nat.ptr(gb), nat.ptr(gc),
                 ctx.gate_stride, n, f_in, f_out, has_res, nat.ptr(dz), dz.stride(0), nat.ptr(dxres),
                 dxres.stride(0) if dxres is not None else 0, nat.ptr(dgate))
@@ -280,23 +306,9 @@ class _DirectGCNFused(torch.autograd.Function):
             nat.call("pg_layer_gemm_bwd_data", *args, st)
         dx = None
         if ctx.needs_input_grad[0]:
-            if ctx.use_tc and ctx.struct.shared and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0:
-                # dX = sum_v (A_v (g_v * dY)) W'_v^T (+ residual): the symmetric structure lets the fan-out kernel gather F_out-wide
-                # rows of dY once for all three matrices instead of the fan-in kernel gathering the 3 F_in-wide gated gradient
-                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride)
-                dx = torch.empty((n, f_in), dtype=torch.float32, device=x.device)
-                ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
-                nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
-                         has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), nat.ptr(ws3), ws3.numel(), st)
-            else:
-                init = dxres if ctx.has_res else (dy if ctx.add_identity else None)
-                dx = _fanin(ctx.struct, dz, f_in, init)
-        if ctx.gate_stride == 1:
-            dga, dgb, dgc = (dgate[v].reshape(ga.shape) for v in range(3))
-        else:
-            dga, dgb, dgc = (dgate[v].sum().reshape(ga.shape) for v in range(3))
-        dconst = dy if ctx.has_const else None
-        return dx, dga, dgb, dgc, dw, dconst, None, None, None, None
+            init = dxres if ctx.has_res else (dy if ctx.add_identity else None)
+            dx = _fanin(ctx.struct, dz, f_in, init)
+        return _finish_backward(ctx, ga, dgate, dx, dw, dy)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -682,6 +682,14 @@ def test_layer_gemm_bwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
     assert rel_err(dgate.cpu().numpy(), dgate_ref.numpy()) <= 2e-5
     if has_res:
         assert rel_err(dxres.cpu().numpy(), dxres_ref.numpy()) <= 2e-5
+    # gate gradients alone (dot-product epilogue, dZ never stored)
+    dgate3 = nan(3, n)
+    need = nat.query("pg_layer_gate_grad_tc_ws_bytes", n, f_in, f_out)
+    ws = _ws(need)
+    nat.call("pg_layer_gate_grad_tc", nat.ptr(dyd), f_out, nat.ptr(wd), nat.ptr(zd), 3 * f_in, n, f_in, f_out, has_res, nat.ptr(dgate3),
+             nat.ptr(ws), ws.numel(), st)
+    nat.call("pg_tc_check", nat.ptr(ws), need, st)
+    assert rel_err(dgate3.cpu().numpy(), dgate_ref.numpy()) <= 2e-5
     # weight gradient
     dw = nan(k_ext, f_out)
     need = nat.query("pg_layer_gemm_bwd_weight_tc_ws_bytes", n, f_in, f_out, has_res)
