@@ -195,3 +195,21 @@ def test_parallel_reader_large_file_threads_and_ranks(tmp_path):
     whole = corpus.read_fasta_parallel(path, threads=4)
     parts = corpus.split_at_separators(whole, 1 << 18)
     assert b"".join(bytes(p.numpy()) for p in parts) == ref and all(bytes(p.numpy()).endswith(b"\xff") for p in parts)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.binary(max_size=300))
+def test_pack5_property(data):
+    """Every buffer over the code's alphabet round-trips; any other byte makes pack5 refuse (never a silent substitution)."""
+    import torch
+    from tests import kernel_spec
+    buf = np.frombuffer(data, dtype=np.uint8)
+    ok = all((c == 0x20) or (0x41 <= c <= 0x5A) or c in (0x2A, 0x2D, 0x2E, 0xFF) for c in data)
+    chunk = corpus.pack5(buf, pinned=False) if len(data) else corpus.pack5(np.zeros(0, dtype=np.uint8), pinned=False)
+    if not ok:
+        assert chunk is None
+        return
+    assert chunk is not None and chunk.n_symbols == len(data)
+    out = torch.zeros(max(len(data), 1), dtype=torch.uint8)
+    kernel_spec.pg_unpack5(chunk.packed, len(data), out)
+    assert bytes(out[:len(data)].numpy()) == data
