@@ -26,22 +26,7 @@ def _write(tmp_path, data: bytes, name="x.fasta"):
     return str(p)
 
 
-CASES = {
-    "ka1": b">seq1\nACGTACT\n>seq2\nTTACGTT\n>seq3\nAGATAGA\n",                       # run_graph_builder.py:24-28
-    "ka2": b">p1\nACGT\n>p2\nTTAC\n>p3\nAGA",                                            # unit_tests.py:41, no trailing newline
-    "crlf_lower_multiline": b">sp|P12345|NAME_HUMAN desc\r\nacde\r\nfghi\r\n\r\n>tr|Q9|x\r\n  klmn  \r\n",
-    "lone_cr": b">a\rACD\rEF\r>b\rGG\r",
-    "junk_before_header": b"ACGT\n\n  \nXX\n>a\nAC\n",
-    "empty_records": b">a\n>b\n\n\n>c\nAC\n>d\n   \n>e",
-    "interior_space_tab": b">a\nAC DE\tFG\n>b\n\tAC\x0b\n",
-    "bare_header_stops": b">a\nAC\n>b\nDE\n>\nFG\n>c\nHI\n",                            # '>' alone: the reference's generator raises there
-    "bare_header_first": b">   \nAC\n>c\nHI\n",
-    "pipes": b">||x\nAC\n>|id|\nDE\n>a|\nFG\n",
-    "control_ws": b">a\n\x1cAC\x1f\n\x1d\n>b\n\x0cDE\x0c\n",
-    "only_text": b"no header at all\nACGT\n",
-    "empty": b"",
-    "header_with_gt": b">a>b\nAC>DE\n",
-}
+from tests.fasta_cases import CASES  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -213,3 +198,21 @@ def test_pack5_property(data):
     out = torch.zeros(max(len(data), 1), dtype=torch.uint8)
     kernel_spec.pg_unpack5(chunk.packed, len(data), out)
     assert bytes(out[:len(data)].numpy()) == data
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_readers_match_reference_generated_golden(name, tmp_path):
+    """tests/golden/fasta_cases.npz holds what the reference's own DataLoader.parse_sequences yields for every edge file
+    (tests/golden/make_golden_fasta.py): the Python twin, the streaming native reader and the multi-threaded one must all
+    produce exactly those records."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fasta_cases.npz"))
+    count = int(g[name + "_count"])
+    ids = str(g[name + "_ids"]).split("\x1f") if count else []
+    seqs = str(g[name + "_seqs"]).split("\x1f") if count else []
+    path = _write(tmp_path, CASES[name])
+    twin = list(DataLoader.parse_sequences(path))
+    assert [r[0] for r in twin] == ids and [r[1] for r in twin] == seqs
+    expect = b"".join(((b" " if i == 0 else b"") + s.encode() + b" \xff") for i, s in enumerate(seqs))
+    stats = {}
+    assert b"".join(_native_chunks(path, stats=stats)) == expect and stats["sequences"] == count
+    assert bytes(corpus.read_fasta_parallel(path, threads=2).numpy()) == expect
