@@ -11,9 +11,10 @@ Fresh restatement of the reference algorithm (citations into /root/reference):
 
 Parity status: pool_proteins and next_node_label_sets are PINNED against outputs of the reference's own
 functions (tests/golden/next_rows.npz, produced by tests/golden/make_golden_next.py, which imports
-models_utils.py and the trainer class verbatim).  init_level_features restates six lines that sit inline in
-the trainer's run() and cannot be called in isolation: "parity unpinned" for that function (the fixture
-holds the restatement's own output so that the CUDA kernel and the oracle cannot drift apart silently).
+models_utils.py and the trainer class verbatim).  init_level_features restates a loop that sits inline in the
+trainer's run(); make_golden_next.py cuts that loop out of the reference module's source at generation time and
+executes it on stand-in locals (`n{n}_x_init_ref` in the fixture), so this function is PINNED as well (bit for bit).
+subgraph (cluster mini-batches) restates torch_geometric.utils.subgraph, which cannot be run here: parity unpinned.
 
 Reference semantics worth spelling out:
   * pooling: `sums[prot_indices] += emb` / `counts[prot_indices] += 1` are numpy fancy-index updates, which apply

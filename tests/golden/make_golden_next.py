@@ -7,8 +7,8 @@ running the UNMODIFIED reference functions (build container only: needs /root/re
     called unbound on a stand-in `self` that only carries config.DEBUG_VERBOSE (all the method reads)
 
 over the same third-party shim as make_golden.py (+ two unused torch_geometric.utils names the trainer imports).
-The feature hand-off (:312-330) sits inline in the trainer's run(); the fixture holds the ORACLE's output for it
-(oracle/next_oracle.py:init_level_features, "parity unpinned" there).
+The feature hand-off (:323-330) sits inline in the trainer's run(): its loop is cut out of the reference module's source at
+generation time and executed on stand-in locals (reference_feature_handoff below), which pins oracle/next_oracle.py:init_level_features.
 
 Outputs: tests/golden/next_rows.npz.    Run: python tests/golden/make_golden_next.py
 """
@@ -24,6 +24,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 import make_golden as mg  # noqa: E402
+
+
+def reference_feature_handoff(ref_tr, node_to_idx, prev_map, prev_emb, n_val):
+    """Runs the reference's OWN feature hand-off loop (protgram_directgcn_trainer.py:323-330, inline in run()): its source lines
+    are cut out of the module at generation time (from the `for ngram_str, idx in tqdm(` line to the `x[idx] = ...` assignment)
+    and executed on stand-in locals -- nothing of it is stored in this repository."""
+    import inspect
+    import textwrap
+    src = inspect.getsource(ref_tr.ProtGramDirectGCNTrainer.run).splitlines()
+    a = next(i for i, l in enumerate(src) if "for ngram_str, idx in tqdm(graph_obj.node_to_idx.items()" in l)
+    b = next(i for i in range(a, len(src)) if "x[idx] = torch.from_numpy(np.mean(" in src[i])
+    loop = textwrap.dedent("\n".join(src[a:b + 1]))
+    env = {
+        "tqdm": lambda it, **kw: it, "np": np, "torch": torch, "n_val": n_val,
+        "graph_obj": types.SimpleNamespace(node_to_idx=node_to_idx),
+        "prev_level_ngram_to_idx_map": prev_map, "prev_level_embeds_np": prev_emb,
+        "self": types.SimpleNamespace(config=types.SimpleNamespace(DEBUG_VERBOSE=False), device=torch.device("cpu")),
+        "x": torch.zeros(len(node_to_idx), prev_emb.shape[1], dtype=torch.float),
+    }
+    exec(loop, env)
+    return env["x"].numpy()
 
 
 def main():
@@ -83,6 +104,8 @@ def main():
         if n > 1:
             prev_nodes, prev_map, prev_emb = embs[n - 1]
             rec[f"n{n}_x_init_oracle"] = next_oracle.init_level_features(nodes, prev_map, prev_emb)
+            rec[f"n{n}_x_init_ref"] = reference_feature_handoff(ref_tr, ngram_map, prev_map, prev_emb, n)
+            assert np.array_equal(rec[f"n{n}_x_init_ref"], rec[f"n{n}_x_init_oracle"])   # the oracle is pinned by the reference's own loop
     np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **rec)
     print("wrote next_rows.npz", {k: v.shape for k, v in rec.items() if k.endswith("pooled")})
 

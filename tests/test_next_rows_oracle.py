@@ -32,3 +32,14 @@ def test_label_oracle_admits_the_reference_labels():
         assert all(int(ref[i]) in set(sets[i].tolist()) for i in range(num))
         single = [i for i in range(num) if sets[i].size == 1]
         assert all(int(ref[i]) == int(sets[i][0]) for i in single) and len(single) > 0
+
+
+def test_feature_handoff_oracle_is_bit_exact_vs_reference_loop():
+    """`n{n}_x_init_ref` was produced by executing the reference's own loop (protgram_directgcn_trainer.py:323-330, cut out of
+    the module's source by make_golden_next.py)."""
+    g = load("next_rows")
+    for n in (2, 3):
+        nodes = [str(x) for x in g[f"n{n}_nodes"]]
+        prev = {str(s): i for i, s in enumerate(g[f"n{n - 1}_nodes"])}
+        x = next_oracle.init_level_features(nodes, prev, g[f"n{n - 1}_emb"])
+        assert np.array_equal(x, g[f"n{n}_x_init_ref"])
