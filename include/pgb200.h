@@ -180,6 +180,39 @@ int pg_normalize_fill(const int64_t *d_src, const int64_t *d_dst, const float *d
                       float *d_val_out, float *d_val_in, float *d_val_und,   /* P each           */
                       void *d_ws, size_t ws_bytes, pg_stream_t stream);
 
+/* The same matrices for ONE ROW BLOCK [row_lo, row_lo + rows) of a graph whose rows are partitioned
+ * over ranks (SURVEY.md 8(e) "Normalisation (a7-a9)": graph_utils.py:140-287 with one exchange).
+ * The owner of the block passes its own out-edges (src in the block; d_out_*) and the in-edges of
+ * its rows (dst in the block; d_in_*, delivered by the host side's all-to-all), both coalesced
+ * (unique pairs), in any order.  Per-node vectors cross ranks between the calls:
+ *   pg_degree_sums_rows         -> weighted out-/in-degree of the block's rows (fp64[rows]); all-gather
+ *   pg_normalize_rows_sizes     -> d_sizes[0] = pattern nnz of the block, d_sizes[1] != 0 if an edge
+ *                                  does not belong to the block or has an id >= num_nodes
+ *   pg_normalize_rows_structure -> rowptr int64[rows+1] (local offsets), col int32 (GLOBAL ids), the
+ *                                  block's rows of A_in_w (row-major sorted), native self-loop flags;
+ *                                  undirected degree of row r = rowptr[r+1] - rowptr[r] + native_loop[r]; all-gather
+ *   pg_normalize_rows_values    -> the three value arrays; d_rs_out / d_rs_in / d_deg are GLOBAL [num_nodes]
+ * The workspace carries the sorted keys from _sizes to _values.  Rows computed here are bitwise
+ * equal to the same rows of pg_normalize_fill on the whole graph. */
+int pg_degree_sums_rows(const int64_t *d_out_src, const float *d_out_w, int64_t nnz_out,
+                        const int64_t *d_in_dst, const float *d_in_w, int64_t nnz_in, int64_t row_lo,
+                        int64_t rows, double *d_rs_out, double *d_rs_in, pg_stream_t stream);
+size_t pg_normalize_rows_ws_bytes(int64_t nnz_out, int64_t nnz_in, int64_t rows);
+int pg_normalize_rows_sizes(const int64_t *d_out_src, const int64_t *d_out_dst, int64_t nnz_out,
+                            const int64_t *d_in_src, const int64_t *d_in_dst, int64_t nnz_in,
+                            int64_t num_nodes, int64_t row_lo, int64_t rows, int64_t *d_sizes,
+                            void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_normalize_rows_structure(const float *d_in_w, int64_t nnz_out, int64_t nnz_in, int64_t num_nodes,
+                                int64_t row_lo, int64_t rows, int64_t pattern_nnz,
+                                int64_t *d_ain_row, int64_t *d_ain_col, float *d_ain_w, /* nnz_in each */
+                                int64_t *d_rowptr, int32_t *d_col, uint8_t *d_native_loop,
+                                void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_normalize_rows_values(const float *d_out_w, const float *d_in_w, int64_t nnz_out, int64_t nnz_in,
+                             int64_t num_nodes, int64_t row_lo, int64_t rows, const double *d_rs_out,
+                             const double *d_rs_in, const int32_t *d_deg, const uint8_t *d_native_loop,
+                             float eps, float *d_val_out, float *d_val_in, float *d_val_und,
+                             void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
 /* CSR row pointers from sorted row ids; COO row ids from row pointers (int64 <-> CSR glue). */
 int pg_rowptr_from_sorted(const int64_t *d_rows, int64_t nnz, int64_t num_rows, int64_t *d_rowptr,
                           pg_stream_t stream);

@@ -52,6 +52,13 @@ _SIGS = {
     "pg_normalize_sizes": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "pg_normalize_fill": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, c_size_t, _P]),
+    "pg_degree_sums_rows": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "pg_normalize_rows_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "pg_normalize_rows_sizes": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "pg_normalize_rows_structure": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P,
+                                            _P, c_size_t, _P]),
+    "pg_normalize_rows_values": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_float, _P, _P, _P,
+                                         _P, c_size_t, _P]),
     "pg_rowptr_from_sorted": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "pg_coo_from_csr": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "pg_edges_to_csr_ws_bytes": (c_size_t, [c_int64]),

@@ -127,3 +127,162 @@ class RowPartitionedPropagation:
         """x_local: [hi-lo (or per), F] -> z_local [per, nv*F] (rows beyond hi-lo are zero)."""
         return _PartitionedFanout.apply(self.pad_rows(x_local), self.local, self.transposed, self.per, self.n,
                                         self.symmetric, self.group)
+
+    @classmethod
+    def from_local(cls, local: _Csr, n: int, group=None, symmetric: bool = True, transposed: Optional[_Csr] = None):
+        """From a row block that already lives on this rank (`normalize_row_partitioned`): rowptr has
+        `per` + 1 entries (rows past the block are empty), columns are global."""
+        self = cls.__new__(cls)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = n
+        self.lo, self.hi, self.per = row_range(n, self.rank, self.world)
+        if local.rowptr.numel() != self.per + 1:
+            raise ValueError(f"local rowptr must hold {self.per + 1} entries (padded block), got {local.rowptr.numel()}")
+        self.local, self.symmetric, self.transposed = local, symmetric, transposed
+        if not symmetric and transposed is None:
+            raise ValueError("general (non-symmetric) matrices need the source-grouped CSR of the local block")
+        return self
+
+
+# ----------------------------------------------------------------------------------------------
+# Row-partitioned normalisation (SURVEY.md 8(e), row "Normalisation (a7-a9)"; reference
+# graph_utils.py:140-287).  Rank r holds the coalesced out-edges of its rows [lo_r, hi_r).  The
+# propagation matrices of a row need the transposed entries too, so there is exactly ONE exchange of
+# edges (every edge i -> j goes to the owner of j) plus all-gathers of three per-node vectors:
+#
+#     all_to_all   (src, dst, w) by owner(dst)                  16 + 4 B per edge that leaves the rank
+#     all_gather   weighted out-/in-degree (fp64)               16 B per node
+#     all_gather   undirected degree (int32)                     4 B per node
+#
+# The local work is the row-block variant of the single-GPU kernels (csrc/graph_rows.cu); each
+# block is bitwise equal to the same rows of DirectedNgramGraph's matrices built on one GPU.
+# ----------------------------------------------------------------------------------------------
+class RowBlockNormalizer:
+    """Local phases for one row block; the caller moves the per-node vectors between them."""
+
+    def __init__(self, o_src, o_dst, o_w, i_src, i_dst, i_w, n: int, lo: int, hi: int, eps: float = 1e-9):
+        for t in (o_src, o_dst, o_w, i_src, i_dst, i_w):
+            nat.check_tensor(t, "edge array")
+        self.o_src, self.o_dst, self.o_w = o_src.contiguous(), o_dst.contiguous(), o_w.contiguous().float()
+        self.i_src, self.i_dst, self.i_w = i_src.contiguous(), i_dst.contiguous(), i_w.contiguous().float()
+        self.n, self.lo, self.rows, self.eps = int(n), int(lo), int(hi - lo), float(eps)
+        self.nnz_o, self.nnz_i = int(o_src.numel()), int(i_src.numel())
+        self.dev = o_src.device
+        self.ws = None
+
+    def degree_sums(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        rs_out = torch.zeros(self.rows, dtype=torch.float64, device=self.dev)
+        rs_in = torch.zeros(self.rows, dtype=torch.float64, device=self.dev)
+        if self.rows:
+            nat.call("pg_degree_sums_rows", nat.ptr(self.o_src), nat.ptr(self.o_w), self.nnz_o, nat.ptr(self.i_dst), nat.ptr(self.i_w),
+                     self.nnz_i, self.lo, self.rows, nat.ptr(rs_out), nat.ptr(rs_in), nat.stream_ptr())
+        return rs_out, rs_in
+
+    def structure(self) -> torch.Tensor:
+        """Sort + pattern of the block -> its undirected degrees (int32[rows]) for the all-gather."""
+        dev, rows = self.dev, self.rows
+        if rows == 0:
+            self.p = 0
+            self.rowptr = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.col = torch.empty(0, dtype=torch.int32, device=dev)
+            self.ain = tuple(torch.empty(0, dtype=dt, device=dev) for dt in (torch.int64, torch.int64, torch.float32))
+            return torch.empty(0, dtype=torch.int32, device=dev)
+        self.ws = nat.workspace(nat.query("pg_normalize_rows_ws_bytes", self.nnz_o, self.nnz_i, rows), dev)
+        sizes = torch.zeros(2, dtype=torch.int64, device=dev)
+        st = nat.stream_ptr()
+        nat.call("pg_normalize_rows_sizes", nat.ptr(self.o_src), nat.ptr(self.o_dst), self.nnz_o, nat.ptr(self.i_src), nat.ptr(self.i_dst),
+                 self.nnz_i, self.n, self.lo, rows, nat.ptr(sizes), nat.ptr(self.ws), self.ws.numel(), st)
+        p, bad = (int(v) for v in sizes.tolist())
+        if bad:
+            raise ValueError(f"row block [{self.lo}, {self.lo + rows}): an out-edge's source or an in-edge's target lies outside "
+                             "the block, or a node id is >= num_nodes")
+        self.p = p
+        self.rowptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+        self.col = torch.empty(p, dtype=torch.int32, device=dev)
+        self.native = torch.zeros(rows, dtype=torch.uint8, device=dev)
+        self.ain = (torch.empty(self.nnz_i, dtype=torch.int64, device=dev), torch.empty(self.nnz_i, dtype=torch.int64, device=dev),
+                    torch.empty(self.nnz_i, dtype=torch.float32, device=dev))
+        nat.call("pg_normalize_rows_structure", nat.ptr(self.i_w), self.nnz_o, self.nnz_i, self.n, self.lo, rows, p, nat.ptr(self.ain[0]),
+                 nat.ptr(self.ain[1]), nat.ptr(self.ain[2]), nat.ptr(self.rowptr), nat.ptr(self.col), nat.ptr(self.native),
+                 nat.ptr(self.ws), self.ws.numel(), st)
+        return ((self.rowptr[1:] - self.rowptr[:-1]) + self.native).to(torch.int32)
+
+    def values(self, rs_out: torch.Tensor, rs_in: torch.Tensor, deg: torch.Tensor) -> dict:
+        """rs_out / rs_in (fp64) and deg (int32) are the GLOBAL [n] vectors."""
+        dev, p = self.dev, self.p
+        v_out, v_in, v_und = (torch.empty(p, dtype=torch.float32, device=dev) for _ in range(3))
+        if self.rows:
+            nat.call("pg_normalize_rows_values", nat.ptr(self.o_w), nat.ptr(self.i_w), self.nnz_o, self.nnz_i, self.n, self.lo, self.rows,
+                     nat.ptr(rs_out), nat.ptr(rs_in), nat.ptr(deg), nat.ptr(self.native), self.eps, nat.ptr(v_out), nat.ptr(v_in),
+                     nat.ptr(v_und), nat.ptr(self.ws), self.ws.numel(), nat.stream_ptr())
+        self.ws = None
+        return {"rowptr": self.rowptr, "col": self.col, "val_out": v_out, "val_in": v_in, "val_und": v_und, "pattern_nnz": p,
+                "in_src": self.ain[0], "in_dst": self.ain[1], "in_w": self.ain[2]}
+
+
+def exchange_in_edges(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int, group=None):
+    """Every rank passes the out-edges of its rows; returns the edges whose TARGET it owns
+    (src, dst, w; one all-to-all of 20 B per edge).  Stable: edges from one peer keep their order."""
+    group = group if group is not None else dist.group.WORLD
+    world = dist.get_world_size(group)
+    per = (n + world - 1) // world
+    e = int(src.numel())
+    dev = src.device
+    owner = torch.div(dst, per, rounding_mode="floor").contiguous()
+    perm = torch.arange(e, dtype=torch.int32, device=dev)
+    if e:
+        # stable partition by owner: one radix pass of the library's own sort
+        alt_k, alt_v = torch.empty_like(owner), torch.empty_like(perm)
+        ws = nat.workspace(nat.query("pg_sort_pairs_ws_bytes", e), dev)
+        nat.call("pg_sort_pairs", nat.ptr(owner), nat.ptr(alt_k), nat.ptr(perm), nat.ptr(alt_v), e, max(1, (world - 1).bit_length()),
+                 nat.ptr(ws), ws.numel(), nat.stream_ptr())
+    send_counts = torch.bincount(owner, minlength=world)[:world]
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    s_split, r_split = send_counts.tolist(), recv_counts.tolist()
+    perm = perm.long()
+    send_sd = torch.stack([src[perm], dst[perm]], dim=1).contiguous()
+    send_w = w[perm].contiguous()
+    total = int(sum(r_split))
+    recv_sd = torch.empty((total, 2), dtype=torch.int64, device=dev)
+    recv_w = torch.empty(total, dtype=w.dtype, device=dev)
+    dist.all_to_all_single(recv_sd, send_sd, output_split_sizes=r_split, input_split_sizes=s_split, group=group)
+    dist.all_to_all_single(recv_w, send_w, output_split_sizes=r_split, input_split_sizes=s_split, group=group)
+    return recv_sd[:, 0].contiguous(), recv_sd[:, 1].contiguous(), recv_w
+
+
+def _all_gather_vector(local: torch.Tensor, per: int, n: int, group) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    padded = torch.zeros(per, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    out = torch.empty(world * per, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return out[:n].contiguous()
+
+
+def normalize_row_partitioned(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int, eps: float = 1e-9, group=None) -> dict:
+    """Propagation matrices of a row-partitioned graph.  `src, dst, w`: the coalesced out-edges of
+    this rank's rows (`row_range(n, rank, world)`), int64 / int64 / fp32 on the GPU.  Returns the
+    block in the layer's format (rowptr int64[per+1] padded with empty rows, col int32 global,
+    val_out / val_in / val_und) plus the block's rows of A_in_w; `local_csr()` of the result feeds
+    `RowPartitionedPropagation.from_local`."""
+    group = group if group is not None else dist.group.WORLD
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi, per = row_range(n, rank, world)
+    i_src, i_dst, i_w = exchange_in_edges(src, dst, w, n, group)
+    blk = RowBlockNormalizer(src, dst, w, i_src, i_dst, i_w, n, lo, hi, eps)
+    rs_out_l, rs_in_l = blk.degree_sums()
+    rs_out = _all_gather_vector(rs_out_l, per, n, group)
+    rs_in = _all_gather_vector(rs_in_l, per, n, group)
+    deg = _all_gather_vector(blk.structure(), per, n, group)
+    res = blk.values(rs_out, rs_in, deg)
+    rp = torch.full((per + 1,), res["pattern_nnz"], dtype=torch.int64, device=src.device)
+    rp[: hi - lo + 1] = res["rowptr"]
+    res.update(rowptr=rp, lo=lo, hi=hi, per=per, rs_out=rs_out, rs_in=rs_in, deg=deg)
+    return res
+
+
+def local_csr(res: dict) -> _Csr:
+    """[val_in, val_out, val_und] in the order the layer consumes them (Z = [A_in X | A_out X | U X])."""
+    return _Csr(res["rowptr"], res["col"], [res["val_in"], res["val_out"], res["val_und"]])

@@ -184,6 +184,85 @@ def pg_normalize_fill(src, dst, w, nnz, n, eps, pattern_nnz, in_src, in_dst, in_
         out.copy_(r)
 
 
+# row-block variant: written independently of _normalize above (dense per-block lookups)
+_rows_state = {}
+
+
+def pg_degree_sums_rows(o_src, o_w, nnz_o, i_dst, i_w, nnz_i, row_lo, rows, rs_out, rs_in, stream=None):
+    rs_out.zero_()
+    rs_in.zero_()
+    rs_out.index_add_(0, o_src[:nnz_o] - row_lo, o_w[:nnz_o].double())
+    rs_in.index_add_(0, i_dst[:nnz_i] - row_lo, i_w[:nnz_i].double())
+
+
+def pg_normalize_rows_ws_bytes(nnz_o, nnz_i, rows):
+    return 256
+
+
+def pg_normalize_rows_sizes(o_src, o_dst, nnz_o, i_src, i_dst, nnz_i, n, row_lo, rows, sizes, ws, ws_bytes, stream=None):
+    o_src, o_dst, i_src, i_dst = o_src[:nnz_o], o_dst[:nnz_o], i_src[:nnz_i], i_dst[:nnz_i]
+    bad = bool(((o_src < row_lo) | (o_src >= row_lo + rows) | (o_dst < 0) | (o_dst >= n)).any()) or \
+        bool(((i_dst < row_lo) | (i_dst >= row_lo + rows) | (i_src < 0) | (i_src >= n)).any())
+    sizes[1] = int(bad)
+    if bad:
+        sizes[0] = rows
+        return
+    loops = torch.arange(rows)
+    key = torch.cat([(o_src - row_lo) * n + o_dst, (i_dst - row_lo) * n + i_src, loops * n + loops + row_lo])
+    ukey = torch.unique(key)
+    _rows_state[ws.data_ptr()] = (ukey, (o_src, o_dst, i_src, i_dst))   # the real workspace carries the sorted keys
+    sizes[0] = ukey.numel()
+
+
+def pg_normalize_rows_structure(i_w, nnz_o, nnz_i, n, row_lo, rows, pattern_nnz, ain_row, ain_col, ain_w, rowptr, col,
+                                native_loop, ws, ws_bytes, stream=None):
+    ukey, (o_src, o_dst, i_src, i_dst) = _rows_state[ws.data_ptr()]
+    rl, c = ukey // n, ukey % n
+    col.copy_(c.to(torch.int32))
+    rowptr[0] = 0
+    rowptr[1:] = torch.cumsum(torch.bincount(rl, minlength=rows), 0)
+    native_loop.zero_()
+    native_loop[(o_src - row_lo)[o_src == o_dst]] = 1      # a self loop is both an out- and an in-edge of its row
+    native_loop[(i_dst - row_lo)[i_src == i_dst]] = 1
+    if nnz_i:
+        order = torch.argsort((i_dst - row_lo) * n + i_src, stable=True)
+        ain_row.copy_(i_dst[order])
+        ain_col.copy_(i_src[order])
+        ain_w.copy_(i_w[:nnz_i][order])
+
+
+def pg_normalize_rows_values(o_w, i_w, nnz_o, nnz_i, n, row_lo, rows, rs_out, rs_in, deg, native_loop, eps, val_out, val_in,
+                             val_und, ws, ws_bytes, stream=None):
+    f32 = torch.float32
+    ukey, (o_src, o_dst, i_src, i_dst) = _rows_state.pop(ws.data_ptr())
+    rl, c = ukey // n, ukey % n
+    r = rl + row_lo
+    P = ukey.numel()
+    pos = lambda kk: torch.searchsorted(ukey, kk)
+    w_rc, w_cr = torch.zeros(P, dtype=f32), torch.zeros(P, dtype=f32)
+    has = torch.zeros(P, dtype=torch.bool)
+    po, pi = pos((o_src - row_lo) * n + o_dst), pos((i_dst - row_lo) * n + i_src)
+    w_rc[po] = o_w[:nnz_o]
+    w_cr[pi] = i_w[:nnz_i]
+    has[po] = True
+    has[pi] = True
+    inv = lambda d: torch.where(d.to(f32) != 0, 1.0 / d.to(f32), torch.zeros(d.numel(), dtype=f32))
+    io, ii = inv(rs_out), inv(rs_in)
+    diag = r == c
+
+    def mathcal(inv_deg, a_rc, a_cr):
+        a, b = a_rc * inv_deg[r], a_cr * inv_deg[c]
+        b = torch.where(diag, a, b)
+        v = torch.sqrt((a * a + b * b) * 0.5 + torch.tensor(eps, dtype=f32))
+        return torch.where(has, torch.where(diag, v + 1.0, v), torch.ones_like(v))
+
+    val_out.copy_(mathcal(io, w_rc, w_cr))
+    val_in.copy_(mathcal(ii, w_cr, w_rc))
+    dis = 1.0 / torch.sqrt(deg.to(f32))
+    vu = dis[r] * dis[c]
+    val_und.copy_(torch.where(diag & (native_loop[rl] != 0), vu + vu, vu))
+
+
 def pg_rowptr_from_sorted(rows, nnz, num_rows, rowptr, stream=None):
     rowptr[0] = 0
     rowptr[1:] = torch.cumsum(torch.bincount(rows[:nnz], minlength=num_rows), 0)

@@ -143,3 +143,100 @@ def test_row_partitioned_propagation_equals_single(symmetric):
     dx = np.concatenate([r[2][: row_range(n, r[0], world)[1] - row_range(n, r[0], world)[0]] for r in res])
     assert np.max(np.abs(z - z_ref.numpy())) <= 1e-4 * np.max(np.abs(z_ref.numpy()))
     assert np.max(np.abs(dx - dx_ref.numpy())) <= 1e-4 * np.max(np.abs(dx_ref.numpy()))
+
+
+def random_count_graph(n, seed, density=0.02, isolated=3):
+    """Coalesced directed edge table with integer counts, reciprocal pairs, native self loops and a few
+    nodes without any edge (what the n-gram builder can emit)."""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((n, n)) < density
+    mask[np.arange(0, n, 7), np.arange(0, n, 7)] = True        # native self loops
+    mask |= (rng.random((n, n)) < density / 2) & mask.T          # extra reciprocal pairs
+    dead = rng.choice(n, size=isolated, replace=False)
+    mask[dead, :] = False
+    mask[:, dead] = False
+    src, dst = np.nonzero(mask)
+    cnt = rng.integers(1, 400, size=src.size).astype(np.int64)
+    return src.astype(np.int64), dst.astype(np.int64), cnt
+
+
+def check_blocks_against_oracle(blocks, src, dst, cnt, n, world, bitwise_vs=None):
+    """blocks: rank -> dict of numpy arrays from normalize_row_partitioned.  Reassemble the full
+    pattern / values / A_in_w and hold them against the full-graph oracle."""
+    from oracle import graph_oracle
+    from protgram_directgcn_b200.host.partitioned import row_range
+    mats = graph_oracle.normalise_all(src, dst, cnt, n)
+    rows, cols, vals, ain = [], [], {"val_out": [], "val_in": [], "val_und": []}, [[], [], []]
+    for r in range(world):
+        b = blocks[r]
+        lo, hi, per = row_range(n, r, world)
+        rp = b["rowptr"]
+        assert rp.shape[0] == per + 1 and rp[0] == 0 and rp[hi - lo] == b["col"].shape[0] and np.all(rp[hi - lo:] == rp[hi - lo])
+        rows.append(np.repeat(np.arange(lo, hi), np.diff(rp[: hi - lo + 1])))
+        cols.append(b["col"].astype(np.int64))
+        for k in vals:
+            vals[k].append(b[k])
+        for i, k in enumerate(("in_src", "in_dst", "in_w")):
+            ain[i].append(b[k])
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    for name, key in (("mathcal_A_out", "val_out"), ("mathcal_A_in", "val_in"), ("A_undirected_norm_sparse", "val_und")):
+        r_ref, c_ref, v_ref = mats[name]
+        assert np.array_equal(rows, r_ref) and np.array_equal(cols, c_ref), name
+        got = np.concatenate(vals[key])
+        assert np.max(np.abs(got - v_ref) / np.abs(v_ref)) <= 2e-7, name
+    r_ref, c_ref, v_ref = mats["A_in_w"]
+    assert np.array_equal(np.concatenate(ain[0]), r_ref) and np.array_equal(np.concatenate(ain[1]), c_ref)
+    assert np.array_equal(np.concatenate(ain[2]), v_ref)
+
+
+def _norm_worker(rank, world, port, payload, q):
+    try:
+        _init(rank, world, port)
+        from protgram_directgcn_b200.host.partitioned import (RowPartitionedPropagation, local_csr, normalize_row_partitioned,
+                                                              row_range)
+        src, dst, cnt, n, x = payload
+        lo, hi, per = row_range(n, rank, world)
+        mine = (src >= lo) & (src < hi)
+        res = normalize_row_partitioned(torch.from_numpy(src[mine]), torch.from_numpy(dst[mine]),
+                                        torch.from_numpy(cnt[mine].astype(np.float32)), n)
+        prop = RowPartitionedPropagation.from_local(local_csr(res), n)
+        z = prop(torch.from_numpy(x[lo:hi]))[: hi - lo]
+        out = {k: res[k].numpy() for k in ("rowptr", "col", "val_out", "val_in", "val_und", "in_src", "in_dst", "in_w")}
+        out["z"] = z.numpy()
+        q.put((rank, out))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,world", [(203, 2), (5, 3), (5, 4)])
+def test_row_partitioned_normalisation_equals_oracle(n, world):
+    """every rank holds the out-edges of its rows; one all-to-all of edges + three
+    all-gathered per-node vectors give each rank its rows of the three propagation matrices and of
+    A_in_w.  Reassembled blocks == the full-graph oracle; the blocks then feed the partitioned SpMM.
+    (5 nodes: per = 2, so the third rank owns a single row and a fourth rank none at all.)"""
+    from oracle import graph_oracle
+    src, dst, cnt = random_count_graph(n, seed=n, density=0.05 if n > 50 else 0.3, isolated=3 if n > 50 else 1)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, 8)).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_norm_worker, args=(r, world, port, (src, dst, cnt, n, x), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(v, str) for v in res.values()), res
+    check_blocks_against_oracle(res, src, dst, cnt, n, world)
+    mats = graph_oracle.normalise_all(src, dst, cnt, n)
+    z = np.concatenate([res[r]["z"] for r in range(world)])
+    for v, name in enumerate(("mathcal_A_in", "mathcal_A_out", "A_undirected_norm_sparse")):
+        rr, cc, vv = mats[name]
+        dense = np.zeros((n, n), dtype=np.float64)
+        dense[rr, cc] = vv
+        ref = dense @ x.astype(np.float64)
+        assert np.max(np.abs(z[:, v * 8:(v + 1) * 8] - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref))), name

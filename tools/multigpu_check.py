@@ -2,6 +2,8 @@
 """Multi-GPU checks over NCCL (run under torchrun with >= 2 GPUs):
   1. sharded graph build (corpus split by sequence range, all-reduce of the tables) == single-GPU build, bit-exact
   2. row-partitioned propagation (all-gather + local SpMM, fwd and bwd) == single-GPU SpMM
+  3. row-partitioned normalisation (all-to-all of edges + all-gathered degree vectors + row-block kernels)
+     == the single-GPU matrices of check 1, bitwise, and the partitioned SpMM on the blocks it returns
 usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multigpu_check.py"""
 import os
 import sys
@@ -72,6 +74,23 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"[ok] row-partitioned propagation over {world} GPUs (all-gather + local SpMM) == single GPU, bitwise, fwd and bwd")
+
+    # ---- 3. row-partitioned normalisation: every rank passes only the out-edges of its rows
+    from protgram_directgcn_b200.host.partitioned import local_csr, normalize_row_partitioned
+    a_out = g_single.A_out_w
+    src, dst, w = a_out.indices()[0].to(dev), a_out.indices()[1].to(dev), a_out.values().to(dev)
+    mine = (src >= lo) & (src < hi)
+    res = normalize_row_partitioned(src[mine].contiguous(), dst[mine].contiguous(), w[mine].contiguous(), N, 1e-9)
+    p0, p1 = int(side["rowptr"][lo]), int(side["rowptr"][hi])
+    assert res["pattern_nnz"] == p1 - p0
+    assert torch.equal(res["rowptr"][: hi - lo + 1], side["rowptr"][lo:hi + 1] - p0) and torch.equal(res["col"], side["col"][p0:p1])
+    for k in ("val_in", "val_out", "val_und"):
+        assert torch.equal(res[k], side[k][p0:p1]), k
+    z2 = RowPartitionedPropagation.from_local(local_csr(res), N)(x[lo:hi].clone())
+    assert torch.equal(z2[: hi - lo], z_full[lo:hi]), "SpMM on the partitioned-normalisation blocks"
+    dist.barrier()
+    if rank == 0:
+        print(f"[ok] row-partitioned normalisation over {world} GPUs == single GPU, bitwise (pattern, three value arrays, SpMM on the blocks)")
     dist.destroy_process_group()
 
 
