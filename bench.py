@@ -300,10 +300,10 @@ def next_node_labels(a_out: torch.Tensor, n: int) -> torch.Tensor:
     return labels
 
 
-def rmat_graph(pipe, log2_nodes, edges_per_node):
+def rmat_edges(pipe, log2_nodes, edges_per_node):
     """R-MAT power-law digraph (a,b,c,d = .57,.19,.19,.05; integer weights 1..7), seeded identically on every
-    rank, pushed through the reference normalisation (coalesce + a8/a9) on the device -> shared-pattern CSR."""
-    gu, dev = pipe.gu, pipe.dev
+    rank; raw edge list (duplicates included) with randomly relabelled node ids."""
+    dev = pipe.dev
     n = 1 << log2_nodes
     e = n * edges_per_node
     g = torch.Generator(device=dev).manual_seed(SEED)
@@ -320,6 +320,13 @@ def rmat_graph(pipe, log2_nodes, edges_per_node):
     perm = torch.randperm(n, generator=g, device=dev)
     src, dst = perm[src], perm[dst]
     del perm
+    return n, e, src, dst, w
+
+
+def rmat_graph(pipe, log2_nodes, edges_per_node):
+    """The R-MAT graph pushed through the reference normalisation (coalesce + a8/a9) on the device -> shared-pattern CSR."""
+    gu = pipe.gu
+    n, e, src, dst, w = rmat_edges(pipe, log2_nodes, edges_per_node)
     s, d, wv = gu.device_coalesce(src, dst, w, n)
     del src, dst, w
     res = gu.device_normalize(s, d, wv, n, 1e-9)
@@ -328,6 +335,43 @@ def rmat_graph(pipe, log2_nodes, edges_per_node):
         res.pop(k)
     torch.cuda.empty_cache()
     return n, e, res
+
+
+def rmat_row_block(pipe, dist, log2_nodes, edges_per_node):
+    """This rank's row block of the same graph WITHOUT ever normalising the whole graph on one GPU:
+    the rank keeps the R-MAT edges that start in its rows, coalesces them, and `normalize_row_partitioned` does the rest
+    (all-to-all of edges by owner of the target, all-gathered degree vectors, row-block kernels).
+    -> (n, e, result dict, ms of the partitioned normalisation as max over ranks)."""
+    from protgram_directgcn_b200.host import partitioned as part
+    gu, dev = pipe.gu, pipe.dev
+    n, e, src, dst, w = rmat_edges(pipe, log2_nodes, edges_per_node)
+    lo, hi, per = part.row_range(n, pipe.rank, pipe.world)
+    keep = (src >= lo) & (src < hi)
+    src, dst, w = src[keep], dst[keep], w[keep]
+    del keep
+    s, d, wv = gu.device_coalesce(src, dst, w, n)
+    del src, dst, w
+    torch.cuda.empty_cache()
+    best, res = None, None
+    for _ in range(2):  # the first call also warms NCCL's all-to-all channels
+        del res
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = part.normalize_row_partitioned(s, d, wv, n, 1e-9, dist.group.WORLD)
+        b.record()
+        torch.cuda.synchronize()
+        best = a.elapsed_time(b)
+    t = torch.tensor([best], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["unique_out_edges_local"] = int(s.numel())
+    res["recv_in_edges_local"] = int(res["in_w"].numel())
+    for k in ("in_src", "in_dst", "in_w", "rs_out", "rs_in", "deg"):
+        res.pop(k)
+    del s, d, wv
+    torch.cuda.empty_cache()
+    return n, e, res, float(t.item())
 
 
 def _time_ms(fn, iters, warm=2):
@@ -372,17 +416,23 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     """Config C5's shape, weak-scaled: R-MAT graph with 2^log2_nodes_per_gpu nodes PER GPU, hidden 128, rows
     partitioned over the ranks (SURVEY 8e).  forward = NCCL all-gather of X over NVLink + local fan-out SpMM;
     backward = all-gather of dZ + local fan-in (symmetric matrices).  Times are max over ranks; edges/s is the
-    whole job (3 * pattern nnz of the full graph per pass).  Every rank builds the full graph redundantly (setup,
-    untimed) and keeps its row block."""
+    whole job (3 * pattern nnz of the full graph per pass).  Every rank generates the seeded edge list, keeps the edges
+    that start in its rows and gets its block of the propagation matrices from the row-partitioned normalisation
+    (`normalise_partitioned`: timed on its own, max over ranks)."""
     import math
     from protgram_directgcn_b200.host import partitioned as part
     nat, dev, world = pipe.nat, pipe.dev, pipe.world
     log2_nodes = log2_nodes_per_gpu + int(round(math.log2(world)))
-    n, e, res = rmat_graph(pipe, log2_nodes, edges_per_node)
-    P = int(res["pattern_nnz"])
-    prop = part.RowPartitionedPropagation(res["rowptr"], res["col"], [res["val_in"], res["val_out"], res["val_und"]], n,
-                                          group=dist.group.WORLD, symmetric=True)
+    n, e, res, ms_norm = rmat_row_block(pipe, dist, log2_nodes, edges_per_node)
+    prop = part.RowPartitionedPropagation.from_local(part.local_csr(res), n, group=dist.group.WORLD, symmetric=True)
     p_local = int(prop.local.col.numel())
+    tot = torch.tensor([p_local, res["unique_out_edges_local"]], device=dev, dtype=torch.int64)
+    dist.all_reduce(tot)
+    P, unique_edges = int(tot[0]), int(tot[1])
+    norm_info = {"ms": ms_norm, "unique_edges": unique_edges, "edges_per_s": unique_edges / (ms_norm * 1e-3),
+                 "exchange": "all_to_all_single of (src, dst, w) by owner of the target (20 B per edge) + all_gather of the "
+                             "weighted out-/in-degrees (fp64) and the undirected degree (int32)",
+                 "note": "each rank starts from the coalesced out-edges of its own rows; the whole graph never exists on one GPU"}
     del res
     torch.cuda.empty_cache()
     per = prop.per
@@ -411,7 +461,7 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}, ids randomly relabelled), {e} directed edges before dedupe, pattern nnz {P}",
            "F": F, "pattern_nnz": P, "rows_per_gpu": per, "partition": "1-D rows, global int32 columns",
            "local_nnz_max_over_mean": mx(float(p_local)) / (P / world),
-           "exchange": "NCCL all_gather_into_tensor (fwd: X [N,F]; bwd: dZ [N,3F])"}
+           "exchange": "NCCL all_gather_into_tensor (fwd: X [N,F]; bwd: dZ [N,3F])", "normalise_partitioned": norm_info}
     for name, fn, comm, local, width in (("fwd", fwd, ag_x, local_fo, F), ("bwd", bwd, ag_dz, local_fi, 3 * F)):
         dist.barrier()
         ms = mx(_time_ms(fn, iters))
