@@ -141,6 +141,34 @@ int pg_graph_extract_fill(const unsigned long long *d_bins, int n, int sigma, in
                           int64_t num_edges, int64_t *d_node_code, int64_t *d_src, int64_t *d_dst,
                           int64_t *d_count, void *d_ws, size_t ws_bytes, pg_stream_t stream);
 
+/* Key-range form of the two steps above for tables merged by an NCCL REDUCE-SCATTER over key ranges
+ * (SURVEY.md 8(e) "Builder"; replaces data_builder.py:151-177 and :267-286 on several GPUs): the caller
+ * holds the summed bins of the source n-gram codes [code_lo, code_lo + codes), i.e. of the keys
+ * [code_lo * sigma, (code_lo + codes) * sigma) -- whole rows of A_out_w -- in d_bins_local (a padded
+ * last range may reach past the table; those bins are never read).
+ *   _range_mark : ORs the presence of the local keys' source / target n-grams into d_present
+ *                 (uint8[sigma^n], preset with the short-sequence flags; the host MAX-reduces it over
+ *                 the ranks afterwards) and reports d_sizes[0] = number of local edges
+ *   pg_node_ids_from_presence : reduced presence -> d_node_id[code] = rank among the present codes
+ *                 (= id of the n-gram in sorted order), d_sizes[0] = number of nodes
+ *   pg_node_codes_emit : d_node_code[id] = code (ascending)
+ *   _range_fill : the local keys' edges (src id, dst id, count) sorted by (src, dst); the ranks' lists
+ *                 concatenated in rank order are the whole coalesced edge table.
+ * The workspace carries the edge offsets from _range_mark to _range_fill. */
+size_t pg_graph_extract_range_ws_bytes(int sigma, int64_t codes);
+int pg_graph_extract_range_mark(const unsigned long long *d_bins_local, int n, int sigma, int64_t code_lo,
+                                int64_t codes, uint8_t *d_present, int64_t *d_sizes, void *d_ws,
+                                size_t ws_bytes, pg_stream_t stream);
+size_t pg_node_ids_ws_bytes(int64_t ngrams);
+int pg_node_ids_from_presence(const uint8_t *d_present, int64_t ngrams, int64_t *d_node_id,
+                              int64_t *d_sizes, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_node_codes_emit(const uint8_t *d_present, const int64_t *d_node_id, int64_t ngrams,
+                       int64_t *d_node_code, pg_stream_t stream);
+int pg_graph_extract_range_fill(const unsigned long long *d_bins_local, int n, int sigma, int64_t code_lo,
+                                int64_t codes, const int64_t *d_node_id, int64_t num_edges_local,
+                                int64_t *d_src, int64_t *d_dst, int64_t *d_count, void *d_ws,
+                                size_t ws_bytes, pg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Hot path A, part 2: adjacency + propagation matrices (graph_utils.py:140-287)
  * ---------------------------------------------------------------------------------------- */

@@ -44,6 +44,12 @@ _SIGS = {
     "pg_graph_extract_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_graph_extract_sizes": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_graph_extract_fill": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pg_graph_extract_range_ws_bytes": (c_size_t, [c_int, c_int64]),
+    "pg_graph_extract_range_mark": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
+    "pg_node_ids_ws_bytes": (c_size_t, [c_int64]),
+    "pg_node_ids_from_presence": (c_int, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "pg_node_codes_emit": (c_int, [_P, _P, c_int64, _P, _P]),
+    "pg_graph_extract_range_fill": (c_int, [_P, c_int, c_int, c_int64, c_int64, _P, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "pg_sort_pairs_ws_bytes": (c_size_t, [c_int64]),
     "pg_sort_pairs": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "pg_coo_coalesce_ws_bytes": (c_size_t, [c_int64]),

@@ -117,6 +117,109 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
                                                n_value=n, assume_coalesced=True)
 
 
+class PartitionedLevelGraph:
+    """One n level of a graph that is never assembled on one GPU (what `build_level_graph_partitioned`
+    returns on every rank): the node list is replicated (ids need the global presence table), edges
+    and matrices exist as this rank's row block [lo, hi) only.
+
+    node_code       int64[N]   packed n-gram codes, ascending = id order (replicated)
+    a_out           (src, dst, count) of the block's rows of A_out_w, sorted by (src, dst)
+    block           dict from partitioned.normalize_row_partitioned (rowptr padded to per + 1, global
+                    int32 columns, val_in / val_out / val_und, the block's rows of A_in_w)"""
+
+    def __init__(self, n_value, symbols, node_code, a_out, block, number_of_edges, group):
+        self.n_value, self.symbols, self.node_code, self.a_out, self.block = n_value, symbols, node_code, a_out, block
+        self.number_of_nodes = int(node_code.numel())
+        self.number_of_edges = number_of_edges
+        self.lo, self.hi, self.per = block["lo"], block["hi"], block["per"]
+        self.group = group
+
+    @property
+    def node_sequences(self):
+        return corpus.LazyNodeNames(self.node_code, self.symbols, self.n_value).resolve()
+
+    def propagation(self):
+        """Row-partitioned SpMM over the block (host/partitioned.py)."""
+        from . import partitioned as part
+        return part.RowPartitionedPropagation.from_local(part.local_csr(self.block), self.number_of_nodes, group=self.group)
+
+
+def merge_tables_by_key_range(bins_padded: torch.Tensor, codes_per: int, sigma: int, group) -> torch.Tensor:
+    """Sum the per-rank tables and leave every rank with ITS key range only: rank r gets the bins of the source codes
+    [r * codes_per, (r + 1) * codes_per) -- the north star's reduce-scatter over key ranges (half the bytes of an
+    all-reduce, and no rank ever holds the merged table)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    chunk = codes_per * sigma
+    if dist.get_backend(group) == "nccl":
+        local = torch.empty(chunk, dtype=bins_padded.dtype, device=bins_padded.device)
+        dist.reduce_scatter_tensor(local, bins_padded, op=dist.ReduceOp.SUM, group=group)
+        return local
+    dist.all_reduce(bins_padded, op=dist.ReduceOp.SUM, group=group)   # gloo (CPU tests) has no reduce_scatter
+    return bins_padded[rank * chunk:(rank + 1) * chunk].clone()
+
+
+def extract_key_range(local_bins: torch.Tensor, short: torch.Tensor, n: int, sigma: int, code_lo: int, codes: int, group):
+    """This rank's key range -> (node_code [N] replicated, src, dst, count of the range's edges with GLOBAL node ids).
+    One small collective: the presence table (sigma^n bytes) is MAX-reduced so every rank numbers the nodes alike."""
+    import torch.distributed as dist
+    dev = local_bins.device
+    pow_n = sigma ** n
+    st = nat.stream_ptr()
+    present = short.clone()
+    ws = nat.workspace(nat.query("pg_graph_extract_range_ws_bytes", sigma, codes), dev)
+    sizes = torch.zeros(2, dtype=torch.int64, device=dev)
+    nat.call("pg_graph_extract_range_mark", nat.ptr(local_bins), n, sigma, code_lo, codes, nat.ptr(present), nat.ptr(sizes),
+             nat.ptr(ws), ws.numel(), st)
+    present_i = present.to(torch.int32)
+    dist.all_reduce(present_i, op=dist.ReduceOp.MAX, group=group)
+    present = present_i.to(torch.uint8)
+    node_id = torch.empty(pow_n, dtype=torch.int64, device=dev)
+    ws_ids = nat.workspace(nat.query("pg_node_ids_ws_bytes", pow_n), dev)
+    nat.call("pg_node_ids_from_presence", nat.ptr(present), pow_n, nat.ptr(node_id), nat.ptr(sizes[1:]), nat.ptr(ws_ids), ws_ids.numel(), st)
+    num_edges, num_nodes = (int(v) for v in sizes.tolist())
+    node_code = torch.empty(num_nodes, dtype=torch.int64, device=dev)
+    if num_nodes:
+        nat.call("pg_node_codes_emit", nat.ptr(present), nat.ptr(node_id), pow_n, nat.ptr(node_code), st)
+    src = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    dst = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    cnt = torch.empty(num_edges, dtype=torch.int64, device=dev)
+    nat.call("pg_graph_extract_range_fill", nat.ptr(local_bins), n, sigma, code_lo, codes, nat.ptr(node_id), num_edges, nat.ptr(src),
+             nat.ptr(dst), nat.ptr(cnt), nat.ptr(ws), ws.numel(), st)
+    return node_code, src, dst, cnt
+
+
+def build_level_graph_partitioned(d_buf: torch.Tensor, n: int, symbols: np.ndarray, d_rank: torch.Tensor, eps: float,
+                                  group) -> PartitionedLevelGraph:
+    """The fully partitioned build of one n level (SURVEY.md 8(e), rows "Builder" + "Normalisation"): every rank counts
+    its corpus shard, the tables are merged by REDUCE-SCATTER over key ranges, every rank extracts the edges of its key
+    range (= whole source rows), the edge lists are re-dealt onto equal row blocks and normalised with one exchange.
+    Neither the merged table nor the graph ever exists on one GPU; results are bit-identical to `build_level_graph`."""
+    import torch.distributed as dist
+    from . import partitioned as part
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sigma = int(symbols.size)
+    pow_n, pow_m = table_sizes(n, sigma)
+    codes_per = (pow_n + world - 1) // world
+    dev = d_rank.device
+    bins_padded = torch.zeros(world * codes_per * sigma, dtype=torch.int64, device=dev)
+    _, short = count_level(d_buf, n, d_rank, sigma, bins=bins_padded[:pow_m])
+    local_bins = merge_tables_by_key_range(bins_padded, codes_per, sigma, group)
+    del bins_padded
+    short_i = short.to(torch.int32)
+    dist.all_reduce(short_i, op=dist.ReduceOp.MAX, group=group)
+    node_code, src, dst, cnt = extract_key_range(local_bins, short_i.to(torch.uint8), n, sigma, rank * codes_per, codes_per, group)
+    num_nodes = int(node_code.numel())
+    if num_nodes == 0:
+        raise ValueError(f"no n-grams for n={n}")
+    total_edges = torch.tensor([int(src.numel())], dtype=torch.int64, device=dev)
+    dist.all_reduce(total_edges, group=group)
+    # key ranges are equal slices of the CODE space; the normalisation wants equal slices of the ID space
+    src, dst, w = part.exchange_in_edges(src, dst, cnt.to(torch.float32), num_nodes, group, by="src")
+    block = part.normalize_row_partitioned(src, dst, w, num_nodes, eps, group)
+    return PartitionedLevelGraph(n, symbols, node_code, (src, dst, w), block, int(total_edges.item()), group)
+
+
 class GraphBuilder:
     def __init__(self, config):
         self.config = config

@@ -221,15 +221,17 @@ class RowBlockNormalizer:
                 "in_src": self.ain[0], "in_dst": self.ain[1], "in_w": self.ain[2]}
 
 
-def exchange_in_edges(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int, group=None):
+def exchange_in_edges(src: torch.Tensor, dst: torch.Tensor, w: torch.Tensor, n: int, group=None, by: str = "dst"):
     """Every rank passes the out-edges of its rows; returns the edges whose TARGET it owns
-    (src, dst, w; one all-to-all of 20 B per edge).  Stable: edges from one peer keep their order."""
+    (src, dst, w; one all-to-all of 20 B per edge).  Stable: edges from one peer keep their order.
+    by="src" sends every edge to the owner of its SOURCE instead (re-dealing an edge table that is
+    partitioned some other way, e.g. by key range, onto the equal row blocks of `row_range`)."""
     group = group if group is not None else dist.group.WORLD
     world = dist.get_world_size(group)
-    per = (n + world - 1) // world
+    per = max(1, (n + world - 1) // world)
     e = int(src.numel())
     dev = src.device
-    owner = torch.div(dst, per, rounding_mode="floor").contiguous()
+    owner = torch.div(dst if by == "dst" else src, per, rounding_mode="floor").contiguous()
     perm = torch.arange(e, dtype=torch.int32, device=dev)
     if e:
         # stable partition by owner: one radix pass of the library's own sort

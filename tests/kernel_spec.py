@@ -87,6 +87,46 @@ def pg_graph_extract_fill(bins, n, sigma, num_nodes, num_edges, node_code, src, 
     count.copy_(bins[nz])
 
 
+# key-range form (tables merged by reduce-scatter)
+def pg_graph_extract_range_ws_bytes(sigma, codes):
+    return 256
+
+
+def _range_keys(bins_local, n, sigma, code_lo, codes):
+    pow_n = sigma ** n
+    nkeys = max(0, min(codes, pow_n - code_lo)) * sigma
+    nz = torch.nonzero(bins_local[:nkeys] != 0).flatten()
+    return nz, nz + code_lo * sigma, pow_n
+
+
+def pg_graph_extract_range_mark(bins_local, n, sigma, code_lo, codes, present, sizes, ws, ws_bytes, stream=None):
+    nz, keys, pow_n = _range_keys(bins_local, n, sigma, code_lo, codes)
+    present[keys // sigma] = 1
+    present[keys % pow_n] = 1
+    sizes[0] = nz.numel()
+
+
+def pg_node_ids_ws_bytes(ngrams):
+    return 256
+
+
+def pg_node_ids_from_presence(present, ngrams, node_id, sizes, ws, ws_bytes, stream=None):
+    flags = (present[:ngrams] != 0).to(torch.int64)
+    node_id.copy_(torch.cumsum(flags, 0) - flags)
+    sizes[0] = int(flags.sum())
+
+
+def pg_node_codes_emit(present, node_id, ngrams, node_code, stream=None):
+    node_code.copy_(torch.nonzero(present[:ngrams] != 0).flatten())
+
+
+def pg_graph_extract_range_fill(bins_local, n, sigma, code_lo, codes, node_id, num_edges, src, dst, count, ws, ws_bytes, stream=None):
+    nz, keys, pow_n = _range_keys(bins_local, n, sigma, code_lo, codes)
+    src.copy_(node_id[keys // sigma])
+    dst.copy_(node_id[keys % pow_n])
+    count.copy_(bins_local[nz])
+
+
 # --------------------------------------------------------------------------- graph
 def pg_sort_pairs_ws_bytes(n):
     return 256

@@ -120,3 +120,85 @@ def test_normalize_row_partitioned_world1_nccl_equals_single_gpu():
         assert float((z[:, :16].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     finally:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ key-range extraction (tables merged by reduce-scatter)
+def _synth_corpus(nseq, seq_len, seed=42):
+    buf = torch.empty(nseq * (seq_len + 2) + 1, dtype=torch.uint8, device=DEV)
+    nat.call("pg_synth_corpus", nat.ptr(buf), 0, nseq, seq_len, seed, 1, nat.stream_ptr())
+    return buf
+
+
+@pytest.mark.parametrize("n,world", [(1, 1), (1, 4), (2, 3), (3, 2), (3, 8)])
+def test_key_range_extraction_equals_full_extraction(n, world):
+    """csrc/extract_range.cu rank by rank on one GPU (presence MAX-reduced by hand): node codes and the concatenated edge
+    lists are exactly what pg_graph_extract_* gives on the whole table.  Few, short sequences so that many n-grams are
+    absent (ids != codes) and some key ranges are empty."""
+    from protgram_directgcn_b200.host import corpus, data_builder
+    buf = _synth_corpus(40 if n == 3 else 12, 30)
+    symbols, d_rank = corpus.discover_alphabet(buf)
+    sigma = int(symbols.size)
+    bins, short = data_builder.count_level(buf, n, d_rank, sigma)
+    node_code, src, dst, cnt = data_builder.extract_level(bins, short, n, sigma)
+    pow_n = sigma ** n
+    assert 0 < node_code.numel() and (n == 1 or node_code.numel() < pow_n)
+    codes_per = (pow_n + world - 1) // world
+    chunk = codes_per * sigma
+    padded = torch.zeros(world * chunk, dtype=torch.int64, device=DEV)
+    padded[: bins.numel()] = bins
+    st = nat.stream_ptr()
+    marks = []
+    for r in range(world):
+        local = padded[r * chunk:(r + 1) * chunk].clone()
+        present = short.clone()
+        ws = torch.empty(nat.query("pg_graph_extract_range_ws_bytes", sigma, codes_per), dtype=torch.uint8, device=DEV)
+        sizes = torch.zeros(1, dtype=torch.int64, device=DEV)
+        nat.call("pg_graph_extract_range_mark", nat.ptr(local), n, sigma, r * codes_per, codes_per, nat.ptr(present), nat.ptr(sizes),
+                 nat.ptr(ws), ws.numel(), st)
+        marks.append((local, present, ws, int(sizes.item())))
+    present = torch.stack([m[1] for m in marks]).max(dim=0).values.contiguous()          # the all-reduce(MAX)
+    node_id = torch.empty(pow_n, dtype=torch.int64, device=DEV)
+    ws_ids = torch.empty(nat.query("pg_node_ids_ws_bytes", pow_n), dtype=torch.uint8, device=DEV)
+    sizes = torch.zeros(1, dtype=torch.int64, device=DEV)
+    nat.call("pg_node_ids_from_presence", nat.ptr(present), pow_n, nat.ptr(node_id), nat.ptr(sizes), nat.ptr(ws_ids), ws_ids.numel(), st)
+    assert int(sizes.item()) == node_code.numel()
+    codes = torch.empty_like(node_code)
+    nat.call("pg_node_codes_emit", nat.ptr(present), nat.ptr(node_id), pow_n, nat.ptr(codes), st)
+    assert torch.equal(codes, node_code)
+    parts = []
+    for r, (local, _, ws, e_local) in enumerate(marks):
+        s, d, c = (torch.empty(e_local, dtype=torch.int64, device=DEV) for _ in range(3))
+        nat.call("pg_graph_extract_range_fill", nat.ptr(local), n, sigma, r * codes_per, codes_per, nat.ptr(node_id), e_local, nat.ptr(s),
+                 nat.ptr(d), nat.ptr(c), nat.ptr(ws), ws.numel(), st)
+        parts.append((s, d, c))
+    assert sum(m[3] for m in marks) == src.numel()
+    for i, ref in enumerate((src, dst, cnt)):
+        assert torch.equal(torch.cat([p[i] for p in parts]), ref)
+
+
+def test_fully_partitioned_build_world1_nccl_equals_build_level_graph():
+    """build_level_graph_partitioned (reduce_scatter_tensor, key-range extraction, re-deal by source, partitioned
+    normalisation) over a one-rank NCCL group == build_level_graph, bitwise, n = 1..3."""
+    import torch.distributed as dist
+    from protgram_directgcn_b200.host import corpus, data_builder
+    from tests.test_multirank_gloo import _free_port
+    buf = _synth_corpus(3000, 60)
+    symbols, d_rank = corpus.discover_alphabet(buf)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        for n in (1, 2, 3):
+            ref = data_builder.build_level_graph(buf, n, symbols, d_rank, 1e-9)
+            got = data_builder.build_level_graph_partitioned(buf, n, symbols, d_rank, 1e-9, dist.group.WORLD)
+            assert got.node_sequences == ref.node_sequences and got.number_of_edges == ref.number_of_edges
+            side = ref._pg_device
+            assert torch.equal(got.block["rowptr"], side["rowptr"]) and torch.equal(got.block["col"], side["col"])
+            for k in ("val_in", "val_out", "val_und"):
+                assert torch.equal(got.block[k], side[k]), (n, k)
+            a_out = ref.A_out_w
+            assert torch.equal(torch.stack([got.a_out[0], got.a_out[1]]).cpu(), a_out.indices())
+            assert torch.equal(got.a_out[2].cpu(), a_out.values())
+            z = got.propagation()(torch.ones(got.number_of_nodes, 4, device=DEV))
+            assert z.shape == (got.number_of_nodes, 12) and bool(torch.isfinite(z).all())
+    finally:
+        dist.destroy_process_group()
