@@ -10,6 +10,8 @@ from the device edge table without the parquet round trip.
 Multi-GPU (one process per GPU, torch.distributed): each rank packs and counts a contiguous
 slice of the sequences; the dense tables are summed with an all-reduce (the merge step of
 SURVEY.md 8(e)); every rank then extracts the identical graph and rank 0 writes the pickles.
+`build_level_graph_partitioned` is the variant for graphs that should never exist on one GPU:
+reduce-scatter of the tables over key ranges, per-range extraction, row-partitioned normalisation.
 """
 from __future__ import annotations
 
