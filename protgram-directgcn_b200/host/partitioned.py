@@ -288,3 +288,98 @@ def normalize_row_partitioned(src: torch.Tensor, dst: torch.Tensor, w: torch.Ten
 def local_csr(res: dict) -> _Csr:
     """[val_in, val_out, val_und] in the order the layer consumes them (Z = [A_in X | A_out X | U X])."""
     return _Csr(res["rowptr"], res["col"], [res["val_in"], res["val_out"], res["val_und"]])
+
+
+# ----------------------------------------------------------------------------------------------
+# Row-partitioned DirectGCN MODEL (SURVEY.md 8(e), row "Propagation (a10-a12)"): the unchanged
+# ProtGramDirectGCN / DirectGCNLayer classes run on the rows of one rank.  Everything in a layer is
+# row-local (gates, dense transform, bias, constant, residual, activation, decoder, log_softmax, L2
+# normalisation) except the three SpMMs, which see all rows: the structure object below answers the
+# layer's fan-out / fan-in calls with an all-gather of the operand + the local kernels.  Weights and
+# biases are replicated (their gradients are partial sums: `allreduce_replicated_grads`); the
+# per-node parameters (`constant`, the gate vectors) exist for the local rows only.
+# ----------------------------------------------------------------------------------------------
+class PartitionedStructure:
+    """What `_DirectGCNFused` needs from a graph structure, for a symmetric shared pattern whose rows
+    are partitioned (reference-built graphs: grouped-by-target == grouped-by-source == the row CSR)."""
+
+    partitioned = True
+    shared = True
+
+    def __init__(self, local: _Csr, n: int, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = n
+        self.lo, self.hi, self.per = row_range(n, self.rank, self.world)
+        if local.rowptr.numel() != self.per + 1 or len(local.vals) != 3:
+            raise ValueError("PartitionedStructure wants the padded block (per + 1 row pointers) with three value arrays")
+        self.local = local
+        self.by_dst = self.by_src = [local]
+        self.nnz_total = 3 * int(local.col.numel())
+
+    def _check(self, t: torch.Tensor):
+        if t.shape[0] != self.per:
+            raise ValueError(f"row-partitioned layers work on the padded block: expected {self.per} rows, got {t.shape[0]}")
+
+    def fanout(self, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
+        self._check(x)
+        x_full = _all_gather_rows(x.contiguous(), self.group)
+        c, per = self.local, self.per
+        z = torch.empty((per, 3 * f), dtype=torch.float32, device=x.device)
+        if scales is None:
+            nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]), 3, per, f,
+                     nat.ptr(x_full), x_full.stride(0), nat.ptr(z), z.stride(0), 0, c.plan(3 * f), nat.stream_ptr())
+            return z
+        if scale_stride == 1:   # per-node gates: the kernel scales by the SOURCE row, so it needs everybody's
+            mine = torch.stack([s.reshape(-1) for s in scales]).contiguous()                 # [3, per]
+            allg = torch.empty((self.world * 3, per), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(allg, mine, group=self.group)
+            full = allg.view(self.world, 3, per).permute(1, 0, 2).reshape(3, self.world * per).contiguous()
+            s0, s1, s2 = full[0], full[1], full[2]
+        else:
+            s0, s1, s2 = scales
+        nat.call("pg_spmm_fanout_scaled", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]), 3, per, f,
+                 nat.ptr(x_full), x_full.stride(0), nat.ptr(z), z.stride(0), 0, nat.ptr(s0), nat.ptr(s1), nat.ptr(s2), int(scale_stride),
+                 c.plan(3 * f), nat.stream_ptr())
+        return z
+
+    def fanin(self, dz: torch.Tensor, f: int, init: Optional[torch.Tensor]) -> torch.Tensor:
+        self._check(dz)
+        g_full = _all_gather_rows(dz.contiguous(), self.group)
+        c, per = self.local, self.per
+        dx = torch.empty((per, f), dtype=torch.float32, device=dz.device)
+        nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]), 3, per, f,
+                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
+                 c.plan(3 * f), nat.stream_ptr())
+        return dx
+
+
+def partitioned_data(x_local: torch.Tensor, local: _Csr, n: int, group=None, **extra):
+    """Data object for `ProtGramDirectGCN` on this rank's row block.  x_local: [hi - lo, F] (padded here to
+    `per` rows); the model must be built with `num_graph_nodes = per` (`row_range(n, rank, world)[2]`).
+    Outputs have `per` rows; rows past hi - lo are padding (mask them in the loss)."""
+    from .protgram_directgcn import Data, register_structure
+    st = PartitionedStructure(local, n, group)
+    x = x_local
+    if x.shape[0] != st.per:
+        x = torch.cat([x, torch.zeros((st.per - x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)], dim=0)
+    # the reference API hands the layer edge tensors; here they only key the structure: this rank's pattern with LOCAL row numbers
+    rows = torch.repeat_interleave(torch.arange(st.per, device=local.col.device), local.rowptr[1:] - local.rowptr[:-1])
+    ei = torch.stack([local.col.to(torch.int64), rows])      # (source = global column, target = local row)
+    ews = (local.vals[0], local.vals[1], local.vals[2])
+    register_structure((ei, ei, ei), ews, st.per, st)
+    return Data(x=x, edge_index_in=ei, edge_weight_in=ews[0], edge_index_out=ei, edge_weight_out=ews[1],
+                edge_index_undirected_norm=ei, edge_weight_undirected_norm=ews[2], num_nodes=st.per, **extra)
+
+
+PER_NODE_PARAMETERS = ("constant", "C_in_vec", "C_out_vec", "C_directed_vec", "C_undirected_vec", "C_all_vec")
+
+
+def allreduce_replicated_grads(model: torch.nn.Module, group=None) -> None:
+    """Sum the gradients of the replicated parameters (weights, biases, scalar gates, PE table, decoder) over the ranks --
+    each rank's backward only saw its rows.  The per-node parameters hold this rank's rows and stay local."""
+    group = group if group is not None else dist.group.WORLD
+    for name, p in model.named_parameters():
+        if p.grad is None or name.rsplit(".", 1)[-1] in PER_NODE_PARAMETERS:
+            continue
+        dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)

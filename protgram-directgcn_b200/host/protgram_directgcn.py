@@ -136,7 +136,16 @@ def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Te
     _STRUCT_CACHE[_cache_key((ei, ei, ei), ews, n)] = st
 
 
+def register_structure(eis, ews, n: int, struct) -> None:
+    """Attach a ready structure object (e.g. partitioned.PartitionedStructure) to the edge tensors a Data object carries:
+    the layer looks at the tag before it consults the cache of CSRs it builds itself."""
+    eis[0]._pg_struct = struct
+
+
 def get_structure(eis, ews, n: int) -> EdgeStructure:
+    tagged = getattr(eis[0], "_pg_struct", None)    # set by register_structure: survives cache eviction
+    if tagged is not None:
+        return tagged
     key = _cache_key(eis, ews, n)
     st = _STRUCT_CACHE.get(key)
     if st is not None and not getattr(st, "_static", False) and st._vers != _versions(eis, ews):
@@ -157,6 +166,8 @@ def get_structure(eis, ews, n: int) -> EdgeStructure:
 # ------------------------------------------------------------------------------------------------
 def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
     """Z = [A_in X | A_out X | U X]; with `scales` = (s_in, s_out, s_und) per SOURCE row: A_v diag(s_v) X (shared structures only)."""
+    if getattr(struct, "partitioned", False):   # rows of this rank only; neighbour rows arrive by all-gather (host/partitioned.py)
+        return struct.fanout(x, f_in, scales, scale_stride)
     n = x.shape[0]
     z = torch.empty((n, 3 * f_in), dtype=torch.float32, device=x.device)
     st = nat.stream_ptr()
@@ -177,6 +188,8 @@ def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int, scales=None, scal
 
 
 def _fanin(struct: EdgeStructure, dz: torch.Tensor, f_in: int, init: Optional[torch.Tensor]) -> torch.Tensor:
+    if getattr(struct, "partitioned", False):
+        return struct.fanin(dz, f_in, init)
     n = dz.shape[0]
     dx = torch.empty((n, f_in), dtype=torch.float32, device=dz.device)
     st = nat.stream_ptr()

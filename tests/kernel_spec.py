@@ -339,6 +339,17 @@ def pg_spmm_fanout(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_o
         z[:, z_off + v * F: z_off + (v + 1) * F] = acc
 
 
+def pg_spmm_fanout_scaled(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, ldz, z_off, s0, s1, s2, scale_stride, plan=None,
+                          stream=None):
+    rows = _rows_of(rowptr, num_rows)
+    xg = x[:, :F][col.long()]
+    for v, (val, sc) in enumerate(list(zip((v0, v1, v2), (s0, s1, s2)))[:nv]):
+        wv = val.to(x.dtype)
+        if sc is not None:
+            wv = wv * (sc.reshape(-1)[col.long()] if scale_stride == 1 else sc.reshape(-1)[0])
+        z[:, z_off + v * F: z_off + (v + 1) * F] = torch.zeros(num_rows, F, dtype=x.dtype).index_add_(0, rows, wv.view(-1, 1) * xg)
+
+
 def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, plan=None,
                   stream=None):
     rows = _rows_of(rowptr, num_rows)

@@ -307,3 +307,156 @@ def test_fully_partitioned_build_equals_reference(name, world):
             assert np.array_equal(np.stack([rows, cat("col").astype(np.int64)]), g[f"n{n}_{m}_idx"]), (n, m)
             ref = g[f"n{n}_{m}_val"]
             assert np.max(np.abs(cat(key) - ref) / np.abs(ref)) <= 2e-7, (n, m)
+
+
+def _model_worker(rank, world, port, payload, q):
+    try:
+        _init(rank, world, port)
+        import protgram_directgcn_b200 as pg
+        from protgram_directgcn_b200.host import partitioned as part
+        src, dst, cnt, n, x, y, dims, classes, state, use_vec = payload
+        lo, hi, per = part.row_range(n, rank, world)
+        mine = (src >= lo) & (src < hi)
+        res = part.normalize_row_partitioned(torch.from_numpy(src[mine]), torch.from_numpy(dst[mine]),
+                                             torch.from_numpy(cnt[mine].astype(np.float32)), n)
+        torch.manual_seed(0)
+        model = pg.ProtGramDirectGCN(dims, per, classes, 1, 0, 0, 0.0, use_vec)
+        sd = {}
+        for k, v in state.items():          # replicated parameters as they are, per-node parameters cut to this rank's rows
+            if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS:
+                blk = torch.zeros((per,) + tuple(v.shape[1:]), dtype=v.dtype)
+                blk[: hi - lo] = v[lo:hi]
+                sd[k] = blk
+            else:
+                sd[k] = v
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        data = part.partitioned_data(torch.from_numpy(x[lo:hi]), part.local_csr(res), n)
+        logp, emb = model(data)
+        yl = torch.full((per,), -100, dtype=torch.int64)
+        yl[: hi - lo] = torch.from_numpy(y[lo:hi])
+        loss = torch.nn.functional.nll_loss(logp, yl, reduction="sum") / n      # ignore_index=-100 masks the padding
+        loss.backward()
+        part.allreduce_replicated_grads(model)
+        grads = {k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None}
+        q.put((rank, {"logp": logp.detach().numpy()[: hi - lo], "emb": emb.detach().numpy()[: hi - lo], "grads": grads}))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_vec", [True, False])
+def test_row_partitioned_model_equals_single_process(use_vec):
+    """SURVEY 8(e) row 3 end to end: the unchanged ProtGramDirectGCN on each rank's row block (partitioned normalisation ->
+    PartitionedStructure -> fused layers with all-gathered SpMM operands) against the same model on the whole graph in one
+    process: log-probs and embeddings row for row, gradients of the replicated parameters after the all-reduce, gradients
+    of the per-node parameters (constant, gate vectors) slice for slice.  Per-node gates exercise the gate exchange."""
+    import protgram_directgcn_b200 as pg
+    from oracle import graph_oracle
+    from protgram_directgcn_b200 import _native as nat
+    from protgram_directgcn_b200.host import partitioned as part
+    from tests import kernel_spec
+    n, world, dims, classes = 157, 2, [12, 16, 16, 8], 5
+    src, dst, cnt = random_count_graph(n, seed=11, density=0.05)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((n, dims[0])).astype(np.float32)
+    y = rng.integers(0, classes, n)
+    torch.manual_seed(1)
+    full = pg.ProtGramDirectGCN(dims, n, classes, 1, 0, 0, 0.0, use_vec)
+    with torch.no_grad():
+        for k, p in full.named_parameters():    # non-trivial gates / biases
+            if "C_" in k or "bias" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    state = {k: v.clone() for k, v in full.state_dict().items()}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    payload = (src, dst, cnt, n, x, y, dims, classes, state, use_vec)
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, payload, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(v, str) for v in res.values()), res
+    # single-process truth on the whole graph (same spec kernels)
+    kernel_spec.install_plain(nat)
+    mats = graph_oracle.normalise_all(src, dst, cnt, n)
+    ei = torch.from_numpy(np.stack([mats["mathcal_A_in"][1], mats["mathcal_A_in"][0]]))     # (source = column, target = row)
+    ew = [torch.from_numpy(mats[m][2]) for m in ("mathcal_A_in", "mathcal_A_out", "A_undirected_norm_sparse")]
+    data = pg.Data(x=torch.from_numpy(x), edge_index_in=ei, edge_weight_in=ew[0], edge_index_out=ei, edge_weight_out=ew[1],
+                   edge_index_undirected_norm=ei, edge_weight_undirected_norm=ew[2])
+    full.eval()
+    logp, emb = full(data)
+    loss = torch.nn.functional.nll_loss(logp, torch.from_numpy(y), reduction="sum") / n
+    loss.backward()
+    got_logp = np.concatenate([res[r]["logp"] for r in range(world)])
+    got_emb = np.concatenate([res[r]["emb"] for r in range(world)])
+    assert np.max(np.abs(got_logp - logp.detach().numpy())) <= 2e-5
+    assert np.max(np.abs(got_emb - emb.detach().numpy())) <= 2e-5
+    for k, p in full.named_parameters():
+        ref = p.grad.numpy() if p.grad is not None else None
+        if ref is None:
+            continue
+        if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS:
+            got = np.concatenate([res[r]["grads"][k][: part.row_range(n, r, world)[1] - part.row_range(n, r, world)[0]] for r in range(world)])
+        else:
+            got = res[0]["grads"][k]
+            assert np.array_equal(got, res[1]["grads"][k]), k          # all-reduced: identical on every rank
+        assert np.max(np.abs(got - ref)) <= 2e-5 * max(1.0, float(np.max(np.abs(ref)))), k
+
+
+def _struct_worker(rank, world, port, payload, q):
+    try:
+        _init(rank, world, port)
+        from protgram_directgcn_b200.host import partitioned as part
+        rowptr, col, vals, n, x, scales, dz = payload
+        lo, hi, per = part.row_range(n, rank, world)
+        st = part.PartitionedStructure(part.slice_rows(rowptr, col, vals, lo, hi, per), n)
+        pad = lambda t: torch.cat([t[lo:hi], torch.zeros((per - (hi - lo),) + tuple(t.shape[1:]), dtype=t.dtype)])
+        z_vec = st.fanout(pad(x), x.shape[1], scales=tuple(pad(s) for s in scales), scale_stride=1)
+        z_sca = st.fanout(pad(x), x.shape[1], scales=tuple(s[:1].clone() for s in scales), scale_stride=0)
+        dx = st.fanin(pad(dz), x.shape[1], pad(x))
+        q.put((rank, z_vec[: hi - lo].numpy(), z_sca[: hi - lo].numpy(), dx[: hi - lo].numpy()))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_structure_scaled_fanout_and_fanin():
+    """The two calls the tensor-core backward makes on a structure (fan-out with per-SOURCE-row gate scales, which must be
+    exchanged; fan-in with a row-local init) against dense algebra, world size 3 with a short last block."""
+    rng = np.random.default_rng(8)
+    n, f, world = 100, 8, 3
+    mask = rng.random((n, n)) < 0.06
+    mask |= mask.T
+    dense = [np.where(mask, rng.standard_normal((n, n)), 0).astype(np.float32) for _ in range(3)]
+    dense = [(d + d.T) / 2 for d in dense]
+    rows, cols = np.nonzero(mask)
+    rowptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64))
+    col = torch.from_numpy(cols.astype(np.int32))
+    vals = [torch.from_numpy(d[rows, cols]) for d in dense]
+    x = torch.from_numpy(rng.standard_normal((n, f)).astype(np.float32))
+    dz = torch.from_numpy(rng.standard_normal((n, 3 * f)).astype(np.float32))
+    scales = [torch.from_numpy(rng.standard_normal(n).astype(np.float32)) for _ in range(3)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_struct_worker, args=(r, world, port, (rowptr, col, vals, n, x, scales, dz), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(r[1], str) for r in res), res
+    z_vec, z_sca, dx = (np.concatenate([r[i] for r in res]) for i in (1, 2, 3))
+    xd = x.numpy().astype(np.float64)
+    ref_vec = np.concatenate([d.astype(np.float64) @ (s.numpy().astype(np.float64)[:, None] * xd) for d, s in zip(dense, scales)], axis=1)
+    ref_sca = np.concatenate([float(s[0]) * (d.astype(np.float64) @ xd) for d, s in zip(dense, scales)], axis=1)
+    ref_dx = xd + sum(d.astype(np.float64) @ dz.numpy().astype(np.float64)[:, v * f:(v + 1) * f] for v, d in enumerate(dense))
+    for got, ref in ((z_vec, ref_vec), (z_sca, ref_sca), (dx, ref_dx)):
+        assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))

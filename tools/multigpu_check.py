@@ -7,6 +7,7 @@
   4. the same at 2^20 nodes, timed
   5. fully partitioned build (reduce-scatter of the tables over key ranges, key-range extraction, partitioned normalisation)
      == the single-GPU build, block by block; timed at n = 4 against the replicated (all-reduce) build
+  6. the unchanged ProtGramDirectGCN on each rank's row block (PartitionedStructure) == the model on the whole graph
 usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multigpu_check.py"""
 import os
 import sys
@@ -161,6 +162,56 @@ def main():
                   f"{t_rep:.2f} ms, fully partitioned build {t_par:.2f} ms ({g4.number_of_nodes} nodes, {g4.number_of_edges} edges)")
     except Exception as exc:  # noqa: BLE001
         print(f"[rank {rank}] partitioned-build section failed: {exc!r}")
+
+    # ---- 6. the unchanged model on row blocks (PartitionedStructure) == the model on the whole graph on one GPU
+    try:
+        from protgram_directgcn_b200.host import partitioned as part
+        dims, classes = [64, 128, 128, 64], 21
+        torch.manual_seed(3)
+        whole = pg.ProtGramDirectGCN(dims, N, classes, n, 0, 0, 0.0, True).to(dev)
+        for p_ in whole.parameters():
+            dist.broadcast(p_.data, 0)
+        xm = torch.randn(N, dims[0], device=dev)
+        ym = torch.randint(0, classes, (N,), device=dev)
+        dist.broadcast(xm, 0)
+        dist.broadcast(ym, 0)
+        whole.eval()
+        logp, emb = whole(g_single.gcn_data(xm, dev))
+        (torch.nn.functional.nll_loss(logp, ym, reduction="sum") / N).backward()
+        lo6, hi6, per6 = row_range(N, rank, world)
+        mine_m = pg.ProtGramDirectGCN(dims, per6, classes, n, 0, 0, 0.0, True).to(dev)
+        sd = {}
+        for k, v in whole.state_dict().items():
+            if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS:
+                blk = torch.zeros((per6,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                blk[: hi6 - lo6] = v[lo6:hi6]
+                sd[k] = blk
+            else:
+                sd[k] = v.clone()
+        mine_m.load_state_dict(sd)
+        mine_m.eval()
+        logp_l, emb_l = mine_m(part.partitioned_data(xm[lo6:hi6], local_csr(res), N))
+        yl = torch.full((per6,), -100, dtype=torch.int64, device=dev)
+        yl[: hi6 - lo6] = ym[lo6:hi6]
+        (torch.nn.functional.nll_loss(logp_l, yl, reduction="sum") / N).backward()
+        part.allreduce_replicated_grads(mine_m)
+        err = float((logp_l[: hi6 - lo6] - logp[lo6:hi6]).abs().max())
+        err = max(err, float((emb_l[: hi6 - lo6] - emb[lo6:hi6]).abs().max()))
+        gerr = 0.0
+        for (k, p_), (_, q_) in zip(whole.named_parameters(), mine_m.named_parameters()):
+            if p_.grad is None:
+                continue
+            ref = p_.grad[lo6:hi6] if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS else p_.grad
+            got = q_.grad[: hi6 - lo6] if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS else q_.grad
+            gerr = max(gerr, float((got - ref).abs().max()) / max(1e-12, float(ref.abs().max())))
+        t = torch.tensor([err, gerr], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert float(t[0]) <= 2e-5 and float(t[1]) <= 1e-4, t.tolist()
+        if rank == 0:
+            print(f"[ok] row-partitioned ProtGramDirectGCN {dims} over {world} GPUs == whole-graph model: outputs {float(t[0]):.1e} abs, "
+                  f"gradients {float(t[1]):.1e} rel (replicated parameters all-reduced, per-node parameters local)")
+    except Exception as exc:  # noqa: BLE001
+        print(f"[rank {rank}] partitioned-model section failed: {exc!r}")
     dist.destroy_process_group()
 
 
