@@ -348,7 +348,7 @@ def _model_worker(rank, world, port, payload, q):
 
 
 @pytest.mark.parametrize("use_vec", [True, False])
-def test_row_partitioned_model_equals_single_process(use_vec):
+def test_row_partitioned_model_equals_single_process(use_vec, monkeypatch):
     """SURVEY 8(e) row 3 end to end: the unchanged ProtGramDirectGCN on each rank's row block (partitioned normalisation ->
     PartitionedStructure -> fused layers with all-gathered SpMM operands) against the same model on the whole graph in one
     process: log-probs and embeddings row for row, gradients of the replicated parameters after the all-reduce, gradients
@@ -382,7 +382,7 @@ def test_row_partitioned_model_equals_single_process(use_vec):
         p.join(timeout=60)
     assert all(not isinstance(v, str) for v in res.values()), res
     # single-process truth on the whole graph (same spec kernels)
-    kernel_spec.install_plain(nat)
+    kernel_spec.install(monkeypatch, nat)      # undone at the end of the test: later tests see the real library again
     mats = graph_oracle.normalise_all(src, dst, cnt, n)
     ei = torch.from_numpy(np.stack([mats["mathcal_A_in"][1], mats["mathcal_A_in"][0]]))     # (source = column, target = row)
     ew = [torch.from_numpy(mats[m][2]) for m in ("mathcal_A_in", "mathcal_A_out", "A_undirected_norm_sparse")]
