@@ -1,4 +1,8 @@
-"""Row-partitioned DirectGCN propagation over several GPUs (one process per GPU, torch.distributed).
+"""Row-partitioned graphs over several GPUs (one process per GPU, torch.distributed).  Three parts:
+  1. RowPartitionedPropagation  the SpMM with one exchange step (below)
+  2. normalize_row_partitioned  the propagation matrices of the rank's rows from the rank's out-edges
+  3. PartitionedStructure / partitioned_data / allreduce_replicated_grads  the unchanged model on a row block
+
 
 SURVEY.md 8(e): the propagation path shards by rows with ONE exchange step per SpMM.  Rank r owns
 the node rows [lo_r, hi_r) of the shared pattern (global int32 columns) and the matching slice of
