@@ -71,6 +71,13 @@ int64_t pg_fasta_next_chunk(pg_fasta_reader *reader, uint8_t *out, int64_t cap, 
  * or a negative code; *n_records = records of all ranks, *stopped_early as above. */
 int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_t cap, int threads, int rank, int world, int block,
                                int64_t *n_records, int *stopped_early);
+/* The same over ONE WINDOW of an open file, for files that do not fit host memory as a single corpus buffer: the caller walks
+ * the file (start with *pos = 0 and first_index = 0; add *n_records to first_index after every call).  The window ends at the
+ * first header line at or after *pos + window_bytes, or at the end of the file; *pos is advanced to it.  out needs the window's
+ * file bytes + 16 at most; PG_FASTA_ETOOSMALL leaves *pos unchanged. */
+int64_t pg_fasta_pack_window(pg_fasta_reader *reader, int64_t *pos, int64_t window_bytes, int64_t first_index, uint8_t *out,
+                             int64_t cap, int threads, int rank, int world, int block, int64_t *n_records,
+                             int *stopped_early);
 
 /* 5-bit host format of the corpus buffer (what crosses PCIe when a corpus is streamed from host memory): 8 symbols in
  * 5 bytes, fixed code ' ' = 0, 'A'..'Z' = 1..26, '*' = 27, '-' = 28, '.' = 29, separator = 31 (also the tail padding).

@@ -34,6 +34,7 @@ _SIGS = {
     "pg_fasta_stopped_early": (c_int, [_P]),
     "pg_fasta_next_chunk": (c_int64, [_P, _P, c_int64, c_int, c_int, c_int]),
     "pg_fasta_pack_parallel": (c_int64, [ctypes.c_char_p, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "pg_fasta_pack_window": (c_int64, [_P, _P, c_int64, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "pg_pack5_bytes": (c_int64, [c_int64]),
     "pg_pack5_host": (c_int64, [_P, c_int64, _P]),
     "pg_unpack5": (c_int, [_P, c_int64, _P, _P]),

@@ -361,18 +361,15 @@ void run_parallel(int n, int threads, F f) {
 }
 }  // namespace
 
-extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_t cap, int threads, int rank, int world, int block,
-                                          int64_t *n_records, int *stopped_early) {
-    if (out == nullptr || cap < 4 || world < 1 || rank < 0 || rank >= world || block < 1 || threads < 1) {
-        pg_set_error("pg_fasta_pack_parallel: bad arguments");
-        return PG_EINVAL;
-    }
-    pg_fasta_reader *rd = pg_fasta_open(path);
-    if (rd == nullptr) return PG_EINVAL;
-    const uint8_t *d = rd->data;
-    const int64_t size = rd->size;
+namespace {
+// Packs the records of the file window [win_lo, win_hi) -- win_lo at a header line (or 0), win_hi at a header line or the
+// end of the file -- whose first record has the global index first_index.  Returns bytes written or a negative code.
+int64_t pack_window(const uint8_t *d, int64_t win_lo, int64_t win_hi, int64_t first_index, uint8_t *out, int64_t cap, int threads,
+                    int rank, int world, int block, int64_t *n_records, int *stopped_early) {
+    const int64_t size = win_hi;
+    const int64_t span = win_hi - win_lo;
     // ranges: nominal cuts moved forward to the next header line
-    const int n_ranges = (int)(size < (1 << 20) ? 1 : (threads * 4 < 256 ? threads * 4 : 256));
+    const int n_ranges = (int)(span < (1 << 20) ? 1 : (threads * 4 < 256 ? threads * 4 : 256));
     std::vector<RangeStat> rs;
     auto next_header = [&](int64_t from) -> int64_t {   // first '>' at or after `from` that directly follows a line break
         int64_t p = from;
@@ -385,9 +382,9 @@ extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_
         }
         return size;
     };
-    int64_t lo = 0;
+    int64_t lo = win_lo;
     for (int i = 1; i <= n_ranges && lo < size; ++i) {
-        const int64_t nominal = size / n_ranges * i;
+        const int64_t nominal = win_lo + span / n_ranges * i;
         const int64_t cut = i == n_ranges ? size : next_header(nominal > lo ? nominal : lo + 1);
         if (cut > lo) {
             rs.push_back(RangeStat{lo, cut, 0, -1, 0, 0, 0, 0});
@@ -404,7 +401,7 @@ extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_
             rs[i].records = 0;
             continue;
         }
-        rs[i].first_index = total_records;
+        rs[i].first_index = first_index + total_records;
         total_records += rs[i].records;
         if (rs[i].stop_at >= 0) stop_range = i;
     }
@@ -435,6 +432,53 @@ extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_
     }
     if (n_records) *n_records = total_records;
     if (stopped_early) *stopped_early = stop_range >= 0 ? 1 : 0;
+    return rcode;
+}
+}  // namespace
+
+extern "C" int64_t pg_fasta_pack_parallel(const char *path, uint8_t *out, int64_t cap, int threads, int rank, int world, int block,
+                                          int64_t *n_records, int *stopped_early) {
+    if (out == nullptr || cap < 4 || world < 1 || rank < 0 || rank >= world || block < 1 || threads < 1) {
+        pg_set_error("pg_fasta_pack_parallel: bad arguments");
+        return PG_EINVAL;
+    }
+    pg_fasta_reader *rd = pg_fasta_open(path);
+    if (rd == nullptr) return PG_EINVAL;
+    const int64_t rcode = pack_window(rd->data, 0, rd->size, 0, out, cap, threads, rank, world, block, n_records, stopped_early);
     pg_fasta_close(rd);
+    return rcode;
+}
+
+// The same over ONE WINDOW of an open file, for files that do not fit host memory as a single corpus buffer: the caller walks
+// the file window by window (start at *pos = 0, first_index = 0; add *n_records to first_index after every call).  The window
+// ends at the first header line at or after *pos + window_bytes (or the end of the file); *pos is advanced to it.  `out` needs
+// (window end - window start) + 16 bytes at most; PG_FASTA_ETOOSMALL leaves *pos unchanged so the call can be repeated.
+extern "C" int64_t pg_fasta_pack_window(pg_fasta_reader *rd, int64_t *pos, int64_t window_bytes, int64_t first_index, uint8_t *out,
+                                        int64_t cap, int threads, int rank, int world, int block, int64_t *n_records,
+                                        int *stopped_early) {
+    if (rd == nullptr || pos == nullptr || out == nullptr || cap < 4 || world < 1 || rank < 0 || rank >= world || block < 1 ||
+        threads < 1 || window_bytes < 1 || first_index < 0 || *pos < 0 || *pos > rd->size) {
+        pg_set_error("pg_fasta_pack_window: bad arguments");
+        return PG_EINVAL;
+    }
+    const uint8_t *d = rd->data;
+    const int64_t size = rd->size, lo = *pos;
+    int64_t hi = size;
+    if (lo + window_bytes < size) {     // first header line at or after the nominal end
+        int64_t p = lo + window_bytes;
+        hi = size;
+        while (p < size) {
+            const uint8_t *q = (const uint8_t *)memchr(d + p, '>', (size_t)(size - p));
+            if (q == nullptr) break;
+            p = (int64_t)(q - d);
+            if (d[p - 1] == '\n' || d[p - 1] == '\r') {
+                hi = p;
+                break;
+            }
+            ++p;
+        }
+    }
+    const int64_t rcode = pack_window(d, lo, hi, first_index, out, cap, threads, rank, world, block, n_records, stopped_early);
+    if (rcode >= 0) *pos = hi;
     return rcode;
 }

@@ -161,6 +161,44 @@ def read_fasta_parallel(fasta_path: str, threads: int = 0, rank: int = 0, world:
     return buf[:got]
 
 
+def stream_fasta_windows(fasta_path: str, window_bytes: int = 1 << 30, threads: int = 0, rank: int = 0, world: int = 1,
+                         block: int = 4096, pinned: bool = False, stats: dict = None):
+    """Files that do not fit host memory as one corpus buffer: walk the file in windows of about window_bytes (cut at header
+    lines), each parsed by several host threads (csrc/fasta.cu:pg_fasta_pack_window).  Yields one uint8 tensor per window
+    (this rank's records; empty windows are skipped); concatenated they are the bytes of read_fasta_parallel()."""
+    import ctypes
+    import os
+    lib = nat.load()
+    path = os.path.normpath(fasta_path)
+    reader = lib.pg_fasta_open(path.encode())
+    if not reader:
+        raise FileNotFoundError(lib.pg_last_error().decode())
+    threads = int(threads) if threads else max(1, min(32, len(os.sched_getaffinity(0))))
+    try:
+        size = int(lib.pg_fasta_file_bytes(reader))
+        pos, first, n_rec, stopped = ctypes.c_int64(0), 0, ctypes.c_int64(0), ctypes.c_int(0)
+        window = max(int(window_bytes), 1)
+        cap = min(window, size) + (1 << 16)
+        while pos.value < size and not stopped.value:
+            buf = torch.empty(cap, dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
+            got = int(lib.pg_fasta_pack_window(reader, ctypes.byref(pos), window, first, ctypes.c_void_p(buf.data_ptr()), cap, threads,
+                                               rank, world, block, ctypes.byref(n_rec), ctypes.byref(stopped)))
+            if got == nat.PG_FASTA_ETOOSMALL:
+                cap *= 2          # a record running far past the nominal window end: grow and retry (pos did not move)
+                continue
+            if got == nat.PG_FASTA_ENONASCII:
+                raise NonAsciiSequence(lib.pg_last_error().decode())
+            if got < 0:
+                raise nat.NativeError(f"pg_fasta_pack_window failed ({got}): {lib.pg_last_error().decode()}")
+            first += int(n_rec.value)
+            if got:
+                yield buf[:got]
+        if stats is not None:
+            stats["sequences"], stats["stopped_early"] = first, bool(stopped.value)
+    finally:
+        lib.pg_fasta_close(reader)
+
+
 def split_at_separators(buf: torch.Tensor, chunk_bytes: int):
     """Views of a host corpus buffer of about chunk_bytes each, cut right after a sequence separator."""
     n = int(buf.numel())

@@ -276,8 +276,11 @@ class GraphBuilder:
                     for buf in corpus.split_at_separators(whole, chunk_bytes):
                         yield buf
                 else:
-                    for buf in corpus.stream_chunks_native(path, chunk_bytes, rank, world, pinned=True, stats=stats):
-                        yield buf
+                    # larger than that: window by window, each window parsed by all host threads
+                    window = int(getattr(self.config, "GRAPH_BUILDER_FASTA_WINDOW_BYTES", max(chunk_bytes, 1 << 30)))
+                    for whole in corpus.stream_fasta_windows(path, window, rank=rank, world=world, pinned=True, stats=stats):
+                        for buf in corpus.split_at_separators(whole, chunk_bytes):
+                            yield buf
                 n_seqs[0] = stats.get("sequences", 0)
                 if stats.get("stopped_early"):
                     print(f"Error parsing FASTA file {self.protein_sequence_file}: list index out of range")  # the reference's message

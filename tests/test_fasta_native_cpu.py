@@ -216,3 +216,97 @@ def test_readers_match_reference_generated_golden(name, tmp_path):
     stats = {}
     assert b"".join(_native_chunks(path, stats=stats)) == expect and stats["sequences"] == count
     assert bytes(corpus.read_fasta_parallel(path, threads=2).numpy()) == expect
+
+
+# ------------------------------------------------------------------------------------------------ windowed parallel reader
+def _windows(path, window_bytes, stats=None, **kw):
+    return b"".join(bytes(w.numpy()) for w in corpus.stream_fasta_windows(path, window_bytes, stats=stats, **kw))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_windowed_reader_matches_reference_golden_on_edge_files(name, tmp_path):
+    """Files larger than host memory are walked window by window (pg_fasta_pack_window); whatever the window size, the bytes
+    are those the reference's own parse_sequences implies (tests/golden/fasta_cases.npz) and the counters those of the
+    streaming reader."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fasta_cases.npz"))
+    count = int(g[name + "_count"])
+    seqs = str(g[name + "_seqs"]).split("\x1f") if count else []
+    expect = b"".join(((b" " if i == 0 else b"") + s.encode() + b" \xff") for i, s in enumerate(seqs))
+    path = _write(tmp_path, CASES[name])
+    ref_stats = {}
+    _native_chunks(path, stats=ref_stats)
+    for window in (1, 2, 5, 11, 1 << 20):
+        stats = {}
+        assert _windows(path, window, stats=stats, threads=2) == expect, window
+        assert stats == ref_stats, window
+
+
+def test_windowed_reader_large_file_threads_ranks_and_stop(tmp_path):
+    rng = np.random.default_rng(12)
+    recs = []
+    for i in range(40_000):
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYacd"), size=int(rng.integers(1, 150))))
+        recs.append(f">id{i} x\n" + "\n".join(seq[j:j + 60] for j in range(0, len(seq), 60)) + ("\r\n" if i % 5 == 0 else "\n"))
+        if i % 9_000 == 0:
+            recs.append(">emptyrecord\n\n")
+    data = "".join(recs).encode()
+    assert len(data) > (3 << 20)
+    path = _write(tmp_path, data)
+    ref_stats = {}
+    ref = bytes(corpus.read_fasta_parallel(path, threads=4, stats=ref_stats).numpy())
+    for window, threads in ((1 << 20, 1), (1 << 20, 8), ((1 << 21) + 12345, 3), (700_001, 4), (1 << 30, 4)):
+        stats = {}
+        assert _windows(path, window, stats=stats, threads=threads) == ref and stats == ref_stats, (window, threads)
+    for rank in range(3):
+        assert _windows(path, (1 << 20) + 7, threads=4, rank=rank, world=3, block=64) == \
+            bytes(corpus.read_fasta_parallel(path, threads=4, rank=rank, world=3, block=64).numpy())
+    stop = data[:len(data) // 2].rsplit(b"\n>", 1)[0] + b"\n>\n" + data[len(data) // 2:]
+    path2 = _write(tmp_path, stop, "stop.fasta")
+    s1, s2 = {}, {}
+    assert _windows(path2, 1 << 20, stats=s1, threads=4) == bytes(corpus.read_fasta_parallel(path2, threads=4, stats=s2).numpy())
+    assert s1 == s2 and s1["stopped_early"]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(LINE, EOL), max_size=25), st.booleans(), st.integers(min_value=1, max_value=40))
+def test_windowed_reader_fuzz(tmp_path_factory, lines, final_eol, window):
+    data = b"".join(l + e for l, e in lines)
+    if not final_eol and lines:
+        data = data[: len(data) - len(lines[-1][1])]
+    path = _write(tmp_path_factory.mktemp("w"), data)
+    try:
+        ref_stats = {}
+        ref = b"".join(_native_chunks(path, stats=ref_stats))
+    except corpus.NonAsciiSequence:
+        with pytest.raises(corpus.NonAsciiSequence):
+            _windows(path, window)
+        return
+    stats = {}
+    assert _windows(path, window, stats=stats, threads=2) == ref and stats == ref_stats
+
+
+def test_graph_builder_takes_the_windowed_reader_for_large_files(monkeypatch, tmp_path):
+    """GraphBuilder.run picks the windowed reader when the file exceeds a quarter of host memory (forced here)."""
+    from tests import kernel_spec
+    from protgram_directgcn_b200.host import data_builder
+    from protgram_directgcn_b200.host.config import Config
+    from tests.helpers import load, fasta_sequences
+    from tests.test_host_logic_cpu import check_graph_against_golden
+    import protgram_directgcn_b200 as pg
+    kernel_spec.install(monkeypatch, nat)
+    g = load("build_protein")
+    cfg = Config()
+    cfg.GCN_INPUT_FASTA_PATH = fasta_sequences(str(g["fasta"]), tmp_path)
+    cfg.BASE_OUTPUT_DIR = str(tmp_path / "o")
+    cfg.GRAPH_OBJECTS_DIR = str(tmp_path / "o" / "g")
+    cfg.GCN_NGRAM_MAX_N = 2
+    cfg.GRAPH_BUILDER_FASTA_WINDOW_BYTES = 97
+    cfg.GRAPH_BUILDER_CHUNK_BYTES = 64
+    used = []
+    real = corpus.stream_fasta_windows
+    monkeypatch.setattr(corpus, "stream_fasta_windows", lambda *a, **k: (used.append(1), real(*a, **k))[1])
+    monkeypatch.setattr(os, "sysconf", lambda name: 1)           # "host memory" of a few bytes
+    data_builder.GraphBuilder(cfg).run()
+    assert used
+    for n in (1, 2):
+        check_graph_against_golden(pg.DataUtils.load_object(os.path.join(cfg.GRAPH_OBJECTS_DIR, f"ngram_graph_n{n}.pkl")), g, n)
