@@ -105,6 +105,7 @@ class _LazyMaps:
         state["node_sequences"] = self.node_sequences
         state["idx_to_node"], state["node_to_idx"] = i2n, n2i
         state.pop("_pg_device", None)  # device-side CSR sidecar never enters the pickle
+        state.pop("_pg_sidecar", None)  # nor the host-side one loaded from <path>.csr.npz
         return state
 
     def __setstate__(self, state):
@@ -298,6 +299,8 @@ class DirectedNgramGraph(Graph):
         from .protgram_directgcn import Data, register_symmetric_structure
         dev = torch.device(device)
         side = getattr(self, "_pg_device", None)
+        if (side is None or side["pattern"].device != dev) and self.__dict__.get("_pg_sidecar") is not None:
+            side = self._upload_sidecar(dev)      # graph loaded from disk with its CSR sidecar: no edge-list sort, 16 B / entry uploaded
         if side is not None and side["pattern"].device == dev:
             ei = side["pattern"]
             ew = (side["val_in"], side["val_out"], side["val_und"])
@@ -307,6 +310,59 @@ class DirectedNgramGraph(Graph):
             ew = tuple(t.values().to(dev) for t in (self.mathcal_A_in, self.mathcal_A_out, self.A_undirected_norm_sparse))
         return Data(x=x.to(dev), edge_index_in=ei, edge_weight_in=ew[0], edge_index_out=ei, edge_weight_out=ew[1],
                     edge_index_undirected_norm=ei, edge_weight_undirected_norm=ew[2], num_nodes=self.number_of_nodes, **extra)
+
+    # -- on-disk hand-off (DataUtils.save_object / load_object)
+    def propagation_csr_host(self):
+        """The three propagation matrices as one shared-pattern CSR in host memory (numpy), or None when the matrices do not
+        share one pattern (graphs not built by this class)."""
+        n = self.number_of_nodes
+        side = self.__dict__.get("_pg_device")
+        if side is not None:
+            return {"n": np.int64(n), "rowptr": side["rowptr"].cpu().numpy(), "col": side["col"].cpu().numpy(),
+                    "val_in": side["val_in"].cpu().numpy(), "val_out": side["val_out"].cpu().numpy(),
+                    "val_und": side["val_und"].cpu().numpy()}
+        host = self.__dict__.get("_pg_sidecar")
+        if host is not None:
+            return dict(host)
+        try:
+            mats = [self.mathcal_A_in, self.mathcal_A_out, self.A_undirected_norm_sparse]
+        except AttributeError:
+            return None
+        if n == 0 or any(m is None or m._nnz() == 0 for m in mats):
+            return None
+        idx = mats[0].indices()
+        if any(m._nnz() != mats[0]._nnz() or not torch.equal(m.indices(), idx) for m in mats[1:]):
+            return None
+        idx = idx.cpu()
+        rowptr = np.zeros(n + 1, dtype=np.int64)
+        rowptr[1:] = np.cumsum(np.bincount(idx[0].numpy(), minlength=n))
+        return {"n": np.int64(n), "rowptr": rowptr, "col": idx[1].numpy().astype(np.int32),
+                "val_in": mats[0].values().cpu().numpy(), "val_out": mats[1].values().cpu().numpy(),
+                "val_und": mats[2].values().cpu().numpy()}
+
+    def attach_propagation_csr(self, csr: dict) -> None:
+        """Accept a sidecar only if it describes THIS graph's pattern (node count, entry count, row lengths)."""
+        n, p = self.number_of_nodes, int(self.mathcal_A_in._nnz())
+        rowptr, col = np.asarray(csr["rowptr"]), np.asarray(csr["col"])
+        ok = (int(csr["n"]) == n and rowptr.shape == (n + 1,) and rowptr.dtype == np.int64 and col.shape == (p,) and col.dtype == np.int32
+              and int(rowptr[0]) == 0 and int(rowptr[-1]) == p
+              and all(np.asarray(csr[k]).shape == (p,) and np.asarray(csr[k]).dtype == np.float32 for k in ("val_in", "val_out", "val_und")))
+        if ok and p:
+            idx = self.mathcal_A_in.indices()
+            ok = bool(np.array_equal(np.diff(rowptr), np.bincount(idx[0].numpy(), minlength=n))) and \
+                bool(np.array_equal(col[: 1 << 16], idx[1][: 1 << 16].numpy().astype(np.int32)))
+        if not ok:
+            raise ValueError("sidecar does not match the pickled graph")
+        self.__dict__["_pg_sidecar"] = {k: np.ascontiguousarray(csr[k]) for k in ("n", "rowptr", "col", "val_in", "val_out", "val_und")}
+
+    def _upload_sidecar(self, dev):
+        host = self.__dict__["_pg_sidecar"]
+        up = lambda k: torch.from_numpy(host[k]).to(dev, non_blocking=True)
+        rowptr, col = up("rowptr"), up("col")
+        side = {"rowptr": rowptr, "col": col, "val_in": up("val_in"), "val_out": up("val_out"), "val_und": up("val_und")}
+        side["pattern"] = csr_to_coo_indices(rowptr, col, self.number_of_nodes)
+        self.__dict__["_pg_device"] = side
+        return side
 
     def _build_from_edges(self, src, dst, w, assume_coalesced: bool = False, result_device="cpu"):
         dev = nat.current_device()

@@ -13,7 +13,7 @@ import protgram_directgcn_b200 as pg
 from protgram_directgcn_b200 import _native as nat
 from protgram_directgcn_b200.host import protgram_directgcn as model_mod
 from tests import kernel_spec
-from tests.helpers import BUILD_FIXTURES, MATS, MODEL_FIXTURES, fasta_sequences, load, rel_err
+from tests.helpers import BUILD_FIXTURES, MATS, MODEL_FIXTURES, fasta_sequences, golden_edges, load, rel_err
 
 
 @pytest.fixture
@@ -262,3 +262,68 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(nat.NativeError):
             pg.DirectedNgramGraph.from_edge_arrays({0: "A", 1: "C"}, np.array([0]), np.array([1]), np.array([2.0]))
+
+
+def test_graph_pickle_csr_sidecar_roundtrip(tmp_path, spec_native):
+    """Row f3, on-disk hand-off: save_object writes the reference-compatible pickle plus `<path>.csr.npz`; load_object
+    attaches the sidecar when it matches, gcn_data() then hands the layer the CSR without sorting edge lists; a stale or
+    foreign sidecar is ignored; the pickle alone still loads."""
+    import pickle
+    import shutil
+    g = load("build_protein")
+    src, dst, w = golden_edges(g, 2)
+    nodes = {i: s for i, s in enumerate(g["n2_nodes"])}
+    graph = pg.DirectedNgramGraph.from_edge_arrays(nodes, src, dst, w.astype(np.float32), n_value=2, assume_coalesced=True)
+    path = str(tmp_path / "g.pkl")
+    pg.DataUtils.save_object(graph, path)
+    side = path + pg.DataUtils.SIDECAR_SUFFIX
+    assert os.path.exists(side)
+    z = np.load(side)
+    p = graph.mathcal_A_in._nnz()
+    assert z["rowptr"].dtype == np.int64 and z["col"].dtype == np.int32 and z["col"].shape == (p,) and int(z["rowptr"][-1]) == p
+    with open(path, "rb") as fh:                       # the pickle knows nothing about the sidecar
+        raw = pickle.load(fh)
+    assert "_pg_sidecar" not in raw.__dict__ and "_pg_device" not in raw.__dict__
+    loaded = pg.DataUtils.load_object(path)
+    assert loaded.__dict__.get("_pg_sidecar") is not None
+    check_graph_against_golden(loaded, g, 2)
+    csr = loaded.propagation_csr_host()
+    for m, k in (("mathcal_A_in", "val_in"), ("mathcal_A_out", "val_out"), ("A_undirected_norm_sparse", "val_und")):
+        assert np.array_equal(csr[k], getattr(loaded, m).values().numpy())
+    assert np.array_equal(csr["col"], loaded.mathcal_A_in.indices()[1].numpy().astype(np.int32))
+    # the layer gets the CSR straight from the sidecar: no edge-list sort (pg_edges_to_csr is never called), same outputs
+    torch.manual_seed(0)
+    n_nodes = loaded.number_of_nodes
+    model = pg.ProtGramDirectGCN([6, 8, 4], n_nodes, 3, 2, 0, 0, 0.0, True).eval()
+    x = torch.randn(n_nodes, 6)
+    calls = []
+    real_call = nat.call
+    nat.call = lambda name, *a: (calls.append(name), real_call(name, *a))[1]
+    try:
+        out_side = model(loaded.gcn_data(x, "cpu"))[1]
+        assert "pg_edges_to_csr" not in calls and "pg_coo_from_csr" in calls
+        del calls[:]
+        raw_data = raw.gcn_data(x, "cpu")                       # no sidecar, no device arrays: the COO route
+        out_coo = model(raw_data)[1]
+        assert "pg_edges_to_csr" in calls
+    finally:
+        nat.call = real_call
+    out_built = model(graph.gcn_data(x, "cpu"))[1]
+    assert torch.equal(out_side, out_built) and rel_err(out_coo.detach().numpy(), out_built.detach().numpy()) <= 1e-6
+    # a graph WITHOUT the device arrays (as after unpickling elsewhere) derives the same sidecar from its COO tensors
+    raw.__dict__.pop("_pg_sidecar", None)
+    derived = raw.propagation_csr_host()
+    assert all(np.array_equal(derived[k], csr[k]) for k in ("rowptr", "col", "val_in", "val_out", "val_und"))
+    # re-saving a loaded graph keeps the sidecar; a foreign sidecar is refused with a warning, not an error
+    pg.DataUtils.save_object(loaded, str(tmp_path / "again.pkl"))
+    assert os.path.exists(str(tmp_path / "again.pkl") + pg.DataUtils.SIDECAR_SUFFIX)
+    src1, dst1, w1 = golden_edges(g, 1)
+    other = pg.DirectedNgramGraph.from_edge_arrays({i: s for i, s in enumerate(g["n1_nodes"])}, src1, dst1, w1.astype(np.float32),
+                                                   n_value=1, assume_coalesced=True)
+    path1 = str(tmp_path / "g1.pkl")
+    pg.DataUtils.save_object(other, path1)
+    shutil.copy(side, path1 + pg.DataUtils.SIDECAR_SUFFIX)
+    os.utime(path1 + pg.DataUtils.SIDECAR_SUFFIX, None)
+    assert pg.DataUtils.load_object(path1).__dict__.get("_pg_sidecar") is None
+    os.remove(side)
+    assert pg.DataUtils.load_object(path).__dict__.get("_pg_sidecar") is None

@@ -245,3 +245,22 @@ def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims):
     for (k, p), (_, p2) in zip(plain.named_parameters(), twin.named_parameters()):
         if p.grad is not None:
             assert float((p2.grad - p.grad).abs().max()) <= 1e-4 * max(1.0, float(p.grad.abs().max())), k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
+                    reason="CSR sidecar upload path: covered on the executable spec (tests/test_host_logic_cpu.py), not yet run on a B200")
+def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
+    import protgram_directgcn_b200 as pg
+    from tests.helpers import golden_edges, load
+    g = load("build_protein")
+    src, dst, w = golden_edges(g, 3)
+    graph = pg.DirectedNgramGraph.from_edge_arrays({i: s for i, s in enumerate(g["n3_nodes"])}, src, dst, w.astype(np.float32),
+                                                   n_value=3, assume_coalesced=True)
+    path = str(tmp_path / "g.pkl")
+    pg.DataUtils.save_object(graph, path)
+    loaded = pg.DataUtils.load_object(path)
+    assert loaded.__dict__.get("_pg_sidecar") is not None
+    torch.manual_seed(0)
+    model = pg.ProtGramDirectGCN([16, 32, 8], graph.number_of_nodes, 3, 3, 0, 0, 0.0, True).to(DEV).eval()
+    x = torch.randn(graph.number_of_nodes, 16, device=DEV)
+    assert torch.equal(model(loaded.gcn_data(x, DEV))[1], model(graph.gcn_data(x, DEV))[1])
