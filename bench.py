@@ -552,6 +552,49 @@ def _max_over_ranks(dist, dev, v):
     return float(t.item())
 
 
+def _build_key_range_variant(pipe, dist, buf, n_level, d_rank, sigma, ws, iters, nodes_expected, edges_expected, transitions_expected):
+    """The same build with the merge the north star words literally: REDUCE-SCATTER of the dense tables over key ranges, then
+    every rank extracts only the edges of its own key range (whole source rows; `csrc/extract_range.cu`) -- the merged table and
+    the edge list never exist on one GPU.  One small extra collective (the sigma^n-byte presence table, MAX) gives every rank
+    the same node numbering.  Timed like the replicated variant (count -> merge -> extract, max over ranks, median of passes)."""
+    db, dev, rank, world = pipe.db, pipe.dev, pipe.rank, pipe.world
+    pow_n, pow_m = db.table_sizes(n_level, sigma)
+    codes_per = (pow_n + world - 1) // world
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_count, t_merge, t_extract = [], [], []
+    res = None
+    for it in range(iters + 1):
+        res = None
+        padded = torch.zeros(world * codes_per * sigma, dtype=torch.int64, device=dev)
+        short = torch.zeros(pow_n, dtype=torch.uint8, device=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        db.count_level(buf, n_level, d_rank, sigma, padded[:pow_m], short, ws)
+        ev[1].record()
+        local = db.merge_tables_by_key_range(padded, codes_per, sigma, pipe.group)
+        s32 = short.to(torch.int32)
+        dist.all_reduce(s32, op=dist.ReduceOp.MAX)
+        short = s32.to(torch.uint8)
+        ev[2].record()
+        res = db.extract_key_range(local, short, n_level, sigma, rank * codes_per, codes_per, pipe.group)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it > 0:
+            t_count.append(ev[0].elapsed_time(ev[1])); t_merge.append(ev[1].elapsed_time(ev[2])); t_extract.append(ev[2].elapsed_time(ev[3]))
+        del padded, short, local
+    node_code, src, dst, cnt = res
+    tot = torch.stack([torch.tensor(int(src.numel()), device=dev, dtype=torch.int64), cnt.sum()])
+    dist.all_reduce(tot)
+    mc, mm, me = (_max_over_ranks(dist, dev, statistics.median(t)) for t in (t_count, t_merge, t_extract))
+    return {"merge": "reduce_scatter_tensor over key ranges (source codes split evenly) + all_reduce(MAX) of the presence table",
+            "count_ms": mc, "merge_reduce_scatter_ms": mm, "extract_own_key_range_ms": me, "build_ms": mc + mm + me,
+            "merge_bytes_per_gpu": world * codes_per * sigma * 8, "presence_bytes": pow_n,
+            "edges_on_this_rank": int(src.numel()),
+            "matches_replicated_build": bool(int(node_code.numel()) == nodes_expected and int(tot[0]) == edges_expected
+                                             and int(tot[1]) == transitions_expected)}
+
+
 def build_scale_leg(pipe, dist, n_level, total_seqs, iters=3, normalise=True):
     """Graph build of one n level at BASELINE configs C3 (n=4) / C4 (n=5, 50 M sequences = 17.5 G residues):
     `total_seqs` 350-residue sequences split over the ranks by contiguous ranges (STRONG scaling: the corpus is
@@ -607,6 +650,12 @@ def build_scale_leg(pipe, dist, n_level, total_seqs, iters=3, normalise=True):
            "count_frac_of_1B_per_residue_hbm_bound": nbytes / (mc * 1e-3) / 1e9 / peaks()[0]}
     if dist is not None:
         out["merge_bytes_per_gpu"] = pow_m * 8
+        try:
+            kr = _build_key_range_variant(pipe, dist, buf, n_level, d_rank, sigma, ws, iters, nodes, edges, out["transitions_counted"])
+            kr["build_residues_per_s"] = residues / (kr["build_ms"] * 1e-3)
+        except Exception as exc:  # noqa: BLE001 - the replicated numbers above stand on their own
+            kr = {"error": repr(exc)}
+        out["key_range_variant"] = kr
     del buf, ws
     if normalise and rank == 0:
         torch.cuda.synchronize()
