@@ -460,3 +460,61 @@ def test_partitioned_structure_scaled_fanout_and_fanin():
     ref_dx = xd + sum(d.astype(np.float64) @ dz.numpy().astype(np.float64)[:, v * f:(v + 1) * f] for v, d in enumerate(dense))
     for got, ref in ((z_vec, ref_vec), (z_sca, ref_sca), (dx, ref_dx)):
         assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
+def _bench_key_range_worker(rank, world, port, seqs, n, q):
+    try:
+        _init(rank, world, port)
+        import types
+        import bench
+        from protgram_directgcn_b200.host import corpus, data_builder
+
+        class _Ev:                                     # CUDA events do not exist here; the choreography is what is under test
+            def __init__(self, enable_timing=True):
+                pass
+
+            def record(self):
+                pass
+
+            def elapsed_time(self, other):
+                return 1.0
+
+        torch.cuda.Event, torch.cuda.synchronize = _Ev, (lambda *a, **k: None)
+        per = (len(seqs) + world - 1) // world
+        mine = seqs[rank * per:(rank + 1) * per]
+        buf = torch.from_numpy(corpus.pack_sequences(mine, global_first=(rank == 0)).copy())
+        symbols, d_rank = corpus.discover_alphabet(buf, dist.group.WORLD)
+        sigma = int(symbols.size)
+        bins, short = data_builder.count_level(buf, n, d_rank, sigma)
+        dist.all_reduce(bins)
+        s32 = short.to(torch.int32)
+        dist.all_reduce(s32, op=dist.ReduceOp.MAX)
+        node_code, src, dst, cnt = data_builder.extract_level(bins, s32.to(torch.uint8), n, sigma)
+        pipe = types.SimpleNamespace(db=data_builder, dev=torch.device("cpu"), rank=rank, world=world, group=dist.group.WORLD)
+        out = bench._build_key_range_variant(pipe, dist, buf, n, d_rank, sigma, None, 2, int(node_code.numel()), int(src.numel()),
+                                             int(cnt.sum()))
+        q.put((rank, out))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_key_range_build_variant_choreography():
+    """bench.py's `key_range_variant` of the multi-GPU build legs at world size 3 (gloo, spec kernels, dummy CUDA events): every
+    rank gets through the same collectives and the totals equal the replicated build's."""
+    from oracle import ngram_oracle
+    seqs = ngram_oracle.synth_sequences(0, 90, 40)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bench_key_range_worker, args=(r, 3, port, seqs, 2, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(isinstance(v, dict) for v in res.values()), res
+    assert all(v["matches_replicated_build"] for v in res.values())
+    assert sum(v["edges_on_this_rank"] for v in res.values()) > 0
