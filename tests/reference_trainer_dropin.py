@@ -113,5 +113,111 @@ def main():
     }))
 
 
+def full_run():
+    """The reference's whole `ProtGramDirectGCNTrainer.run()` (graph loading, per-level feature hand-off, label generation,
+    training with the config's Adam / scheduler / early stopping, embedding extraction, protein pooling, H5 writing) executed
+    unmodified twice: with the reference's classes on the reference-built pickles, and with `ProtGramDirectGCN`,
+    `DirectedNgramGraph`, `DataUtils` of the trainer module swapped for this package's on pickles written by this package's
+    GraphBuilder.  Prints the max difference of the pooled protein embeddings it "saves" (h5py is a recording stub)."""
+    import make_golden as mg
+    ref_db, ref_du, ref_gu, ref_model, ref_mu = mg.import_reference()
+    tgu = sys.modules["torch_geometric.utils"]
+    tgu.subgraph = tgu.to_networkx = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("not on this path"))
+    saved = {}
+
+    class _H5File:
+        def __init__(self, path, mode="r"):
+            self.store = saved.setdefault(os.path.basename(path), {})
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def create_dataset(self, key, data=None):
+            self.store[key] = np.array(data)
+
+    sys.modules["h5py"].File = _H5File
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        from src.pipeline import protgram_directgcn_trainer as ref_tr
+        from config import Config
+    finally:
+        os.chdir(cwd)
+    import protgram_directgcn_b200 as pg
+    from protgram_directgcn_b200 import _native as nat
+    from tests import kernel_spec
+    kernel_spec.install_plain(nat)
+
+    rng = np.random.default_rng(21)
+    fasta_text = mg.synth_fasta(rng, 60, 12, 50, "ACDEFGHIKLMNPQRSTVWY", weird=True)
+    n_max = 2
+    results = {}
+    for tag in ("R", "M"):
+        tmp = tempfile.mkdtemp()
+        fasta = os.path.join(tmp, "in.fasta")
+        with open(fasta, "w") as fh:
+            fh.write(fasta_text)
+        os.chdir(tmp)
+        try:
+            cfg = Config()
+        finally:
+            os.chdir(cwd)
+        from pathlib import Path
+        cfg.GCN_INPUT_FASTA_PATH = Path(fasta)
+        cfg.BASE_OUTPUT_DIR = Path(tmp) / "out"
+        cfg.GRAPH_OBJECTS_DIR = cfg.BASE_OUTPUT_DIR / "1_graph_objects"
+        cfg.GCN_EMBEDDINGS_DIR = cfg.BASE_OUTPUT_DIR / "2_gcn_embeddings"
+        cfg.GCN_NGRAM_MAX_N = n_max
+        cfg.GCN_HIDDEN_LAYER_DIMS = [24, 16]
+        cfg.GCN_1GRAM_INIT_DIM = 12
+        cfg.GCN_EPOCHS_PER_LEVEL = 4
+        cfg.GCN_TASK_TYPES_PER_LEVEL = {1: "next_node", 2: "next_node"}
+        cfg.GCN_USE_CLUSTER_TRAINING = False
+        # the reference's own _apply_pe (protgram_directgcn.py:185-191) raises "a leaf Variable that requires grad is being used in an
+        # in-place operation" under this torch (2.11) when x carries no grad, i.e. in its own n=1 training: positional encoding off
+        cfg.GCN_MAX_PE_LEN = 0
+        cfg.ID_MAPPING_MODE = "none"
+        cfg.APPLY_PCA_TO_GCN = False
+        cfg.GCN_RUN_SANITY_CHECK_PPI = False
+        cfg.DEBUG_VERBOSE = False
+        os.makedirs(cfg.GRAPH_OBJECTS_DIR, exist_ok=True)
+        if tag == "R":
+            # reference pickles: run()'s data flow with the reference's helpers (Dask replaced by set / Counter, see make_golden.py)
+            recs = mg.reference_build(ref_db, ref_du, ref_gu, fasta_text, n_max)
+            for n, rec in recs.items():
+                edge_file = os.path.join(tmp, f"e{n}.parquet")
+                pd.DataFrame({"source": rec["A_out_w_idx"][0], "target": rec["A_out_w_idx"][1],
+                              "weight": rec["A_out_w_val"].astype(np.int64)}).to_parquet(edge_file, index=False)
+                g = ref_gu.DirectedNgramGraph(nodes={i: str(s) for i, s in enumerate(rec["nodes"])}, edge_file_path=edge_file,
+                                              epsilon_propagation=1e-9, n_value=n)
+                ref_du.DataUtils.save_object(g, str(cfg.GRAPH_OBJECTS_DIR / f"ngram_graph_n{n}.pkl"))
+            ref_tr.ProtGramDirectGCN, ref_tr.DirectedNgramGraph, ref_tr.DataUtils = ref_model.ProtGramDirectGCN, ref_gu.DirectedNgramGraph, ref_du.DataUtils
+        else:
+            with redirect_stdout(io.StringIO()):
+                pg.GraphBuilder(cfg).run()          # the reference Config object drives this package's builder
+            ref_tr.ProtGramDirectGCN, ref_tr.DirectedNgramGraph, ref_tr.DataUtils = pg.ProtGramDirectGCN, pg.DirectedNgramGraph, pg.DataUtils
+        trainer = ref_tr.ProtGramDirectGCNTrainer(cfg)
+        trainer.device = torch.device("cpu")
+        torch.manual_seed(5)
+        random.seed(5)
+        np.random.seed(5)
+        saved.clear()
+        log = io.StringIO()
+        with redirect_stdout(log):
+            trainer.run()
+        assert "SUCCESS: Primary embeddings saved" in log.getvalue(), log.getvalue()[-2000:]
+        (fname, store), = saved.items()
+        results[tag] = (fname, {k: v.copy() for k, v in store.items()})
+    (fr, r), (fm, m) = results["R"], results["M"]
+    keys_equal = fr == fm and sorted(r) == sorted(m)
+    diff = max(float(np.max(np.abs(r[k].astype(np.float64) - m[k].astype(np.float64)))) for k in r) if keys_equal else float("inf")
+    scale = max(float(np.max(np.abs(v))) for v in r.values())
+    print(json.dumps({"mode": "full_run", "file": fr, "proteins": len(r), "keys_equal": bool(keys_equal), "dim": int(next(iter(r.values())).shape[0]),
+                      "pooled_max_abs_diff": diff, "pooled_max_abs": scale}))
+
+
 if __name__ == "__main__":
-    main()
+    full_run() if "--full-run" in sys.argv else main()
