@@ -518,3 +518,75 @@ def test_bench_key_range_build_variant_choreography():
     assert all(isinstance(v, dict) for v in res.values()), res
     assert all(v["matches_replicated_build"] for v in res.values())
     assert sum(v["edges_on_this_rank"] for v in res.values()) > 0
+
+
+def _corpus_to_model_worker(rank, world, port, seqs, n, dims, classes, state, x, q):
+    try:
+        _init(rank, world, port)
+        import protgram_directgcn_b200 as pg
+        from protgram_directgcn_b200.host import corpus, data_builder, partitioned as part
+        per_seq = (len(seqs) + world - 1) // world
+        mine = seqs[rank * per_seq:(rank + 1) * per_seq]
+        buf = torch.from_numpy(corpus.pack_sequences(mine, global_first=(rank == 0)).copy())
+        symbols, d_rank = corpus.discover_alphabet(buf, dist.group.WORLD)
+        g = data_builder.build_level_graph_partitioned(buf, n, symbols, d_rank, 1e-9, dist.group.WORLD)
+        lo, hi, per = g.lo, g.hi, g.per
+        model = pg.ProtGramDirectGCN(dims, per, classes, n, 0, 0, 0.0, True)
+        sd = {}
+        for k, v in state.items():
+            if k.rsplit(".", 1)[-1] in part.PER_NODE_PARAMETERS:
+                blk = torch.zeros((per,) + tuple(v.shape[1:]), dtype=v.dtype)
+                blk[: hi - lo] = v[lo:hi]
+                sd[k] = blk
+            else:
+                sd[k] = v
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        data = part.partitioned_data(torch.from_numpy(x[lo:hi]), part.local_csr(g.block), g.number_of_nodes)
+        _, emb = model(data)
+        q.put((rank, g.node_sequences, emb.detach().numpy()[: hi - lo]))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_corpus_to_embeddings_without_a_whole_graph_anywhere(monkeypatch):
+    """The whole chain on 2 ranks -- corpus shards -> counts -> reduce-scatter over key ranges -> key-range extraction ->
+    re-deal -> partitioned normalisation -> the unchanged model on row blocks -- against the single-process pipeline
+    (GraphBuilder-style build_level_graph + the model on the whole graph): same nodes, same embeddings."""
+    import protgram_directgcn_b200 as pg
+    from oracle import ngram_oracle
+    from protgram_directgcn_b200 import _native as nat
+    from protgram_directgcn_b200.host import corpus, data_builder
+    from tests import kernel_spec
+    seqs = ngram_oracle.synth_sequences(0, 120, 45)
+    n, dims, classes, world = 2, [10, 16, 8], 4, 2
+    kernel_spec.install(monkeypatch, nat)
+    buf = torch.from_numpy(corpus.pack_sequences(seqs).copy())
+    symbols, d_rank = corpus.discover_alphabet(buf)
+    whole = data_builder.build_level_graph(buf, n, symbols, d_rank, 1e-9)
+    N = whole.number_of_nodes
+    torch.manual_seed(2)
+    full = pg.ProtGramDirectGCN(dims, N, classes, n, 0, 0, 0.0, True).eval()
+    with torch.no_grad():
+        for k, p in full.named_parameters():
+            if "C_" in k or "bias" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    x = np.random.default_rng(0).standard_normal((N, dims[0])).astype(np.float32)
+    _, emb_ref = full(whole.gcn_data(torch.from_numpy(x), "cpu"))
+    state = {k: v.clone() for k, v in full.state_dict().items()}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_corpus_to_model_worker, args=(r, world, port, seqs, n, dims, classes, state, x, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(r[1], str) for r in res), res
+    assert all(r[1] == whole.node_sequences for r in res)
+    emb = np.concatenate([r[2] for r in res])
+    assert emb.shape == tuple(emb_ref.shape) and np.max(np.abs(emb - emb_ref.detach().numpy())) <= 2e-5
