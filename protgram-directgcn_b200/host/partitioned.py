@@ -80,6 +80,42 @@ def _spmm_fanin(csr: _Csr, g_full: torch.Tensor, rows: int, f: int) -> torch.Ten
     return y
 
 
+MAX_EXCHANGE_BYTES = 16 << 30   # all-gathered operand of one backward call; wider gradients go through in column chunks
+
+
+def _fanin_exchanged(csr: _Csr, dz_local: torch.Tensor, per: int, f: int, init: Optional[torch.Tensor], group,
+                     limit: Optional[int] = None) -> torch.Tensor:
+    """dX_local = (init) + sum_v A_v[rows of this rank] dZ_v for symmetric matrices: all-gather of dZ + local fan-in.
+    dZ is [N, 3F]: at C5's size (50 M nodes, F = 128) that is 77 GB, so beyond `limit` bytes the F columns are cut into
+    chunks -- every chunk gathers its three column blocks [per, 3 fc] and the kernel writes the matching fc columns of dX."""
+    world = dist.get_world_size(group)
+    limit = MAX_EXCHANGE_BYTES if limit is None else int(limit)
+    nv = len(csr.vals)
+    full_bytes = world * per * nv * f * 4
+    if full_bytes <= limit or f <= 4:
+        g_full = _all_gather_rows(dz_local.contiguous(), group)
+        dx = torch.empty((per, f), dtype=torch.float32, device=dz_local.device)
+        v = csr.vals + [None] * (3 - nv)
+        nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, f,
+                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
+                 csr.plan(3 * f), nat.stream_ptr())
+        return dx
+    chunks = -(-full_bytes // limit)
+    fc = max(4, (-(-f // chunks) + 3) // 4 * 4)                  # multiple of 4 floats: the kernels' 128-bit path
+    dx = torch.empty((per, f), dtype=torch.float32, device=dz_local.device)
+    v = csr.vals + [None] * (3 - nv)
+    for c0 in range(0, f, fc):
+        w = min(fc, f - c0)
+        part = torch.cat([dz_local[:, k * f + c0: k * f + c0 + w] for k in range(nv)], dim=1).contiguous()    # [per, nv * w]
+        g_full = _all_gather_rows(part, group)
+        init_c = init[:, c0:] if init is not None else None
+        nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, w,
+                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init_c), init.stride(0) if init is not None else 0, nat.ptr(dx[:, c0:]),
+                 dx.stride(0), 0, csr.plan(3 * f), nat.stream_ptr())
+        del g_full
+    return dx
+
+
 class _PartitionedFanout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, local_csr, local_csr_t, per, n_total, symmetric, group):
@@ -94,8 +130,7 @@ class _PartitionedFanout(torch.autograd.Function):
         local_csr, local_csr_t, per, n_total, symmetric, group, f = ctx.meta
         dz_local = dz_local.contiguous().float()
         if symmetric:
-            g_full = _all_gather_rows(dz_local, group)
-            dx = _spmm_fanin(local_csr, g_full, per, f)
+            dx = _fanin_exchanged(local_csr, dz_local, per, f, None, group)
         else:
             world = dist.get_world_size(group)
             part = _spmm_fanin(local_csr_t, dz_local, world * per, f)  # rows = global sources, cols = local targets
@@ -349,13 +384,7 @@ class PartitionedStructure:
 
     def fanin(self, dz: torch.Tensor, f: int, init: Optional[torch.Tensor]) -> torch.Tensor:
         self._check(dz)
-        g_full = _all_gather_rows(dz.contiguous(), self.group)
-        c, per = self.local, self.per
-        dx = torch.empty((per, f), dtype=torch.float32, device=dz.device)
-        nat.call("pg_spmm_fanin", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]), 3, per, f,
-                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
-                 c.plan(3 * f), nat.stream_ptr())
-        return dx
+        return _fanin_exchanged(self.local, dz.contiguous(), self.per, f, init, self.group)
 
 
 def partitioned_data(x_local: torch.Tensor, local: _Csr, n: int, group=None, **extra):

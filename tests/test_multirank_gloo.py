@@ -412,7 +412,9 @@ def _struct_worker(rank, world, port, payload, q):
     try:
         _init(rank, world, port)
         from protgram_directgcn_b200.host import partitioned as part
-        rowptr, col, vals, n, x, scales, dz = payload
+        rowptr, col, vals, n, x, scales, dz, limit = payload
+        if limit is not None:
+            part.MAX_EXCHANGE_BYTES = limit        # force the column-chunked exchange of the fan-in
         lo, hi, per = part.row_range(n, rank, world)
         st = part.PartitionedStructure(part.slice_rows(rowptr, col, vals, lo, hi, per), n)
         pad = lambda t: torch.cat([t[lo:hi], torch.zeros((per - (hi - lo),) + tuple(t.shape[1:]), dtype=t.dtype)])
@@ -427,11 +429,13 @@ def _struct_worker(rank, world, port, payload, q):
         dist.destroy_process_group()
 
 
-def test_partitioned_structure_scaled_fanout_and_fanin():
+@pytest.mark.parametrize("limit", [None, 3000])
+def test_partitioned_structure_scaled_fanout_and_fanin(limit):
     """The two calls the tensor-core backward makes on a structure (fan-out with per-SOURCE-row gate scales, which must be
-    exchanged; fan-in with a row-local init) against dense algebra, world size 3 with a short last block."""
+    exchanged; fan-in with a row-local init) against dense algebra, world size 3 with a short last block.  With a small
+    exchange limit the fan-in gathers dZ in column chunks (what C5's 77 GB gradient needs): same result."""
     rng = np.random.default_rng(8)
-    n, f, world = 100, 8, 3
+    n, f, world = 100, 12, 3
     mask = rng.random((n, n)) < 0.06
     mask |= mask.T
     dense = [np.where(mask, rng.standard_normal((n, n)), 0).astype(np.float32) for _ in range(3)]
@@ -446,7 +450,7 @@ def test_partitioned_structure_scaled_fanout_and_fanin():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_struct_worker, args=(r, world, port, (rowptr, col, vals, n, x, scales, dz), q)) for r in range(world)]
+    procs = [ctx.Process(target=_struct_worker, args=(r, world, port, (rowptr, col, vals, n, x, scales, dz, limit), q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
