@@ -450,11 +450,21 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
         ag_x()
         holder["z"] = part._spmm_fanout(prop.local, holder["x"], per, F)
 
+    # at config C5's full size (--large-log2-nodes 23 on 8 GPUs) the all-gathered dZ [N, 3F] would be 103 GB: beyond 48 GiB the
+    # backward exchanges it in column chunks (partitioned._fanin_exchanged) and only its total time is reported
+    leg_limit = 48 << 30
+    big_bwd = world * per * 3 * F * 4 > leg_limit
+
     def bwd():
+        if big_bwd:
+            holder["dx"] = part._fanin_exchanged(prop.local, dz_local, per, F, None, prop.group, limit=leg_limit)
+            return
         ag_dz()
         holder["dx"] = part._spmm_fanin(prop.local, holder["g"], per, F)
 
-    ag_x(); ag_dz()
+    ag_x()
+    if not big_bwd:
+        ag_dz()
     local_fo = lambda: part._spmm_fanout(prop.local, holder["x"], per, F)
     local_fi = lambda: part._spmm_fanin(prop.local, holder["g"], per, F)
     mx = lambda v: (lambda t: (dist.all_reduce(t, op=dist.ReduceOp.MAX), float(t.item()))[1])(torch.tensor([v], device=dev, dtype=torch.float64))
@@ -465,6 +475,10 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     for name, fn, comm, local, width in (("fwd", fwd, ag_x, local_fo, F), ("bwd", bwd, ag_dz, local_fi, 3 * F)):
         dist.barrier()
         ms = mx(_time_ms(fn, iters))
+        if name == "bwd" and big_bwd:
+            out[name] = {"ms": ms, "edges_per_s": 3 * P / (ms * 1e-3), "exchange": "dZ all-gathered in column chunks (exceeds 48 GiB in one piece)",
+                         "nvlink_recv_bytes_per_gpu": 4 * width * per * (world - 1)}
+            continue
         dist.barrier()
         ms_comm = mx(_time_ms(comm, iters))
         dist.barrier()
