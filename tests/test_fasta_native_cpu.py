@@ -310,3 +310,13 @@ def test_graph_builder_takes_the_windowed_reader_for_large_files(monkeypatch, tm
     assert used
     for n in (1, 2):
         check_graph_against_golden(pg.DataUtils.load_object(os.path.join(cfg.GRAPH_OBJECTS_DIR, f"ngram_graph_n{n}.pkl")), g, n)
+
+
+def test_windowed_reader_grows_its_buffer_for_a_record_far_longer_than_the_window(tmp_path):
+    rng = np.random.default_rng(5)
+    long_seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=300_000))
+    data = (">short\nACDE\n>long\n" + "\n".join(long_seq[i:i + 80] for i in range(0, len(long_seq), 80)) + "\n>tail\nGG\n").encode()
+    path = _write(tmp_path, data)
+    expect = b" ACDE \xff" + long_seq.encode() + b" \xffGG \xff"
+    stats = {}
+    assert _windows(path, 10, stats=stats, threads=2) == expect and stats["sequences"] == 3
