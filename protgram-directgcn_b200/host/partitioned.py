@@ -311,6 +311,16 @@ def normalize_row_partitioned(src: torch.Tensor, dst: torch.Tensor, w: torch.Ten
     group = group if group is not None else dist.group.WORLD
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi, per = row_range(n, rank, world)
+    total = torch.tensor([int(src.numel())], dtype=torch.int64, device=src.device)
+    dist.all_reduce(total, group=group)
+    if int(total.item()) == 0:
+        # no edge anywhere: the reference leaves all matrices EMPTY (graph_utils.py:219-223 and the constructor's else branch), not the identity
+        dev = src.device
+        e_i, e_f = torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.float32, device=dev)
+        return {"rowptr": torch.zeros(per + 1, dtype=torch.int64, device=dev), "col": torch.empty(0, dtype=torch.int32, device=dev),
+                "val_out": e_f, "val_in": e_f.clone(), "val_und": e_f.clone(), "pattern_nnz": 0, "in_src": e_i, "in_dst": e_i.clone(),
+                "in_w": e_f.clone(), "lo": lo, "hi": hi, "per": per, "rs_out": torch.zeros(n, dtype=torch.float64, device=dev),
+                "rs_in": torch.zeros(n, dtype=torch.float64, device=dev), "deg": torch.zeros(n, dtype=torch.int32, device=dev)}
     i_src, i_dst, i_w = exchange_in_edges(src, dst, w, n, group)
     blk = RowBlockNormalizer(src, dst, w, i_src, i_dst, i_w, n, lo, hi, eps)
     rs_out_l, rs_in_l = blk.degree_sums()

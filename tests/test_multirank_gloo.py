@@ -199,6 +199,9 @@ def _norm_worker(rank, world, port, payload, q):
         mine = (src >= lo) & (src < hi)
         res = normalize_row_partitioned(torch.from_numpy(src[mine]), torch.from_numpy(dst[mine]),
                                         torch.from_numpy(cnt[mine].astype(np.float32)), n)
+        if src.size == 0:           # a graph without any edge: empty matrices on every rank, like the reference
+            q.put((rank, {"pattern_nnz": res["pattern_nnz"], "rowptr": res["rowptr"].numpy()}))
+            return
         prop = RowPartitionedPropagation.from_local(local_csr(res), n)
         z = prop(torch.from_numpy(x[lo:hi]))[: hi - lo]
         out = {k: res[k].numpy() for k in ("rowptr", "col", "val_out", "val_in", "val_und", "in_src", "in_dst", "in_w")}
@@ -594,3 +597,19 @@ def test_corpus_to_embeddings_without_a_whole_graph_anywhere(monkeypatch):
     assert all(r[1] == whole.node_sequences for r in res)
     emb = np.concatenate([r[2] for r in res])
     assert emb.shape == tuple(emb_ref.shape) and np.max(np.abs(emb - emb_ref.detach().numpy())) <= 2e-5
+
+
+def test_row_partitioned_normalisation_of_an_edgeless_graph_is_empty():
+    """Nodes but no edges (every sequence exactly n residues long): the reference leaves all matrices empty
+    (graph_utils.py:219-223), so do the blocks -- not the identity pattern the tagged-key sort would give."""
+    z = np.zeros(0, dtype=np.int64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_norm_worker, args=(r, 2, port, (z, z, z, 5, np.zeros((5, 4), dtype=np.float32)), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(isinstance(v, dict) and v["pattern_nnz"] == 0 and not v["rowptr"].any() for v in res.values()), res
