@@ -264,3 +264,26 @@ def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
     model = pg.ProtGramDirectGCN([16, 32, 8], graph.number_of_nodes, 3, 3, 0, 0, 0.0, True).to(DEV).eval()
     x = torch.randn(graph.number_of_nodes, 16, device=DEV)
     assert torch.equal(model(loaded.gcn_data(x, DEV))[1], model(graph.gcn_data(x, DEV))[1])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
+                    reason="column-chunked exchange of the partitioned fan-in: gloo-tested on the spec, not yet run on a B200")
+def test_partitioned_fanin_column_chunks_equal_single_exchange():
+    import torch.distributed as dist
+    from protgram_directgcn_b200.host import partitioned as part
+    from tests.test_multirank_gloo import _free_port
+    n, f = 5003, 64
+    src, dst, cnt = random_count_graph(n, seed=31, density=0.004)
+    s, d, w = (torch.from_numpy(a).to(DEV) for a in (src, dst, cnt.astype(np.float32)))
+    full = graph_utils.device_normalize(s, d, w, n, 1e-9)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        csr = part.slice_rows(full["rowptr"], full["col"], [full["val_in"], full["val_out"], full["val_und"]], 0, n, n)
+        dz = torch.randn(n, 3 * f, device=DEV)
+        init = torch.randn(n, f, device=DEV)
+        one = part._fanin_exchanged(csr, dz, n, f, init, dist.group.WORLD)
+        for limit in (n * 3 * f * 4 // 2, n * 3 * f * 4 // 7):
+            assert torch.equal(part._fanin_exchanged(csr, dz, n, f, init, dist.group.WORLD, limit=limit), one)
+    finally:
+        dist.destroy_process_group()
