@@ -15,6 +15,24 @@ from tests.test_multirank_gloo import check_blocks_against_oracle, random_count_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+BACKEND = "nccl"
+
+
+@pytest.fixture(scope="module")
+def world1():
+    """ONE one-rank process group for all tests of this module that drive the collective code paths (initialised once per
+    process: NCCL communicators are not re-created between tests)."""
+    import torch.distributed as dist
+    from tests.test_multirank_gloo import _free_port
+    created = not dist.is_initialized()
+    if created:
+        kw = {"device_id": torch.device("cuda", torch.cuda.current_device())} if BACKEND == "nccl" else {}
+        dist.init_process_group(BACKEND, init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1, **kw)
+    try:
+        yield dist.group.WORLD
+    finally:
+        if created:
+            dist.destroy_process_group()
 
 
 def _play_ranks(src, dst, w, n, world, seed=0, eps=1e-9):
@@ -95,31 +113,24 @@ def test_row_block_rejects_foreign_edges():
     assert lib.pg_normalize_rows_sizes(None, None, 0, None, None, 0, 10, 8, 5, None, None, 0, None) == -1   # row_lo + rows > num_nodes
 
 
-def test_normalize_row_partitioned_world1_nccl_equals_single_gpu():
+def test_normalize_row_partitioned_world1_nccl_equals_single_gpu(world1):
     """The whole driver (owner partition with pg_sort_pairs, all_to_all_single / all_gather over NCCL,
     padding) on a one-rank NCCL group: identical to device_normalize."""
-    import torch.distributed as dist
     from protgram_directgcn_b200.host.partitioned import RowPartitionedPropagation, local_csr, normalize_row_partitioned
-    from tests.test_multirank_gloo import _free_port
     n = 1003
     src, dst, cnt = random_count_graph(n, seed=21, density=0.01)
     s, d, w = (torch.from_numpy(a).to(DEV) for a in (src, dst, cnt.astype(np.float32)))
     full = graph_utils.device_normalize(s, d, w, n, 1e-9)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        perm = torch.randperm(s.numel(), generator=torch.Generator().manual_seed(1)).to(DEV)
-        res = normalize_row_partitioned(s[perm], d[perm], w[perm], n)
-        for k in ("rowptr", "col", "val_out", "val_in", "val_und", "in_src", "in_dst", "in_w"):
-            assert torch.equal(res[k], full[k]), k
-        x = torch.randn(n, 16, device=DEV)
-        z = RowPartitionedPropagation.from_local(local_csr(res), n)(x)
-        ref = torch.zeros(n, 16, device=DEV, dtype=torch.float64)
-        rows = torch.repeat_interleave(torch.arange(n, device=DEV), full["rowptr"][1:] - full["rowptr"][:-1])
-        ref.index_add_(0, rows, full["val_in"].double().view(-1, 1) * x.double()[full["col"].long()])
-        assert float((z[:, :16].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
-    finally:
-        dist.destroy_process_group()
+    perm = torch.randperm(s.numel(), generator=torch.Generator().manual_seed(1)).to(DEV)
+    res = normalize_row_partitioned(s[perm], d[perm], w[perm], n, group=world1)
+    for k in ("rowptr", "col", "val_out", "val_in", "val_und", "in_src", "in_dst", "in_w"):
+        assert torch.equal(res[k], full[k]), k
+    x = torch.randn(n, 16, device=DEV)
+    z = RowPartitionedPropagation.from_local(local_csr(res), n, group=world1)(x)
+    ref = torch.zeros(n, 16, device=DEV, dtype=torch.float64)
+    rows = torch.repeat_interleave(torch.arange(n, device=DEV), full["rowptr"][1:] - full["rowptr"][:-1])
+    ref.index_add_(0, rows, full["val_in"].double().view(-1, 1) * x.double()[full["col"].long()])
+    assert float((z[:, :16].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
 
 
 # ------------------------------------------------------------------ key-range extraction (tables merged by reduce-scatter)
@@ -176,32 +187,25 @@ def test_key_range_extraction_equals_full_extraction(n, world):
         assert torch.equal(torch.cat([p[i] for p in parts]), ref)
 
 
-def test_fully_partitioned_build_world1_nccl_equals_build_level_graph():
+def test_fully_partitioned_build_world1_nccl_equals_build_level_graph(world1):
     """build_level_graph_partitioned (reduce_scatter_tensor, key-range extraction, re-deal by source, partitioned
     normalisation) over a one-rank NCCL group == build_level_graph, bitwise, n = 1..3."""
-    import torch.distributed as dist
     from protgram_directgcn_b200.host import corpus, data_builder
-    from tests.test_multirank_gloo import _free_port
     buf = _synth_corpus(3000, 60)
     symbols, d_rank = corpus.discover_alphabet(buf)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        for n in (1, 2, 3):
-            ref = data_builder.build_level_graph(buf, n, symbols, d_rank, 1e-9)
-            got = data_builder.build_level_graph_partitioned(buf, n, symbols, d_rank, 1e-9, dist.group.WORLD)
-            assert got.node_sequences == ref.node_sequences and got.number_of_edges == ref.number_of_edges
-            side = ref._pg_device
-            assert torch.equal(got.block["rowptr"], side["rowptr"]) and torch.equal(got.block["col"], side["col"])
-            for k in ("val_in", "val_out", "val_und"):
-                assert torch.equal(got.block[k], side[k]), (n, k)
-            a_out = ref.A_out_w
-            assert torch.equal(torch.stack([got.a_out[0], got.a_out[1]]).cpu(), a_out.indices())
-            assert torch.equal(got.a_out[2].cpu(), a_out.values())
-            z = got.propagation()(torch.ones(got.number_of_nodes, 4, device=DEV))
-            assert z.shape == (got.number_of_nodes, 12) and bool(torch.isfinite(z).all())
-    finally:
-        dist.destroy_process_group()
+    for n in (1, 2, 3):
+        ref = data_builder.build_level_graph(buf, n, symbols, d_rank, 1e-9)
+        got = data_builder.build_level_graph_partitioned(buf, n, symbols, d_rank, 1e-9, world1)
+        assert got.node_sequences == ref.node_sequences and got.number_of_edges == ref.number_of_edges
+        side = ref._pg_device
+        assert torch.equal(got.block["rowptr"], side["rowptr"]) and torch.equal(got.block["col"], side["col"])
+        for k in ("val_in", "val_out", "val_und"):
+            assert torch.equal(got.block[k], side[k]), (n, k)
+        a_out = ref.A_out_w
+        assert torch.equal(torch.stack([got.a_out[0], got.a_out[1]]).cpu(), a_out.indices())
+        assert torch.equal(got.a_out[2].cpu(), a_out.values())
+        z = got.propagation()(torch.ones(got.number_of_nodes, 4, device=DEV))
+        assert z.shape == (got.number_of_nodes, 12) and bool(torch.isfinite(z).all())
 
 
 @pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
@@ -209,13 +213,11 @@ def test_fully_partitioned_build_world1_nccl_equals_build_level_graph():
                            "executable spec (tests/test_multirank_gloo.py) and uses only entry points verified on the GPU, but this "
                            "test itself has not run on a B200 yet; opt in with PGB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("n,dims", [(301, [12, 16, 8]), (6000, [64, 128, 128])])
-def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims):
+def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims, world1):
     """ProtGramDirectGCN on the padded row block of a one-rank NCCL group == the plain model on the same graph (forward,
     loss, every gradient); the second shape takes the tensor-core path (scaled fan-out with exchanged gates in backward)."""
-    import torch.distributed as dist
     import protgram_directgcn_b200 as pg
     from protgram_directgcn_b200.host import partitioned as part
-    from tests.test_multirank_gloo import _free_port
     src, dst, cnt = random_count_graph(n, seed=5, density=min(0.05, 20.0 / n))
     s, d, w = (torch.from_numpy(a).to(DEV) for a in (src, dst, cnt.astype(np.float32)))
     full = graph_utils.device_normalize(s, d, w, n, 1e-9)
@@ -231,16 +233,11 @@ def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims):
                    edge_index_undirected_norm=ei, edge_weight_undirected_norm=full["val_und"])
     logp, emb = plain(data)
     torch.nn.functional.nll_loss(logp, y).backward()
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        res = part.normalize_row_partitioned(s, d, w, n)
-        pdata = part.partitioned_data(x, part.local_csr(res), n)
-        logp2, emb2 = twin(pdata)
-        torch.nn.functional.nll_loss(logp2, y).backward()
-        part.allreduce_replicated_grads(twin)
-    finally:
-        dist.destroy_process_group()
+    res = part.normalize_row_partitioned(s, d, w, n, group=world1)
+    pdata = part.partitioned_data(x, part.local_csr(res), n, group=world1)
+    logp2, emb2 = twin(pdata)
+    torch.nn.functional.nll_loss(logp2, y).backward()
+    part.allreduce_replicated_grads(twin, group=world1)
     assert float((logp2 - logp).abs().max()) <= 2e-5 and float((emb2 - emb).abs().max()) <= 2e-5
     for (k, p), (_, p2) in zip(plain.named_parameters(), twin.named_parameters()):
         if p.grad is not None:
@@ -268,22 +265,15 @@ def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
 
 @pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
                     reason="column-chunked exchange of the partitioned fan-in: gloo-tested on the spec, not yet run on a B200")
-def test_partitioned_fanin_column_chunks_equal_single_exchange():
-    import torch.distributed as dist
+def test_partitioned_fanin_column_chunks_equal_single_exchange(world1):
     from protgram_directgcn_b200.host import partitioned as part
-    from tests.test_multirank_gloo import _free_port
     n, f = 5003, 64
     src, dst, cnt = random_count_graph(n, seed=31, density=0.004)
     s, d, w = (torch.from_numpy(a).to(DEV) for a in (src, dst, cnt.astype(np.float32)))
     full = graph_utils.device_normalize(s, d, w, n, 1e-9)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        csr = part.slice_rows(full["rowptr"], full["col"], [full["val_in"], full["val_out"], full["val_und"]], 0, n, n)
-        dz = torch.randn(n, 3 * f, device=DEV)
-        init = torch.randn(n, f, device=DEV)
-        one = part._fanin_exchanged(csr, dz, n, f, init, dist.group.WORLD)
-        for limit in (n * 3 * f * 4 // 2, n * 3 * f * 4 // 7):
-            assert torch.equal(part._fanin_exchanged(csr, dz, n, f, init, dist.group.WORLD, limit=limit), one)
-    finally:
-        dist.destroy_process_group()
+    csr = part.slice_rows(full["rowptr"], full["col"], [full["val_in"], full["val_out"], full["val_und"]], 0, n, n)
+    dz = torch.randn(n, 3 * f, device=DEV)
+    init = torch.randn(n, f, device=DEV)
+    one = part._fanin_exchanged(csr, dz, n, f, init, world1)
+    for limit in (n * 3 * f * 4 // 2, n * 3 * f * 4 // 7):
+        assert torch.equal(part._fanin_exchanged(csr, dz, n, f, init, world1, limit=limit), one)
