@@ -414,6 +414,58 @@ def pg_layer_gemm_bwd_weight(z, ldz, x, ldx, ga, gb, gc, gate_stride, dy, lddy, 
     dw_ext.copy_(_a_ext(z, x, ga, gb, gc, n, f_in, has_res).t() @ dy)
 
 
+# tensor-core entry points: same mathematics as the SIMT ones (the CUDA side differs in precision handling only).  They are
+# reachable on CPU only when a test forces TC_MODE and flips pg_layer_gemm_fwd_tc_supported (host wiring of that path).
+def pg_layer_gemm_fwd_tc_ws_bytes(f_in, f_out, has_res):
+    return 256
+
+
+def pg_layer_gemm_fwd_tc(z, ldz, x, ldx, ga, gb, gc, gate_stride, w_ext, constant, ldconst, n, f_in, f_out, has_res, add_identity,
+                         slope, h, ldh, ws=None, ws_bytes=0, stream=None):
+    pg_layer_gemm_fwd(z, ldz, x, ldx, ga, gb, gc, gate_stride, w_ext, constant, ldconst, n, f_in, f_out, has_res, add_identity, slope, h, ldh)
+
+
+def pg_layer_gemm_bwd_weight_tc_ws_bytes(n, f_in, f_out, has_res):
+    return 256
+
+
+def pg_layer_gemm_bwd_weight_tc(*args):
+    pg_layer_gemm_bwd_weight(*args)
+
+
+def pg_layer_gemm_bwd_data_tc_ws_bytes(f_in, f_out, has_res):
+    return 256
+
+
+def pg_layer_gemm_bwd_data_tc(dy, lddy, w_ext, z, ldz, ga, gb, gc, gate_stride, n, f_in, f_out, has_res, dz, lddz, dxres, lddxres, dgate,
+                              ws=None, ws_bytes=0, stream=None):
+    pg_layer_gemm_bwd_data(dy, lddy, w_ext, z, ldz, ga, gb, gc, gate_stride, n, f_in, f_out, has_res, dz, lddz, dxres, lddxres, dgate)
+
+
+def pg_layer_gate_grad_tc_ws_bytes(n, f_in, f_out):
+    return 256
+
+
+def pg_layer_gate_grad_tc(dy, lddy, w_ext, z, ldz, n, f_in, f_out, has_res, dgate, ws=None, ws_bytes=0, stream=None):
+    k_data = 3 * f_in + (f_in if has_res else 0)
+    for v in range(3):
+        seg = slice(v * f_in, (v + 1) * f_in)
+        dgate[v] = ((dy @ w_ext[seg].t()) * z[:, seg]).sum(1) + dy @ w_ext[k_data + v]
+
+
+def pg_layer_gemm_bwd_dx_tc_ws_bytes(f_in, f_out, has_res):
+    return 256
+
+
+def pg_layer_gemm_bwd_dx_tc(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, add_identity, dx, lddx, ws=None, ws_bytes=0, stream=None):
+    acc = sum(t[:, v * f_out:(v + 1) * f_out] @ w_ext[v * f_in:(v + 1) * f_in].t() for v in range(3))
+    if has_res:
+        acc = acc + dy @ w_ext[3 * f_in:4 * f_in].t()
+    elif add_identity:
+        acc = acc + dy
+    dx.copy_(acc)
+
+
 def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
     out.copy_(h / (torch.norm(h, p=2, dim=1, keepdim=True) + eps))
 

@@ -327,3 +327,37 @@ def test_graph_pickle_csr_sidecar_roundtrip(tmp_path, spec_native):
     assert pg.DataUtils.load_object(path1).__dict__.get("_pg_sidecar") is None
     os.remove(side)
     assert pg.DataUtils.load_object(path).__dict__.get("_pg_sidecar") is None
+
+
+def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch):
+    """The tensor-core branch of the fused layer (forward TC GEMM, weight gradient, gate gradients from the dot-product epilogue,
+    input gradient through the SCALED FAN-OUT + one GEMM instead of the fan-in) wired on the executable spec: same outputs and
+    gradients as the SIMT branch, with and without residual projections, vector and scalar gates."""
+    for use_vec in (True, False):
+        g = load("model_refgraph")
+        outs = {}
+        for mode in ("off", "force"):
+            monkeypatch.setattr(model_mod, "TC_MODE", mode)
+            monkeypatch.setattr(kernel_spec, "pg_layer_gemm_fwd_tc_supported", lambda f_in, f_out: 1)
+            torch.manual_seed(0)
+            n = int(g["num_graph_nodes"])
+            model = pg.ProtGramDirectGCN([8, 16, 16, 4], n, 3, 1, 0, 0, 0.0, use_vec).eval()
+            with torch.no_grad():
+                for k, p in model.named_parameters():
+                    if "C_" in k or "bias" in k:
+                        p.add_(0.3 * torch.randn_like(p))
+            data = _data(g)
+            data.x = torch.randn(n, 8, generator=torch.Generator().manual_seed(1)).requires_grad_(True)
+            calls = []
+            real_call = nat.call
+            monkeypatch.setattr(nat, "call", lambda name, *a, _c=calls, _r=real_call: (_c.append(name), _r(name, *a))[1])
+            logp, emb = model(data)
+            (logp.sum() + (emb * emb).sum()).backward()
+            monkeypatch.setattr(nat, "call", real_call)
+            outs[mode] = (logp.detach(), emb.detach(), data.x.grad.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, calls)
+        assert "pg_spmm_fanout_scaled" in outs["force"][4] and "pg_layer_gate_grad_tc" in outs["force"][4] and "pg_spmm_fanin" not in outs["force"][4]
+        assert "pg_spmm_fanin" in outs["off"][4] and "pg_layer_gemm_fwd_tc" not in outs["off"][4]
+        for a, b in zip(outs["off"][:3], outs["force"][:3]):
+            assert rel_err(b.numpy(), a.numpy()) <= 2e-5
+        for k, v in outs["off"][3].items():
+            assert rel_err(outs["force"][3][k].numpy(), v.numpy()) <= 5e-5, k

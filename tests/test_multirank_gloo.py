@@ -317,7 +317,12 @@ def _model_worker(rank, world, port, payload, q):
         _init(rank, world, port)
         import protgram_directgcn_b200 as pg
         from protgram_directgcn_b200.host import partitioned as part
-        src, dst, cnt, n, x, y, dims, classes, state, use_vec = payload
+        src, dst, cnt, n, x, y, dims, classes, state, use_vec, tc = payload
+        if tc:   # tensor-core branch of the layer (spec kernels): backward goes through the scaled fan-out with EXCHANGED gates
+            from protgram_directgcn_b200.host import protgram_directgcn as model_mod
+            from tests import kernel_spec
+            model_mod.TC_MODE = "force"
+            kernel_spec.pg_layer_gemm_fwd_tc_supported = lambda f_in, f_out: 1
         lo, hi, per = part.row_range(n, rank, world)
         mine = (src >= lo) & (src < hi)
         res = part.normalize_row_partitioned(torch.from_numpy(src[mine]), torch.from_numpy(dst[mine]),
@@ -350,8 +355,8 @@ def _model_worker(rank, world, port, payload, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_vec", [True, False])
-def test_row_partitioned_model_equals_single_process(use_vec, monkeypatch):
+@pytest.mark.parametrize("use_vec,tc", [(True, False), (False, False), (True, True)])
+def test_row_partitioned_model_equals_single_process(use_vec, tc, monkeypatch):
     """SURVEY 8(e) row 3 end to end: the unchanged ProtGramDirectGCN on each rank's row block (partitioned normalisation ->
     PartitionedStructure -> fused layers with all-gathered SpMM operands) against the same model on the whole graph in one
     process: log-probs and embeddings row for row, gradients of the replicated parameters after the all-reduce, gradients
@@ -376,7 +381,7 @@ def test_row_partitioned_model_equals_single_process(use_vec, monkeypatch):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    payload = (src, dst, cnt, n, x, y, dims, classes, state, use_vec)
+    payload = (src, dst, cnt, n, x, y, dims, classes, state, use_vec, tc)
     procs = [ctx.Process(target=_model_worker, args=(r, world, port, payload, q)) for r in range(world)]
     for p in procs:
         p.start()
