@@ -35,7 +35,8 @@ class GraphedDirectGCNStep:
         self.rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=dev)
         self.col = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
         self.vals = [torch.zeros(self.capacity, dtype=torch.float32, device=dev) for _ in range(3)]
-        self._ei = torch.zeros((2, 1), dtype=torch.int64, device=dev)  # placeholder: the CSR is pre-registered
+        self._ei = torch.zeros((2, 1), dtype=torch.int64, device=dev)  # placeholder: the CSR is pre-registered (rides on the tensor)
+        self._ei._pg_placeholder = True     # get_structure refuses to build a structure from it
         register_symmetric_structure(self._ei, tuple(self.vals), self.num_nodes, self.rowptr, self.col)
         self.data = Data(x=self.x, edge_index_in=self._ei, edge_weight_in=self.vals[0], edge_index_out=self._ei,
                          edge_weight_out=self.vals[1], edge_index_undirected_norm=self._ei,
@@ -75,6 +76,11 @@ class GraphedDirectGCNStep:
         loss = nll.detach()
         if self.l2_lambda > 0.0:
             l2 = torch.stack(torch._foreach_norm(self.params)).square().sum()
+            # reference trainer :96: the L2 term covers EVERY trainable parameter, also those the loss did not reach
+            # (grad None after zero_grad(set_to_none=True)): their whole gradient is the decay term
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
             torch._foreach_add_([p.grad for p in self.params], self.params, alpha=2.0 * self.l2_lambda)
             loss = loss + self.l2_lambda * l2
         self.opt.step()

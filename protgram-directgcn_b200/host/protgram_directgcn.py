@@ -105,7 +105,10 @@ class EdgeStructure:
         self.nnz_total = sum(int(e.shape[1]) for e in eis)
 
 
-_STRUCT_CACHE: Dict[tuple, EdgeStructure] = {}
+import collections as _collections
+
+_STRUCT_CACHE: "_collections.OrderedDict[tuple, EdgeStructure]" = _collections.OrderedDict()
+STRUCT_CACHE_ENTRIES = 64      # least-recently-used eviction; pre-registered structures also ride on their edge tensor (tag)
 
 
 def _cache_key(eis, ews, n):
@@ -116,74 +119,99 @@ def _versions(eis, ews):
     return tuple(t._version if t is not None else -1 for t in (*eis, *ews))
 
 
+def _cache_put(key, st) -> None:
+    _STRUCT_CACHE[key] = st
+    _STRUCT_CACHE.move_to_end(key)
+    while len(_STRUCT_CACHE) > STRUCT_CACHE_ENTRIES:
+        _STRUCT_CACHE.popitem(last=False)
+
+
+def _ews_key(ews):
+    return tuple((t.data_ptr(), tuple(t.shape)) if t is not None else None for t in ews)
+
+
 def register_symmetric_structure(ei: torch.Tensor, ews, n: int, rowptr: torch.Tensor, col: torch.Tensor,
                                  static: bool = True) -> None:
     """Hand the layer a ready CSR for a shared, row-major sorted, value-symmetric pattern (what the
     normalisation kernels emit for reference-built graphs): ews = (in, out, undirected) values in
     pattern order.  Symmetry makes grouped-by-target == grouped-by-source == the row CSR.
     static=True: the buffers are rewritten in place by their owner (CUDA-graph replay), so the
-    cached structure stays valid across version bumps of the tensors."""
+    cached structure stays valid across version bumps of the tensors.
+    The structure is attached to `ei` itself (not to the LRU cache of structures built from edge lists): it
+    lives exactly as long as the edge tensor the caller hands to the model, whatever passes through that cache."""
     st = EdgeStructure.__new__(EdgeStructure)
     st.n, st.shared = n, True
     csr = _Csr(rowptr, col, [w.contiguous() for w in ews])
     st.by_dst, st.by_src = [csr], [csr]
     st.nnz_total = 3 * int(col.numel())
-    st._keepalive = (ei, ews)
+    st._keepalive = (ews,)          # not `ei`: the tag below would make that a reference cycle
     st._static = static
     st._vers = _versions((ei, ei, ei), ews)
-    if len(_STRUCT_CACHE) > 16:
-        _STRUCT_CACHE.clear()
-    _STRUCT_CACHE[_cache_key((ei, ei, ei), ews, n)] = st
+    st._tag_ews = _ews_key(ews)
+    st._tag_n = n
+    ei._pg_struct = st
 
 
 def register_structure(eis, ews, n: int, struct) -> None:
     """Attach a ready structure object (e.g. partitioned.PartitionedStructure) to the edge tensors a Data object carries:
     the layer looks at the tag before it consults the cache of CSRs it builds itself."""
+    struct._tag_ews = _ews_key(ews)
+    struct._tag_n = n
     eis[0]._pg_struct = struct
 
 
 def get_structure(eis, ews, n: int) -> EdgeStructure:
-    tagged = getattr(eis[0], "_pg_struct", None)    # set by register_structure: survives cache eviction
-    if tagged is not None:
+    tagged = getattr(eis[0], "_pg_struct", None)    # set by register_*structure: survives cache eviction
+    if tagged is not None and all(e is eis[0] for e in eis[1:]) and getattr(tagged, "_tag_n", n) == n \
+            and getattr(tagged, "_tag_ews", None) in (None, _ews_key(ews)):
         return tagged
     key = _cache_key(eis, ews, n)
     st = _STRUCT_CACHE.get(key)
     if st is not None and not getattr(st, "_static", False) and st._vers != _versions(eis, ews):
         st = None  # tensors were modified in place since the CSR was built
     if st is None:
-        if len(_STRUCT_CACHE) > 16:
-            _STRUCT_CACHE.clear()
+        if eis[0].numel() == 2 and eis[0].shape[-1] == 1 and getattr(eis[0], "_pg_placeholder", False):
+            raise RuntimeError("placeholder edge_index without its pre-registered structure (it must be registered with "
+                               "register_symmetric_structure before the model sees it)")
         st = EdgeStructure(eis, ews, n)
         st._keepalive = (eis, ews)  # data_ptr keys stay valid while cached
         st._static = False
         st._vers = _versions(eis, ews)
-        _STRUCT_CACHE[key] = st
+    _cache_put(key, st)
     return st
 
 
 # ------------------------------------------------------------------------------------------------
 # kernels as autograd function
 # ------------------------------------------------------------------------------------------------
-def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
-    """Z = [A_in X | A_out X | U X]; with `scales` = (s_in, s_out, s_und) per SOURCE row: A_v diag(s_v) X (shared structures only)."""
-    if getattr(struct, "partitioned", False):   # rows of this rank only; neighbour rows arrive by all-gather (host/partitioned.py)
+def _fanout(struct: EdgeStructure, x: torch.Tensor, f_in: int, scales=None, scale_stride: int = 1, transposed: bool = False) -> torch.Tensor:
+    """Z = [A_in X | A_out X | U X]; with `scales` = (s_in, s_out, s_und) indexed by the GATHERED row: A_v diag(s_v) X.
+    transposed=True runs over the source-grouped structure: Z_v = A_v^T diag(s_v) X (the regrouped input gradient of the
+    backward pass; for value-symmetric matrices both structures are the same object)."""
+    if getattr(struct, "partitioned", False):   # rows of this rank only; neighbour rows arrive by exchange (host/partitioned.py)
         return struct.fanout(x, f_in, scales, scale_stride)
     n = x.shape[0]
     z = torch.empty((n, 3 * f_in), dtype=torch.float32, device=x.device)
     st = nat.stream_ptr()
+    csrs = struct.by_src if transposed else struct.by_dst
     if struct.shared and scales is not None:
-        c = struct.by_dst[0]
+        c = csrs[0]
         nat.call("pg_spmm_fanout_scaled", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
                  3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, nat.ptr(scales[0]), nat.ptr(scales[1]),
                  nat.ptr(scales[2]), int(scale_stride), c.plan(3 * f_in), st)
     elif struct.shared:
-        c = struct.by_dst[0]
+        c = csrs[0]
         nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), nat.ptr(c.vals[1]), nat.ptr(c.vals[2]),
                  3, n, f_in, nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), 0, c.plan(3 * f_in), st)
     else:
-        for v, c in enumerate(struct.by_dst):
-            nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
-                     nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, c.plan(3 * f_in), st)
+        for v, c in enumerate(csrs):
+            if scales is not None:
+                nat.call("pg_spmm_fanout_scaled", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
+                         nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, nat.ptr(scales[v]), None, None, int(scale_stride),
+                         c.plan(3 * f_in), st)
+            else:
+                nat.call("pg_spmm_fanout", nat.ptr(c.rowptr), nat.ptr(c.col), nat.ptr(c.vals[0]), None, None, 1, n, f_in,
+                         nat.ptr(x), x.stride(0), nat.ptr(z), z.stride(0), v * f_in, c.plan(3 * f_in), st)
     return z
 
 
@@ -290,7 +318,9 @@ class _DirectGCNFused(torch.autograd.Function):
                  nat.ptr(gc), ctx.gate_stride, nat.ptr(dy), dy.stride(0), n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws),
                  ws.numel(), st)
         dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
-        fanout_bwd = ctx.use_tc and ctx.struct.shared and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0
+        # dX = sum_v A_v^T (g_v * dY) W'_v^T: the gather runs over the SOURCE-grouped structure (== the forward structure only
+        # for value-symmetric matrices; shared-but-unsymmetric and unshared edge lists take their by_src CSRs)
+        fanout_bwd = ctx.use_tc and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0
         if fanout_bwd:
             # gate gradients from the data-gradient GEMM with a dot-product epilogue (dZ is never written); the input gradient
             # regrouped as dX = sum_v (A_v (g_v * dY)) W'_v^T (+ residual): the symmetric structure lets the fan-out kernel gather
@@ -300,7 +330,7 @@ class _DirectGCNFused(torch.autograd.Function):
                      nat.ptr(dgate), nat.ptr(wsg), wsg.numel(), st)
             dx = None
             if ctx.needs_input_grad[0]:
-                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride)
+                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride, transposed=True)
                 dx = torch.empty((n, f_in), dtype=torch.float32, device=x.device)
                 ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
                 nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,

@@ -782,6 +782,59 @@ def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec):
         assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("shared", [True, False])
+def test_tensor_core_backward_on_unsymmetric_edge_lists(monkeypatch, shared):
+    """the regrouped input gradient gathers over the SOURCE-grouped structure.  A directed (unsymmetric)
+    edge list reused for in / out / undirected (shared pattern, by_src != by_dst) and three different unsymmetric lists
+    (benchmarker contract, gnn_benchmarker.py:297-305) must give the same gradients through the fan-out regrouping as through
+    the fan-in gather, and both must match the torch-CPU oracle."""
+    from oracle import directgcn_oracle
+    n, dims = 700, [16, 32, 16]
+    g = torch.Generator().manual_seed(11)
+    def edges(e):
+        ei = torch.stack([torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)])
+        return ei, torch.rand(e, generator=g) + 0.1
+    if shared:
+        ei, w = edges(6000)
+        lists = [(ei, w), (ei, w * 0.5 + 0.2), (ei, 1.0 / (w + 1.0))]
+    else:
+        lists = [edges(6000), edges(5000), edges(7000)]
+    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    x0 = torch.randn(n, dims[0], generator=g)
+    y = torch.randint(0, 5, (n,), generator=g)
+    torch.manual_seed(5)
+    model = pg.ProtGramDirectGCN(dims, n, 5, 2, 0, 16, 0.0, True)
+    with torch.no_grad():
+        for p_ in model.parameters():
+            if p_.ndim == 1 or p_.shape[-1] == 1:
+                p_.add_(0.3 * torch.randn_like(p_))
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    flat = [t for pair in lists for t in pair]
+    xr = x0.clone().requires_grad_(True)
+    logp_ref, _ = directgcn_oracle.protgram_forward(params, xr, *flat, n_gram_len=2, one_gram_dim=0)
+    torch.nn.functional.nll_loss(logp_ref, y).backward()
+    model = model.to(DEV).eval()
+    grads = {}
+    for mode in ("fanin", "fanout"):
+        monkeypatch.setattr(model_mod, "BWD_DX_MODE", mode)
+        model_mod._STRUCT_CACHE.clear()
+        x = x0.to(DEV).requires_grad_(True)
+        dl = [t.to(DEV) for t in flat]
+        data = pg.Data(x=x, edge_index_in=dl[0], edge_weight_in=dl[1], edge_index_out=dl[2], edge_weight_out=dl[3],
+                       edge_index_undirected_norm=dl[4], edge_weight_undirected_norm=dl[5])
+        st = model_mod.get_structure((dl[0], dl[2], dl[4]), (dl[1], dl[3], dl[5]), n)
+        assert st.shared == shared and st.by_src is not st.by_dst
+        loss = torch.nn.functional.nll_loss(model(data)[0], y.to(DEV))
+        named = [(k, p_) for k, p_ in model.named_parameters()]
+        g_ = torch.autograd.grad(loss, [x] + [p_ for _, p_ in named], allow_unused=True)
+        grads[mode] = dict(zip(["x"] + [k for k, _ in named], g_))
+    for k, ref in [("x", xr.grad)] + [(k, params[k].grad) for k, _ in named]:
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        for mode in ("fanin", "fanout"):
+            assert rel_err(grads[mode][k].cpu().numpy(), ref.numpy()) <= 1e-4, (mode, k)
+
+
 def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     """Force the tcgen05 dense transform inside the model and re-check the reference goldens
     (model_refgraph has widths 24/40/16/8 -> only the 16-wide layer qualifies; the C2-shaped oracle
@@ -789,6 +842,9 @@ def test_model_with_tensor_core_transform_matches_reference(monkeypatch):
     monkeypatch.setattr(model_mod, "TC_MODE", "force")
     model_mod._STRUCT_CACHE.clear()
     run_model_case(load("model_refgraph"), DEV, 2e-5, 1e-4)
+    for name in ("model_general_scalar", "model_cluster_batch", "model_n1_pe"):   # unsymmetric / unshared edge lists, sub-graph gates, PE
+        model_mod._STRUCT_CACHE.clear()
+        run_model_case(load(name), DEV, 5e-5, 1e-4)
     # 3 x TF32 (truncating split, lo*lo dropped) carries ~2^-21 per product: after three stacked layers
     # the worst element sits at ~2e-5 of the layer maximum -- 5x inside the 1e-4 north-star bar
     test_per_layer_embeddings_vs_oracle_c2_shape(tol=5e-5)

@@ -329,12 +329,15 @@ def test_graph_pickle_csr_sidecar_roundtrip(tmp_path, spec_native):
     assert pg.DataUtils.load_object(path).__dict__.get("_pg_sidecar") is None
 
 
-def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch):
+@pytest.mark.parametrize("fixture", ["model_refgraph", "model_general_scalar"])
+def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch, fixture):
     """The tensor-core branch of the fused layer (forward TC GEMM, weight gradient, gate gradients from the dot-product epilogue,
     input gradient through the SCALED FAN-OUT + one GEMM instead of the fan-in) wired on the executable spec: same outputs and
-    gradients as the SIMT branch, with and without residual projections, vector and scalar gates."""
+    gradients as the SIMT branch, with and without residual projections, vector and scalar gates.  model_general_scalar carries
+    three different UNSYMMETRIC edge lists (benchmarker contract): the regrouped input gradient must run over the
+    source-grouped CSRs there."""
     for use_vec in (True, False):
-        g = load("model_refgraph")
+        g = load(fixture)
         outs = {}
         for mode in ("off", "force"):
             monkeypatch.setattr(model_mod, "TC_MODE", mode)
@@ -361,3 +364,33 @@ def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch
             assert rel_err(b.numpy(), a.numpy()) <= 2e-5
         for k, v in outs["off"][3].items():
             assert rel_err(outs["force"][3][k].numpy(), v.numpy()) <= 5e-5, k
+
+
+def test_preregistered_structure_survives_cache_pressure(spec_native):
+    """a structure registered for a placeholder edge_index (CUDA-graph step, cluster sub-CSRs) rides on the
+    tensor itself: however many other graphs pass through the LRU cache in between, the layer finds it again; and a
+    placeholder WITHOUT its structure raises instead of silently training on one self-loop."""
+    g = load("model_refgraph")
+    n = int(g["num_graph_nodes"])
+    ei_real = torch.from_numpy(g["ei_in"]) if "ei_in" in g.files else _data(g).edge_index_in
+    d = _data(g)
+    st_real = model_mod.get_structure((d.edge_index_in, d.edge_index_out, d.edge_index_undirected_norm),
+                                      (d.edge_weight_in, d.edge_weight_out, d.edge_weight_undirected_norm), n)
+    csr = st_real.by_dst[0]
+    ph = torch.zeros((2, 1), dtype=torch.int64)
+    ph._pg_placeholder = True
+    vals = tuple(v.clone() for v in csr.vals)
+    model_mod.register_symmetric_structure(ph, vals, n, csr.rowptr, csr.col)
+    for i in range(model_mod.STRUCT_CACHE_ENTRIES + 8):       # cache pressure: > capacity other structures
+        e = torch.tensor([[0, i % n], [i % n, 0]], dtype=torch.int64)
+        model_mod.get_structure((e, e, e), (None, None, None), n)
+    assert len(model_mod._STRUCT_CACHE) <= model_mod.STRUCT_CACHE_ENTRIES
+    got = model_mod.get_structure((ph, ph, ph), vals, n)
+    assert got.by_dst[0].col is csr.col and got.shared
+    naked = torch.zeros((2, 1), dtype=torch.int64)
+    naked._pg_placeholder = True
+    with pytest.raises(RuntimeError):
+        model_mod.get_structure((naked, naked, naked), vals, n)
+    # same tensor, other weights: the tag does not apply (a fresh structure is built from the edge list instead)
+    other = tuple(v.clone() for v in vals)
+    assert model_mod.get_structure((ei_real, ei_real, ei_real), (None, None, None), n) is not got

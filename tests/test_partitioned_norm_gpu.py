@@ -208,10 +208,6 @@ def test_fully_partitioned_build_world1_nccl_equals_build_level_graph(world1):
         assert z.shape == (got.number_of_nodes, 12) and bool(torch.isfinite(z).all())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
-                    reason="written after this round's GPU budget was spent: the composition is covered over gloo on the kernels' "
-                           "executable spec (tests/test_multirank_gloo.py) and uses only entry points verified on the GPU, but this "
-                           "test itself has not run on a B200 yet; opt in with PGB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("n,dims", [(301, [12, 16, 8]), (6000, [64, 128, 128])])
 def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims, world1):
     """ProtGramDirectGCN on the padded row block of a one-rank NCCL group == the plain model on the same graph (forward,
@@ -244,8 +240,6 @@ def test_row_partitioned_model_world1_nccl_equals_plain_model(n, dims, world1):
             assert float((p2.grad - p.grad).abs().max()) <= 1e-4 * max(1.0, float(p.grad.abs().max())), k
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
-                    reason="CSR sidecar upload path: covered on the executable spec (tests/test_host_logic_cpu.py), not yet run on a B200")
 def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
     import protgram_directgcn_b200 as pg
     from tests.helpers import golden_edges, load
@@ -263,8 +257,6 @@ def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
     assert torch.equal(model(loaded.gcn_data(x, DEV))[1], model(graph.gcn_data(x, DEV))[1])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PGB200_RUN_UNVERIFIED") != "1",
-                    reason="column-chunked exchange of the partitioned fan-in: gloo-tested on the spec, not yet run on a B200")
 def test_partitioned_fanin_column_chunks_equal_single_exchange(world1):
     from protgram_directgcn_b200.host import partitioned as part
     n, f = 5003, 64
