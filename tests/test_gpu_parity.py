@@ -514,6 +514,29 @@ def test_c2_full_size_properties():
     assert torch.equal(lin, lin_t)  # pattern symmetric
 
 
+def test_c2_full_size_bit_exact_vs_c_oracle():
+    """BASELINE config C2 at FULL size, bit for bit: the whole 176 MB corpus goes through
+    oracle/ngram_count.c on the host (about a second per level) and the dense (n+1)-gram table, the node list and the
+    extracted edge table (src, dst, count) of the CUDA path must equal it exactly, n = 1, 2, 3."""
+    from oracle import c_oracle
+    nseq, L = 500_000, 350
+    d_buf = _device_corpus(nseq, L)
+    host = d_buf.cpu().numpy()
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    o_symbols, o_rank = c_oracle.alphabet(host)
+    assert np.array_equal(symbols, o_symbols)
+    sigma = int(symbols.size)
+    for n in (1, 2, 3):
+        ref_bins, ref_present = c_oracle.count_level(host, n, o_rank, sigma)
+        bins, short = data_builder.count_level(d_buf, n, d_rank, sigma)
+        assert np.array_equal(bins.cpu().numpy().astype(np.uint64), ref_bins), n
+        node_code, src, dst, cnt = data_builder.extract_level(bins, short, n, sigma)
+        assert np.array_equal(node_code.cpu().numpy(), np.nonzero(ref_present)[0]), n
+        _, r_src, r_dst, r_cnt = c_oracle.bins_to_graph(ref_bins, ref_present, symbols, n)
+        assert np.array_equal(src.cpu().numpy(), r_src) and np.array_equal(dst.cpu().numpy(), r_dst), n
+        assert np.array_equal(cnt.cpu().numpy().astype(np.int64), r_cnt), n
+
+
 # ------------------------------------------------------------------------------- model
 @pytest.mark.parametrize("name", MODEL_FIXTURES)
 def test_model_matches_reference_gpu(name):
