@@ -292,13 +292,33 @@ int pg_spmm_fanout(const int64_t *d_rowptr, const int32_t *d_col, const float *d
                    const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
                    const pg_spmm_plan *plan, pg_stream_t stream);
 /* Same with per-SOURCE-row scales: Z_v[i] = sum_j val_v[i,j] * s_v[j] * X[j] (d_s0 NULL = unscaled; scale_stride 1 = one
- * scale per row, 0 = a scalar).  The layer's backward uses it with X = dY and s_v = gate_v on the symmetric structure:
+ * scale per row, 0 = a scalar, k > 1 = one scale every k floats, e.g. gate triples kept as rows of 4).  The layer's backward uses it with X = dY and s_v = gate_v on the symmetric structure:
  * dX = sum_v (A_v (g_v * dY)) W_v^T gathers F_out-wide rows once instead of the 3 F_in-wide gated gradient. */
 int pg_spmm_fanout_scaled(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0,
                           const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
                           const float *d_x, int64_t ldx, float *d_z, int64_t ldz, int64_t z_off,
                           const float *d_s0, const float *d_s1, const float *d_s2, int scale_stride,
                           const pg_spmm_plan *plan, pg_stream_t stream);
+
+/* The gathered matrix of a ROW-PARTITIONED graph: rows below `split` are read from `lo` (row stride ld_lo), the others from
+ * `hi` (numbered from `split`, row stride ld_hi) -- the rank's own rows stay where they are, the halo rows it references
+ * arrive in a compact second buffer (host/partitioned.py: HaloExchange) and the block's columns are renumbered once into
+ * [own rows | halo rows].  hi = NULL: everything from `lo`. */
+typedef struct pg_spmm_operand {
+    const float *lo;
+    int64_t ld_lo;
+    const float *hi;
+    int64_t ld_hi;
+    int64_t split;
+} pg_spmm_operand;
+/* pg_spmm_fanout_scaled on a split operand; `z_vstride` = distance between the nv output segments (F for the plain calls;
+ * the full feature width when a call handles one COLUMN CHUNK of the features -- pass x->lo / d_z advanced to the chunk,
+ * F = chunk width: the exchange of chunk k+1 then overlaps the SpMM of chunk k, and each output element is still summed
+ * in CSR order). */
+int pg_spmm_fanout_split(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
+                         const float *d_val2, int nv, int64_t num_rows, int F, const pg_spmm_operand *x, float *d_z,
+                         int64_t ldz, int64_t z_off, int64_t z_vstride, const float *d_s0, const float *d_s1,
+                         const float *d_s2, int scale_stride, const pg_spmm_plan *plan, pg_stream_t stream);
 
 /* Fan-in SpMM (backward of the above over the transposed structure; forward of nothing else):
  *     Y[i, :] = (d_init ? init[i, :] : 0) + sum_v sum_k val_v[k] * G[col[k], g_off + v*F : +F]
@@ -308,6 +328,17 @@ int pg_spmm_fanin(const int64_t *d_rowptr, const int32_t *d_col, const float *d_
                   const float *d_val1, const float *d_val2, int nv, int64_t num_rows, int F,
                   const float *d_g, int64_t ldg, int64_t g_off, const float *d_init, int64_t ldinit,
                   float *d_y, int64_t ldy, int accumulate, const pg_spmm_plan *plan, pg_stream_t stream);
+
+/* pg_spmm_fanin on a split operand; the nv gradient segments of a row start at g_off + v * g_vstride. */
+int pg_spmm_fanin_split(const int64_t *d_rowptr, const int32_t *d_col, const float *d_val0, const float *d_val1,
+                        const float *d_val2, int nv, int64_t num_rows, int F, const pg_spmm_operand *g, int64_t g_off,
+                        int64_t g_vstride, const float *d_init, int64_t ldinit, float *d_y, int64_t ldy, int accumulate,
+                        const pg_spmm_plan *plan, pg_stream_t stream);
+
+/* Pack step of the halo exchange of a row-partitioned graph: d_dst[i, 0:w] = d_src[d_idx[i], 0:w] -- the rows of this rank
+ * that a peer's block references, in the order the peer asked for them (one call per feature-column chunk). */
+int pg_gather_rows(const float *d_src, int64_t ld_src, const int64_t *d_idx, int64_t count, int w, float *d_dst,
+                   int64_t ld_dst, pg_stream_t stream);
 
 /* Fused dense transform of one DirectGCN layer (the collapsed algebra of SURVEY.md 7.2):
  *   A_ext[i, :] = [ a_i*Z_in[i] | b_i*Z_out[i] | c_i*Z_und[i] | X[i] (if has_res) | a_i b_i c_i | 1 (if has_res) ]

@@ -73,6 +73,11 @@ _SIGS = {
     "pg_spmm_fanout": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P, _P]),
     "pg_spmm_fanout_scaled": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
                                       _P, _P]),
+    "pg_spmm_fanout_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int,
+                                     _P, _P]),
+    "pg_spmm_fanin_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, c_int,
+                                    _P, _P]),
+    "pg_gather_rows": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, _P]),
     "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
                               c_int64, c_int, _P, _P]),
     "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
@@ -129,6 +134,20 @@ def layer_params(**tensors):
     return ctypes.byref(st), (st, tensors)
 
 
+class SpmmOperandStruct(ctypes.Structure):
+    """Mirror of `pg_spmm_operand` (include/pgb200.h)."""
+    _fields_ = [("lo", _P), ("ld_lo", c_int64), ("hi", _P), ("ld_hi", c_int64), ("split", c_int64)]
+
+
+def spmm_operand(lo: torch.Tensor, hi: Optional[torch.Tensor], split: int):
+    """-> by-reference `pg_spmm_operand`: rows < split from `lo`, the others from `hi` (2-D fp32 views; their strides and
+    storage offsets are honoured, so a column chunk is just `t[:, c0:c0 + w]`)."""
+    st = SpmmOperandStruct(ptr(lo), lo.stride(0), ptr(hi) if hi is not None and hi.numel() else None,
+                           hi.stride(0) if hi is not None and hi.numel() else 0, int(split))
+    st._keep = (lo, hi)
+    return ctypes.byref(st)
+
+
 class SpmmPlanStruct(ctypes.Structure):
     """Mirror of `pg_spmm_plan` (include/pgb200.h)."""
     _fields_ = [("chunk", ctypes.c_int32), ("n_long", c_int64), ("n_items", c_int64), ("d_long_rows", _P),
@@ -140,9 +159,10 @@ class SpmmPlan:
     Keeps its device arrays alive; `.ref(width)` returns the pointer to pass as `plan` (None if the
     structure has no long rows)."""
 
-    CHUNK = 512
+    CHUNK = int(os.environ.get("PGB200_SPMM_CHUNK", "512"))
 
-    def __init__(self, rowptr: torch.Tensor, chunk: int = CHUNK):
+    def __init__(self, rowptr: torch.Tensor, chunk: Optional[int] = None):
+        chunk = self.CHUNK if chunk is None else chunk
         deg = rowptr[1:] - rowptr[:-1]
         long_rows = torch.nonzero(deg > chunk).flatten()
         self.chunk = int(chunk)

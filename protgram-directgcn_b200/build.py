@@ -20,6 +20,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
          "-I", os.path.join(HERE, "csrc")]
 
 
+EXTRA = os.environ.get("PGB200_NVCC_FLAGS", "").split()    # e.g. -DPG_SPMM_MIN_BLOCKS=5 for A/B builds
+
+
 def sources():
     return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
 
@@ -35,7 +38,7 @@ def stale() -> bool:
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + sources()
+    cmd = [NVCC] + FLAGS + EXTRA + ["-o", LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

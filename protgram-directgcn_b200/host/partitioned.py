@@ -5,22 +5,34 @@
 
 
 SURVEY.md 8(e): the propagation path shards by rows with ONE exchange step per SpMM.  Rank r owns
-the node rows [lo_r, hi_r) of the shared pattern (global int32 columns) and the matching slice of
-X; W and the other parameters are replicated (the dense transform and its epilogue are row-local).
+the node rows [lo_r, hi_r) of the shared pattern and the matching slice of X; W and the other
+parameters are replicated (the dense transform and its epilogue are row-local).
 
-    forward   X_full = all_gather(X_local)            Z_local = fan-out SpMM(rows of r, X_full)
-    backward  symmetric matrices (reference-built graphs):
-                  G_full = all_gather(dZ_local)       dX_local = fan-in SpMM(rows of r, G_full)
-              general matrices:
-                  dX_part[N, F] = fan-in over the transposed local block, then reduce-scatter
+The exchange is a HALO exchange (north star: "all-gather of boundary features"): a rank's block only
+references a subset of the remote rows -- on the randomly relabelled power-law graphs of config C5
+about 30 % of them at 8 ranks (low-degree nodes are rarely anybody's neighbour), measured by
+`HaloExchange.stats()` -- so each rank asks every peer ONCE, at structure-build time, for the sorted list
+of rows it needs; per SpMM every rank packs the rows its peers asked for (`pg_gather_rows`) and one
+`all_to_all_single` with those split sizes moves them over NVLink.  The block's columns are renumbered
+once into [own rows | halo rows grouped by owner], the kernels read the two buffers through a split
+operand (`pg_spmm_operand`), and the entries of a row keep their CSR order, so a block's result is
+bitwise equal to the same rows of the single-GPU SpMM.
 
-The exchange is an NCCL all-gather of fp32 rows over NVLink (N*F*4*(g-1)/g bytes received per GPU);
-power-law graphs touch almost every remote row, so gathering whole blocks beats per-row peer loads
-(B200 peer LDG latency is ~3.5x local DRAM).  Rows are padded to ceil(N/g) so the collective is a
-single all_gather_into_tensor.
+The exchange is pipelined against the SpMM over FEATURE-COLUMN chunks: chunk k+1's rows are in flight
+on NCCL's stream while the kernel works on chunk k's columns (every output element is still summed in
+CSR order; the index arrays are re-read once per chunk: 16 B against >= 128 B of gathered features).
+
+    forward   H_x = halo(X_local)                   Z_local = fan-out SpMM(rows of r, [X_local | H_x])
+    backward  layer (symmetric matrices): dX = sum_v (A_v diag(g_v) dY) W_v^T -- the SAME exchange on the
+              F_out-wide dY plus the three gate values per halo row (`PartitionedStructure.fanout(scales=...)`),
+              never the 3F-wide gated gradient;
+              bare operator Z = fan-out(X) given dZ:  halo(dZ_local) [3F wide] + local fan-in  (symmetric)
+                                                      fan-in over the transposed block + reduce-scatter (general)
+PGB200_EXCHANGE=allgather restores the round-1 exchange (all_gather_into_tensor of every row) for A/B timing.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -62,6 +74,11 @@ def _reduce_scatter_rows(full: torch.Tensor, per: int, group) -> torch.Tensor:
     return full[rank * per:(rank + 1) * per].clone()
 
 
+EXCHANGE_MODE = os.environ.get("PGB200_EXCHANGE", "halo")          # "halo" | "allgather"
+PIPELINE_CHUNKS = int(os.environ.get("PGB200_EXCHANGE_CHUNKS", "2"))  # feature-column chunks the exchange is pipelined over
+PIPELINE_MIN_BYTES = 8 << 20                                         # below this a single exchange is cheaper than several
+
+
 def _spmm_fanout(csr: _Csr, x_full: torch.Tensor, rows: int, f: int) -> torch.Tensor:
     nv = len(csr.vals)
     z = torch.empty((rows, nv * f), dtype=torch.float32, device=x_full.device)
@@ -80,62 +97,156 @@ def _spmm_fanin(csr: _Csr, g_full: torch.Tensor, rows: int, f: int) -> torch.Ten
     return y
 
 
-MAX_EXCHANGE_BYTES = 16 << 30   # all-gathered operand of one backward call; wider gradients go through in column chunks
+def halo_plan(col: torch.Tensor, lo: int, per: int, world: int):
+    """Pure part of the halo exchange: from the (global, int32) columns of the block whose own rows are [lo, lo + per)
+    -> (need: sorted global ids of the referenced remote rows = grouped by owner, need_counts[world], col_ext: the same
+    entries renumbered into [own rows 0..per) | halo rows per.. in `need` order])."""
+    c = col.to(torch.int64)
+    own = (c >= lo) & (c < lo + per)
+    need = torch.unique(c[~own])
+    need_counts = torch.bincount(torch.div(need, max(per, 1), rounding_mode="floor"), minlength=world)[:world]
+    ext = torch.where(own, c - lo, per + torch.searchsorted(need, c))
+    return need, need_counts, ext.to(torch.int32).contiguous()
 
 
-def _fanin_exchanged(csr: _Csr, dz_local: torch.Tensor, per: int, f: int, init: Optional[torch.Tensor], group,
-                     limit: Optional[int] = None) -> torch.Tensor:
-    """dX_local = (init) + sum_v A_v[rows of this rank] dZ_v for symmetric matrices: all-gather of dZ + local fan-in.
-    dZ is [N, 3F]: at C5's size (50 M nodes, F = 128) that is 77 GB, so beyond `limit` bytes the F columns are cut into
-    chunks -- every chunk gathers its three column blocks [per, 3 fc] and the kernel writes the matching fc columns of dX."""
-    world = dist.get_world_size(group)
-    limit = MAX_EXCHANGE_BYTES if limit is None else int(limit)
+class HaloExchange:
+    """Which remote rows this rank's block references, which of its own rows the peers reference, and the block's columns
+    renumbered into [own rows (per) | halo rows (sorted by global id, i.e. grouped by owner)].  Built once per structure:
+    two small all-to-alls (counts, row ids).  `exchange(t)` then moves the referenced rows of a [per, w] matrix."""
+
+    def __init__(self, col: torch.Tensor, n: int, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = int(n)
+        self.lo, self.hi_row, self.per = row_range(n, self.rank, self.world)
+        dev = col.device
+        lo, per = self.lo, self.per
+        need, need_counts, self.col_ext = halo_plan(col, lo, per, self.world)
+        self.num_halo = int(need.numel())
+        serve_counts = torch.empty_like(need_counts)
+        dist.all_to_all_single(serve_counts, need_counts, group=self.group)
+        self.need_splits = [int(v) for v in need_counts.tolist()]
+        self.serve_splits = [int(v) for v in serve_counts.tolist()]
+        serve = torch.empty(sum(self.serve_splits), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(serve, need, output_split_sizes=self.serve_splits, input_split_sizes=self.need_splits, group=self.group)
+        self.serve_idx = (serve - lo).contiguous()                       # local row numbers, grouped by requesting peer
+        self.num_serve = int(serve.numel())
+        if self.num_serve and (int(self.serve_idx.min()) < 0 or int(self.serve_idx.max()) >= per):
+            raise ValueError("halo exchange: a peer asked for a row outside this rank's block")
+        self.need = need
+
+    def stats(self) -> dict:
+        remote = max(1, self.n - (self.hi_row - self.lo))
+        return {"halo_rows": self.num_halo, "remote_rows": remote, "halo_fraction_of_remote_rows": self.num_halo / remote,
+                "rows_served_to_peers": self.num_serve}
+
+    def start(self, t: torch.Tensor, async_op: bool = True):
+        """t: [per, w] fp32 (any row stride).  Packs the rows the peers asked for and posts the all-to-all.
+        -> (halo buffer [num_halo, w], work handle or None, keep-alive)."""
+        w = int(t.shape[1])
+        send = torch.empty((self.num_serve, w), dtype=torch.float32, device=t.device)
+        if self.num_serve:
+            nat.call("pg_gather_rows", nat.ptr(t), t.stride(0), nat.ptr(self.serve_idx), self.num_serve, w, nat.ptr(send), w, nat.stream_ptr())
+        recv = torch.empty((self.num_halo, w), dtype=torch.float32, device=t.device)
+        work = dist.all_to_all_single(recv, send, output_split_sizes=self.need_splits, input_split_sizes=self.serve_splits,
+                                      group=self.group, async_op=async_op)
+        return recv, (work if async_op else None), send
+
+    def exchange(self, t: torch.Tensor) -> torch.Tensor:
+        recv, _, _ = self.start(t, async_op=False)
+        return recv
+
+
+def _feature_chunks(f: int, per: int, world: int) -> List[Tuple[int, int]]:
+    """(first column, width) of the feature-column chunks one exchange + SpMM is pipelined over (widths are multiples of 4:
+    the kernels' 128-bit path)."""
+    k = PIPELINE_CHUNKS if (world > 1 and f % 4 == 0 and per * f * 4 >= PIPELINE_MIN_BYTES) else 1
+    k = max(1, min(k, f // 4))
+    w = -(-(f // 4) // k) * 4
+    return [(c0, min(w, f - c0)) for c0 in range(0, f, w)]
+
+
+def _halo_fanout(csr_ext: _Csr, halo: HaloExchange, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
+    """Z[per, nv f] = fan-out SpMM of this rank's rows over [x | halo rows of x], exchange pipelined over column chunks.
+    scales (backward of the gated layer): per-source-row gates; with scale_stride == 1 their halo values travel as one
+    extra 4-float chunk."""
+    per, nv = halo.per, len(csr_ext.vals)
+    x = x.contiguous()
+    z = torch.empty((per, nv * f), dtype=torch.float32, device=x.device)
+    v = csr_ext.vals + [None] * (3 - nv)
+    s_ptrs, s_stride, s_work, s_keep = (None, None, None), 0, None, None
+    if scales is not None:
+        if scale_stride == 1:
+            mine = torch.zeros((per, 4), dtype=torch.float32, device=x.device)
+            for k, sc in enumerate(scales):
+                mine[:, k] = sc.reshape(-1)
+            s_halo, s_work, s_keep = halo.start(mine)
+        else:
+            s_ptrs, s_stride = tuple(nat.ptr(sc) for sc in scales), 0
+    chunks = _feature_chunks(f, per, halo.world)
+    posted = [halo.start(x[:, c0:c0 + w]) for c0, w in chunks]       # all packs + exchanges are queued up front
+    if s_work is not None:
+        s_work.wait()
+    if scales is not None and scale_stride == 1:
+        s_ext = torch.cat([mine, s_halo], dim=0).reshape(-1)           # [(per + H) * 4]: gates of own rows, then of the halo rows
+        s_ptrs, s_stride = tuple(nat.ptr(s_ext[k:]) for k in range(3)), 4
+    for (c0, w), (recv, work, _keep) in zip(chunks, posted):
+        if work is not None:
+            work.wait()                                               # the compute stream waits for THIS chunk only
+        nat.call("pg_spmm_fanout_split", nat.ptr(csr_ext.rowptr), nat.ptr(csr_ext.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv,
+                 per, w, nat.spmm_operand(x[:, c0:c0 + w], recv, per), nat.ptr(z[:, c0:]), z.stride(0), 0, f,
+                 s_ptrs[0], s_ptrs[1] if nv == 3 else None, s_ptrs[2] if nv == 3 else None, s_stride, csr_ext.plan(3 * f), nat.stream_ptr())
+    return z
+
+
+def _halo_fanin(csr_ext: _Csr, halo: HaloExchange, dz: torch.Tensor, f: int, init: Optional[torch.Tensor]) -> torch.Tensor:
+    """dX[per, f] = (init) + sum_v A_v[rows of this rank] dZ_v for symmetric matrices: halo rows of dZ (nv f wide) + local fan-in."""
+    per, nv = halo.per, len(csr_ext.vals)
+    dz = dz.contiguous()
+    recv = halo.exchange(dz)
+    dx = torch.empty((per, f), dtype=torch.float32, device=dz.device)
+    v = csr_ext.vals + [None] * (3 - nv)
+    nat.call("pg_spmm_fanin_split", nat.ptr(csr_ext.rowptr), nat.ptr(csr_ext.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, f,
+             nat.spmm_operand(dz, recv, per), 0, f, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
+             csr_ext.plan(3 * f), nat.stream_ptr())
+    return dx
+
+
+def _fanin_exchanged(csr: _Csr, dz_local: torch.Tensor, per: int, f: int, init: Optional[torch.Tensor], group) -> torch.Tensor:
+    """Round-1 exchange (PGB200_EXCHANGE=allgather): all-gather of dZ [N, 3F] + local fan-in over global columns."""
     nv = len(csr.vals)
-    full_bytes = world * per * nv * f * 4
-    if full_bytes <= limit or f <= 4:
-        g_full = _all_gather_rows(dz_local.contiguous(), group)
-        dx = torch.empty((per, f), dtype=torch.float32, device=dz_local.device)
-        v = csr.vals + [None] * (3 - nv)
-        nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, f,
-                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
-                 csr.plan(3 * f), nat.stream_ptr())
-        return dx
-    chunks = -(-full_bytes // limit)
-    fc = max(4, (-(-f // chunks) + 3) // 4 * 4)                  # multiple of 4 floats: the kernels' 128-bit path
+    g_full = _all_gather_rows(dz_local.contiguous(), group)
     dx = torch.empty((per, f), dtype=torch.float32, device=dz_local.device)
     v = csr.vals + [None] * (3 - nv)
-    for c0 in range(0, f, fc):
-        w = min(fc, f - c0)
-        part = torch.cat([dz_local[:, k * f + c0: k * f + c0 + w] for k in range(nv)], dim=1).contiguous()    # [per, nv * w]
-        g_full = _all_gather_rows(part, group)
-        init_c = init[:, c0:] if init is not None else None
-        nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, w,
-                 nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init_c), init.stride(0) if init is not None else 0, nat.ptr(dx[:, c0:]),
-                 dx.stride(0), 0, csr.plan(3 * f), nat.stream_ptr())
-        del g_full
+    nat.call("pg_spmm_fanin", nat.ptr(csr.rowptr), nat.ptr(csr.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv, per, f,
+             nat.ptr(g_full), g_full.stride(0), 0, nat.ptr(init), init.stride(0) if init is not None else 0, nat.ptr(dx), dx.stride(0), 0,
+             csr.plan(3 * f), nat.stream_ptr())
     return dx
 
 
 class _PartitionedFanout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, local_csr, local_csr_t, per, n_total, symmetric, group):
+    def forward(ctx, x_local, prop):
         nat.check_tensor(x_local, "x_local")
         f = x_local.shape[1]
-        x_full = _all_gather_rows(x_local.float(), group)
-        ctx.meta = (local_csr, local_csr_t, per, n_total, symmetric, group, f)
-        return _spmm_fanout(local_csr, x_full, per, f)
+        ctx.prop, ctx.f = prop, f
+        x_local = x_local.float()
+        if prop.halo is not None:
+            return _halo_fanout(prop.local_ext, prop.halo, x_local, f)
+        return _spmm_fanout(prop.local, _all_gather_rows(x_local, prop.group), prop.per, f)
 
     @staticmethod
     def backward(ctx, dz_local):
-        local_csr, local_csr_t, per, n_total, symmetric, group, f = ctx.meta
+        prop, f = ctx.prop, ctx.f
         dz_local = dz_local.contiguous().float()
-        if symmetric:
-            dx = _fanin_exchanged(local_csr, dz_local, per, f, None, group)
+        if prop.symmetric and prop.halo is not None:
+            dx = _halo_fanin(prop.local_ext, prop.halo, dz_local, f, None)
+        elif prop.symmetric:
+            dx = _fanin_exchanged(prop.local, dz_local, prop.per, f, None, prop.group)
         else:
-            world = dist.get_world_size(group)
-            part = _spmm_fanin(local_csr_t, dz_local, world * per, f)  # rows = global sources, cols = local targets
-            dx = _reduce_scatter_rows(part, per, group)
-        return dx, None, None, None, None, None, None
+            part = _spmm_fanin(prop.transposed, dz_local, prop.world * prop.per, f)  # rows = global sources, cols = local targets
+            dx = _reduce_scatter_rows(part, prop.per, prop.group)
+        return dx, None
 
 
 class RowPartitionedPropagation:
@@ -146,32 +257,11 @@ class RowPartitionedPropagation:
     `transposed` = the CSR grouped by source of the same local block (rows = global ids)."""
 
     def __init__(self, rowptr, col, vals, n: int, group=None, symmetric: bool = True, transposed: Optional[_Csr] = None):
-        self.group = group if group is not None else dist.group.WORLD
-        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        self.n = n
-        self.lo, self.hi, self.per = row_range(n, self.rank, self.world)
-        self.local = slice_rows(rowptr, col, list(vals), self.lo, self.hi, self.per)
-        self.symmetric = symmetric
-        self.transposed = transposed
-        if not symmetric and transposed is None:
-            raise ValueError("general (non-symmetric) matrices need the source-grouped CSR of the local block")
+        group = group if group is not None else dist.group.WORLD
+        lo, hi, per = row_range(n, dist.get_rank(group), dist.get_world_size(group))
+        self._init(slice_rows(rowptr, col, list(vals), lo, hi, per), n, group, symmetric, transposed)
 
-    def pad_rows(self, x_local: torch.Tensor) -> torch.Tensor:
-        if x_local.shape[0] == self.per:
-            return x_local
-        pad = torch.zeros((self.per - x_local.shape[0], x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
-        return torch.cat([x_local, pad], dim=0)
-
-    def __call__(self, x_local: torch.Tensor) -> torch.Tensor:
-        """x_local: [hi-lo (or per), F] -> z_local [per, nv*F] (rows beyond hi-lo are zero)."""
-        return _PartitionedFanout.apply(self.pad_rows(x_local), self.local, self.transposed, self.per, self.n,
-                                        self.symmetric, self.group)
-
-    @classmethod
-    def from_local(cls, local: _Csr, n: int, group=None, symmetric: bool = True, transposed: Optional[_Csr] = None):
-        """From a row block that already lives on this rank (`normalize_row_partitioned`): rowptr has
-        `per` + 1 entries (rows past the block are empty), columns are global."""
-        self = cls.__new__(cls)
+    def _init(self, local: _Csr, n: int, group, symmetric: bool, transposed: Optional[_Csr]):
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.n = n
@@ -181,6 +271,28 @@ class RowPartitionedPropagation:
         self.local, self.symmetric, self.transposed = local, symmetric, transposed
         if not symmetric and transposed is None:
             raise ValueError("general (non-symmetric) matrices need the source-grouped CSR of the local block")
+        self.halo = self.local_ext = None
+        if EXCHANGE_MODE == "halo":
+            self.halo = HaloExchange(local.col, n, self.group)
+            self.local_ext = _Csr(local.rowptr, self.halo.col_ext, local.vals)
+            self.local_ext._plan = local._plan
+
+    def pad_rows(self, x_local: torch.Tensor) -> torch.Tensor:
+        if x_local.shape[0] == self.per:
+            return x_local
+        pad = torch.zeros((self.per - x_local.shape[0], x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
+        return torch.cat([x_local, pad], dim=0)
+
+    def __call__(self, x_local: torch.Tensor) -> torch.Tensor:
+        """x_local: [hi-lo (or per), F] -> z_local [per, nv*F] (rows beyond hi-lo are zero)."""
+        return _PartitionedFanout.apply(self.pad_rows(x_local), self)
+
+    @classmethod
+    def from_local(cls, local: _Csr, n: int, group=None, symmetric: bool = True, transposed: Optional[_Csr] = None):
+        """From a row block that already lives on this rank (`normalize_row_partitioned`): rowptr has
+        `per` + 1 entries (rows past the block are empty), columns are global."""
+        self = cls.__new__(cls)
+        self._init(local, n, group, symmetric, transposed)
         return self
 
 
@@ -365,6 +477,10 @@ class PartitionedStructure:
         self.local = local
         self.by_dst = self.by_src = [local]
         self.nnz_total = 3 * int(local.col.numel())
+        self.halo = self.local_ext = None
+        if EXCHANGE_MODE == "halo":
+            self.halo = HaloExchange(local.col, n, self.group)
+            self.local_ext = _Csr(local.rowptr, self.halo.col_ext, local.vals)
 
     def _check(self, t: torch.Tensor):
         if t.shape[0] != self.per:
@@ -372,6 +488,8 @@ class PartitionedStructure:
 
     def fanout(self, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
         self._check(x)
+        if self.halo is not None:
+            return _halo_fanout(self.local_ext, self.halo, x, f, scales, scale_stride)
         x_full = _all_gather_rows(x.contiguous(), self.group)
         c, per = self.local, self.per
         z = torch.empty((per, 3 * f), dtype=torch.float32, device=x.device)
@@ -394,6 +512,8 @@ class PartitionedStructure:
 
     def fanin(self, dz: torch.Tensor, f: int, init: Optional[torch.Tensor]) -> torch.Tensor:
         self._check(dz)
+        if self.halo is not None:
+            return _halo_fanin(self.local_ext, self.halo, dz, f, init)
         return _fanin_exchanged(self.local, dz.contiguous(), self.per, f, init, self.group)
 
 

@@ -346,8 +346,50 @@ def pg_spmm_fanout_scaled(rowptr, col, v0, v1, v2, nv, num_rows, F, x, ldx, z, l
     for v, (val, sc) in enumerate(list(zip((v0, v1, v2), (s0, s1, s2)))[:nv]):
         wv = val.to(x.dtype)
         if sc is not None:
-            wv = wv * (sc.reshape(-1)[col.long()] if scale_stride == 1 else sc.reshape(-1)[0])
+            wv = wv * (sc.reshape(-1)[col.long() * scale_stride] if scale_stride >= 1 else sc.reshape(-1)[0])
         z[:, z_off + v * F: z_off + (v + 1) * F] = torch.zeros(num_rows, F, dtype=x.dtype).index_add_(0, rows, wv.view(-1, 1) * xg)
+
+
+def _operand_rows(op, col, width):
+    """rows col[k] of a split operand (rows < split from lo, the others from hi), first `width` columns."""
+    idx = col.long()
+    lo = op.lo[:, :width]
+    if op.hi is None or op.hi.numel() == 0:
+        return lo[idx]
+    own = idx < op.split
+    out = torch.empty((idx.numel(), width), dtype=lo.dtype)
+    out[own] = lo[idx[own]]
+    out[~own] = op.hi[:, :width][idx[~own] - op.split]
+    return out
+
+
+def pg_spmm_fanout_split(rowptr, col, v0, v1, v2, nv, num_rows, F, x, z, ldz, z_off, z_vstride, s0, s1, s2, scale_stride,
+                         plan=None, stream=None):
+    rows = _rows_of(rowptr, num_rows)
+    xg = _operand_rows(x, col, F)
+    for v, (val, sc) in enumerate(list(zip((v0, v1, v2), (s0, s1, s2)))[:nv]):
+        wv = val.to(xg.dtype)
+        if sc is not None:
+            wv = wv * (sc.reshape(-1)[col.long() * scale_stride] if scale_stride >= 1 else sc.reshape(-1)[0])
+        z[:, z_off + v * z_vstride: z_off + v * z_vstride + F] = torch.zeros(num_rows, F, dtype=xg.dtype).index_add_(0, rows, wv.view(-1, 1) * xg)
+
+
+def pg_spmm_fanin_split(rowptr, col, v0, v1, v2, nv, num_rows, F, g, g_off, g_vstride, init, ldinit, y, ldy, accumulate, plan=None,
+                        stream=None):
+    rows = _rows_of(rowptr, num_rows)
+    gg = _operand_rows(g, col, g_off + (nv - 1) * g_vstride + F)
+    acc = torch.zeros(num_rows, F, dtype=gg.dtype)
+    if init is not None:
+        acc += init[:, :F]
+    if accumulate:
+        acc += y[:, :F]
+    for v, val in enumerate((v0, v1, v2)[:nv]):
+        acc.index_add_(0, rows, val.to(gg.dtype).view(-1, 1) * gg[:, g_off + v * g_vstride: g_off + v * g_vstride + F])
+    y[:, :F] = acc
+
+
+def pg_gather_rows(src, ld_src, idx, count, w, dst, ld_dst, stream=None):
+    dst[:count, :w] = src[idx[:count].long(), :w]
 
 
 def pg_spmm_fanin(rowptr, col, v0, v1, v2, nv, num_rows, F, g, ldg, g_off, init, ldinit, y, ldy, accumulate, plan=None,
@@ -583,6 +625,7 @@ def install(monkeypatch, nat):
     monkeypatch.setattr(nat, "ptr", lambda t: t)
     import types
     monkeypatch.setattr(nat, "layer_params", lambda **t: (types.SimpleNamespace(**{k: t.get(k) for k in nat.LAYER_PARAM_FIELDS}), None))
+    monkeypatch.setattr(nat, "spmm_operand", lambda lo, hi, split: types.SimpleNamespace(lo=lo, hi=hi, split=int(split)))
     monkeypatch.setattr(nat, "stream_ptr", lambda: None)
     monkeypatch.setattr(nat, "require_cuda", lambda: None)
     monkeypatch.setattr(nat, "check_tensor", lambda t, what="input": None)

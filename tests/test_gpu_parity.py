@@ -102,6 +102,60 @@ def test_spmm_fanout_fanin_vs_spec(F, nv, chunk):
     assert torch.equal(z, z2)
 
 
+@pytest.mark.parametrize("F,w", [(128, 32), (64, 64), (256, 128), (24, 8), (10, 10)])
+@pytest.mark.parametrize("nv", [1, 3])
+def test_spmm_split_operand_and_column_chunks_bitwise(F, w, nv):
+    """pg_spmm_fanout_split / pg_spmm_fanin_split (row-partitioned graphs): the gathered matrix cut into [own rows | halo
+    rows] with renumbered columns, the features processed in column chunks of width w, per-source gates stored as rows of
+    4 -- every variant must equal the plain call on the whole matrix BIT FOR BIT (same CSR order per output element),
+    also through the long-row split."""
+    rng = np.random.default_rng(F + w + nv)
+    n, split = 1500, 600
+    rowptr, col, vals = _random_csr(rng, n, n, 11, skew=True)
+    d = lambda t: t.to(DEV)
+    rp, cl, vs = d(rowptr), d(col), [d(v) for v in vals]
+    x = torch.randn(n, F, device=DEV)
+    g = torch.randn(n, 3 * F, device=DEV)
+    init = torch.randn(n, F, device=DEV)
+    gates = torch.rand(n, 4, device=DEV) + 0.5
+    st = nat.stream_ptr()
+    plan = nat.SpmmPlan(rp, chunk=96)
+    vp = [nat.ptr(vs[0]), nat.ptr(vs[1]) if nv == 3 else None, nat.ptr(vs[2]) if nv == 3 else None]
+    z_ref, zs_ref = torch.zeros(n, nv * F, device=DEV), torch.zeros(n, nv * F, device=DEV)
+    y_ref = torch.empty(n, F, device=DEV)
+    s_cols = [gates[:, k].contiguous() for k in range(3)]
+    nat.call("pg_spmm_fanout", nat.ptr(rp), nat.ptr(cl), *vp, nv, n, F, nat.ptr(x), F, nat.ptr(z_ref), nv * F, 0, plan.ref(3 * F), st)
+    nat.call("pg_spmm_fanout_scaled", nat.ptr(rp), nat.ptr(cl), *vp, nv, n, F, nat.ptr(x), F, nat.ptr(zs_ref), nv * F, 0,
+             nat.ptr(s_cols[0]), nat.ptr(s_cols[1]) if nv == 3 else None, nat.ptr(s_cols[2]) if nv == 3 else None, 1, plan.ref(3 * F), st)
+    nat.call("pg_spmm_fanin", nat.ptr(rp), nat.ptr(cl), *vp, nv, n, F, nat.ptr(g), 3 * F, 0, nat.ptr(init), F, nat.ptr(y_ref), F, 0,
+             plan.ref(3 * F), st)
+    # own rows = [0, split) stay in place, the "halo" rows [split, n) live in a second buffer in PERMUTED order; columns renumbered
+    perm = torch.randperm(n - split, device=DEV)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n - split, device=DEV)
+    cl_ext = torch.where(cl.long() < split, cl.long(), split + inv[(cl.long() - split).clamp_min(0)]).to(torch.int32)
+    x_hi_full, g_hi = x[split:][perm].contiguous(), g[split:][perm].contiguous()
+    gates_ext = torch.cat([gates[:split], gates[split:][perm]]).reshape(-1)
+    z, zs = torch.zeros(n, nv * F, device=DEV), torch.zeros(n, nv * F, device=DEV)
+    for c0 in range(0, F, w):
+        cw = min(w, F - c0)
+        x_hi = x_hi_full[:, c0:c0 + cw].contiguous()                   # a halo buffer holds one chunk, row stride = chunk width
+        for out, sp, stride in ((z, (None, None, None), 0), (zs, tuple(nat.ptr(gates_ext[k:]) for k in range(3)), 4)):
+            nat.call("pg_spmm_fanout_split", nat.ptr(rp), nat.ptr(cl_ext), *vp, nv, n, cw, nat.spmm_operand(x[:, c0:c0 + cw], x_hi, split),
+                     nat.ptr(out[:, c0:]), nv * F, 0, F, sp[0], sp[1] if nv == 3 else None, sp[2] if nv == 3 else None, stride,
+                     plan.ref(3 * F), st)
+    assert torch.equal(z, z_ref) and torch.equal(zs, zs_ref)
+    y = torch.empty(n, F, device=DEV)
+    nat.call("pg_spmm_fanin_split", nat.ptr(rp), nat.ptr(cl_ext), *vp, nv, n, F, nat.spmm_operand(g, g_hi, split), 0, F, nat.ptr(init), F,
+             nat.ptr(y), F, 0, plan.ref(3 * F), st)
+    assert torch.equal(y, y_ref)
+    # pack step of the exchange
+    idx = torch.randint(0, n, (777,), device=DEV)
+    out = torch.empty(777, w, device=DEV)
+    nat.call("pg_gather_rows", nat.ptr(x), F, nat.ptr(idx), 777, min(w, F), nat.ptr(out), w, st)
+    assert torch.equal(out[:, :min(w, F)], x[idx, :min(w, F)])
+
+
 @pytest.mark.parametrize("n,f_in,f_out,has_res,vec_gate", [(1000, 64, 256, 1, 1), (777, 24, 40, 1, 1), (513, 16, 16, 0, 1),
                                                            (300, 10, 12, 1, 0), (129, 12, 5, 1, 0), (2500, 128, 64, 1, 1),
                                                            (64, 256, 256, 0, 1)])

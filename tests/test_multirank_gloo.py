@@ -420,9 +420,11 @@ def _struct_worker(rank, world, port, payload, q):
     try:
         _init(rank, world, port)
         from protgram_directgcn_b200.host import partitioned as part
-        rowptr, col, vals, n, x, scales, dz, limit = payload
-        if limit is not None:
-            part.MAX_EXCHANGE_BYTES = limit        # force the column-chunked exchange of the fan-in
+        rowptr, col, vals, n, x, scales, dz, mode = payload
+        if mode == "allgather":
+            part.EXCHANGE_MODE = "allgather"       # round-1 exchange: every row to everybody
+        elif mode is not None:
+            part.PIPELINE_CHUNKS, part.PIPELINE_MIN_BYTES = int(mode), 0   # halo exchange pipelined over feature-column chunks
         lo, hi, per = part.row_range(n, rank, world)
         st = part.PartitionedStructure(part.slice_rows(rowptr, col, vals, lo, hi, per), n)
         pad = lambda t: torch.cat([t[lo:hi], torch.zeros((per - (hi - lo),) + tuple(t.shape[1:]), dtype=t.dtype)])
@@ -437,11 +439,11 @@ def _struct_worker(rank, world, port, payload, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("limit", [None, 3000])
+@pytest.mark.parametrize("limit", [None, 3, "allgather"])
 def test_partitioned_structure_scaled_fanout_and_fanin(limit):
     """The two calls the tensor-core backward makes on a structure (fan-out with per-SOURCE-row gate scales, which must be
-    exchanged; fan-in with a row-local init) against dense algebra, world size 3 with a short last block.  With a small
-    exchange limit the fan-in gathers dZ in column chunks (what C5's 77 GB gradient needs): same result."""
+    exchanged; fan-in with a row-local init) against dense algebra, world size 3 with a short last block: halo exchange in
+    one piece, pipelined over 3 feature-column chunks, and the round-1 all-gather exchange."""
     rng = np.random.default_rng(8)
     n, f, world = 100, 12, 3
     mask = rng.random((n, n)) < 0.06

@@ -257,15 +257,134 @@ def test_loaded_graph_with_csr_sidecar_feeds_the_layer(tmp_path):
     assert torch.equal(model(loaded.gcn_data(x, DEV))[1], model(graph.gcn_data(x, DEV))[1])
 
 
-def test_partitioned_fanin_column_chunks_equal_single_exchange(world1):
+def test_partitioned_halo_exchange_equals_allgather_exchange_bitwise(world1, monkeypatch):
+    """One-rank NCCL group: the halo path (split operand, feature-column chunks, scaled fan-out with exchanged gates, fan-in)
+    against the round-1 all-gather path and against the plain single-GPU kernels -- bitwise (same CSR order per row)."""
     from protgram_directgcn_b200.host import partitioned as part
     n, f = 5003, 64
     src, dst, cnt = random_count_graph(n, seed=31, density=0.004)
     s, d, w = (torch.from_numpy(a).to(DEV) for a in (src, dst, cnt.astype(np.float32)))
     full = graph_utils.device_normalize(s, d, w, n, 1e-9)
     csr = part.slice_rows(full["rowptr"], full["col"], [full["val_in"], full["val_out"], full["val_und"]], 0, n, n)
+    x = torch.randn(n, f, device=DEV)
     dz = torch.randn(n, 3 * f, device=DEV)
     init = torch.randn(n, f, device=DEV)
-    one = part._fanin_exchanged(csr, dz, n, f, init, world1)
-    for limit in (n * 3 * f * 4 // 2, n * 3 * f * 4 // 7):
-        assert torch.equal(part._fanin_exchanged(csr, dz, n, f, init, world1, limit=limit), one)
+    gates = tuple(torch.rand(n, device=DEV) + 0.5 for _ in range(3))
+    outs = {}
+    for mode, chunks in (("allgather", 1), ("halo", 1), ("halo", 4)):
+        monkeypatch.setattr(part, "EXCHANGE_MODE", mode)
+        monkeypatch.setattr(part, "PIPELINE_CHUNKS", chunks)
+        monkeypatch.setattr(part, "PIPELINE_MIN_BYTES", 0)
+        st = part.PartitionedStructure(csr, n, world1)
+        outs[(mode, chunks)] = (st.fanout(x, f), st.fanout(x, f, scales=gates, scale_stride=1),
+                                st.fanout(x, f, scales=tuple(g[:1] for g in gates), scale_stride=0), st.fanin(dz, f, init))
+    ref = outs[("allgather", 1)]
+    for key, got in outs.items():
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b), key
+
+
+def _rmat_edges(log2_nodes, edges_per_node, seed=42):
+    """bench.py's R-MAT generator (a, b, c, d = .57, .19, .19, .05; ids randomly relabelled; integer weights)."""
+    n, e = 1 << log2_nodes, (1 << log2_nodes) * edges_per_node
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    src = torch.zeros(e, dtype=torch.int64, device=DEV)
+    dst = torch.zeros(e, dtype=torch.int64, device=DEV)
+    for _ in range(log2_nodes):
+        r = torch.rand(e, generator=g, device=DEV)
+        src = src * 2 + (r >= 0.76).to(torch.int64)
+        dst = dst * 2 + (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).to(torch.int64)
+    w = torch.randint(1, 8, (e,), generator=g, device=DEV).to(torch.float32)
+    perm = torch.randperm(n, generator=g, device=DEV)
+    return n, perm[src], perm[dst], w
+
+
+@pytest.mark.parametrize("world,chunks", [(4, 1), (8, 2)])
+def test_partitioned_spmm_on_rmat_blocks_vs_oracle_sampled_rows(world, chunks):
+    """Config C5's shape at test size (VERDICT r1 missing #1): an R-MAT power-law digraph (2^17 nodes, 2 M edges, hub rows of
+    several thousand entries) through the reference normalisation, its rows cut into `world` blocks that are played one after
+    the other on this GPU with the PRODUCT's halo plan (`partitioned.halo_plan`: referenced remote rows, renumbered columns),
+    pack kernel and split-operand kernels.  Each block's forward fan-out, gated (backward) fan-out and fan-in must
+      (1) equal the same rows of the single-GPU kernels bit for bit, and
+      (2) agree with oracle/directgcn_oracle.py's `propagate` (reference message passing, torch CPU) on 256 sampled rows
+          to 1e-4 relative (the north star's bar; fp32 sums over hub rows differ by summation order only)."""
+    from oracle import directgcn_oracle
+    from protgram_directgcn_b200.host import partitioned as part
+    from protgram_directgcn_b200.host.protgram_directgcn import _Csr
+    n, src, dst, w = _rmat_edges(17, 16)
+    s, d, wv = graph_utils.device_coalesce(src, dst, w, n)
+    full = graph_utils.device_normalize(s, d, wv, n, 1e-9)
+    rowptr, col = full["rowptr"], full["col"]
+    vals = [full["val_in"], full["val_out"], full["val_und"]]
+    F = 64
+    torch.manual_seed(1)
+    x = torch.randn(n, F, device=DEV)
+    dz = torch.randn(n, 3 * F, device=DEV)
+    gates = torch.rand(n, 4, device=DEV) + 0.5
+    st = nat.stream_ptr()
+    whole = _Csr(rowptr, col, vals)
+    plan = whole.plan(3 * F)
+    assert whole._plan.n_long > 0                                       # hub rows take the long-row split
+    vp = [nat.ptr(v) for v in vals]
+    z_ref, zs_ref, y_ref = torch.empty(n, 3 * F, device=DEV), torch.empty(n, 3 * F, device=DEV), torch.empty(n, F, device=DEV)
+    g_cols = [gates[:, k].contiguous() for k in range(3)]
+    nat.call("pg_spmm_fanout", nat.ptr(rowptr), nat.ptr(col), *vp, 3, n, F, nat.ptr(x), F, nat.ptr(z_ref), 3 * F, 0, plan, st)
+    nat.call("pg_spmm_fanout_scaled", nat.ptr(rowptr), nat.ptr(col), *vp, 3, n, F, nat.ptr(x), F, nat.ptr(zs_ref), 3 * F, 0,
+             nat.ptr(g_cols[0]), nat.ptr(g_cols[1]), nat.ptr(g_cols[2]), 1, plan, st)
+    nat.call("pg_spmm_fanin", nat.ptr(rowptr), nat.ptr(col), *vp, 3, n, F, nat.ptr(dz), 3 * F, 0, None, 0, nat.ptr(y_ref), F, 0, plan, st)
+    halo_rows = []
+    z_all, zs_all, y_all = (torch.empty_like(t) for t in (z_ref, zs_ref, y_ref))
+    w_chunk = F // chunks
+    for r in range(world):
+        lo, hi, per = row_range(n, r, world)
+        blk = part.slice_rows(rowptr, col, vals, lo, hi, per)
+        need, need_counts, col_ext = part.halo_plan(blk.col, lo, per, world)
+        assert int(need_counts[r]) == 0 and int(need_counts.sum()) == need.numel()
+        halo_rows.append(int(need.numel()))
+        bp = [nat.ptr(v) for v in blk.vals]
+        bplan = blk.plan(3 * F)
+        # the peers' pack step: owner o gathers the rows this block asked it for (local row numbers), in `need` order
+        def halo_of(t, c0, cw):
+            out = torch.empty((need.numel(), cw), dtype=torch.float32, device=DEV)
+            pos = 0
+            for o in range(world):
+                k = int(need_counts[o])
+                if k:
+                    olo = row_range(n, o, world)[0]
+                    idx = (need[pos:pos + k] - olo).contiguous()
+                    own_rows = t[olo:olo + per]
+                    nat.call("pg_gather_rows", nat.ptr(own_rows[:, c0:]), t.stride(0), nat.ptr(idx), k, cw, nat.ptr(out[pos:]), cw, st)
+                pos += k
+            return out
+        xl, gl, dzl = x[lo:lo + per], gates[lo:lo + per], dz[lo:lo + per]
+        z, zs = torch.empty(per, 3 * F, device=DEV), torch.empty(per, 3 * F, device=DEV)
+        g_ext = torch.cat([gl, halo_of(gates, 0, 4)]).reshape(-1)
+        for c0 in range(0, F, w_chunk):
+            hx = halo_of(x, c0, w_chunk)
+            for out, sp, stride in ((z, (None, None, None), 0), (zs, tuple(nat.ptr(g_ext[k:]) for k in range(3)), 4)):
+                nat.call("pg_spmm_fanout_split", nat.ptr(blk.rowptr), nat.ptr(col_ext), *bp, 3, hi - lo, w_chunk,
+                         nat.spmm_operand(xl[:, c0:c0 + w_chunk], hx, per), nat.ptr(out[:, c0:]), 3 * F, 0, F, sp[0], sp[1], sp[2], stride, bplan, st)
+        y = torch.empty(per, F, device=DEV)
+        nat.call("pg_spmm_fanin_split", nat.ptr(blk.rowptr), nat.ptr(col_ext), *bp, 3, hi - lo, F, nat.spmm_operand(dzl, halo_of(dz, 0, 3 * F), per),
+                 0, F, None, 0, nat.ptr(y), F, 0, bplan, st)
+        z_all[lo:hi], zs_all[lo:hi], y_all[lo:hi] = z[: hi - lo], zs[: hi - lo], y[: hi - lo]
+    assert torch.equal(z_all, z_ref) and torch.equal(zs_all, zs_ref) and torch.equal(y_all, y_ref)
+    # power-law graph, random relabelling: a block references well under all remote rows (what makes the halo exchange pay)
+    assert max(halo_rows) < 0.8 * (n - n // world), halo_rows
+    # (2) reference message passing on 256 sampled target rows
+    sample = torch.from_numpy(np.random.default_rng(0).choice(n, 256, replace=False))
+    rows_of = torch.repeat_interleave(torch.arange(n, device=DEV), rowptr[1:] - rowptr[:-1]).cpu()
+    keep = torch.zeros(n, dtype=torch.bool)
+    keep[sample] = True
+    keep = keep[rows_of]
+    ei = torch.stack([col.cpu().long()[keep], rows_of[keep]])          # (source = column, target = row)
+    xc, dzc, gc = x.cpu(), dz.cpu(), gates.cpu()
+    err = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    for v in range(3):
+        ew = vals[v].cpu()[keep]
+        ref = directgcn_oracle.propagate(ei, xc, ew)[sample]
+        assert err(z_all[sample, v * F:(v + 1) * F].cpu(), ref) <= 1e-4, v
+        ref_s = directgcn_oracle.propagate(ei, xc * gc[:, v:v + 1], ew)[sample]
+        assert err(zs_all[sample, v * F:(v + 1) * F].cpu(), ref_s) <= 1e-4, v
+    ref_y = sum(directgcn_oracle.propagate(ei, dzc[:, v * F:(v + 1) * F], vals[v].cpu()[keep]) for v in range(3))[sample]
+    assert err(y_all[sample].cpu(), ref_y) <= 1e-4
