@@ -38,30 +38,37 @@ __device__ __forceinline__ const float *operand_row(const Operand &x, int c) {
     return c < x.split ? x.lo + (int64_t)c * x.ld_lo : x.hi + ((int64_t)c - x.split) * x.ld_hi;
 }
 
-// Work mapping.  Rows mode: group g owns row g; rows longer than `skip_above` nnz are left to the
-// long-row pass.  Items mode (long_rows != nullptr): group g owns one `chunk`-nnz slice of a long
-// row and writes a partial sum to its own output row g (combined afterwards in item order, so the
-// result stays bitwise reproducible however skewed the degrees are).
+// Work mapping of ONE launch.  The first n_items groups each own one `chunk`-nnz slice of a long row and write a partial sum
+// to the plan's scratch (combined afterwards in item order, so the result stays bitwise reproducible however skewed the
+// degrees are); the following num_rows groups own one row each and skip the long ones.  Slices first: they are the
+// longest-running groups, and the short rows that follow fill the SMs' gaps while they drain.
 struct RowMap {
-    int64_t num_groups;
-    int64_t skip_above;           // rows mode: 0 = no limit
-    const int32_t *long_rows;     // items mode
+    int64_t num_rows;
+    int64_t skip_above;           // rows longer than this are handled as slices (0 = no long-row plan)
+    int64_t n_items;
+    const int32_t *long_rows;
     const int64_t *item_ptr;
     const int32_t *item_row;
+    float *partials;
     int32_t chunk;
 };
 
+// -> false: nothing to do for this group.  *item: the group is a slice (output row = slice index in the scratch).
 __device__ __forceinline__ bool map_group(const RowMap &m, const int64_t *__restrict__ rowptr, int64_t g, int64_t *rb,
-                                          int64_t *re, int64_t *out_row) {
-    if (m.long_rows != nullptr) {
+                                          int64_t *re, int64_t *out_row, bool *item) {
+    if (g < m.n_items) {
         const int32_t li = m.item_row[g];
         const int64_t row = m.long_rows[li];
         const int64_t b = rowptr[row] + (g - m.item_ptr[li]) * (int64_t)m.chunk;
         *rb = b;
         *re = min(b + m.chunk, rowptr[row + 1]);
         *out_row = g;
+        *item = true;
         return true;
     }
+    g -= m.n_items;
+    *item = false;
+    if (g >= m.num_rows) return false;
     *rb = rowptr[g];
     *re = rowptr[g + 1];
     *out_row = g;
@@ -69,10 +76,13 @@ __device__ __forceinline__ bool map_group(const RowMap &m, const int64_t *__rest
 }
 
 #ifndef PG_SPMM_MIN_BLOCKS
-#define PG_SPMM_MIN_BLOCKS 4   // register cap 127: ptxas then keeps all UNROLL gathers of a batch in flight (at 5+ it serialises them again)
+#define PG_SPMM_MIN_BLOCKS 6   // CTAs per SM the fan-out kernel is compiled for when a lane holds ONE float4 (register cap 80; wider rows: 4 / 3).  Measured on the R-MAT leg (fan-out, ms): 4 blocks x 8 gathers 8.1, 5 x 8 7.2, 6 x 4 6.0, 8 x 4 7.5, 4 x 4 7.1
+#endif
+#ifndef PG_SPMM_HALF_WARP_ROWS
+#define PG_SPMM_HALF_WARP_ROWS 0
 #endif
 #ifndef PG_SPMM_UNROLL1
-#define PG_SPMM_UNROLL1 8      // gathers in flight per lane when a lane holds one float4 of the row
+#define PG_SPMM_UNROLL1 4      // gathers in flight per lane when a lane holds one float4 of the row
 #endif
 constexpr int SPMM_THREADS = 128;   // small CTAs: a CTA lives as long as its longest row, the other warps' slots idle meanwhile
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
@@ -96,7 +106,7 @@ struct __align__(16) StagedEntry {
 //     them (double-buffered stage), so the index latency stays hidden.
 // Accumulation stays in CSR order (bitwise reproducible; a partitioned block equals the same rows of the whole matrix).
 template <int NV, int LPR, int CHUNKS, bool FULL>   // FULL: F == 4 * LPR * CHUNKS, no lane is idle -> unpredicated gathers
-__global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanout_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+__global__ void __launch_bounds__(SPMM_THREADS, CHUNKS == 1 ? PG_SPMM_MIN_BLOCKS : (CHUNKS == 2 ? 4 : 3)) spmm_fanout_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                                    const float *__restrict__ val0, const float *__restrict__ val1,
                                                                    const float *__restrict__ val2, RowMap map, int F, Operand x,
                                                                    float *__restrict__ z, int64_t ldz, int64_t z_off, int64_t z_vstride,
@@ -112,9 +122,9 @@ __global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanout_
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
     StagedEntry(*st)[32] = stage[threadIdx.x >> 5];
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    if (gid >= map.num_groups) return;
     int64_t rb, re, row;
-    if (!map_group(map, rowptr, gid, &rb, &re, &row)) return;
+    bool item;
+    if (!map_group(map, rowptr, gid, &rb, &re, &row, &item)) return;
     const int nvec = F >> 2;                               // float4 per feature row
     float4 acc[NV][CHUNKS];
 #pragma unroll
@@ -185,9 +195,11 @@ __global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanout_
         if (more) put_entry(buf ^ 1, n_row, n0, n1, n2);
         __syncwarp(gmask);                                  // stage[buf^1] complete; every lane is done reading stage[buf]
     }
+    float *zrow = item ? map.partials + row * (int64_t)(NV * F) : z + row * ldz + z_off;
+    const int64_t vstride = item ? (int64_t)F : z_vstride;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-        float4 *zp = reinterpret_cast<float4 *>(z + row * ldz + z_off + (int64_t)v * z_vstride);
+        float4 *zp = reinterpret_cast<float4 *>(zrow + (int64_t)v * vstride);
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int f4 = lg + c * LPR;
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanout_
 }
 
 template <int NV, int LPR, int CHUNKS, bool FULL>
-__global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanin_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+__global__ void __launch_bounds__(SPMM_THREADS, NV * CHUNKS <= 3 ? 6 : (NV * CHUNKS <= 6 ? 4 : 2)) spmm_fanin_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                                   const float *__restrict__ val0, const float *__restrict__ val1,
                                                                   const float *__restrict__ val2, RowMap map, int F, Operand g,
                                                                   int64_t g_off, int64_t g_vstride, const float *__restrict__ init,
@@ -210,16 +222,16 @@ __global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanin_k
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
     StagedEntry(*st)[32] = stage[threadIdx.x >> 5];
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    if (gid >= map.num_groups) return;
     int64_t rb, re, row;
-    if (!map_group(map, rowptr, gid, &rb, &re, &row)) return;
+    bool item;
+    if (!map_group(map, rowptr, gid, &rb, &re, &row, &item)) return;
     const int nvec = F >> 2;
     float4 acc[CHUNKS];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int f4 = lg + c * LPR;
         acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f4 < nvec) {
+        if (f4 < nvec && !item) {
             if (init) acc[c] = __ldg(reinterpret_cast<const float4 *>(init + row * ldinit) + f4);
             if (accumulate) {
                 const float4 o = reinterpret_cast<const float4 *>(y + row * ldy)[f4];
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, PG_SPMM_MIN_BLOCKS) spmm_fanin_k
         if (more) put_entry(buf ^ 1, n_row, n0, n1, n2);
         __syncwarp(gmask);
     }
-    float4 *yp = reinterpret_cast<float4 *>(y + row * ldy);
+    float4 *yp = reinterpret_cast<float4 *>(item ? map.partials + row * (int64_t)F : y + row * ldy);
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int f4 = lg + c * LPR;
@@ -389,6 +401,7 @@ inline bool pick_shape(int F, int *lpr, int *chunks) {
     const int nvec = F / 4;
     int l = 4;
     while (l < nvec && l < 32) l <<= 1;
+    if (l == 32 && nvec == 32 && PG_SPMM_HALF_WARP_ROWS) l = 16;   // F = 128: two rows per warp, two float4 per lane
     int c = (nvec + l - 1) / l;
     if (c == 3) c = 4;
     *lpr = l;
@@ -396,18 +409,17 @@ inline bool pick_shape(int F, int *lpr, int *chunks) {
     return true;
 }
 
-inline RowMap rows_map(int64_t num_rows, const pg_spmm_plan *plan) {
+inline RowMap work_map(int64_t num_rows, const pg_spmm_plan *plan) {
     RowMap m;
-    m.num_groups = num_rows;
-    m.skip_above = (plan && plan->n_long > 0) ? plan->chunk : 0;
-    m.long_rows = nullptr; m.item_ptr = nullptr; m.item_row = nullptr; m.chunk = 0;
-    return m;
-}
-inline RowMap items_map(const pg_spmm_plan *plan) {
-    RowMap m;
-    m.num_groups = plan->n_items;
-    m.skip_above = 0;
-    m.long_rows = plan->d_long_rows; m.item_ptr = plan->d_item_ptr; m.item_row = plan->d_item_row; m.chunk = plan->chunk;
+    const bool lng = plan && plan->n_long > 0;
+    m.num_rows = num_rows;
+    m.skip_above = lng ? plan->chunk : 0;
+    m.n_items = lng ? plan->n_items : 0;
+    m.long_rows = lng ? plan->d_long_rows : nullptr;
+    m.item_ptr = lng ? plan->d_item_ptr : nullptr;
+    m.item_row = lng ? plan->d_item_row : nullptr;
+    m.partials = lng ? plan->d_partials : nullptr;
+    m.chunk = lng ? plan->chunk : 0;
     return m;
 }
 inline bool plan_ok(const pg_spmm_plan *plan) {
@@ -439,6 +451,7 @@ inline Operand to_operand(const pg_spmm_operand *x) {
         const bool full = (F == 4 * lpr * chunks);                                                    \
         if (lpr == 4) PG_SPMM_LAUNCH(KERNEL, NV, 4, 1, __VA_ARGS__);                                  \
         else if (lpr == 8) PG_SPMM_LAUNCH(KERNEL, NV, 8, 1, __VA_ARGS__);                             \
+        else if (lpr == 16 && chunks == 2) PG_SPMM_LAUNCH(KERNEL, NV, 16, 2, __VA_ARGS__);            \
         else if (lpr == 16) PG_SPMM_LAUNCH(KERNEL, NV, 16, 1, __VA_ARGS__);                           \
         else if (chunks == 1) PG_SPMM_LAUNCH(KERNEL, NV, 32, 1, __VA_ARGS__);                         \
         else if (chunks == 2) PG_SPMM_LAUNCH(KERNEL, NV, 32, 2, __VA_ARGS__);                         \
@@ -482,16 +495,13 @@ extern "C" int pg_spmm_fanout_split(const int64_t *d_rowptr, const int32_t *d_co
     int lpr = 0, chunks = 0;
     const bool vec = pick_shape(F, &lpr, &chunks) && operand_vec(x) && aligned16(d_z) && ldz % 4 == 0 && z_off % 4 == 0 && z_vstride % 4 == 0;
     if (vec) {
-        const RowMap rm = rows_map(num_rows, plan);
-        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, xo, d_z, ldz, z_off, z_vstride, d_s0, s1, s2, scale_stride);
-        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, xo, d_z, ldz, z_off, z_vstride, d_s0, s1, s2, scale_stride);
+        const RowMap wm = work_map(num_rows, plan);                    // long-row slices and plain rows in ONE launch
+        const int64_t groups = wm.n_items + num_rows;
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, groups, d_rowptr, d_col, d_val0, v1, v2, wm, F, xo, d_z, ldz, z_off, z_vstride, d_s0, s1, s2, scale_stride);
+        else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, groups, d_rowptr, d_col, d_val0, v1, v2, wm, F, xo, d_z, ldz, z_off, z_vstride, d_s0, s1, s2, scale_stride);
         PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel");
-        if (plan && plan->n_long > 0) {
-            const RowMap im = items_map(plan);
+        if (wm.n_items > 0) {
             const int64_t w = (int64_t)nv * F;
-            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanout_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, xo, plan->d_partials, w, 0, (int64_t)F, d_s0, s1, s2, scale_stride);
-            else PG_SPMM_DISPATCH(spmm_fanout_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, xo, plan->d_partials, w, 0, (int64_t)F, d_s0, s1, s2, scale_stride);
-            PG_CUDA_LAUNCH_CHECK("spmm_fanout_kernel(long rows)");
             spmm_reduce_long_kernel<<<(unsigned)plan->n_long, 256, 0, st>>>(plan->d_long_rows, plan->d_item_ptr, plan->n_long, (int)w, F,
                                                                             plan->d_partials, d_z, ldz, z_off, z_vstride, nullptr, 0, 0);
             PG_CUDA_LAUNCH_CHECK("spmm_reduce_long_kernel");
@@ -533,15 +543,12 @@ extern "C" int pg_spmm_fanin_split(const int64_t *d_rowptr, const int32_t *d_col
     const bool vec = pick_shape(F, &lpr, &chunks) && operand_vec(g) && aligned16(d_y) && ldy % 4 == 0 && g_off % 4 == 0 &&
                      g_vstride % 4 == 0 && (!d_init || (aligned16(d_init) && ldinit % 4 == 0));
     if (vec) {
-        const RowMap rm = rows_map(num_rows, plan);
-        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, go, g_off, g_vstride, d_init, ldinit, d_y, ldy, accumulate);
-        else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, num_rows, d_rowptr, d_col, d_val0, v1, v2, rm, F, go, g_off, g_vstride, d_init, ldinit, d_y, ldy, accumulate);
+        const RowMap wm = work_map(num_rows, plan);
+        const int64_t groups = wm.n_items + num_rows;
+        if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, groups, d_rowptr, d_col, d_val0, v1, v2, wm, F, go, g_off, g_vstride, d_init, ldinit, d_y, ldy, accumulate);
+        else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, groups, d_rowptr, d_col, d_val0, v1, v2, wm, F, go, g_off, g_vstride, d_init, ldinit, d_y, ldy, accumulate);
         PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel");
-        if (plan && plan->n_long > 0) {
-            const RowMap im = items_map(plan);
-            if (nv == 3) PG_SPMM_DISPATCH(spmm_fanin_kernel, 3, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, go, g_off, g_vstride, nullptr, 0, plan->d_partials, (int64_t)F, 0);
-            else PG_SPMM_DISPATCH(spmm_fanin_kernel, 1, plan->n_items, d_rowptr, d_col, d_val0, v1, v2, im, F, go, g_off, g_vstride, nullptr, 0, plan->d_partials, (int64_t)F, 0);
-            PG_CUDA_LAUNCH_CHECK("spmm_fanin_kernel(long rows)");
+        if (wm.n_items > 0) {
             spmm_reduce_long_kernel<<<(unsigned)plan->n_long, 256, 0, st>>>(plan->d_long_rows, plan->d_item_ptr, plan->n_long, F, F, plan->d_partials,
                                                                             d_y, ldy, 0, 0, d_init, ldinit, accumulate);
             PG_CUDA_LAUNCH_CHECK("spmm_reduce_long_kernel");

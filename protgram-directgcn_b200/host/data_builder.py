@@ -107,6 +107,8 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
         up.release()
     if bins is None:
         bins, short = count_level(torch.empty(0, dtype=torch.uint8, device=d_rank.device), n, d_rank, sigma)
+    if group is not None and _use_key_range_merge(n, sigma, group):
+        return _finish_by_key_range(bins, short, n, symbols, sigma, eps, group)
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
@@ -117,6 +119,74 @@ def build_level_graph(d_buf, n: int, symbols: np.ndarray, d_rank: torch.Tensor, 
     names = corpus.LazyNodeNames(node_code, symbols, n)   # id -> n-gram string, id order; decoded on first access
     return DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), epsilon_propagation=eps,
                                                n_value=n, assume_coalesced=True)
+
+
+KEY_RANGE_MERGE_MIN_TABLE_BYTES = 126 << 20     # B200's L2: beyond it the all-reduced table is re-read from HBM by every rank's extraction
+
+
+def _use_key_range_merge(n: int, sigma: int, group) -> bool:
+    """Multi-GPU merge policy of one level: tables that fit L2 (n <= 4 at sigma = 21: 33 MB) are all-reduced and every rank
+    extracts the identical graph; larger ones (n = 5: 686 MB) are REDUCE-SCATTERED over key ranges, every rank extracts the
+    edges of its own range only and the edge lists (16 B per edge, not 8 B per bin) are gathered on rank 0 for the pickle."""
+    import torch.distributed as dist
+    return dist.get_world_size(group) > 1 and table_sizes(n, sigma)[1] * 8 > KEY_RANGE_MERGE_MIN_TABLE_BYTES
+
+
+def gather_edges_on_root(src, dst, cnt, group, root: int = 0):
+    """Variable-size gather of the per-rank edge lists (already globally sorted in rank order: key ranges ascend) onto `root`
+    -- one all_to_all_single in which only the root receives.  -> (src, dst, cnt) on root, three empty tensors elsewhere."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = src.device
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = src.numel()
+    dist.all_reduce(sizes, group=group)
+    sizes = [int(v) for v in sizes.tolist()]
+    send = torch.stack([src, dst, cnt], dim=1).contiguous()                       # [e, 3] int64
+    in_split = [send.shape[0] if r == root else 0 for r in range(world)]
+    out_split = sizes if rank == root else [0] * world
+    recv = torch.empty((sum(out_split), 3), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+    return recv[:, 0].contiguous(), recv[:, 1].contiguous(), recv[:, 2].contiguous()
+
+
+def _finish_by_key_range(bins, short, n: int, symbols, sigma: int, eps: float, group):
+    """count tables -> reduce-scatter over key ranges -> per-range extraction -> edge lists gathered on rank 0, which alone
+    builds (and later pickles) the whole-graph object; the other ranks return a node-list-only stub (`edges_on_rank0`)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    pow_n, pow_m = table_sizes(n, sigma)
+    codes_per = (pow_n + world - 1) // world
+    padded = torch.zeros(world * codes_per * sigma, dtype=torch.int64, device=bins.device)
+    padded[:pow_m] = bins
+    del bins
+    local = merge_tables_by_key_range(padded, codes_per, sigma, group)
+    del padded
+    short_i = short.to(torch.int32)
+    dist.all_reduce(short_i, op=dist.ReduceOp.MAX, group=group)
+    node_code, src, dst, cnt = extract_key_range(local, short_i.to(torch.uint8), n, sigma, rank * codes_per, codes_per, group)
+    total = torch.tensor([int(src.numel())], dtype=torch.int64, device=src.device)
+    dist.all_reduce(total, group=group)
+    src, dst, cnt = gather_edges_on_root(src, dst, cnt, group)
+    names = corpus.LazyNodeNames(node_code, symbols, n)
+    if rank == 0:
+        return DirectedNgramGraph.from_edge_arrays(names, src, dst, cnt.to(torch.float32), epsilon_propagation=eps, n_value=n,
+                                                   assume_coalesced=True)
+    return _RemoteLevelGraph(n, names, int(node_code.numel()), int(total.item()))
+
+
+class _RemoteLevelGraph:
+    """What the non-root ranks of a key-range merged level hold: the (replicated) node list and the totals; the edges and
+    matrices live on rank 0 (`GraphBuilder.run` only pickles there)."""
+    edges_on_rank0 = True
+
+    def __init__(self, n_value, names, number_of_nodes, number_of_edges):
+        self.n_value, self._names = n_value, names
+        self.number_of_nodes, self.number_of_edges = number_of_nodes, number_of_edges
+
+    @property
+    def node_sequences(self):
+        return self._names.resolve()
 
 
 class PartitionedLevelGraph:
@@ -240,6 +310,19 @@ class GraphBuilder:
         import torch.distributed as dist
         return dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
 
+    def _agree(self, flag: int, count: int) -> Tuple[int, int]:
+        """-> (max of `flag`, sum of `count`) over the ranks of the process group (identity without one)."""
+        if self.process_group is None:
+            return flag, count
+        import torch.distributed as dist
+        dev = nat.current_device() if dist.get_backend(self.process_group) == "nccl" else torch.device("cpu")
+        t = torch.tensor([flag, count], dtype=torch.int64, device=dev)
+        f = t[:1].clone()
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.process_group)
+        c = t[1:].clone()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.process_group)
+        return int(f.item()), int(c.item())
+
     def run(self):
         t0 = time.monotonic()
         DataUtils.print_header("PIPELINE STEP 1: Building N-gram Graphs")
@@ -291,6 +374,7 @@ class GraphBuilder:
             yield from corpus.stream_chunks(sequences(), chunk_bytes, rank, world)
 
         chunks, resident = [], 0
+        failed = None
         try:
             for buf in host_chunks():
                 size = int(buf.numel()) if torch.is_tensor(buf) else int(buf.size)
@@ -300,15 +384,22 @@ class GraphBuilder:
                 else:                                       # larger than the budget: re-streamed per level, 5 bits per symbol on the wire
                     chunks.append(corpus.pack5(buf) or buf)
         except ValueError as exc:
-            print(f"ERROR: {exc}")
+            failed = str(exc)
+        # ranks agree on failure BEFORE the first collective: a rank that returned alone would leave the others blocked in it
+        any_failed, total_seqs = self._agree(1 if failed else 0, n_seqs[0])
+        if failed:
+            print(f"ERROR: {failed}")
+        if any_failed:
+            if not failed:
+                print("ERROR: another rank could not read its shard of the FASTA file. Cannot proceed.")
             return
-        if n_seqs[0] == 0:
+        if total_seqs == 0:
             print("ERROR: No sequences found in the FASTA file. Cannot proceed.")
             return
         print(f"  Loaded {n_seqs[0]} sequences from FASTA ({len(chunks)} corpus chunk(s) on this rank).")
         try:
             symbols, d_rank = corpus.discover_alphabet(chunks, self.process_group)
-        except ValueError as exc:
+        except ValueError as exc:          # raised from the all-reduced presence table: every rank sees the same error
             print(f"ERROR: {exc}")
             return
         d_buf = chunks

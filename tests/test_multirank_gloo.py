@@ -28,10 +28,13 @@ def _init(rank, world, port):
     return nat
 
 
-def _builder_worker(rank, world, port, fasta_path, out_dir, n_max, q):
+def _builder_worker(rank, world, port, fasta_path, out_dir, n_max, q, key_range=False):
     try:
         _init(rank, world, port)
         import protgram_directgcn_b200 as pg
+        if key_range:    # force the merge policy of tables beyond L2 (reduce-scatter over key ranges, edges gathered on rank 0)
+            from protgram_directgcn_b200.host import data_builder
+            data_builder.KEY_RANGE_MERGE_MIN_TABLE_BYTES = 0
         cfg = pg.Config()
         cfg.GCN_INPUT_FASTA_PATH = fasta_path
         cfg.BASE_OUTPUT_DIR = out_dir
@@ -48,8 +51,8 @@ def _builder_worker(rank, world, port, fasta_path, out_dir, n_max, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["build_protein", "build_ragged"])
-def test_sharded_builder_equals_reference(name, tmp_path):
+@pytest.mark.parametrize("name,key_range", [("build_protein", False), ("build_ragged", False), ("build_protein", True), ("build_ragged", True)])
+def test_sharded_builder_equals_reference(name, key_range, tmp_path):
     """Corpus split over 2 ranks by sequence range, tables merged by all-reduce: bit-exact nodes,
     edges and counts against the reference goldens (== the single-rank result)."""
     g = load(name)
@@ -58,7 +61,7 @@ def test_sharded_builder_equals_reference(name, tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_builder_worker, args=(r, 2, port, fasta, str(tmp_path), n_max, q)) for r in range(2)]
+    procs = [ctx.Process(target=_builder_worker, args=(r, 2, port, fasta, str(tmp_path), n_max, q, key_range)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
