@@ -514,8 +514,8 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}, ids randomly relabelled), {e} directed edges before dedupe, pattern nnz {P}",
            "nodes": n, "F": F, "pattern_nnz": P, "rows_per_gpu": per, "partition": "1-D rows; block columns renumbered into [own rows | halo rows]",
            "local_nnz_max_over_mean": mx(float(p_local)) / (P / world),
-           "exchange": f"halo: pg_gather_rows + NCCL all_to_all_single of the referenced rows, pipelined over {len(part._feature_chunks(F, per, world))} "
-                       "feature-column chunk(s) against the SpMM",
+           "exchange": "halo: pg_gather_rows + NCCL all_to_all_single of the referenced rows, then the local SpMM over [own rows | halo rows] "
+                       f"({len(part._feature_chunks(F, per, world))} feature-column chunk(s))",
            "halo": {"rows_received_per_gpu_mean": int(tot[2]) / world, "rows_served_per_gpu_mean": int(tot[3]) / world,
                     "fraction_of_remote_rows": (int(tot[2]) / world) / max(1, n - per), "plan_build_s_once_per_graph": mx(plan_s)},
            "normalise_partitioned": norm_info}
@@ -525,6 +525,14 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
         recv = 4 * (width + extra_cols) * recv_rows
         out[name] = {"ms": ms, "edges_per_s": 3 * P / (ms * 1e-3), "nvlink_recv_bytes_this_gpu": recv,
                      "all_gather_would_receive_bytes": 4 * width * per * (world - 1)}
+    # the feature-column pipelining of the exchange (off by default, see host/partitioned.py): measured for the record
+    saved = (part.PIPELINE_CHUNKS, part.PIPELINE_MIN_BYTES)
+    try:
+        part.PIPELINE_CHUNKS, part.PIPELINE_MIN_BYTES = 2, 0
+        dist.barrier()
+        out["fwd"]["ms_with_2_feature_chunks_pipelined"] = mx(_time_ms(fwd, iters))
+    finally:
+        part.PIPELINE_CHUNKS, part.PIPELINE_MIN_BYTES = saved
     dist.barrier()
     ms_comm = mx(_time_ms(comm, iters))
     fwd()
@@ -537,6 +545,39 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
                        "nvlink_gbs_this_gpu_exchange_alone": recv / (ms_comm * 1e-3) / 1e9, "nvlink_frac_of_measured_770": recv / (ms_comm * 1e-3) / 1e9 / 770.0,
                        "local_spmm_algorithmic_bytes": alg_local, "local_spmm_gbs": alg_local / (ms_local * 1e-3) / 1e9,
                        "local_spmm_frac_of_hbm_peak": alg_local / (ms_local * 1e-3) / 1e9 / peak_gbs})
+    # one whole DirectGCN layer (F -> F, identity residual, tensor-core transform) on the block, forward + backward: in the backward
+    # the halo exchange of dY is posted before the weight- and gate-gradient GEMMs and waited for after them
+    try:
+        import protgram_directgcn_b200 as pg
+        data = part.partitioned_data(x_local, prop.local, n, group)
+        st_obj = data.edge_index_in._pg_struct
+        layer = pg.DirectGCNLayer(F, F, per, True).to(dev)
+        edges = (data.edge_index_in, data.edge_weight_in, data.edge_index_out, data.edge_weight_out, data.edge_index_undirected_norm,
+                 data.edge_weight_undirected_norm)
+        xr = x_local.clone().requires_grad_(True)
+        dh = torch.randn(per, F, device=dev, generator=g)
+
+        def layer_step():
+            xr.grad = None
+            layer.zero_grad(set_to_none=True)
+            layer._run(xr, edges, None, None, None, True, 0.01).backward(dh)
+
+        dist.barrier()
+        ms_layer = mx(_time_ms(layer_step, iters))
+        begin = type(st_obj).fanout_begin
+        try:
+            type(st_obj).fanout_begin = lambda self, *a, **k: None          # same step with the exchange NOT overlapped
+            dist.barrier()
+            ms_layer_serial = mx(_time_ms(layer_step, iters))
+        finally:
+            type(st_obj).fanout_begin = begin
+        out["layer_fwd_bwd"] = {"what": f"DirectGCNLayer({F}, {F}) forward + backward on the row block (fan-out SpMM, tcgen05 transform, weight / gate / "
+                                        "input gradients), exchanges included", "ms": ms_layer, "ms_backward_exchange_not_overlapped": ms_layer_serial,
+                                "edges_per_s": 2 * 3 * P / (ms_layer * 1e-3)}
+        del data, layer, edges, xr, dh, st_obj
+    except Exception as exc:  # noqa: BLE001
+        out["layer_fwd_bwd"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
     x_full = None
     if compare_allgather and world * per * F * 4 <= 40 << 30:
         def ag_fwd():

@@ -423,6 +423,27 @@ int pg_layer_gate_grad_tc(const float *d_dy, int64_t lddy, const float *d_w_ext,
                           int64_t num_rows, int F_in, int F_out, int has_res, float *d_dgate /* [3 x num_rows] */,
                           void *d_ws, size_t ws_bytes, pg_stream_t stream);
 int pg_tc_check(const void *d_ws, size_t need, pg_stream_t stream);
+/* The same two steps of the regrouped backward on the SIMT fp32 path (layers narrower than the tensor-core threshold, i.e. every
+ * n <= 3 graph's last layers and the benchmarker's small models): identical contracts, any F_in / F_out / alignment. */
+size_t pg_layer_gate_grad_ws_bytes(int64_t num_rows, int F_in, int F_out);
+int pg_layer_gate_grad(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z, int64_t ldz,
+                       int64_t num_rows, int F_in, int F_out, int has_res, float *d_dgate /* [3 x num_rows] */,
+                       void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_layer_gemm_bwd_dx(const float *d_t, int64_t ldt, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                         int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx,
+                         int64_t lddx, pg_stream_t stream);
+
+/* Plain Linear layers on the SIMT fp32 mainloop (the decoder MLP, reference protgram_directgcn.py:173-180,219: row f1), torch.nn.Linear
+ * layout W [C x K]:  out = act(x W^T + bias);  dx = g W;  dW = g^T x (rows split over CTAs, fixed-order reduction);  column sums of
+ * g (the bias gradient).  Any shape / alignment. */
+int pg_linear_fwd(const float *d_x, int64_t ldx, int64_t num_rows, int K, const float *d_w, const float *d_bias, int C, int relu,
+                  float *d_out, int64_t ldo, pg_stream_t stream);
+int pg_linear_bwd_data(const float *d_g, int64_t ldg, int64_t num_rows, int C, const float *d_w, int K, float *d_dx, int64_t lddx,
+                       pg_stream_t stream);
+size_t pg_linear_bwd_weight_ws_bytes(int64_t num_rows, int C, int K);
+int pg_linear_bwd_weight(const float *d_g, int64_t ldg, const float *d_x, int64_t ldx, int64_t num_rows, int C, int K, float *d_dw,
+                         void *d_ws, size_t ws_bytes, pg_stream_t stream);
+int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, pg_stream_t stream);
 
 /* Plain Linear on the same tensor-core kernel: out[N, C] = x[N, K] @ W[C, K]^T + bias (torch.nn.Linear layout, bias may be
  * NULL).  Used for the decoder's output layer (protgram_directgcn.py:177-180 with C = N classes, row f1).  K % 4 == 0,

@@ -104,6 +104,14 @@ _SIGS = {
     "pg_layer_gate_grad_tc_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "pg_layer_gate_grad_tc": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_tc_check": (c_int, [_P, c_size_t, _P]),
+    "pg_layer_gate_grad_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "pg_layer_gate_grad": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pg_layer_gemm_bwd_dx": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "pg_linear_fwd": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, c_int, _P, c_int64, _P]),
+    "pg_linear_bwd_data": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int, _P, c_int64, _P]),
+    "pg_linear_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "pg_linear_bwd_weight": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pg_colsum": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "pg_linear_tc_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_linear_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),

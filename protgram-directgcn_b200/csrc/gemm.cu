@@ -221,6 +221,217 @@ struct Epi_Partial {  // split-K partial of dW_ext
     }
 };
 
+// ---- plain Linear layers (the decoder MLP of reference protgram_directgcn.py:173-180; row f1) on the same mainloop ----
+struct OpA_PlainT {  // A(m, k) = p[k, m]: the transposed operand of a weight gradient (m = column of p, k = row of p)
+    const float *p;
+    int64_t ld, nrows;   // nrows = extent of k (rows beyond read as zero: split-K tails)
+    int ncols;           // extent of m
+    bool vec;
+    template <int BM_>
+    __device__ __forceinline__ void load(float4 (&r)[BM_ / 64], int64_t m0, int64_t k0, int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            r[rep] = ld4_guard(p, ld, k0 + idx / (BM_ / 4), nrows, (int)m0 + (idx % (BM_ / 4)) * 4, ncols, vec);
+        }
+    }
+    template <int BM_>
+    __device__ __forceinline__ void store(float (*As)[BM_ + PAD], const float4 (&r)[BM_ / 64], int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            *reinterpret_cast<float4 *>(&As[idx / (BM_ / 4)][(idx % (BM_ / 4)) * 4]) = r[rep];
+        }
+    }
+};
+
+struct Epi_BiasAct {  // out = act(acc + bias)
+    const float *bias;
+    float *out;
+    int64_t ldo, M;
+    int ncols, relu;
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int) const {
+        if (r >= M) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            if (c < ncols) {
+                float v = acc[j] + (bias ? bias[c] : 0.f);
+                if (relu) v = v > 0.f ? v : 0.f;
+                out[r * ldo + c] = v;
+            }
+        }
+    }
+};
+
+// column sums of a row-major matrix in fixed order: one CTA per 32 columns, 8 row-strided partials per column combined by thread 0..31
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ g, int64_t ld, int64_t M, int ncols, float *__restrict__ out) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int slice = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < ncols)
+        for (int64_t r = slice; r < M; r += 8) acc += g[r * ld + c];
+    part[slice][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (slice == 0 && c < ncols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+        out[c] = t;
+    }
+}
+
+// ---- operands / epilogues of the regrouped backward on the SIMT path (the tensor-core path has its own in gemm_tc.cu):
+//   gate gradients   dgate_v[i] = <dY[i] W'_v^T, Z_v[i]> + <dY[i], beta_v>      (data-gradient GEMM with a dot-product epilogue:
+//                                                                               the 3 F_in-wide dZ is never written)
+//   input gradient   dX = [T_in | T_out | T_und | dY] @ [W'_in^T; W'_out^T; W'_und^T; W_res^T] (+ dY),  T_v = A_v^T (g_v * dY)
+struct OpA_Cat2 {  // A(m, k) = k < k_first ? p0[m, k] : p1[m, k - k_first]
+    const float *p0;
+    int64_t ld0;
+    int k_first;
+    const float *p1;
+    int64_t ld1;
+    int k_total;
+    int64_t M;
+    bool vec;      // k_first % 4 == 0 and both matrices 16 B aligned with row strides % 4 == 0
+    __device__ __forceinline__ float4 at4(int64_t m, int k0) const {
+        if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec && k0 + 3 < k_total)
+            return k0 < k_first ? __ldg(reinterpret_cast<const float4 *>(p0 + m * ld0 + k0))
+                                : __ldg(reinterpret_cast<const float4 *>(p1 + m * ld1 + (k0 - k_first)));
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            t[j] = k >= k_total ? 0.f : (k < k_first ? p0[m * ld0 + k] : p1[m * ld1 + (k - k_first)]);
+        }
+        return make_float4(t[0], t[1], t[2], t[3]);
+    }
+    template <int BM_>
+    __device__ __forceinline__ void load(float4 (&r)[BM_ / 64], int64_t m0, int64_t k0, int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            r[rep] = at4(m0 + (idx >> 2), (int)k0 + (idx & 3) * 4);
+        }
+    }
+    template <int BM_>
+    __device__ __forceinline__ void store(float (*As)[BM_ + PAD], const float4 (&r)[BM_ / 64], int tid) const {
+#pragma unroll
+        for (int rep = 0; rep < BM_ / 64; ++rep) {
+            const int idx = tid + rep * 256;
+            const int m = idx >> 2, kq = (idx & 3) * 4;
+            As[kq + 0][m] = r[rep].x; As[kq + 1][m] = r[rep].y; As[kq + 2][m] = r[rep].z; As[kq + 3][m] = r[rep].w;
+        }
+    }
+};
+
+struct OpB_WextBlocksT {  // B(k = v * F_out + o, n) = W_ext[v * F_in + n, o]   (v < blocks; n < F_in)
+    const float *w;       // [k_ext, F_out] row-major
+    int F_in, F_out, blocks;
+    bool vec;             // F_out % 4 == 0, w 16 B aligned
+    __device__ __forceinline__ void load(float4 &r, int n0, int64_t k0, int tid) const {
+        const int n = n0 + (tid >> 2);
+        const int k = (int)k0 + (tid & 3) * 4;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < F_in) {
+            if (vec && k + 3 < blocks * F_out) {
+                const int v = k / F_out, o = k - v * F_out;
+                r = __ldg(reinterpret_cast<const float4 *>(w + ((int64_t)v * F_in + n) * F_out + o));
+                return;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kk = k + j;
+                if (kk < blocks * F_out) {
+                    const int v = kk / F_out, o = kk - v * F_out;
+                    t[j] = w[((int64_t)v * F_in + n) * F_out + o];
+                }
+            }
+        }
+        r = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    __device__ __forceinline__ void store(float (*Bs)[BN + PAD], const float4 &r, int tid) const {
+        const int n = tid >> 2, kq = (tid & 3) * 4;
+        Bs[kq + 0][n] = r.x; Bs[kq + 1][n] = r.y; Bs[kq + 2][n] = r.z; Bs[kq + 3][n] = r.w;
+    }
+};
+
+struct Epi_Dx {  // dX = acc (+ dY)
+    float *dx;
+    int64_t lddx;
+    const float *dy;
+    int64_t lddy, M;
+    int F_in, add_identity;
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int) const {
+        if (r >= M) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            if (c < F_in) dx[r * lddx + c] = acc[j] + (add_identity ? dy[r * lddy + c] : 0.f);
+        }
+    }
+};
+
+struct Epi_GateDot {  // per row and 64-column block: the three <dA_v[i], Z_v[i]> parts (fixed-order reduction over the blocks afterwards)
+    const float *z;
+    int64_t ldz, M;
+    int F_in;
+    float *partial;      // [gridDim.y][3][M]
+    __device__ __forceinline__ void operator()(const float (&acc)[4], int64_t r, int c0, int) const {
+        float dot[3] = {0.f, 0.f, 0.f};
+        if (r < M) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < 3 * F_in) {
+                    const float p = acc[j] * z[r * ldz + c];
+                    const int v = c / F_in;
+                    dot[0] += v == 0 ? p : 0.f;
+                    dot[1] += v == 1 ? p : 0.f;
+                    dot[2] += v == 2 ? p : 0.f;
+                }
+            }
+        }
+        // the 16 threads that share a row of the tile are 16 consecutive lanes (tid = tm * 16 + tn)
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int s = 8; s > 0; s >>= 1) dot[v] += __shfl_xor_sync(0xffffffffu, dot[v], s);
+        if ((threadIdx.x & 15) == 0 && r < M) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) partial[((int64_t)blockIdx.y * 3 + v) * M + r] = dot[v];
+        }
+    }
+};
+
+// dgate[v][r] = sum over column blocks of partial + <dY[r], W_ext[k_data + v]>   (one warp per row, fixed order)
+__global__ void __launch_bounds__(256) gate_dot_reduce_kernel(const float *__restrict__ partial, int blocks, const float *__restrict__ dy,
+                                                              int64_t lddy, const float *__restrict__ w_ext, int64_t M, int F_out,
+                                                              int k_data, float *__restrict__ dgate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps) {
+        float dot[3] = {0.f, 0.f, 0.f};
+        for (int f = lane; f < F_out; f += 32) {
+            const float d = dy[r * lddy + f];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) dot[v] = fmaf(d, w_ext[(int64_t)(k_data + v) * F_out + f], dot[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) dot[v] += __shfl_xor_sync(0xffffffffu, dot[v], s);
+            if (lane == 0) {
+                float acc = 0.f;
+                for (int b = 0; b < blocks; ++b) acc += partial[((int64_t)b * 3 + v) * M + r];
+                dgate[(int64_t)v * M + r] = acc + dot[v];
+            }
+        }
+    }
+}
+
 template <int BM_, class OpA, class OpB, class Epi>
 __global__ void __launch_bounds__(256) gemm_kernel(OpA opa, OpB opb, Epi epi, int64_t k_total, int64_t k_per_z) {
     constexpr int TM = BM_ / 16;
@@ -501,5 +712,118 @@ extern "C" int pg_l2_normalize_rows(const float *d_h, int64_t ldh, int64_t num_r
     PG_CHECK_ARG(d_h && d_out, "pg_l2_normalize_rows: null buffer");
     l2_normalize_kernel<<<grid_for(num_rows * 32), 256, 0, pg_cu(stream)>>>(d_h, ldh, num_rows, F, eps, d_out, ldout);
     PG_CUDA_LAUNCH_CHECK("l2_normalize_kernel");
+    return PG_OK;
+}
+
+// ---- regrouped backward, SIMT path (same contracts as pg_layer_gate_grad_tc / pg_layer_gemm_bwd_dx_tc) ----
+extern "C" size_t pg_layer_gate_grad_ws_bytes(int64_t num_rows, int F_in, int F_out) {
+    (void)F_out;
+    return (size_t)pg_ceil_div(3 * (int64_t)F_in, BN) * 3 * (size_t)num_rows * sizeof(float) + 256;
+}
+
+extern "C" int pg_layer_gate_grad(const float *d_dy, int64_t lddy, const float *d_w_ext, const float *d_z, int64_t ldz,
+                                  int64_t num_rows, int F_in, int F_out, int has_res, float *d_dgate, void *d_ws, size_t ws_bytes,
+                                  pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 1 && F_out >= 1 && lddy >= F_out && ldz >= 3 * (int64_t)F_in, "pg_layer_gate_grad: bad shape");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_dy && d_w_ext && d_z && d_dgate && d_ws, "pg_layer_gate_grad: null buffer");
+    if (ws_bytes < pg_layer_gate_grad_ws_bytes(num_rows, F_in, F_out) - 256) {
+        pg_set_error("pg_layer_gate_grad: workspace too small (%zu bytes)", ws_bytes);
+        return PG_EWORKSPACE;
+    }
+    const int k_data = 3 * F_in + (has_res ? F_in : 0);
+    const int blocks = (int)pg_ceil_div(3 * (int64_t)F_in, BN);
+    const bool dy_vec = F_out % 4 == 0 && al16(d_dy) && lddy % 4 == 0;
+    const bool w_vec = F_out % 4 == 0 && al16(d_w_ext);
+    cudaStream_t st = pg_cu(stream);
+    OpA_Plain opa{d_dy, lddy, num_rows, F_out, dy_vec};
+    OpB_Trans opb{d_w_ext, F_out, 3 * F_in, F_out, w_vec};
+    Epi_GateDot epi{d_z, ldz, num_rows, F_in, (float *)d_ws};
+    int rc = launch_gemm(opa, opb, epi, num_rows, 3 * (int64_t)F_in, F_out, F_out, 1, st);
+    if (rc != PG_OK) return rc;
+    gate_dot_reduce_kernel<<<grid_for(num_rows * 32), 256, 0, st>>>((const float *)d_ws, blocks, d_dy, lddy, d_w_ext, num_rows, F_out, k_data,
+                                                                   d_dgate);
+    PG_CUDA_LAUNCH_CHECK("gate_dot_reduce_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_layer_gemm_bwd_dx(const float *d_t, int64_t ldt, const float *d_dy, int64_t lddy, const float *d_w_ext,
+                                    int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx, int64_t lddx,
+                                    pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && F_in >= 1 && F_out >= 1 && ldt >= 3 * (int64_t)F_out && lddy >= F_out && lddx >= F_in,
+                 "pg_layer_gemm_bwd_dx: bad shape");
+    PG_CHECK_ARG(!(has_res && add_identity) && (!add_identity || F_in == F_out), "pg_layer_gemm_bwd_dx: bad residual flags");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_t && d_dy && d_w_ext && d_dx, "pg_layer_gemm_bwd_dx: null buffer");
+    const int blocks = has_res ? 4 : 3;
+    const int k_total = blocks * F_out;
+    const bool a_vec = F_out % 4 == 0 && al16(d_t) && ldt % 4 == 0 && al16(d_dy) && lddy % 4 == 0;
+    const bool w_vec = F_out % 4 == 0 && al16(d_w_ext);
+    OpA_Cat2 opa{d_t, ldt, 3 * F_out, d_dy, lddy, k_total, num_rows, a_vec};
+    OpB_WextBlocksT opb{d_w_ext, F_in, F_out, blocks, w_vec};
+    Epi_Dx epi{d_dx, lddx, d_dy, lddy, num_rows, F_in, add_identity};
+    return launch_gemm(opa, opb, epi, num_rows, F_in, k_total, k_total, 1, pg_cu(stream));
+}
+
+// ---- plain Linear (decoder MLP, row f1): forward with fused bias + ReLU, both gradients, column sums (bias gradient) ----
+extern "C" int pg_linear_fwd(const float *d_x, int64_t ldx, int64_t num_rows, int K, const float *d_w, const float *d_bias, int C, int relu,
+                             float *d_out, int64_t ldo, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && K >= 1 && C >= 1 && ldx >= K && ldo >= C, "pg_linear_fwd: bad shape");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_x && d_w && d_out, "pg_linear_fwd: null buffer");
+    OpA_Plain opa{d_x, ldx, num_rows, K, K % 4 == 0 && al16(d_x) && ldx % 4 == 0};
+    OpB_Trans opb{d_w, K, C, K, K % 4 == 0 && al16(d_w)};
+    Epi_BiasAct epi{d_bias, d_out, ldo, num_rows, C, relu};
+    return launch_gemm(opa, opb, epi, num_rows, C, K, K, 1, pg_cu(stream));
+}
+
+extern "C" int pg_linear_bwd_data(const float *d_g, int64_t ldg, int64_t num_rows, int C, const float *d_w, int K, float *d_dx,
+                                  int64_t lddx, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && K >= 1 && C >= 1 && ldg >= C && lddx >= K, "pg_linear_bwd_data: bad shape");
+    if (num_rows == 0) return PG_OK;
+    PG_CHECK_ARG(d_g && d_w && d_dx, "pg_linear_bwd_data: null buffer");
+    OpA_Plain opa{d_g, ldg, num_rows, C, C % 4 == 0 && al16(d_g) && ldg % 4 == 0};
+    OpB_Rows opb{d_w, K, C, K, K % 4 == 0 && al16(d_w)};
+    Epi_BiasAct epi{nullptr, d_dx, lddx, num_rows, K, 0};
+    return launch_gemm(opa, opb, epi, num_rows, K, C, C, 1, pg_cu(stream));
+}
+
+extern "C" size_t pg_linear_bwd_weight_ws_bytes(int64_t num_rows, int C, int K) {
+    return (size_t)split_count(num_rows, C, K) * C * K * sizeof(float) + 256;
+}
+
+extern "C" int pg_linear_bwd_weight(const float *d_g, int64_t ldg, const float *d_x, int64_t ldx, int64_t num_rows, int C, int K,
+                                    float *d_dw, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && K >= 1 && C >= 1 && ldg >= C && ldx >= K, "pg_linear_bwd_weight: bad shape");
+    PG_CHECK_ARG(d_dw, "pg_linear_bwd_weight: null output");
+    cudaStream_t st = pg_cu(stream);
+    const int64_t numel = (int64_t)C * K;
+    if (num_rows == 0) {
+        PG_CUDA_CALL(cudaMemsetAsync(d_dw, 0, (size_t)numel * sizeof(float), st));
+        return PG_OK;
+    }
+    PG_CHECK_ARG(d_g && d_x && d_ws, "pg_linear_bwd_weight: null buffer");
+    const int splits = split_count(num_rows, C, K);
+    if (ws_bytes < (size_t)splits * numel * sizeof(float)) {
+        pg_set_error("pg_linear_bwd_weight: workspace too small (%zu < %zu)", ws_bytes, (size_t)splits * numel * sizeof(float));
+        return PG_EWORKSPACE;
+    }
+    int64_t rows_per_split = pg_ceil_div(num_rows, splits);
+    rows_per_split = pg_ceil_div(rows_per_split, BK) * BK;
+    OpA_PlainT opa{d_g, ldg, num_rows, C, C % 4 == 0 && al16(d_g) && ldg % 4 == 0};
+    OpB_Rows opb{d_x, ldx, num_rows, K, K % 4 == 0 && al16(d_x) && ldx % 4 == 0};
+    Epi_Partial epi{(float *)d_ws, C, K};
+    int rc = launch_gemm(opa, opb, epi, C, K, num_rows, rows_per_split, splits, st);
+    if (rc != PG_OK) return rc;
+    reduce_splits_kernel<<<grid_for(numel), 256, 0, st>>>((const float *)d_ws, splits, numel, d_dw);
+    PG_CUDA_LAUNCH_CHECK("reduce_splits_kernel");
+    return PG_OK;
+}
+
+extern "C" int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, pg_stream_t stream) {
+    PG_CHECK_ARG(num_rows >= 0 && C >= 1 && ldg >= C, "pg_colsum: bad shape");
+    PG_CHECK_ARG(d_out && (num_rows == 0 || d_g), "pg_colsum: null buffer");
+    colsum_kernel<<<(unsigned)pg_ceil_div(C, 32), 256, 0, pg_cu(stream)>>>(d_g, ldg, num_rows, C, d_out);
+    PG_CUDA_LAUNCH_CHECK("colsum_kernel");
     return PG_OK;
 }

@@ -18,9 +18,12 @@ once into [own rows | halo rows grouped by owner], the kernels read the two buff
 operand (`pg_spmm_operand`), and the entries of a row keep their CSR order, so a block's result is
 bitwise equal to the same rows of the single-GPU SpMM.
 
-The exchange is pipelined against the SpMM over FEATURE-COLUMN chunks: chunk k+1's rows are in flight
-on NCCL's stream while the kernel works on chunk k's columns (every output element is still summed in
-CSR order; the index arrays are re-read once per chunk: 16 B against >= 128 B of gathered features).
+Overlap.  In the layer's BACKWARD the exchange of dY is posted first and the weight-gradient and gate-gradient GEMMs
+(which need dY but no halo rows) run under it (`fanout_begin` / `fanout_finish`).  The forward has no independent work
+to put there; the kernels can process the features in COLUMN CHUNKS so that chunk k+1's rows are in flight while the
+SpMM works on chunk k (every output element is still summed in CSR order, `PGB200_EXCHANGE_CHUNKS`), but measured on
+2 x B200 (R-MAT 2^22 nodes, F = 128) two 64-wide passes cost 2.5 ms more than one 128-wide pass and only 1.2 ms of
+exchange is there to hide, so the default is ONE chunk; the chunked path stays for fabrics where the exchange dominates.
 
     forward   H_x = halo(X_local)                   Z_local = fan-out SpMM(rows of r, [X_local | H_x])
     backward  layer (symmetric matrices): dX = sum_v (A_v diag(g_v) dY) W_v^T -- the SAME exchange on the
@@ -75,7 +78,7 @@ def _reduce_scatter_rows(full: torch.Tensor, per: int, group) -> torch.Tensor:
 
 
 EXCHANGE_MODE = os.environ.get("PGB200_EXCHANGE", "halo")          # "halo" | "allgather"
-PIPELINE_CHUNKS = int(os.environ.get("PGB200_EXCHANGE_CHUNKS", "2"))  # feature-column chunks the exchange is pipelined over
+PIPELINE_CHUNKS = int(os.environ.get("PGB200_EXCHANGE_CHUNKS", "1"))  # feature-column chunks one exchange + SpMM is pipelined over (see module docstring: 1 = off)
 PIPELINE_MIN_BYTES = 8 << 20                                         # below this a single exchange is cheaper than several
 
 
@@ -166,37 +169,56 @@ def _feature_chunks(f: int, per: int, world: int) -> List[Tuple[int, int]]:
     return [(c0, min(w, f - c0)) for c0 in range(0, f, w)]
 
 
-def _halo_fanout(csr_ext: _Csr, halo: HaloExchange, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
-    """Z[per, nv f] = fan-out SpMM of this rank's rows over [x | halo rows of x], exchange pipelined over column chunks.
-    scales (backward of the gated layer): per-source-row gates; with scale_stride == 1 their halo values travel as one
-    extra 4-float chunk."""
+class _PendingFanout:
+    """A fan-out whose halo exchange has been posted (NCCL's stream) but whose SpMM has not been launched yet: whatever the
+    caller enqueues between `_halo_fanout_begin` and `_halo_fanout_finish` runs UNDER the exchange (the layer's backward puts
+    its weight-gradient and gate-gradient GEMMs there, which need dY but no halo rows)."""
+    __slots__ = ("csr_ext", "halo", "x", "f", "chunks", "posted", "mine", "s_halo", "s_work", "s_keep", "scales", "scale_stride")
+
+
+def _halo_fanout_begin(csr_ext: _Csr, halo: HaloExchange, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> _PendingFanout:
+    p = _PendingFanout()
+    p.csr_ext, p.halo, p.f, p.scales, p.scale_stride = csr_ext, halo, f, scales, scale_stride
+    p.x = x.contiguous()
+    per = halo.per
+    p.mine = p.s_halo = p.s_work = p.s_keep = None
+    if scales is not None and scale_stride == 1:     # per-node gates: the kernel scales by the SOURCE row -> the halo rows' gates travel too
+        p.mine = torch.zeros((per, 4), dtype=torch.float32, device=x.device)
+        for k, sc in enumerate(scales):
+            p.mine[:, k] = sc.reshape(-1)
+        p.s_halo, p.s_work, p.s_keep = halo.start(p.mine)
+    p.chunks = _feature_chunks(f, per, halo.world)
+    p.posted = [halo.start(p.x[:, c0:c0 + w]) for c0, w in p.chunks]       # all packs + exchanges are queued up front
+    return p
+
+
+def _halo_fanout_finish(p: _PendingFanout) -> torch.Tensor:
+    csr_ext, halo, x, f = p.csr_ext, p.halo, p.x, p.f
     per, nv = halo.per, len(csr_ext.vals)
-    x = x.contiguous()
     z = torch.empty((per, nv * f), dtype=torch.float32, device=x.device)
     v = csr_ext.vals + [None] * (3 - nv)
-    s_ptrs, s_stride, s_work, s_keep = (None, None, None), 0, None, None
-    if scales is not None:
-        if scale_stride == 1:
-            mine = torch.zeros((per, 4), dtype=torch.float32, device=x.device)
-            for k, sc in enumerate(scales):
-                mine[:, k] = sc.reshape(-1)
-            s_halo, s_work, s_keep = halo.start(mine)
+    s_ptrs, s_stride = (None, None, None), 0
+    if p.scales is not None:
+        if p.scale_stride == 1:
+            if p.s_work is not None:
+                p.s_work.wait()
+            s_ext = torch.cat([p.mine, p.s_halo], dim=0).reshape(-1)    # [(per + H) * 4]: gates of own rows, then of the halo rows
+            s_ptrs, s_stride = tuple(nat.ptr(s_ext[k:]) for k in range(3)), 4
         else:
-            s_ptrs, s_stride = tuple(nat.ptr(sc) for sc in scales), 0
-    chunks = _feature_chunks(f, per, halo.world)
-    posted = [halo.start(x[:, c0:c0 + w]) for c0, w in chunks]       # all packs + exchanges are queued up front
-    if s_work is not None:
-        s_work.wait()
-    if scales is not None and scale_stride == 1:
-        s_ext = torch.cat([mine, s_halo], dim=0).reshape(-1)           # [(per + H) * 4]: gates of own rows, then of the halo rows
-        s_ptrs, s_stride = tuple(nat.ptr(s_ext[k:]) for k in range(3)), 4
-    for (c0, w), (recv, work, _keep) in zip(chunks, posted):
+            s_ptrs, s_stride = tuple(nat.ptr(sc) for sc in p.scales), 0
+    for (c0, w), (recv, work, _keep) in zip(p.chunks, p.posted):
         if work is not None:
             work.wait()                                               # the compute stream waits for THIS chunk only
         nat.call("pg_spmm_fanout_split", nat.ptr(csr_ext.rowptr), nat.ptr(csr_ext.col), nat.ptr(v[0]), nat.ptr(v[1]), nat.ptr(v[2]), nv,
                  per, w, nat.spmm_operand(x[:, c0:c0 + w], recv, per), nat.ptr(z[:, c0:]), z.stride(0), 0, f,
                  s_ptrs[0], s_ptrs[1] if nv == 3 else None, s_ptrs[2] if nv == 3 else None, s_stride, csr_ext.plan(3 * f), nat.stream_ptr())
     return z
+
+
+def _halo_fanout(csr_ext: _Csr, halo: HaloExchange, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
+    """Z[per, nv f] = fan-out SpMM of this rank's rows over [x | halo rows of x].  scales (backward of the gated layer):
+    per-source-row gates; with scale_stride == 1 their halo values travel as one extra 4-float exchange."""
+    return _halo_fanout_finish(_halo_fanout_begin(csr_ext, halo, x, f, scales, scale_stride))
 
 
 def _halo_fanin(csr_ext: _Csr, halo: HaloExchange, dz: torch.Tensor, f: int, init: Optional[torch.Tensor]) -> torch.Tensor:
@@ -485,6 +507,17 @@ class PartitionedStructure:
     def _check(self, t: torch.Tensor):
         if t.shape[0] != self.per:
             raise ValueError(f"row-partitioned layers work on the padded block: expected {self.per} rows, got {t.shape[0]}")
+
+    def fanout_begin(self, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1):
+        """Post the exchange of a fan-out now, launch its SpMM later (`fanout_finish`): what is enqueued in between overlaps
+        with the NVLink transfer.  None when this structure exchanges by all-gather (nothing to split)."""
+        self._check(x)
+        if self.halo is None:
+            return None
+        return _halo_fanout_begin(self.local_ext, self.halo, x, f, scales, scale_stride)
+
+    def fanout_finish(self, pending) -> torch.Tensor:
+        return _halo_fanout_finish(pending)
 
     def fanout(self, x: torch.Tensor, f: int, scales=None, scale_stride: int = 1) -> torch.Tensor:
         self._check(x)

@@ -293,6 +293,8 @@ class _DirectGCNFused(torch.autograd.Function):
                      float(slope), nat.ptr(h), h.stride(0), nat.stream_ptr())
         ctx.save_for_backward(x, ga, gb, gc, w_ext, z, h)
         ctx.use_tc = use_tc
+        # the regrouped backward needs 128-bit rows on the tensor-core path; the SIMT kernels take any width
+        ctx.bwd_regrouped = (f_in % 4 == 0 and f_out % 4 == 0) if use_tc else True
         ctx.struct, ctx.has_res, ctx.add_identity, ctx.slope = struct, bool(has_res), bool(add_identity), float(slope)
         ctx.gate_stride, ctx.has_const = gate_stride, const_rows is not None
         return h
@@ -310,6 +312,11 @@ class _DirectGCNFused(torch.autograd.Function):
         else:
             dy = dh
         has_res = int(ctx.has_res)
+        fanout_bwd = ctx.bwd_regrouped and BWD_DX_MODE == "fanout"
+        # row-partitioned graphs: post the halo exchange of dY (and of the gates) NOW; the two GEMMs below run under it
+        pending = None
+        if fanout_bwd and ctx.needs_input_grad[0] and getattr(ctx.struct, "partitioned", False) and hasattr(ctx.struct, "fanout_begin"):
+            pending = ctx.struct.fanout_begin(dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride)
         # dW_ext = A_ext^T dY
         dw = torch.empty_like(w_ext)
         tc = "_tc" if ctx.use_tc and (n >= TC_BWD_WEIGHT_MIN_ROWS or TC_MODE == "force") else ""
@@ -318,23 +325,29 @@ class _DirectGCNFused(torch.autograd.Function):
                  nat.ptr(gc), ctx.gate_stride, nat.ptr(dy), dy.stride(0), n, f_in, f_out, has_res, nat.ptr(dw), nat.ptr(ws),
                  ws.numel(), st)
         dgate = torch.empty((3, n), dtype=torch.float32, device=x.device)
-        # dX = sum_v A_v^T (g_v * dY) W'_v^T: the gather runs over the SOURCE-grouped structure (== the forward structure only
-        # for value-symmetric matrices; shared-but-unsymmetric and unshared edge lists take their by_src CSRs)
-        fanout_bwd = ctx.use_tc and BWD_DX_MODE == "fanout" and f_in % 4 == 0 and f_out % 4 == 0
         if fanout_bwd:
             # gate gradients from the data-gradient GEMM with a dot-product epilogue (dZ is never written); the input gradient
-            # regrouped as dX = sum_v (A_v (g_v * dY)) W'_v^T (+ residual): the symmetric structure lets the fan-out kernel gather
-            # F_out-wide rows of dY once for all three matrices instead of the fan-in kernel gathering the 3 F_in-wide gated gradient
-            wsg = nat.workspace(nat.query("pg_layer_gate_grad_tc_ws_bytes", n, f_in, f_out), x.device)
-            nat.call("pg_layer_gate_grad_tc", nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), n, f_in, f_out, has_res,
+            # regrouped as dX = sum_v (A_v^T (g_v * dY)) W'_v^T (+ residual): the gather runs over the SOURCE-grouped structure
+            # (== the forward structure for value-symmetric matrices) and moves F_out-wide rows of dY once for all three matrices
+            # instead of the fan-in kernel gathering the 3 F_in-wide gated gradient.  Tensor-core and SIMT GEMMs alike.
+            t_ = "_tc" if ctx.use_tc else ""
+            wsg = nat.workspace(nat.query(f"pg_layer_gate_grad{t_}_ws_bytes", n, f_in, f_out), x.device)
+            nat.call(f"pg_layer_gate_grad{t_}", nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), nat.ptr(z), z.stride(0), n, f_in, f_out, has_res,
                      nat.ptr(dgate), nat.ptr(wsg), wsg.numel(), st)
             dx = None
             if ctx.needs_input_grad[0]:
-                t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride, transposed=True)
+                if pending is not None:
+                    t = ctx.struct.fanout_finish(pending)
+                else:
+                    t = _fanout(ctx.struct, dy, f_out, scales=(ga, gb, gc), scale_stride=ctx.gate_stride, transposed=True)
                 dx = torch.empty((n, f_in), dtype=torch.float32, device=x.device)
-                ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
-                nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
-                         has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), nat.ptr(ws3), ws3.numel(), st)
+                if ctx.use_tc:
+                    ws3 = nat.workspace(nat.query("pg_layer_gemm_bwd_dx_tc_ws_bytes", f_in, f_out, has_res), x.device)
+                    nat.call("pg_layer_gemm_bwd_dx_tc", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
+                             has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), nat.ptr(ws3), ws3.numel(), st)
+                else:
+                    nat.call("pg_layer_gemm_bwd_dx", nat.ptr(t), t.stride(0), nat.ptr(dy), dy.stride(0), nat.ptr(w_ext), n, f_in, f_out,
+                             has_res, int(ctx.add_identity), nat.ptr(dx), dx.stride(0), st)
             return _finish_backward(ctx, ga, dgate, dx, dw, dy)
         # dA = dY W_ext^T  -> dZ (gated), dXres, dgates
         dz = torch.empty_like(z)

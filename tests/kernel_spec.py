@@ -508,6 +508,18 @@ def pg_layer_gemm_bwd_dx_tc(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, ad
     dx.copy_(acc)
 
 
+def pg_layer_gate_grad_ws_bytes(n, f_in, f_out):
+    return 256
+
+
+def pg_layer_gate_grad(dy, lddy, w_ext, z, ldz, n, f_in, f_out, has_res, dgate, ws=None, ws_bytes=0, stream=None):
+    pg_layer_gate_grad_tc(dy, lddy, w_ext, z, ldz, n, f_in, f_out, has_res, dgate)
+
+
+def pg_layer_gemm_bwd_dx(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, add_identity, dx, lddx, stream=None):
+    pg_layer_gemm_bwd_dx_tc(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, add_identity, dx, lddx)
+
+
 def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):
     out.copy_(h / (torch.norm(h, p=2, dim=1, keepdim=True) + eps))
 

@@ -785,6 +785,36 @@ def test_layer_gemm_bwd_tensor_core_vs_spec(n, f_in, f_out, has_res, vec_gate):
     assert rel_err(dz.cpu().numpy(), dz2.cpu().numpy()) <= 2e-5 and rel_err(dw.cpu().numpy(), dw2.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("n,f_in,f_out,has_res,identity", [(1000, 64, 256, 1, 0), (777, 24, 40, 1, 0), (513, 16, 16, 0, 1), (300, 10, 12, 1, 0),
+                                                           (129, 12, 5, 1, 0), (2500, 128, 64, 1, 0), (4000, 64, 64, 0, 1), (70, 7, 3, 0, 0)])
+def test_layer_regrouped_backward_simt_vs_spec(n, f_in, f_out, has_res, identity):
+    """The two GEMMs of the regrouped backward on the SIMT fp32 path (pg_layer_gate_grad: data-gradient GEMM with the
+    dot-product epilogue; pg_layer_gemm_bwd_dx: [T | dY] @ [W'^T blocks; W_res^T] (+ dY)) against the fp64 spec, any width and
+    alignment (odd F_in / F_out take the scalar loaders)."""
+    g = torch.Generator().manual_seed(11 * n + f_in)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    z, dy, t = rnd(n, 3 * f_in), rnd(n, f_out), rnd(n, 3 * f_out)
+    k_ext = 3 * f_in + (f_in if has_res else 0) + 3 + (1 if has_res else 0)
+    w_ext = rnd(k_ext, f_out) * 0.2
+    D = lambda a: a.double()
+    dgate_ref = torch.empty(3, n, dtype=torch.float64)
+    spec.pg_layer_gate_grad_tc(D(dy), f_out, D(w_ext), D(z), 3 * f_in, n, f_in, f_out, has_res, dgate_ref)
+    dx_ref = torch.empty(n, f_in, dtype=torch.float64)
+    spec.pg_layer_gemm_bwd_dx_tc(D(t), 3 * f_out, D(dy), f_out, D(w_ext), n, f_in, f_out, has_res, identity, dx_ref, f_in)
+    d = lambda a: a.to(DEV).contiguous()
+    zd, dyd, td, wd = d(z), d(dy), d(t), d(w_ext)
+    st = nat.stream_ptr()
+    dgate = torch.full((3, n), float("nan"), device=DEV)
+    ws = _ws(nat.query("pg_layer_gate_grad_ws_bytes", n, f_in, f_out))
+    nat.call("pg_layer_gate_grad", nat.ptr(dyd), f_out, nat.ptr(wd), nat.ptr(zd), 3 * f_in, n, f_in, f_out, has_res, nat.ptr(dgate),
+             nat.ptr(ws), ws.numel(), st)
+    assert rel_err(dgate.cpu().numpy(), dgate_ref.numpy()) <= 5e-6
+    dx = torch.full((n, f_in), float("nan"), device=DEV)
+    nat.call("pg_layer_gemm_bwd_dx", nat.ptr(td), 3 * f_out, nat.ptr(dyd), f_out, nat.ptr(wd), n, f_in, f_out, has_res, identity,
+             nat.ptr(dx), f_in, st)
+    assert rel_err(dx.cpu().numpy(), dx_ref.numpy()) <= 5e-6
+
+
 @pytest.mark.parametrize("n,k,c,with_bias", [(8401, 32, 8401, True), (300, 4, 17, True), (1000, 64, 256, False), (129, 32, 1000, True)])
 def test_linear_tensor_core_vs_fp64(n, k, c, with_bias):
     """pg_linear_tc (decoder output layer, row f1): out = x W^T + b on tcgen05 with the 3 x TF32 split, odd class counts
@@ -823,8 +853,9 @@ def test_fused_loss_with_tensor_core_logits_matches_torch(monkeypatch):
         assert rel_err(a.cpu().numpy(), r.cpu().numpy()) <= 5e-5
 
 
-@pytest.mark.parametrize("dims,vec", [([32, 64, 48, 16], True), ([16, 16, 16], True), ([24, 32, 64], False)])
-def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec):
+@pytest.mark.parametrize("tc_mode", ["force", "off"])
+@pytest.mark.parametrize("dims,vec", [([32, 64, 48, 16], True), ([16, 16, 16], True), ([24, 32, 64], False), ([10, 14, 6], True)])
+def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec, tc_mode):
     """Backward on the tensor-core path: dX = sum_v (A_v (g_v * dY)) W_v^T via the scaled fan-out kernel + one GEMM must equal
     the fan-in formulation (gather of the gated 3 F_in-wide gradient) in every gradient: residual projection, identity
     residual, vector and scalar gates."""
@@ -834,7 +865,9 @@ def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec):
     symbols, d_rank = corpus.discover_alphabet(d_buf)
     graph = data_builder.build_level_graph(d_buf, 2, symbols, d_rank, 1e-9)
     n = graph.number_of_nodes
-    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    if tc_mode == "force" and any(d % 4 for d in dims):
+        pytest.skip("the tensor-core kernels take widths that are multiples of 4")
+    monkeypatch.setattr(model_mod, "TC_MODE", tc_mode)      # "off": the SIMT GEMMs of the same regrouping (F_out < 128 layers, any width)
     torch.manual_seed(3)
     x = torch.randn(n, dims[0], device=DEV, requires_grad=True)
     y = torch.randint(0, 5, (n,), device=DEV)
@@ -859,8 +892,9 @@ def test_input_gradient_through_fanout_matches_fanin(monkeypatch, dims, vec):
         assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("tc_mode", ["force", "off"])
 @pytest.mark.parametrize("shared", [True, False])
-def test_tensor_core_backward_on_unsymmetric_edge_lists(monkeypatch, shared):
+def test_tensor_core_backward_on_unsymmetric_edge_lists(monkeypatch, shared, tc_mode):
     """the regrouped input gradient gathers over the SOURCE-grouped structure.  A directed (unsymmetric)
     edge list reused for in / out / undirected (shared pattern, by_src != by_dst) and three different unsymmetric lists
     (benchmarker contract, gnn_benchmarker.py:297-305) must give the same gradients through the fan-out regrouping as through
@@ -876,7 +910,7 @@ def test_tensor_core_backward_on_unsymmetric_edge_lists(monkeypatch, shared):
         lists = [(ei, w), (ei, w * 0.5 + 0.2), (ei, 1.0 / (w + 1.0))]
     else:
         lists = [edges(6000), edges(5000), edges(7000)]
-    monkeypatch.setattr(model_mod, "TC_MODE", "force")
+    monkeypatch.setattr(model_mod, "TC_MODE", tc_mode)       # the SIMT GEMMs ("off") run the same regrouping
     x0 = torch.randn(n, dims[0], generator=g)
     y = torch.randint(0, 5, (n,), generator=g)
     torch.manual_seed(5)

@@ -339,8 +339,9 @@ def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch
     for use_vec in (True, False):
         g = load(fixture)
         outs = {}
-        for mode in ("off", "force"):
+        for mode, bwd in (("off", "fanin"), ("off", "fanout"), ("force", "fanout")):
             monkeypatch.setattr(model_mod, "TC_MODE", mode)
+            monkeypatch.setattr(model_mod, "BWD_DX_MODE", bwd)
             monkeypatch.setattr(kernel_spec, "pg_layer_gemm_fwd_tc_supported", lambda f_in, f_out: 1)
             torch.manual_seed(0)
             n = int(g["num_graph_nodes"])
@@ -357,13 +358,17 @@ def test_tensor_core_path_host_wiring_matches_simt_path(spec_native, monkeypatch
             logp, emb = model(data)
             (logp.sum() + (emb * emb).sum()).backward()
             monkeypatch.setattr(nat, "call", real_call)
-            outs[mode] = (logp.detach(), emb.detach(), data.x.grad.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, calls)
-        assert "pg_spmm_fanout_scaled" in outs["force"][4] and "pg_layer_gate_grad_tc" in outs["force"][4] and "pg_spmm_fanin" not in outs["force"][4]
-        assert "pg_spmm_fanin" in outs["off"][4] and "pg_layer_gemm_fwd_tc" not in outs["off"][4]
-        for a, b in zip(outs["off"][:3], outs["force"][:3]):
-            assert rel_err(b.numpy(), a.numpy()) <= 2e-5
-        for k, v in outs["off"][3].items():
-            assert rel_err(outs["force"][3][k].numpy(), v.numpy()) <= 5e-5, k
+            outs[(mode, bwd)] = (logp.detach(), emb.detach(), data.x.grad.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, calls)
+        legacy, simt, tc = outs[("off", "fanin")], outs[("off", "fanout")], outs[("force", "fanout")]
+        assert "pg_spmm_fanout_scaled" in tc[4] and "pg_layer_gate_grad_tc" in tc[4] and "pg_spmm_fanin" not in tc[4]
+        assert "pg_spmm_fanout_scaled" in simt[4] and "pg_layer_gate_grad" in simt[4] and "pg_layer_gemm_bwd_dx" in simt[4]
+        assert "pg_spmm_fanin" not in simt[4] and "pg_layer_gemm_fwd_tc" not in simt[4]
+        assert "pg_spmm_fanin" in legacy[4] and "pg_layer_gemm_bwd_data" in legacy[4]
+        for other in (simt, tc):
+            for a, b in zip(legacy[:3], other[:3]):
+                assert rel_err(b.numpy(), a.numpy()) <= 2e-5
+            for k, v in legacy[3].items():
+                assert rel_err(other[3][k].numpy(), v.numpy()) <= 5e-5, k
 
 
 def test_preregistered_structure_survives_cache_pressure(spec_native):
