@@ -1135,6 +1135,23 @@ def run_b200(args):
         "wall_ms_per_step": wall_step * 1e3,
         "per_step_ms": {"resident": step_ms_resident, "e2e": pipe.step_ms},
     }
+    # the concurrent host -> device bound of this box: every rank uploads its corpus bytes from its pinned buffer at the same time
+    # (what every e2e step must do); max over ranks.  e2e cannot beat it: on an 8-GPU node the ranks share the host's PCIe / memory system
+    try:
+        src = pipe.h_buf if torch.is_tensor(pipe.h_buf) else None
+        if src is not None and src.is_pinned():
+            dst = torch.empty(src.numel(), dtype=torch.uint8, device=dev)
+            def _up():
+                dst.copy_(src, non_blocking=True)
+            barrier()
+            bound_ms = _max_over_ranks(dist, dev, _time_ms(_up, 8, warm=2))
+            line["e2e"]["h2d_concurrent_bound"] = {"ms_per_upload": bound_ms, "gbs_per_gpu": src.numel() / (bound_ms * 1e-3) / 1e9,
+                                                   "gbs_aggregate": world * src.numel() / (bound_ms * 1e-3) / 1e9,
+                                                   "e2e_step_over_bound": e2e_ms / bound_ms,
+                                                   "note": "all ranks copy their step's corpus bytes pinned host -> HBM simultaneously, nothing else running"}
+            del dst
+    except Exception as exc:  # noqa: BLE001
+        line["e2e"]["h2d_concurrent_bound"] = {"error": repr(exc)}
     if count_ms:
         alg = pipe.nbytes
         # the same call timed alone (no DirectGCN replay of the previous batch sharing the SMs)

@@ -340,6 +340,23 @@ int pg_spmm_fanin_split(const int64_t *d_rowptr, const int32_t *d_col, const flo
 int pg_gather_rows(const float *d_src, int64_t ld_src, const int64_t *d_idx, int64_t count, int w, float *d_dst,
                    int64_t ld_dst, pg_stream_t stream);
 
+/* ---- halo exchange over NVLink peer memory (csrc/peer.cu; one process per GPU, one node) ------------------------------------
+ * pg_peer_alloc: device buffer (zeroed) + its 64-byte CUDA-IPC handle, which the host side all-gathers; pg_peer_open maps a
+ * peer's buffer into this process.  pg_halo_push: ONE kernel stores the rows d_src[d_idx[i], 0:w] that peer p asked for
+ * (rows h_row_begin[p] .. h_row_begin[p+1] of d_idx) into h_peer_dst[p] (row stride ld_dst) and, when all stores are fenced,
+ * writes `epoch` to h_peer_flag[p] for every peer (NULL = no flag: the rank itself).  pg_halo_wait: one CTA on the consumer's
+ * stream that returns once every peer's flag word in d_flags has reached `epoch`; it gives up after ~4 s and raises
+ * *d_error_flag (1 + peer) instead of hanging.  h_* arrays are HOST arrays of `world` (row_begin: world + 1) entries. */
+#define PG_MAX_PEERS 16
+int pg_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle64);
+int pg_peer_open(const unsigned char *handle64, void **d_ptr);
+int pg_peer_close(void *d_ptr);
+int pg_peer_free(void *d_ptr);
+int pg_halo_push(const float *d_src, int64_t ld_src, const int64_t *d_idx, const int64_t *h_row_begin, float *const *h_peer_dst,
+                 uint32_t *const *h_peer_flag, int world, int w, int64_t ld_dst, uint32_t epoch, unsigned int *d_done_counter,
+                 pg_stream_t stream);
+int pg_halo_wait(const uint32_t *d_flags, int world, int self, uint32_t epoch, int *d_error_flag, pg_stream_t stream);
+
 /* Fused dense transform of one DirectGCN layer (the collapsed algebra of SURVEY.md 7.2):
  *   A_ext[i, :] = [ a_i*Z_in[i] | b_i*Z_out[i] | c_i*Z_und[i] | X[i] (if has_res) | a_i b_i c_i | 1 (if has_res) ]
  *   Y = A_ext @ W_ext (+ X if add_identity) + constant[i]        W_ext: [K_ext x F_out] row-major
@@ -433,6 +450,14 @@ int pg_layer_gemm_bwd_dx(const float *d_t, int64_t ldt, const float *d_dy, int64
                          int64_t num_rows, int F_in, int F_out, int has_res, int add_identity, float *d_dx,
                          int64_t lddx, pg_stream_t stream);
 
+/* The two gradient GEMMs of the decoder's output layer in ONE pass over the N x C gradient matrix g that pg_softmax_nll leaves
+ * behind (row f1; reference protgram_directgcn.py:177-180 under autograd):  dd = scale * g @ W2 [C x K],  dW2 = scale * g^T @ d [N x K].
+ * K in {32, 64, 128} (pg_decoder_grads_supported); any N, C, row strides.  Fixed-order partial sums: bitwise reproducible. */
+int pg_decoder_grads_supported(int K);
+size_t pg_decoder_grads_ws_bytes(int64_t N, int C, int K);
+int pg_decoder_grads(const float *d_g, int64_t ldg, const float *d_d, int64_t ldd, const float *d_w2, int64_t N, int C, int K,
+                     float scale, float *d_dd, float *d_dw2, void *d_ws, size_t ws_bytes, pg_stream_t stream);
+
 /* Plain Linear layers on the SIMT fp32 mainloop (the decoder MLP, reference protgram_directgcn.py:173-180,219: row f1), torch.nn.Linear
  * layout W [C x K]:  out = act(x W^T + bias);  dx = g W;  dW = g^T x (rows split over CTAs, fixed-order reduction);  column sums of
  * g (the bias gradient).  Any shape / alignment. */
@@ -443,7 +468,8 @@ int pg_linear_bwd_data(const float *d_g, int64_t ldg, int64_t num_rows, int C, c
 size_t pg_linear_bwd_weight_ws_bytes(int64_t num_rows, int C, int K);
 int pg_linear_bwd_weight(const float *d_g, int64_t ldg, const float *d_x, int64_t ldx, int64_t num_rows, int C, int K, float *d_dw,
                          void *d_ws, size_t ws_bytes, pg_stream_t stream);
-int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, pg_stream_t stream);
+size_t pg_colsum_ws_bytes(int64_t num_rows, int C);
+int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, void *d_ws, size_t ws_bytes, pg_stream_t stream);
 
 /* Plain Linear on the same tensor-core kernel: out[N, C] = x[N, K] @ W[C, K]^T + bias (torch.nn.Linear layout, bias may be
  * NULL).  Used for the decoder's output layer (protgram_directgcn.py:177-180 with C = N classes, row f1).  K % 4 == 0,

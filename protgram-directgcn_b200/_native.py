@@ -78,6 +78,12 @@ _SIGS = {
     "pg_spmm_fanin_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, c_int,
                                     _P, _P]),
     "pg_gather_rows": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, _P]),
+    "pg_peer_alloc": (c_int, [c_size_t, _P, _P]),
+    "pg_peer_open": (c_int, [_P, _P]),
+    "pg_peer_close": (c_int, [_P]),
+    "pg_peer_free": (c_int, [_P]),
+    "pg_halo_push": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int64, c_uint32, _P, _P]),
+    "pg_halo_wait": (c_int, [_P, c_int, c_int, c_uint32, _P, _P]),
     "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
                               c_int64, c_int, _P, _P]),
     "pg_layer_gemm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int64, c_int64, c_int,
@@ -107,11 +113,15 @@ _SIGS = {
     "pg_layer_gate_grad_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "pg_layer_gate_grad": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pg_layer_gemm_bwd_dx": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "pg_decoder_grads_supported": (c_int, [c_int]),
+    "pg_decoder_grads_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "pg_decoder_grads": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "pg_linear_fwd": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, c_int, _P, c_int64, _P]),
     "pg_linear_bwd_data": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int, _P, c_int64, _P]),
     "pg_linear_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "pg_linear_bwd_weight": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, c_size_t, _P]),
-    "pg_colsum": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
+    "pg_colsum_ws_bytes": (c_size_t, [c_int64, c_int]),
+    "pg_colsum": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_size_t, _P]),
     "pg_linear_tc_ws_bytes": (c_size_t, [c_int, c_int]),
     "pg_linear_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),
     "pg_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
@@ -154,6 +164,37 @@ def spmm_operand(lo: torch.Tensor, hi: Optional[torch.Tensor], split: int):
                            hi.stride(0) if hi is not None and hi.numel() else 0, int(split))
     st._keep = (lo, hi)
     return ctypes.byref(st)
+
+
+class DeviceView:
+    """A device buffer that torch did not allocate (a CUDA-IPC receive slot), exposed through `__cuda_array_interface__` so that
+    `torch.as_tensor(view, device=...)` wraps it without a copy."""
+
+    def __init__(self, pointer: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(pointer), False),
+                                         "version": 2, "strides": None}
+
+
+def view_tensor(pointer: int, shape, device) -> torch.Tensor:
+    """fp32 tensor over raw device memory at `pointer` (kept alive by its owner, not by the tensor)."""
+    if int(shape[0]) == 0 or pointer == 0:
+        return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    return torch.as_tensor(DeviceView(pointer, shape), device=device)
+
+
+def peer_alloc(nbytes: int):
+    """-> (device pointer, 64-byte IPC handle as bytes) of a zeroed cudaMalloc'ed buffer peers can map (pg_peer_alloc)."""
+    ptr_out = c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    call("pg_peer_alloc", c_size_t(max(256, int(nbytes))), ctypes.byref(ptr_out), handle)
+    return int(ptr_out.value), bytes(handle)
+
+
+def peer_open(handle: bytes) -> int:
+    ptr_out = c_void_p()
+    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    call("pg_peer_open", buf, ctypes.byref(ptr_out))
+    return int(ptr_out.value)
 
 
 class SpmmPlanStruct(ctypes.Structure):
@@ -268,6 +309,13 @@ def call(name: str, *args):
 
 def query(name: str, *args) -> int:
     return int(getattr(load(), name)(*args))
+
+
+_CONSTS = {"PG_MAX_PEERS": 16}     # include/pgb200.h
+
+
+def query_const(name: str) -> int:
+    return _CONSTS[name]
 
 
 def kernel_launches() -> int:

@@ -264,21 +264,24 @@ struct Epi_BiasAct {  // out = act(acc + bias)
     }
 };
 
-// column sums of a row-major matrix in fixed order: one CTA per 32 columns, 8 row-strided partials per column combined by thread 0..31
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ g, int64_t ld, int64_t M, int ncols, float *__restrict__ out) {
+// column sums of a row-major matrix in fixed order: CTA (x, y) sums 32 columns over row slice y (8 row-strided partials per column
+// combined by the first warp), a second pass adds the slices in order
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ g, int64_t ld, int64_t M, int ncols, int64_t rows_per_slice,
+                                                     float *__restrict__ partial) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int slice = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(M, r0 + rows_per_slice);
     float acc = 0.f;
     if (c < ncols)
-        for (int64_t r = slice; r < M; r += 8) acc += g[r * ld + c];
+        for (int64_t r = r0 + slice; r < r1; r += 8) acc += g[r * ld + c];
     part[slice][threadIdx.x & 31] = acc;
     __syncthreads();
     if (slice == 0 && c < ncols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
-        out[c] = t;
+        partial[(int64_t)blockIdx.y * ncols + c] = t;
     }
 }
 
@@ -820,10 +823,29 @@ extern "C" int pg_linear_bwd_weight(const float *d_g, int64_t ldg, const float *
     return PG_OK;
 }
 
-extern "C" int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, pg_stream_t stream) {
+extern "C" size_t pg_colsum_ws_bytes(int64_t num_rows, int C) {
+    int64_t slices = pg_ceil_div(num_rows, 512);
+    if (slices > 256) slices = 256;
+    if (slices < 1) slices = 1;
+    return (size_t)slices * C * sizeof(float) + 256;
+}
+
+extern "C" int pg_colsum(const float *d_g, int64_t ldg, int64_t num_rows, int C, float *d_out, void *d_ws, size_t ws_bytes, pg_stream_t stream) {
     PG_CHECK_ARG(num_rows >= 0 && C >= 1 && ldg >= C, "pg_colsum: bad shape");
-    PG_CHECK_ARG(d_out && (num_rows == 0 || d_g), "pg_colsum: null buffer");
-    colsum_kernel<<<(unsigned)pg_ceil_div(C, 32), 256, 0, pg_cu(stream)>>>(d_g, ldg, num_rows, C, d_out);
+    PG_CHECK_ARG(d_out && d_ws && (num_rows == 0 || d_g), "pg_colsum: null buffer");
+    int64_t slices = pg_ceil_div(num_rows, 512);
+    if (slices > 256) slices = 256;
+    if (slices < 1) slices = 1;
+    if (ws_bytes < (size_t)slices * C * sizeof(float)) {
+        pg_set_error("pg_colsum: workspace too small (%zu bytes)", ws_bytes);
+        return PG_EWORKSPACE;
+    }
+    const int64_t rows_per_slice = pg_ceil_div(num_rows > 0 ? num_rows : 1, slices);
+    cudaStream_t st = pg_cu(stream);
+    const dim3 grid((unsigned)pg_ceil_div(C, 32), (unsigned)slices, 1);
+    colsum_kernel<<<grid, 256, 0, st>>>(d_g, ldg, num_rows, C, rows_per_slice, (float *)d_ws);
     PG_CUDA_LAUNCH_CHECK("colsum_kernel");
+    reduce_splits_kernel<<<grid_for(C), 256, 0, st>>>((const float *)d_ws, (int)slices, C, d_out);
+    PG_CUDA_LAUNCH_CHECK("reduce_splits_kernel");
     return PG_OK;
 }

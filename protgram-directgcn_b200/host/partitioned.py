@@ -143,9 +143,23 @@ class HaloExchange:
         return {"halo_rows": self.num_halo, "remote_rows": remote, "halo_fraction_of_remote_rows": self.num_halo / remote,
                 "rows_served_to_peers": self.num_serve}
 
+    def _peer_transport(self):
+        if getattr(self, "_transport", None) is None:
+            self._transport = False
+            if (HALO_TRANSPORT == "p2p" and self.world > 1 and dist.get_backend(self.group) == "nccl" and self.serve_idx.is_cuda):
+                self._transport = PeerMemoryTransport(self)
+        return self._transport or None
+
     def start(self, t: torch.Tensor, async_op: bool = True):
-        """t: [per, w] fp32 (any row stride).  Packs the rows the peers asked for and posts the all-to-all.
-        -> (halo buffer [num_halo, w], work handle or None, keep-alive)."""
+        """t: [per, w] fp32 (any row stride).  Moves the rows the peers asked for: the peer-memory push kernel on an NVLink
+        node (PeerMemoryTransport), else pack + all_to_all_single.  -> (halo buffer [num_halo, w], work handle or None, keep-alive)."""
+        tr = self._peer_transport()
+        if tr is not None and tr.fits(int(t.shape[1])):
+            recv, work, keep = tr.start(t)
+            if not async_op:
+                work.wait()
+                work = None
+            return recv, work, keep
         w = int(t.shape[1])
         send = torch.empty((self.num_serve, w), dtype=torch.float32, device=t.device)
         if self.num_serve:
@@ -158,6 +172,104 @@ class HaloExchange:
     def exchange(self, t: torch.Tensor) -> torch.Tensor:
         recv, _, _ = self.start(t, async_op=False)
         return recv
+
+
+HALO_TRANSPORT = os.environ.get("PGB200_HALO_TRANSPORT", "p2p")    # "p2p": peer-memory push kernel (NCCL groups on one node) | "nccl"
+
+
+class _ReadyWork:
+    """`work.wait()` of the peer-memory transport: enqueue the one-CTA wait kernel for this exchange's epoch on the current stream."""
+
+    def __init__(self, transport, epoch):
+        self.transport, self.epoch = transport, epoch
+
+    def wait(self):
+        t = self.transport
+        nat.call("pg_halo_wait", t.ctrl_ptr, t.world, t.rank, self.epoch, nat.ptr(t.err), nat.stream_ptr())
+
+
+class PeerMemoryTransport:
+    """The halo exchange as ONE kernel over NVLink peer memory (csrc/peer.cu) instead of pack + all_to_all_single.
+    Every rank owns, per exchanged width, a ring of RING receive slots that its peers map through CUDA IPC; `start` launches
+    pg_halo_push on a side stream (rows read straight out of the operand, stored into the peers' current slot, epoch flag
+    published when the stores are fenced) and returns the local slot as a tensor plus a handle whose `wait()` puts
+    pg_halo_wait in front of the consumer.  Setting it up is collective (IPC handles are all-gathered)."""
+
+    RING = 4
+    MAX_RING_BYTES = 40 << 30      # wider exchanges (the bare operator's 3F-wide gradient at C5 size) stay on all_to_all_single
+
+    def fits(self, w: int) -> bool:
+        """Same answer on every rank (decided from the all-gathered halo sizes): is the receive ring of this width affordable?"""
+        return self.RING * max(1, max(self.peer_halo_rows)) * int(w) * 4 <= self.MAX_RING_BYTES
+
+    def check(self):
+        """Raise if a wait kernel ever gave up (host sync)."""
+        code = int(self.err.item())
+        if code:
+            raise nat.NativeError(f"halo exchange: peer {code - 1} never published its epoch (pg_halo_wait gave up)")
+
+    def __init__(self, halo: "HaloExchange"):
+        self.halo, self.group, self.rank, self.world = halo, halo.group, halo.rank, halo.world
+        dev = halo.serve_idx.device
+        self.dev = dev
+        if self.world > nat.query_const("PG_MAX_PEERS"):
+            raise ValueError("peer-memory halo transport supports up to PG_MAX_PEERS ranks")
+        # who needs how many rows from whom: counts[p][q] = rows rank p receives from rank q
+        mine = torch.tensor(halo.need_splits, dtype=torch.int64, device=dev)
+        allc = torch.empty((self.world, self.world), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        counts = allc.tolist()
+        self.peer_halo_rows = [int(sum(counts[p])) for p in range(self.world)]
+        self.my_offset_on_peer = [int(sum(counts[p][:self.rank])) for p in range(self.world)]   # first row of MY rows in peer p's halo order
+        self.row_begin = [0]
+        for n_rows in halo.serve_splits:
+            self.row_begin.append(self.row_begin[-1] + int(n_rows))
+        # control block: one flag word per sender
+        self.ctrl_ptr, handle = nat.peer_alloc(256)
+        self.peer_ctrl = self._exchange_and_open(handle, self.ctrl_ptr)
+        self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 0
+        self.slots = {}
+        self.stream = torch.cuda.Stream(device=dev)
+        self._keep = []
+
+    def _exchange_and_open(self, handle: bytes, own_ptr: int):
+        h = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.dev)
+        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, h, group=self.group)
+        allh = allh.cpu().numpy()
+        return [own_ptr if p == self.rank else nat.peer_open(bytes(allh[p].tobytes())) for p in range(self.world)]
+
+    def _slots_for(self, w: int):
+        if w not in self.slots:      # collective: every rank meets the widths in the same order (same model, same calls)
+            rows = max(1, self.halo.num_halo)
+            local_ptr, handle = nat.peer_alloc(self.RING * rows * w * 4)
+            self.slots[w] = (local_ptr, self._exchange_and_open(handle, local_ptr))
+        return self.slots[w]
+
+    def start(self, t: torch.Tensor):
+        """t: [per, w] fp32.  -> (receive slot [num_halo, w] as a tensor, wait handle, keep-alive)."""
+        import ctypes
+        w = int(t.shape[1])
+        local_ptr, peer_ptrs = self._slots_for(w)
+        self.epoch += 1
+        if self.epoch % 256 == 0 and int(self.err.item()):
+            raise nat.NativeError(f"halo exchange: peer {int(self.err.item()) - 1} never published its epoch (pg_halo_wait gave up)")
+        slot = self.epoch % self.RING
+        P = ctypes.c_void_p
+        dst = (P * self.world)(*[P(peer_ptrs[p] + (slot * max(1, self.peer_halo_rows[p]) + self.my_offset_on_peer[p]) * w * 4)
+                                 if p != self.rank and self.halo.serve_splits[p] else P(None) for p in range(self.world)])
+        flag = (P * self.world)(*[P(self.peer_ctrl[p] + 4 * self.rank) if p != self.rank else P(None) for p in range(self.world)])
+        rb = (ctypes.c_int64 * (self.world + 1))(*self.row_begin)
+        cur = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(cur)                       # the operand is complete
+        with torch.cuda.stream(self.stream):
+            nat.call("pg_halo_push", nat.ptr(t), t.stride(0), nat.ptr(self.halo.serve_idx), rb, dst, flag, self.world, w, w, self.epoch,
+                     nat.ptr(self.done), nat.stream_ptr())
+        t.record_stream(self.stream)
+        recv = nat.view_tensor(local_ptr + slot * max(1, self.halo.num_halo) * w * 4, (self.halo.num_halo, w), self.dev)
+        return recv, _ReadyWork(self, self.epoch), t
 
 
 def _feature_chunks(f: int, per: int, world: int) -> List[Tuple[int, int]]:

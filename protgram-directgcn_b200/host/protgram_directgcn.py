@@ -243,6 +243,8 @@ import os as _os
 TC_MODE = _os.environ.get("PGB200_TC", "auto")
 TC_MIN_WIDTH, TC_MIN_ROWS = 128, 4096
 BWD_DX_MODE = _os.environ.get("PGB200_BWD_DX", "fanout")   # "fanin": gather the gated gradient (the SIMT path's way) also on the TC path
+DECODER_GRADS = _os.environ.get("PGB200_DECODER_GRADS", "auto")    # "auto" | "fused" | "simt" | "library" (see _LinearLogSoftmaxNLL.backward)
+DECODER_GRADS_FUSED_MAX_CLASSES = 1024
 TC_BWD_WEIGHT_MIN_ROWS = 65536   # the weight gradient splits the ROWS over CTAs: below this the SIMT kernel (more, smaller tiles) is faster
 
 
@@ -435,7 +437,10 @@ class _LinearLogSoftmaxNLL(torch.autograd.Function):
                      c, nat.ptr(buf), ld, nat.ptr(ws_tc), ws_tc.numel(), nat.stream_ptr())
             logits = buf[:, :c]
         else:
-            logits = torch.addmm(bias, d, weight.t()) if bias is not None else d @ weight.t()
+            d32, w32 = d.contiguous().float(), weight.contiguous().float()
+            logits = torch.empty((n, c), dtype=torch.float32, device=dev)
+            nat.call("pg_linear_fwd", nat.ptr(d32), d32.stride(0), n, k, nat.ptr(w32), nat.ptr(bias.contiguous().float()) if bias is not None else None,
+                     c, 0, nat.ptr(logits), logits.stride(0), nat.stream_ptr())
         # grad_scale is a host scalar of the C ABI: with every row counted (the trainer's case) it is 1/n and no
         # device->host read is needed; masked labels take the exact count from the device
         scale = 1.0 / max(n, 1)
@@ -455,13 +460,103 @@ class _LinearLogSoftmaxNLL(torch.autograd.Function):
     def backward(ctx, grad_out):
         d, weight, g, colsum = ctx.saved_tensors
         dd = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dd = (g @ weight).mul_(grad_out)
-        if ctx.needs_input_grad[1]:
-            dw = (g.t() @ d).mul_(grad_out)
+        n, k = d.shape
+        c = weight.shape[0]
+        dev = d.device
+        st = nat.stream_ptr()
+        need_dd, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if (need_dd or need_dw) and nat.query("pg_decoder_grads_supported", k) and (c <= DECODER_GRADS_FUSED_MAX_CLASSES or DECODER_GRADS == "fused") \
+                and DECODER_GRADS != "library":
+            # both gradient GEMMs in ONE pass over the N x C gradient matrix (csrc/decoder.cu: decoder_grads_kernel)
+            d32, w32 = d.contiguous().float(), weight.contiguous().float()
+            dd = torch.empty((n, k), dtype=torch.float32, device=dev)
+            dw = torch.empty((c, k), dtype=torch.float32, device=dev)
+            ws = nat.workspace(nat.query("pg_decoder_grads_ws_bytes", n, c, k), dev)
+            nat.call("pg_decoder_grads", nat.ptr(g), g.stride(0), nat.ptr(d32), d32.stride(0), nat.ptr(w32), n, c, k, 1.0, nat.ptr(dd),
+                     nat.ptr(dw), nat.ptr(ws), ws.numel(), st)
+            dd, dw = (dd.mul_(grad_out) if need_dd else None), (dw.mul_(grad_out) if need_dw else None)
+        elif DECODER_GRADS == "simt":
+            if need_dd:
+                dd = _linear_bwd_data(g, weight, c, k).mul_(grad_out)
+            if need_dw:
+                dw = _linear_bwd_weight(g, d, c, k).mul_(grad_out)
+        else:
+            # C = N classes (next_node task, 8401^2 at config C2) with K = 32: two tall-skinny reductions over the 282 MB gradient
+            # matrix.  Measured on B200 (profiles/r02_launches_c2_step.txt): library SGEMM pair 0.40 ms, decoder_grads_kernel<1>
+            # 0.89 ms (shared-memory bound at 0.37 LDS per FMA), generic SIMT mainloop ~0.8 ms (half of its 64-wide tile idle at
+            # K = 32) -- so this one shape stays on the library until the fused kernel is rebuilt on tensor cores.
+            if need_dd:
+                dd = (g @ weight).mul_(grad_out)
+            if need_dw:
+                dw = (g.t() @ d).mul_(grad_out)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum * grad_out
         return dd, dw, db, None, None
+
+
+def _linear_bwd_data(g: torch.Tensor, weight: torch.Tensor, c: int, k: int) -> torch.Tensor:
+    """dx [N, K] = g [N, C] @ W [C, K] (SIMT fp32 mainloop, csrc/gemm.cu)."""
+    n = g.shape[0]
+    w32 = weight.contiguous().float()
+    dx = torch.empty((n, k), dtype=torch.float32, device=g.device)
+    nat.call("pg_linear_bwd_data", nat.ptr(g), g.stride(0), n, c, nat.ptr(w32), k, nat.ptr(dx), dx.stride(0), nat.stream_ptr())
+    return dx
+
+
+def _linear_bwd_weight(g: torch.Tensor, x: torch.Tensor, c: int, k: int) -> torch.Tensor:
+    """dW [C, K] = g^T [C, N] @ x [N, K] (rows split over CTAs, fixed-order reduction)."""
+    n = g.shape[0]
+    x32 = x.contiguous().float()
+    dw = torch.empty((c, k), dtype=torch.float32, device=g.device)
+    ws = nat.workspace(nat.query("pg_linear_bwd_weight_ws_bytes", n, c, k), g.device)
+    nat.call("pg_linear_bwd_weight", nat.ptr(g), g.stride(0), nat.ptr(x32), x32.stride(0), n, c, k, nat.ptr(dw), nat.ptr(ws), ws.numel(),
+             nat.stream_ptr())
+    return dw
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b) through libpgb200 (the decoder MLP, reference :173-180): SIMT fp32 mainloop with bias / ReLU fused into the
+    epilogue, or the tcgen05 kernel for wide outputs; backward = two GEMMs + fixed-order column sums.  No library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        nat.check_tensor(x, "decoder input")
+        x32, w32 = x.contiguous().float(), weight.contiguous().float()
+        b32 = bias.contiguous().float() if bias is not None else None
+        n, k = x32.shape
+        c = w32.shape[0]
+        if (not relu and TC_MODE != "off" and k % 4 == 0 and (TC_MODE == "force" or (n >= TC_MIN_ROWS and c >= TC_MIN_WIDTH))):
+            ld = (c + 3) // 4 * 4
+            buf = torch.empty((n, ld), dtype=torch.float32, device=x.device)
+            ws_tc = nat.workspace(nat.query("pg_linear_tc_ws_bytes", k, c), x.device)
+            nat.call("pg_linear_tc", nat.ptr(x32), x32.stride(0), n, k, nat.ptr(w32), nat.ptr(b32), c, nat.ptr(buf), ld, nat.ptr(ws_tc),
+                     ws_tc.numel(), nat.stream_ptr())
+            out = buf[:, :c]
+        else:
+            out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            nat.call("pg_linear_fwd", nat.ptr(x32), x32.stride(0), n, k, nat.ptr(w32), nat.ptr(b32), c, int(relu), nat.ptr(out), out.stride(0),
+                     nat.stream_ptr())
+        ctx.save_for_backward(x32, w32, out if relu else None)
+        ctx.relu, ctx.has_bias = bool(relu), bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x32, w32, out = ctx.saved_tensors
+        n, k = x32.shape
+        c = w32.shape[0]
+        g = gout.float()
+        if ctx.relu:
+            g = g * (out > 0)
+        g = g.contiguous()
+        dx = _linear_bwd_data(g, w32, c, k) if ctx.needs_input_grad[0] else None
+        dw = _linear_bwd_weight(g, x32, c, k) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(c, dtype=torch.float32, device=g.device)
+            wsc = nat.workspace(nat.query("pg_colsum_ws_bytes", n, c), g.device)
+            nat.call("pg_colsum", nat.ptr(g), g.stride(0), n, c, nat.ptr(db), nat.ptr(wsc), wsc.numel(), nat.stream_ptr())
+        return dx, dw, db, None
 
 
 def linear_log_softmax_nll(d: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor,
@@ -638,17 +733,26 @@ class ProtGramDirectGCN(nn.Module):
             layers.append(h)
         return (h, layers) if return_layers else h
 
+    def _decoder_hidden(self, h: torch.Tensor) -> torch.Tensor:
+        """decoder_fc[0..2] of the reference (:173-176): Linear + ReLU (one kernel, fused epilogue) + Dropout(0.5)."""
+        first, drop = self.decoder_fc[0], self.decoder_fc[2]
+        return drop(_Linear.apply(h, first.weight, first.bias, True))
+
     def nll_loss(self, data, labels: torch.Tensor, has_ignored: bool = False) -> torch.Tensor:
         """`F.nll_loss(self(data)[0], labels)` of the reference trainer (protgram_directgcn_trainer.py:92-94)
         without materialising log_softmax: the decoder's output Linear, log_softmax and nll_loss (and their
         backward) run through the fused loss (row f1)."""
         h = self.embed(data)
-        d = self.decoder_fc[:-1](h)
+        d = self._decoder_hidden(h)
         last = self.decoder_fc[-1]
         return linear_log_softmax_nll(d, last.weight, last.bias, labels, has_ignored)
 
     def forward(self, data) -> Tuple[torch.Tensor, torch.Tensor]:
         h = self.embed(data)
-        task_logits = self.decoder_fc(h)
+        last = self.decoder_fc[-1]
+        # The reference's call pattern F.nll_loss(model(data)[0], y) needs the N x C log-probabilities as a tensor, so they are
+        # materialised here (the decoder GEMMs run through libpgb200, log_softmax is torch's elementwise kernel); `nll_loss()`
+        # above is the fused form that never writes them.
+        task_logits = _Linear.apply(self._decoder_hidden(h), last.weight, last.bias, False)
         emb = EmbeddingProcessor.l2_normalize_torch(h, eps=self.l2_eps)
         return F.log_softmax(task_logits, dim=-1), emb

@@ -388,6 +388,14 @@ def pg_spmm_fanin_split(rowptr, col, v0, v1, v2, nv, num_rows, F, g, g_off, g_vs
     y[:, :F] = acc
 
 
+def pg_halo_push(*a, **k):
+    raise NotImplementedError("peer-memory kernels have no CPU specification (GPU test only)")
+
+
+def pg_halo_wait(*a, **k):
+    raise NotImplementedError("peer-memory kernels have no CPU specification (GPU test only)")
+
+
 def pg_gather_rows(src, ld_src, idx, count, w, dst, ld_dst, stream=None):
     dst[:count, :w] = src[idx[:count].long(), :w]
 
@@ -518,6 +526,46 @@ def pg_layer_gate_grad(dy, lddy, w_ext, z, ldz, n, f_in, f_out, has_res, dgate, 
 
 def pg_layer_gemm_bwd_dx(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, add_identity, dx, lddx, stream=None):
     pg_layer_gemm_bwd_dx_tc(t, ldt, dy, lddy, w_ext, n, f_in, f_out, has_res, add_identity, dx, lddx)
+
+
+def pg_decoder_grads_supported(K):
+    return 1 if K in (32, 64, 128) else 0
+
+
+def pg_decoder_grads_ws_bytes(N, C, K):
+    return 256
+
+
+def pg_decoder_grads(g, ldg, d, ldd, w2, N, C, K, scale, dd, dw2, ws=None, ws_bytes=0, stream=None):
+    dd.copy_(scale * (g[:, :C] @ w2))
+    dw2.copy_(scale * (g[:, :C].t() @ d[:, :K]))
+
+
+def pg_linear_fwd(x, ldx, n, K, w, bias, C, relu, out, ldo, stream=None):
+    y = x[:, :K] @ w.t()
+    if bias is not None:
+        y = y + bias
+    out[:, :C] = torch.relu(y) if relu else y
+
+
+def pg_linear_bwd_data(g, ldg, n, C, w, K, dx, lddx, stream=None):
+    dx[:, :K] = g[:, :C] @ w
+
+
+def pg_linear_bwd_weight_ws_bytes(n, C, K):
+    return 256
+
+
+def pg_linear_bwd_weight(g, ldg, x, ldx, n, C, K, dw, ws=None, ws_bytes=0, stream=None):
+    dw.copy_(g[:, :C].t() @ x[:, :K])
+
+
+def pg_colsum_ws_bytes(n, C):
+    return 256
+
+
+def pg_colsum(g, ldg, n, C, out, ws=None, ws_bytes=0, stream=None):
+    out.copy_(g[:, :C].sum(0))
 
 
 def pg_l2_normalize_rows(h, ldh, n, F, eps, out, ldout, stream=None):

@@ -834,6 +834,92 @@ def test_linear_tensor_core_vs_fp64(n, k, c, with_bias):
     assert bool(torch.isnan(out[:, c:]).all())        # the padding columns are never written
 
 
+@pytest.mark.parametrize("n,c,k,ld", [(8401, 8401, 32, 8404), (300, 17, 32, 17), (1000, 21, 128, 24), (129, 1000, 64, 1000), (5000, 130, 32, 131)])
+def test_decoder_grads_fused_vs_fp64(n, c, k, ld):
+    """pg_decoder_grads (row f1): dd = g W2 and dW2 = g^T d in ONE pass over the N x C gradient matrix, against fp64 and bitwise
+    run to run (fixed-order partial sums); aligned and unaligned row strides, the C2 shape (8401^2, K = 32) included."""
+    gen = torch.Generator().manual_seed(n + c + k)
+    g = torch.randn(n, ld, generator=gen)
+    d, w2 = torch.randn(n, k, generator=gen), torch.randn(c, k, generator=gen) * 0.3
+    ref_dd = 0.5 * (g[:, :c].double() @ w2.double())
+    ref_dw = 0.5 * (g[:, :c].double().t() @ d.double())
+    gd, dd_, wd = g.to(DEV), d.to(DEV), w2.to(DEV)
+    assert nat.query("pg_decoder_grads_supported", k) == 1 and nat.query("pg_decoder_grads_supported", 48) == 0
+    ws = _ws(nat.query("pg_decoder_grads_ws_bytes", n, c, k))
+    outs = []
+    for _ in range(2):
+        dd = torch.full((n, k), float("nan"), device=DEV)
+        dw = torch.full((c, k), float("nan"), device=DEV)
+        nat.call("pg_decoder_grads", nat.ptr(gd), ld, nat.ptr(dd_), k, nat.ptr(wd), n, c, k, 0.5, nat.ptr(dd), nat.ptr(dw), nat.ptr(ws), ws.numel(),
+                 nat.stream_ptr())
+        outs.append((dd, dw))
+    assert rel_err(outs[0][0].cpu().numpy(), ref_dd.numpy()) <= 5e-6 and rel_err(outs[0][1].cpu().numpy(), ref_dw.numpy()) <= 5e-6
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("n,k,c,relu", [(8401, 64, 32, 1), (300, 5, 7, 0), (1000, 128, 21, 0), (4099, 32, 130, 1)])
+def test_linear_simt_kernels_vs_fp64(n, k, c, relu):
+    """pg_linear_fwd (bias + ReLU fused), pg_linear_bwd_data, pg_linear_bwd_weight, pg_colsum: the decoder MLP without library GEMMs."""
+    gen = torch.Generator().manual_seed(n + c + k)
+    x, w, b, g = torch.randn(n, k, generator=gen), torch.randn(c, k, generator=gen) * 0.3, torch.randn(c, generator=gen), torch.randn(n, c, generator=gen)
+    y_ref = x.double() @ w.double().t() + b.double()
+    if relu:
+        y_ref = torch.relu(y_ref)
+    xd, wd, bd, gd = (t.to(DEV) for t in (x, w, b, g))
+    st = nat.stream_ptr()
+    y = torch.full((n, c), float("nan"), device=DEV)
+    nat.call("pg_linear_fwd", nat.ptr(xd), k, n, k, nat.ptr(wd), nat.ptr(bd), c, relu, nat.ptr(y), c, st)
+    assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= 5e-6
+    dx = torch.full((n, k), float("nan"), device=DEV)
+    nat.call("pg_linear_bwd_data", nat.ptr(gd), c, n, c, nat.ptr(wd), k, nat.ptr(dx), k, st)
+    assert rel_err(dx.cpu().numpy(), (g.double() @ w.double()).numpy()) <= 5e-6
+    dw = torch.full((c, k), float("nan"), device=DEV)
+    ws = _ws(nat.query("pg_linear_bwd_weight_ws_bytes", n, c, k))
+    nat.call("pg_linear_bwd_weight", nat.ptr(gd), c, nat.ptr(xd), k, n, c, k, nat.ptr(dw), nat.ptr(ws), ws.numel(), st)
+    assert rel_err(dw.cpu().numpy(), (g.double().t() @ x.double()).numpy()) <= 5e-6
+    cs = torch.full((c,), float("nan"), device=DEV)
+    ws = _ws(nat.query("pg_colsum_ws_bytes", n, c))
+    nat.call("pg_colsum", nat.ptr(gd), c, n, c, nat.ptr(cs), nat.ptr(ws), ws.numel(), st)
+    assert rel_err(cs.cpu().numpy(), g.double().sum(0).numpy()) <= 5e-6
+
+
+def test_train_step_launches_no_library_gemm(monkeypatch):
+    """one training step of the C2-shaped model (fused loss path and the reference's F.nll_loss(model(data)[0], y)
+    pattern) CAN run every GEMM through libpgb200 -- with the fused decoder-gradient kernel selected the profiler sees no cuBLAS /
+    CUTLASS kernel.  (The default keeps the library pair for the C = N decoder gradients only, where it is 2x faster.)"""
+    from torch.profiler import ProfilerActivity, profile
+    from oracle import ngram_oracle
+    seqs = ngram_oracle.synth_sequences(0, 3000, 120)
+    d_buf = corpus.to_device(corpus.pack_sequences(seqs), DEV)
+    symbols, d_rank = corpus.discover_alphabet(d_buf)
+    graph = data_builder.build_level_graph(d_buf, 3, symbols, d_rank, 1e-9)
+    n = graph.number_of_nodes
+    torch.manual_seed(0)
+    model = pg.ProtGramDirectGCN([64, 256, 128, 64], n, n, 3, 0, 512, 0.5, True).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    data = graph.gcn_data(torch.randn(n, 64), DEV)
+    y = pg.generate_next_node_labels(graph)[0].to(DEV)
+
+    def step(fused):
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        loss = model.nll_loss(data, y) if fused else torch.nn.functional.nll_loss(model(data)[0], y)
+        loss.backward()
+        opt.step()
+
+    monkeypatch.setattr(model_mod, "DECODER_GRADS", "fused")     # C = N classes: "auto" keeps the library pair for this one shape (it is faster)
+    for fused in (True, False):
+        step(fused)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(fused)
+            torch.cuda.synchronize()
+        names = [e.key for e in prof.key_averages()]
+        lib = [k for k in names if any(t in k.lower() for t in ("cutlass", "cublas", "gemm", "sgemm")) and "tc_rows_gemm" not in k and "gemm_kernel" not in k]
+        assert not lib, (fused, lib)
+        assert any("gemm_kernel" in k or "tc_rows_gemm" in k for k in names)
+
+
 def test_fused_loss_with_tensor_core_logits_matches_torch(monkeypatch):
     """linear_log_softmax_nll with the output layer on tensor cores (forced) against torch's Linear + log_softmax + nll_loss:
     loss and all three gradients."""

@@ -195,8 +195,10 @@ def main():
         yl[: hi6 - lo6] = ym[lo6:hi6]
         (torch.nn.functional.nll_loss(logp_l, yl, reduction="sum") / N).backward()
         part.allreduce_replicated_grads(mine_m)
-        err = float((logp_l[: hi6 - lo6] - logp[lo6:hi6]).abs().max())
-        err = max(err, float((emb_l[: hi6 - lo6] - emb[lo6:hi6]).abs().max()))
+        # relative to the output's scale: a block below the tensor-core row threshold runs the SIMT GEMMs while the whole graph
+        # runs the 3 x TF32 ones (8 ranks: 1051 rows per block), so the two sides may differ by the kernels' own 2e-5, not bitwise
+        err = float((logp_l[: hi6 - lo6] - logp[lo6:hi6]).abs().max() / logp.abs().max())
+        err = max(err, float((emb_l[: hi6 - lo6] - emb[lo6:hi6]).abs().max() / emb.abs().max()))
         gerr = 0.0
         for (k, p_), (_, q_) in zip(whole.named_parameters(), mine_m.named_parameters()):
             if p_.grad is None:
@@ -206,9 +208,9 @@ def main():
             gerr = max(gerr, float((got - ref).abs().max()) / max(1e-12, float(ref.abs().max())))
         t = torch.tensor([err, gerr], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        assert float(t[0]) <= 2e-5 and float(t[1]) <= 1e-4, t.tolist()
+        assert float(t[0]) <= 1e-4 and float(t[1]) <= 1e-4, t.tolist()      # the north star's bar
         if rank == 0:
-            print(f"[ok] row-partitioned ProtGramDirectGCN {dims} over {world} GPUs == whole-graph model: outputs {float(t[0]):.1e} abs, "
+            print(f"[ok] row-partitioned ProtGramDirectGCN {dims} over {world} GPUs == whole-graph model: outputs {float(t[0]):.1e} rel, "
                   f"gradients {float(t[1]):.1e} rel (replicated parameters all-reduced, per-node parameters local)")
     except Exception as exc:  # noqa: BLE001
         print(f"[rank {rank}] partitioned-model section failed: {exc!r}")
