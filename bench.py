@@ -514,8 +514,10 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     out = {"graph": f"R-MAT 2^{log2_nodes} nodes ({world} x 2^{log2_nodes_per_gpu}, ids randomly relabelled), {e} directed edges before dedupe, pattern nnz {P}",
            "nodes": n, "F": F, "pattern_nnz": P, "rows_per_gpu": per, "partition": "1-D rows; block columns renumbered into [own rows | halo rows]",
            "local_nnz_max_over_mean": mx(float(p_local)) / (P / world),
-           "exchange": "halo: pg_gather_rows + NCCL all_to_all_single of the referenced rows, then the local SpMM over [own rows | halo rows] "
-                       f"({len(part._feature_chunks(F, per, world))} feature-column chunk(s))",
+           "exchange": ("halo, peer-memory transport: ONE kernel (pg_halo_push) stores the referenced rows into the peers' CUDA-IPC mapped receive "
+                        "slots over NVLink and publishes an epoch flag; pg_halo_wait in front of the SpMM" if halo._peer_transport() is not None else
+                        "halo, NCCL transport: pg_gather_rows + all_to_all_single of the referenced rows") +
+                       f", then the local SpMM over [own rows | halo rows] ({len(part._feature_chunks(F, per, world))} feature-column chunk(s))",
            "halo": {"rows_received_per_gpu_mean": int(tot[2]) / world, "rows_served_per_gpu_mean": int(tot[3]) / world,
                     "fraction_of_remote_rows": (int(tot[2]) / world) / max(1, n - per), "plan_build_s_once_per_graph": mx(plan_s)},
            "normalise_partitioned": norm_info}
