@@ -450,7 +450,7 @@ def spmm_large_leg(pipe, peak_gbs, log2_nodes=21, edges_per_node=16, F=128, iter
 
 
 def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_node=16, F=128, iters=5, compare_allgather=True,
-                         parity_rows=256):
+                         parity_rows=256, transport=None):
     """Config C5's shape: R-MAT graph with 2^log2_nodes_per_gpu nodes PER GPU, hidden 128, rows partitioned over the ranks
     (SURVEY 8e).  Every rank generates the seeded edge list, keeps the edges that start in its rows and gets its block of the
     propagation matrices from the row-partitioned normalisation (`normalise_partitioned`, timed, max over ranks).
@@ -468,6 +468,9 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     log2_nodes = log2_nodes_per_gpu + int(round(math.log2(world)))
     n, e, res, ms_norm = rmat_row_block(pipe, dist, log2_nodes, edges_per_node)
     group = dist.group.WORLD
+    saved_transport = part.HALO_TRANSPORT
+    if transport is not None:
+        part.HALO_TRANSPORT = transport
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     prop = part.RowPartitionedPropagation.from_local(part.local_csr(res), n, group=group, symmetric=True)
@@ -551,7 +554,7 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
     # the halo exchange of dY is posted before the weight- and gate-gradient GEMMs and waited for after them
     try:
         import protgram_directgcn_b200 as pg
-        data = part.partitioned_data(x_local, prop.local, n, group)
+        data = part.partitioned_data(x_local, prop.local, n, group, halo=prop.halo)
         st_obj = data.edge_index_in._pg_struct
         layer = pg.DirectGCNLayer(F, F, per, True).to(dev)
         edges = (data.edge_index_in, data.edge_weight_in, data.edge_index_out, data.edge_weight_out, data.edge_index_undirected_norm,
@@ -608,6 +611,11 @@ def spmm_partitioned_leg(pipe, peak_gbs, dist, log2_nodes_per_gpu=21, edges_per_
         out["parity"] = {"rows_sampled_per_rank": int(rows.numel()), "max_rel_err_vs_fp64_over_ranks": mx(worst), "bar": 1e-4}
         del x_full
     holder.clear()
+    tr = halo._peer_transport()
+    if tr is not None:
+        tr.check()
+    halo.close()                      # collective: the peer-memory receive rings are cudaMalloc'ed outside torch's allocator
+    part.HALO_TRANSPORT = saved_transport
     torch.cuda.empty_cache()
     return out
 
@@ -1035,7 +1043,9 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails alone must not leave the others in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("PGB200_NCCL_TIMEOUT_S", "150"))))
     pipe = B200Pipeline(rank, world, dev)
     pipe.use_cuda_graph = not args.no_cuda_graph
     pipe.pipelined = not args.no_pipeline
@@ -1233,7 +1243,9 @@ def run_b200(args):
         if world == 8 and not args.no_c5_full and args.large_log2_nodes < 23:
             torch.cuda.empty_cache()
             try:
-                leg = spmm_partitioned_leg(pipe, peak_gbs, dist, 23, iters=3, compare_allgather=False)
+                # NCCL transport here: at this size every byte of HBM headroom goes to the operands (the peer-memory ring of this
+                # width alone is 30 GB); the weak-scaled leg above runs the peer-memory transport
+                leg = spmm_partitioned_leg(pipe, peak_gbs, dist, 23, iters=3, compare_allgather=False, transport="nccl")
             except Exception as exc:  # noqa: BLE001
                 leg = {"error": repr(exc)}
             if rank == 0:

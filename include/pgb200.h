@@ -344,7 +344,8 @@ int pg_gather_rows(const float *d_src, int64_t ld_src, const int64_t *d_idx, int
  * pg_peer_alloc: device buffer (zeroed) + its 64-byte CUDA-IPC handle, which the host side all-gathers; pg_peer_open maps a
  * peer's buffer into this process.  pg_halo_push: ONE kernel stores the rows d_src[d_idx[i], 0:w] that peer p asked for
  * (rows h_row_begin[p] .. h_row_begin[p+1] of d_idx) into h_peer_dst[p] (row stride ld_dst) and, when all stores are fenced,
- * writes `epoch` to h_peer_flag[p] for every peer (NULL = no flag: the rank itself).  pg_halo_wait: one CTA on the consumer's
+ * writes `epoch` to h_peer_flag[p] for every peer (NULL = no flag: the rank itself); the work is ordered by peer self + 1,
+ * self + 2, ... so that the ranks never all store into the same GPU.  pg_halo_wait: one CTA on the consumer's
  * stream that returns once every peer's flag word in d_flags has reached `epoch`; it gives up after ~4 s and raises
  * *d_error_flag (1 + peer) instead of hanging.  h_* arrays are HOST arrays of `world` (row_begin: world + 1) entries. */
 #define PG_MAX_PEERS 16
@@ -353,8 +354,8 @@ int pg_peer_open(const unsigned char *handle64, void **d_ptr);
 int pg_peer_close(void *d_ptr);
 int pg_peer_free(void *d_ptr);
 int pg_halo_push(const float *d_src, int64_t ld_src, const int64_t *d_idx, const int64_t *h_row_begin, float *const *h_peer_dst,
-                 uint32_t *const *h_peer_flag, int world, int w, int64_t ld_dst, uint32_t epoch, unsigned int *d_done_counter,
-                 pg_stream_t stream);
+                 uint32_t *const *h_peer_flag, int world, int self, int w, int64_t ld_dst, uint32_t epoch,
+                 unsigned int *d_done_counter, pg_stream_t stream);
 int pg_halo_wait(const uint32_t *d_flags, int world, int self, uint32_t epoch, int *d_error_flag, pg_stream_t stream);
 
 /* Fused dense transform of one DirectGCN layer (the collapsed algebra of SURVEY.md 7.2):

@@ -82,7 +82,7 @@ _SIGS = {
     "pg_peer_open": (c_int, [_P, _P]),
     "pg_peer_close": (c_int, [_P]),
     "pg_peer_free": (c_int, [_P]),
-    "pg_halo_push": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int64, c_uint32, _P, _P]),
+    "pg_halo_push": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_uint32, _P, _P]),
     "pg_halo_wait": (c_int, [_P, c_int, c_int, c_uint32, _P, _P]),
     "pg_spmm_fanin": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P, c_int64, c_int64, _P, c_int64, _P,
                               c_int64, c_int, _P, _P]),

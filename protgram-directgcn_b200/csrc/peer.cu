@@ -16,7 +16,8 @@ struct PushArgs {
     float *dst[PG_MAX_PEERS];        // peer p: base of the slot region that receives THIS rank's rows (already offset)
     uint32_t *flag[PG_MAX_PEERS];    // peer p: the flag word this rank sets there
     int64_t row_begin[PG_MAX_PEERS + 1];   // rows [row_begin[p], row_begin[p+1]) of d_idx go to peer p
-    int world;
+    int64_t rot_begin[PG_MAX_PEERS + 1];   // the same row counts, prefix-summed in ROTATED peer order (self + 1, self + 2, ...)
+    int world, self;
 };
 
 // grid-stride over (row, float4) items; the last CTA to finish publishes the epoch to every peer
@@ -24,13 +25,19 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) halo_push_kernel(const float *__restrict__ src, int64_t ld_src, const int64_t *__restrict__ idx,
                                                         PushArgs a, int w, int64_t ld_dst, uint32_t epoch, unsigned int *done_counter) {
     const int per_row = VEC ? (w >> 2) : w;
-    const int64_t total = a.row_begin[a.world] * per_row;
+    const int64_t total = a.rot_begin[a.world] * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / per_row;
-        const int c = (int)(i - r * per_row);
-        int p = 0;
+        // work is laid out in rotated peer order: rank r's first CTAs write to peer r + 1, the next ones to r + 2, ... so that at any
+        // moment the ranks store into DIFFERENT peers (all ranks starting with peer 0 made one GPU's ingress the bottleneck:
+        // 247 GB/s per GPU at 8 ranks against 585 GB/s at 2)
+        const int64_t rr = i / per_row;
+        const int c = (int)(i - rr * per_row);
+        int q = 0;
 #pragma unroll
-        for (int q = 1; q < PG_MAX_PEERS; ++q) p += (q < a.world && r >= a.row_begin[q]) ? 1 : 0;
+        for (int t = 1; t < PG_MAX_PEERS; ++t) q += (t < a.world && rr >= a.rot_begin[t]) ? 1 : 0;
+        int p = a.self + 1 + q;
+        if (p >= a.world) p -= a.world;
+        const int64_t r = a.row_begin[p] + (rr - a.rot_begin[q]);
         const int64_t s = __ldg(idx + r);
         float *drow = a.dst[p] + (r - a.row_begin[p]) * ld_dst;
         if (VEC) reinterpret_cast<float4 *>(drow)[c] = __ldg(reinterpret_cast<const float4 *>(src + s * ld_src) + c);
@@ -98,9 +105,10 @@ extern "C" int pg_peer_free(void *d_ptr) {
 }
 
 extern "C" int pg_halo_push(const float *d_src, int64_t ld_src, const int64_t *d_idx, const int64_t *h_row_begin, float *const *h_peer_dst,
-                            uint32_t *const *h_peer_flag, int world, int w, int64_t ld_dst, uint32_t epoch, unsigned int *d_done_counter,
-                            pg_stream_t stream) {
-    PG_CHECK_ARG(world >= 1 && world <= PG_MAX_PEERS && w >= 1 && ld_src >= w && ld_dst >= w, "pg_halo_push: bad shape (world <= %d)", PG_MAX_PEERS);
+                            uint32_t *const *h_peer_flag, int world, int self, int w, int64_t ld_dst, uint32_t epoch,
+                            unsigned int *d_done_counter, pg_stream_t stream) {
+    PG_CHECK_ARG(world >= 1 && world <= PG_MAX_PEERS && self >= 0 && self < world && w >= 1 && ld_src >= w && ld_dst >= w,
+                 "pg_halo_push: bad shape (world <= %d)", PG_MAX_PEERS);
     PG_CHECK_ARG(h_row_begin && h_peer_dst && h_peer_flag && d_done_counter, "pg_halo_push: null argument");
     PushArgs a;
     a.world = world;
@@ -111,6 +119,12 @@ extern "C" int pg_halo_push(const float *d_src, int64_t ld_src, const int64_t *d
         if (p < world && a.dst[p] && (((uintptr_t)a.dst[p]) & 15) != 0) vec = false;
     }
     for (int p = 0; p <= PG_MAX_PEERS; ++p) a.row_begin[p] = h_row_begin[p < world ? p : world];
+    a.self = self;
+    a.rot_begin[0] = 0;
+    for (int q = 0; q < PG_MAX_PEERS; ++q) {
+        const int p = (self + 1 + q) % world;
+        a.rot_begin[q + 1] = a.rot_begin[q] + (q < world ? a.row_begin[p + 1] - a.row_begin[p] : 0);
+    }
     const int64_t rows = a.row_begin[world];
     PG_CHECK_ARG(rows >= 0 && (rows == 0 || (d_src && d_idx)), "pg_halo_push: null buffer");
     for (int p = 0; p < world; ++p)

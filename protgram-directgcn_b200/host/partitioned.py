@@ -138,6 +138,13 @@ class HaloExchange:
             raise ValueError("halo exchange: a peer asked for a row outside this rank's block")
         self.need = need
 
+    def close(self):
+        """Release the peer-memory transport's buffers (collective; a no-op for the NCCL transport)."""
+        tr = getattr(self, "_transport", None)
+        if tr:
+            tr.close()
+        self._transport = False
+
     def stats(self) -> dict:
         remote = max(1, self.n - (self.hi_row - self.lo))
         return {"halo_rows": self.num_halo, "remote_rows": remote, "halo_fraction_of_remote_rows": self.num_halo / remote,
@@ -154,7 +161,7 @@ class HaloExchange:
         """t: [per, w] fp32 (any row stride).  Moves the rows the peers asked for: the peer-memory push kernel on an NVLink
         node (PeerMemoryTransport), else pack + all_to_all_single.  -> (halo buffer [num_halo, w], work handle or None, keep-alive)."""
         tr = self._peer_transport()
-        if tr is not None and tr.fits(int(t.shape[1])):
+        if tr is not None and tr.fits(int(t.shape[1])) and tr._slots_for(int(t.shape[1])) is not None:
             recv, work, keep = tr.start(t)
             if not async_op:
                 work.wait()
@@ -242,11 +249,41 @@ class PeerMemoryTransport:
         return [own_ptr if p == self.rank else nat.peer_open(bytes(allh[p].tobytes())) for p in range(self.world)]
 
     def _slots_for(self, w: int):
-        if w not in self.slots:      # collective: every rank meets the widths in the same order (same model, same calls)
+        """Receive ring of one width; None when some rank could not allocate it (then EVERY rank uses all_to_all_single for this
+        width).  Collective: every rank meets the widths in the same order (same model, same calls)."""
+        if w not in self.slots:
             rows = max(1, self.halo.num_halo)
-            local_ptr, handle = nat.peer_alloc(self.RING * rows * w * 4)
-            self.slots[w] = (local_ptr, self._exchange_and_open(handle, local_ptr))
+            torch.cuda.empty_cache()                       # cudaMalloc competes with torch's cached blocks
+            local_ptr, handle = 0, bytes(64)
+            try:
+                local_ptr, handle = nat.peer_alloc(self.RING * rows * w * 4)
+            except nat.NativeError:
+                local_ptr = 0
+            ok = torch.tensor([1 if local_ptr else 0], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if local_ptr:
+                    nat.call("pg_peer_free", local_ptr)
+                self.slots[w] = None
+            else:
+                self.slots[w] = (local_ptr, self._exchange_and_open(handle, local_ptr))
         return self.slots[w]
+
+    def close(self):
+        """Collective teardown: unmap the peers' buffers, then free the own ones (no rank may still be exchanging)."""
+        if self.ctrl_ptr == 0:
+            return
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)
+        own = [self.ctrl_ptr] + [v[0] for v in self.slots.values() if v]
+        for ptrs in [self.peer_ctrl] + [v[1] for v in self.slots.values() if v]:
+            for p, ptr in enumerate(ptrs):
+                if p != self.rank:
+                    nat.call("pg_peer_close", ptr)
+        dist.barrier(group=self.group)
+        for ptr in own:
+            nat.call("pg_peer_free", ptr)
+        self.ctrl_ptr, self.slots = 0, {}
 
     def start(self, t: torch.Tensor):
         """t: [per, w] fp32.  -> (receive slot [num_halo, w] as a tensor, wait handle, keep-alive)."""
@@ -265,7 +302,7 @@ class PeerMemoryTransport:
         cur = torch.cuda.current_stream(self.dev)
         self.stream.wait_stream(cur)                       # the operand is complete
         with torch.cuda.stream(self.stream):
-            nat.call("pg_halo_push", nat.ptr(t), t.stride(0), nat.ptr(self.halo.serve_idx), rb, dst, flag, self.world, w, w, self.epoch,
+            nat.call("pg_halo_push", nat.ptr(t), t.stride(0), nat.ptr(self.halo.serve_idx), rb, dst, flag, self.world, self.rank, w, w, self.epoch,
                      nat.ptr(self.done), nat.stream_ptr())
         t.record_stream(self.stream)
         recv = nat.view_tensor(local_ptr + slot * max(1, self.halo.num_halo) * w * 4, (self.halo.num_halo, w), self.dev)
@@ -601,7 +638,7 @@ class PartitionedStructure:
     partitioned = True
     shared = True
 
-    def __init__(self, local: _Csr, n: int, group=None):
+    def __init__(self, local: _Csr, n: int, group=None, halo: Optional["HaloExchange"] = None):
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.n = n
@@ -613,7 +650,7 @@ class PartitionedStructure:
         self.nnz_total = 3 * int(local.col.numel())
         self.halo = self.local_ext = None
         if EXCHANGE_MODE == "halo":
-            self.halo = HaloExchange(local.col, n, self.group)
+            self.halo = halo if halo is not None else HaloExchange(local.col, n, self.group)   # an existing plan of the SAME block is shared
             self.local_ext = _Csr(local.rowptr, self.halo.col_ext, local.vals)
 
     def _check(self, t: torch.Tensor):
@@ -662,12 +699,12 @@ class PartitionedStructure:
         return _fanin_exchanged(self.local, dz.contiguous(), self.per, f, init, self.group)
 
 
-def partitioned_data(x_local: torch.Tensor, local: _Csr, n: int, group=None, **extra):
+def partitioned_data(x_local: torch.Tensor, local: _Csr, n: int, group=None, halo: Optional[HaloExchange] = None, **extra):
     """Data object for `ProtGramDirectGCN` on this rank's row block.  x_local: [hi - lo, F] (padded here to
     `per` rows); the model must be built with `num_graph_nodes = per` (`row_range(n, rank, world)[2]`).
     Outputs have `per` rows; rows past hi - lo are padding (mask them in the loss)."""
     from .protgram_directgcn import Data, register_structure
-    st = PartitionedStructure(local, n, group)
+    st = PartitionedStructure(local, n, group, halo=halo)
     x = x_local
     if x.shape[0] != st.per:
         x = torch.cat([x, torch.zeros((st.per - x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)], dim=0)

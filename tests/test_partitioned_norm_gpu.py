@@ -390,17 +390,20 @@ def test_partitioned_spmm_on_rmat_blocks_vs_oracle_sampled_rows(world, chunks):
     assert err(y_all[sample].cpu(), ref_y) <= 1e-4
 
 
-def test_halo_push_and_wait_kernels_two_emulated_ranks():
-    """csrc/peer.cu on ONE GPU: two ranks' buffers live in this process (plain pointers instead of CUDA-IPC mappings; the IPC
-    plumbing itself runs in tools/multigpu_check.py on real peers).  Rank 0 and rank 1 push the rows the other asked for into
-    the other's receive slot and publish the epoch; the wait kernels return at once (the pushes are earlier in stream order);
-    a wait for an epoch nobody publishes gives up after its bounded spin and raises the error word instead of hanging."""
+def test_halo_push_and_wait_kernels_emulated_ranks():
+    """csrc/peer.cu on ONE GPU: three ranks' buffers live in this process (plain pointers instead of CUDA-IPC mappings; the IPC
+    plumbing itself runs in tools/multigpu_check.py on real peers).  Every rank pushes the rows each other rank asked for into
+    that rank's receive slot (work in rotated peer order) and publishes the epoch; the wait kernels return at once (the pushes
+    are earlier in stream order); a wait for an epoch nobody publishes gives up after its bounded spin and raises the error
+    word instead of hanging."""
     import ctypes
-    per, w, world = 1000, 64, 2
+    per, w, world = 1000, 64, 3
     g = torch.Generator(device=DEV).manual_seed(0)
     x = [torch.randn(per, w, device=DEV, generator=g) for _ in range(world)]
-    serve = [torch.randint(0, per, (n_rows,), device=DEV, generator=g) for n_rows in (700, 300)]    # rows rank r sends to the other rank
-    recv = [torch.full((serve[1 - r].numel(), w), float("nan"), device=DEV) for r in range(world)]
+    counts = [[0, 700, 13], [300, 0, 0], [129, 511, 0]]                 # counts[r][p]: rows rank r sends to rank p
+    serve = [torch.randint(0, per, (sum(counts[r]),), device=DEV, generator=g) for r in range(world)]
+    off_on = [[sum(counts[q][p] for q in range(r)) for p in range(world)] for r in range(world)]    # rank r's first row in p's halo order
+    recv = [torch.full((sum(counts[q][p] for q in range(world)), w), float("nan"), device=DEV) for p in range(world)]
     flags = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
     done = torch.zeros(1, dtype=torch.int32, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
@@ -408,20 +411,24 @@ def test_halo_push_and_wait_kernels_two_emulated_ranks():
     P = ctypes.c_void_p
     for epoch in (1, 2):
         for r in range(world):
-            o = 1 - r
-            rb = (ctypes.c_int64 * (world + 1))(*([0, 0, serve[r].numel()] if o == 1 else [0, serve[r].numel(), serve[r].numel()]))
-            dst = (P * world)(*[P(recv[o].data_ptr()) if p == o else P(None) for p in range(world)])
-            flg = (P * world)(*[P(flags[o].data_ptr() + 4 * r) if p == o else P(None) for p in range(world)])
-            nat.call("pg_halo_push", nat.ptr(x[r]), w, nat.ptr(serve[r]), rb, dst, flg, world, w, w, epoch, nat.ptr(done), st)
+            begin = [0]
+            for p in range(world):
+                begin.append(begin[-1] + counts[r][p])
+            rb = (ctypes.c_int64 * (world + 1))(*begin)
+            dst = (P * world)(*[P(recv[p].data_ptr() + off_on[r][p] * w * 4) if counts[r][p] else P(None) for p in range(world)])
+            flg = (P * world)(*[P(flags[p].data_ptr() + 4 * r) if p != r else P(None) for p in range(world)])
+            nat.call("pg_halo_push", nat.ptr(x[r]), w, nat.ptr(serve[r]), rb, dst, flg, world, r, w, w, epoch, nat.ptr(done), st)
         for r in range(world):
             nat.call("pg_halo_wait", nat.ptr(flags[r]), world, r, epoch, nat.ptr(err), st)
         torch.cuda.synchronize()
-        for r in range(world):
-            assert torch.equal(recv[r], x[1 - r][serve[1 - r]]) and int(flags[r][1 - r]) == epoch
+        for p in range(world):
+            want = torch.cat([x[r][serve[r][sum(counts[r][:p]):sum(counts[r][:p + 1])]] for r in range(world)])
+            assert torch.equal(recv[p], want)
+            assert all(int(flags[p][r]) == epoch for r in range(world) if r != p)
         assert int(err) == 0 and int(done) == 0
         x = [t + 1.0 for t in x]
     import time
     t0 = time.time()
     nat.call("pg_halo_wait", nat.ptr(flags[0]), world, 0, 7, nat.ptr(err), st)     # nobody publishes epoch 7
     torch.cuda.synchronize()
-    assert int(err) == 2 and time.time() - t0 < 30.0                                # 1 + the peer that stayed silent
+    assert int(err) in (2, 3) and time.time() - t0 < 30.0                          # 1 + a peer that stayed silent

@@ -22,7 +22,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     import protgram_directgcn_b200 as pg
     from protgram_directgcn_b200 import _native as nat
     from protgram_directgcn_b200.host import corpus, data_builder
