@@ -725,6 +725,10 @@ def allreduce_replicated_grads(model: torch.nn.Module, group=None) -> None:
     each rank's backward only saw its rows.  The per-node parameters hold this rank's rows and stay local."""
     group = group if group is not None else dist.group.WORLD
     for name, p in model.named_parameters():
-        if p.grad is None or name.rsplit(".", 1)[-1] in PER_NODE_PARAMETERS:
+        if not p.requires_grad or name.rsplit(".", 1)[-1] in PER_NODE_PARAMETERS:
             continue
+        if p.grad is None:
+            # a parameter the loss did not reach on THIS rank (e.g. an all-padding block) still takes part: every rank must issue
+            # the same collectives in the same order (ADVICE r1)
+            p.grad = torch.zeros_like(p)
         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)

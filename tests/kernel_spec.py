@@ -541,6 +541,15 @@ def pg_decoder_grads(g, ldg, d, ldd, w2, N, C, K, scale, dd, dw2, ws=None, ws_by
     dw2.copy_(scale * (g[:, :C].t() @ d[:, :K]))
 
 
+def pg_linear_tc_ws_bytes(K, C):
+    return 256
+
+
+def pg_linear_tc(x, ldx, n, K, w, bias, C, out, ldo, ws=None, ws_bytes=0, stream=None):
+    y = x[:, :K] @ w.t()
+    out[:, :C] = y + bias if bias is not None else y
+
+
 def pg_linear_fwd(x, ldx, n, K, w, bias, C, relu, out, ldo, stream=None):
     y = x[:, :K] @ w.t()
     if bias is not None:
