@@ -90,7 +90,8 @@ def subgraph(subset, edge_index, edge_attr, num_nodes):
     """torch_geometric.utils.subgraph(subset, edge_index, edge_attr, relabel_nodes=True, num_nodes=N) restated from its
     published semantics (PyG is not installed here; call site protgram_directgcn_trainer.py:183-186): keep the edges
     whose two end points are in `subset`, in their original order, relabelled by node_idx[subset] = arange(len(subset)).
-    PARITY UNPINNED: torch_geometric (unpinned dependency of the reference, absent here) cannot be run to generate a fixture."""
+    PARITY PARTLY PINNED: torch_geometric (unpinned dependency of the reference, absent here) cannot be run to generate fixtures; the
+    restatement is held against the known answer of PyG's own docstring example (tests/test_next_rows_oracle.py), nothing more."""
     import numpy as np
     subset = np.asarray(subset, dtype=np.int64)
     edge_index = np.asarray(edge_index)

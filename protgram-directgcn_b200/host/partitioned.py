@@ -314,6 +314,8 @@ def _feature_chunks(f: int, per: int, world: int) -> List[Tuple[int, int]]:
     the kernels' 128-bit path)."""
     k = PIPELINE_CHUNKS if (world > 1 and f % 4 == 0 and per * f * 4 >= PIPELINE_MIN_BYTES) else 1
     k = max(1, min(k, f // 4))
+    if k == 1:
+        return [(0, f)]
     w = -(-(f // 4) // k) * 4
     return [(c0, min(w, f - c0)) for c0 in range(0, f, w)]
 

@@ -43,3 +43,20 @@ def test_feature_handoff_oracle_is_bit_exact_vs_reference_loop():
         prev = {str(s): i for i, s in enumerate(g[f"n{n - 1}_nodes"])}
         x = next_oracle.init_level_features(nodes, prev, g[f"n{n - 1}_emb"])
         assert np.array_equal(x, g[f"n{n}_x_init_ref"])
+
+
+def test_subgraph_oracle_matches_the_published_pyg_example():
+    """`torch_geometric.utils.subgraph` cannot run here (PyG is an unpinned, absent dependency of the reference), so the
+    restatement is held against the one known answer PyG itself publishes: the example of the function's docstring
+    (torch_geometric/utils/subgraph.py, `subgraph`): a path 0-1-...-6 stored in both directions, subset {3, 4, 5}
+    -> edges (3,4) (4,3) (4,5) (5,4) with attributes 7, 8, 9, 10; with relabel_nodes=True (what the reference's call site
+    protgram_directgcn_trainer.py:183-186 passes) the same edges renumbered 0..2.  A partial pin: one vector, not a fixture set."""
+    edge_index = np.array([[0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6],
+                           [1, 0, 2, 1, 3, 2, 4, 3, 5, 4, 6, 5]])
+    edge_attr = np.arange(1, 13, dtype=np.float32)
+    ei, ea = next_oracle.subgraph([3, 4, 5], edge_index, edge_attr, 7)
+    assert np.array_equal(ea, np.array([7, 8, 9, 10], dtype=np.float32))
+    assert np.array_equal(ei, np.array([[0, 1, 1, 2], [1, 0, 2, 1]]))          # relabelled: 3 -> 0, 4 -> 1, 5 -> 2
+    # a permuted subset relabels by POSITION in the subset (node_idx[subset] = arange), edge order stays the edge list's
+    ei2, ea2 = next_oracle.subgraph([5, 3, 4], edge_index, edge_attr, 7)
+    assert np.array_equal(ea2, ea) and np.array_equal(ei2, np.array([[1, 2, 2, 0], [2, 1, 0, 2]]))
