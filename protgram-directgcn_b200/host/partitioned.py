@@ -339,6 +339,9 @@ def _halo_fanout_begin(csr_ext: _Csr, halo: HaloExchange, x: torch.Tensor, f: in
             p.mine[:, k] = sc.reshape(-1)
         p.s_halo, p.s_work, p.s_keep = halo.start(p.mine)
     p.chunks = _feature_chunks(f, per, halo.world)
+    tr = halo._peer_transport()
+    if tr is not None and len(p.chunks) + (1 if p.mine is not None else 0) > tr.RING - 2:
+        p.chunks = [(0, f)]      # the receive ring holds two exchanges per consume phase safely (see PeerMemoryTransport); no deeper pipelining there
     p.posted = [halo.start(p.x[:, c0:c0 + w]) for c0, w in p.chunks]       # all packs + exchanges are queued up front
     return p
 
